@@ -1,0 +1,314 @@
+"""CPU oracle for the Normalisr association-testing hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a numpy restatement of the reference algorithm
+(lingfeiwang/normalisr v1.0.0, ``src/normalisr/association.py``, ``coex.py``,
+``de.py``).  It exists so that the CUDA path can be checked on a box where
+``/root/reference`` is absent.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
+product package ``normalisr_b200`` never does.
+
+Parity status: PINNED.  The reference ships no tests or golden vectors
+(SURVEY.md section 4), so the oracle is pinned against outputs of the reference
+itself, run in the authoring container by ``tests/golden/make_golden.py`` and
+committed as ``tests/golden/*.npz`` (``tests/test_oracle.py`` checks every one).
+
+Third-party arithmetic the reference calls and that is not under /root/reference:
+``numpy.matmul`` (BLAS dgemm), ``scipy.linalg.svd`` (LAPACK gesdd) and
+``scipy.stats.beta.cdf`` -> ``scipy.special.betainc`` (unpinned in setup.py:29;
+fixtures were made with numpy 2.3.5 / scipy 1.18.1).  matmul and svd are used
+as-is from numpy; the incomplete beta function is used from scipy when it is
+importable and otherwise (or with ``pvalue_backend='c'``) from the plain-C
+restatement of its published algorithm in ``oracle/betainc_cf.c``.
+
+All arrays follow the reference convention: float64, rows = variables
+(genes / groupings / covariates), columns = cells.
+"""
+import ctypes
+import itertools
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CLIB = None
+
+
+# --------------------------------------------------------------------------------------
+# P-value: regularised incomplete beta I_x(a, 1/2)       (association.py:249, 563)
+# --------------------------------------------------------------------------------------
+def _load_c():
+    global _CLIB
+    if _CLIB is None:
+        path = os.path.join(_HERE, "_build", "liboracle.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle C library missing: run `make -C oracle`")
+        lib = ctypes.CDLL(path)
+        lib.oracle_betainc_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                             ctypes.c_void_p, ctypes.c_int64]
+        lib.oracle_betainc_array.restype = None
+        _CLIB = lib
+    return _CLIB
+
+
+def beta_cdf(x, a, b=0.5, backend="auto"):
+    """``scipy.stats.beta.cdf(x, a, b)`` as the reference calls it
+    (association.py:249: ``beta.cdf(1 - R2, (n - 1 - dcr - dimreduce) / 2, 0.5)``).
+    ``a`` may be a scalar or an array broadcastable against ``x``."""
+    x = np.asarray(x, dtype=np.float64)
+    if backend == "auto":
+        try:
+            import scipy.special  # noqa: F401
+            backend = "scipy"
+        except Exception:  # pragma: no cover
+            backend = "c"
+    if backend == "scipy":
+        from scipy.special import betainc
+        xc = np.clip(x, 0.0, 1.0)           # beta.cdf is 0 below and 1 above the support
+        return betainc(a, b, xc)
+    lib = _load_c()
+    xa = np.ascontiguousarray(np.broadcast_to(x, np.broadcast(x, a).shape), dtype=np.float64)
+    aa = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), xa.shape))
+    out = np.empty_like(xa)
+    lib.oracle_betainc_array(xa.ctypes.data, aa.ctypes.data, float(b), out.ctypes.data, xa.size)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# inv_rank                                                (association.py:4-134)
+# --------------------------------------------------------------------------------------
+def pinv_rank(m, tol=1e-8, **unsupported):
+    """SVD pseudo-inverse and rank of a square matrix; singular values below
+    ``tol * s_max`` count as zero (association.py:66-80, the ``method='scipy'``
+    branch with mpc == 0, which is the only one the hot path reaches by default)."""
+    if unsupported.get("mpc", 0) or unsupported.get("method", "auto") not in ("auto", "scipy"):
+        raise NotImplementedError("oracle covers the exact-SVD branch of inv_rank only")
+    m = np.asarray(m, dtype=np.float64)
+    if m.ndim != 2 or m.shape[0] != m.shape[1]:
+        raise ValueError("Wrong shape for m.")
+    if tol <= 0:
+        raise ValueError("tol must be positive.")
+    u, s, vt = np.linalg.svd(m)
+    # number kept = n - #(s < tol*s0), exactly the searchsorted rule at :77
+    keep = m.shape[0] - int(np.searchsorted(s[::-1], tol * s[0]))
+    v = vt[:keep]
+    return (v.T / s[:keep]) @ v, keep      # symmetric input, so this equals the reference's .T
+
+
+# --------------------------------------------------------------------------------------
+# association_test_1 : one tile, single=0                 (association.py:137-260)
+# --------------------------------------------------------------------------------------
+def tile_single0(dx, dy, dc, dci, dcr, dimreduce=0, lowmem=True, pvalue_backend="auto"):
+    if dx.ndim != 2 or dy.ndim != 2 or dc.ndim != 2:
+        raise ValueError("Incorrect dx/dy/dc size.")
+    n = dx.shape[1]
+    if dy.shape[1] != n or dc.shape[1] != n:
+        raise ValueError("Unmatching dx/dy/dc dimensions.")
+    if n <= dcr + dimreduce + 1:
+        raise ValueError("Insufficient number of cells: must be greater than degrees of "
+                         "freedom removed + covariate + 1.")
+    rx, ry = dx, dy
+    if dcr > 0:                                            # :224-229
+        cx = (dci @ (dc @ dx.T)).T
+        cy = (dci @ (dc @ dy.T)).T
+        rx = dx - cx @ dc
+        ry = dy - cy @ dc
+    vx = np.mean(rx * rx, axis=1)                          # :230-233
+    vx[vx == 0] = 1
+    vy = np.mean(ry * ry, axis=1)
+    vy[vy == 0] = 1
+    gamma = (ry @ rx.T / (n * vx)).T                       # :234
+    r2 = (gamma * gamma) * vx[:, None] / vy[None, :]       # :235
+    if lowmem:
+        alpha = None
+    elif dcr > 0:                                          # :238-243  alpha = cy - gamma*cx
+        alpha = cy[None, :, :] - gamma[:, :, None] * cx[:, None, :]
+    else:
+        alpha = np.zeros((dx.shape[0], dy.shape[0], dc.shape[0]))
+    assert (r2 >= 0).all() and (r2 <= 1 + 1e-8).all()     # :248
+    pv = beta_cdf(1 - r2, (n - 1 - dcr - dimreduce) / 2, 0.5, backend=pvalue_backend)  # :249
+    return pv, gamma, alpha, vx, vy
+
+
+# --------------------------------------------------------------------------------------
+# association_test_4 : single=4 from Gram matrices        (association.py:421-576)
+# --------------------------------------------------------------------------------------
+def tile_single4(vx, prod, prody, prodyy, nx, nc, n, lenx, dimreduce=0, pvalue_backend="auto",
+                 **ka):
+    """dx != dy branch only (de never passes dy=None).  ``prod`` = A A^T with
+    A = [dx; dc], ``prody`` = A dy^T, ``prodyy`` = rowsum(dy^2)."""
+    ny = prody.shape[1]
+    m = nx + nc
+    pv = np.zeros((lenx, ny))
+    gam = np.zeros((lenx, ny))
+    varx = np.zeros(lenx)
+    vary = np.zeros((lenx, ny))
+    rank = np.zeros((lenx, ny), dtype=int)
+    for i in range(lenx):
+        x = vx + i
+        oth = [k for k in range(m) if k != x]              # :523
+        r = 0
+        if oth:
+            ginv, r = pinv_rank(prod[np.ix_(oth, oth)], **ka)   # :527-528
+        rank[i] = r
+        if r == 0:                                         # :532-536
+            dxx = prod[x, x] / n
+            dyy = prodyy / n
+            dxy = prody[x] / n
+        else:                                              # :537-544
+            cx = prod[x, oth] @ ginv
+            dxx = (prod[x, x] - cx @ prod[oth, x]) / n
+            cy = prody[oth].T @ ginv
+            dyy = (prodyy - np.sum(cy.T * prody[oth], axis=0)) / n
+            dxy = (prody[x] - cy @ prod[oth, x]) / n
+        if dxx == 0:                                       # :545-547
+            dxx = 1
+        varx[i] = dxx
+        vary[i] = dyy
+        gam[i] = dxy / dxx
+        pv[i] = dxy * dxy / (dxx * dyy)
+    assert (pv >= 0).all() and (pv <= 1 + 1e-8).all()      # :557
+    dof = n - 1 - rank - dimreduce
+    if (dof <= 0).any():
+        raise RuntimeError("Insufficient number of cells: must be greater than degrees of "
+                           "freedom removed + covariate + 1.")
+    pv = beta_cdf(1 - pv, dof / 2, 0.5, backend=pvalue_backend)   # :563
+    return pv, gam, varx, vary
+
+
+# --------------------------------------------------------------------------------------
+# _auto_batchsize / association_tests                     (association.py:731-1093)
+# --------------------------------------------------------------------------------------
+def _batch(bs, itemsize, nc, ns, cap, sizemax=2 ** 30):
+    if bs == 0:                                            # :743-746: two tiles <= 1 GiB
+        bs = min(int((sizemax - itemsize * nc * ns) // (2 * itemsize * ns)), cap)
+    return bs
+
+
+def _blocks(n, bs):
+    return [(s, min(s + bs, n)) for s in range(0, n, bs)]
+
+
+def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=True, single=0,
+                      bs4=500, pvalue_backend="auto", **ka):
+    """Driver: tiling, per-tile kernels, assembly, gamma<->dot conversion and (for
+    dy=None) symmetrisation.  ``nth`` > 1 maps tiles over a thread pool exactly like
+    the reference's ``autopooler(..., dummy=True)`` (parallel.py:49-71)."""
+    if single not in (0, 4):
+        raise ValueError("oracle covers single=0 and single=4 (the BASELINE configs)")
+    samexy = dy is None
+    if samexy:
+        dy = dx
+        if single == 4:
+            raise NotImplementedError("oracle: single=4 with dy=None is not on the hot path")
+    nx, ns = dx.shape
+    ny = dy.shape[0]
+    nc = dc.shape[0]
+    dimreduce = ka.pop("dimreduce", 0)
+    capx, capy = (500, 500) if single == 0 else (10, 500000)     # :854-875
+    bsx = _batch(bsx, dx.dtype.itemsize, nc, ns, capx)
+    bsy = bsx if samexy else _batch(bsy, dy.dtype.itemsize, nc, ns, capy)
+    tiles = list(itertools.product(_blocks(nx, bsx), _blocks(ny, bsy)))
+    if samexy:
+        tiles = [t for t in tiles if t[0][0] <= t[1][0]]            # :892-893
+
+    def pmap(fn, items):
+        if nth == 1:
+            return [fn(i) for i in items]
+        from multiprocessing.dummy import Pool
+        with Pool(nth if nth > 0 else os.cpu_count()) as p:
+            return p.map(fn, items)
+
+    P = np.ones((nx, ny))
+    coef = np.zeros((nx, ny))
+    alpha = None if lowmem else np.zeros((nx, ny, nc))
+    varx = None if samexy else np.zeros(nx)
+    if single == 0:
+        if nc > 0 and (dc != 0).any():                              # :899-903
+            dci, dcr = pinv_rank(dc @ dc.T)
+        else:
+            dci, dcr = None, 0
+        vary = np.zeros(ny)
+
+        def run(t):
+            (x0, x1), (y0, y1) = t
+            return t, tile_single0(dx[x0:x1], dy[y0:y1], dc, dci, dcr, dimreduce, lowmem,
+                                   pvalue_backend)
+        for ((x0, x1), (y0, y1)), (pv, g, al, vx, vy) in pmap(run, tiles):
+            P[x0:x1, y0:y1] = pv
+            coef[x0:x1, y0:y1] = g
+            if not lowmem:
+                alpha[x0:x1, y0:y1] = al
+            if not samexy:
+                varx[x0:x1] = vx
+            vary[y0:y1] = vy
+    else:
+        A = np.concatenate([dx, dc], axis=0)                        # :935
+        m = nx + nc
+        prod = np.zeros((m, m))
+        for (i0, i1), (j0, j1) in itertools.product(_blocks(m, bs4), _blocks(m, bs4)):
+            if i0 <= j0:                                            # :936-950
+                prod[i0:i1, j0:j1] = A[i0:i1] @ A[j0:j1].T
+        prod = np.triu(prod).T + np.triu(prod, 1)
+        prody = np.zeros((m, ny))
+        for (i0, i1), (j0, j1) in itertools.product(_blocks(m, bs4), _blocks(ny, bs4)):
+            prody[i0:i1, j0:j1] = A[i0:i1] @ dy[j0:j1].T            # :952-966
+        prodyy = (dy ** 2).sum(axis=1)                              # :968
+        vary = np.zeros((nx, ny))
+
+        def run4(t):
+            (x0, x1), (y0, y1) = t
+            return t, tile_single4(x0, prod, prody[:, y0:y1], prodyy[y0:y1], nx, nc, ns, x1 - x0,
+                                   dimreduce, pvalue_backend, **ka)
+        for ((x0, x1), (y0, y1)), (pv, g, vx, vy) in pmap(run4, tiles):
+            P[x0:x1, y0:y1] = pv
+            coef[x0:x1, y0:y1] = g
+            varx[x0:x1] = vx
+            vary[x0:x1, y0:y1] = vy
+    # gamma -> dot, symmetrise                                     :1036-1065
+    if samexy:
+        dot = coef * vary[:, None]            # row x times var of x (== vary for dy=dx)
+        P = np.triu(P, 1)
+        P = P + P.T
+        dot = np.triu(dot, 1)
+        dot = dot + dot.T
+        if not return_dot:
+            dot = dot / vary[:, None]
+        if not lowmem:
+            a = np.triu(alpha.transpose(2, 0, 1))
+            alpha = (a + a.transpose(0, 2, 1)).transpose(1, 2, 0)
+        coef = dot
+    elif return_dot:
+        coef = coef * varx[:, None]
+    return P, coef, alpha, varx, vary
+
+
+# --------------------------------------------------------------------------------------
+# coex / de                                                (coex.py:4-48, de.py:4-132)
+# --------------------------------------------------------------------------------------
+def coex(dt, dc, **ka):
+    """(P, dot, var) for all gene pairs (coex.py:46-48)."""
+    ans = association_tests(dt, None, dc, **ka)
+    return ans[0], ans[1], ans[4]
+
+
+def de(dg, dt, dc, bs=0, **ka):
+    """(P, gamma, alpha|None, varg, vart); constant groupings are dropped and
+    back-filled with P=1 / 0 (de.py:92-122)."""
+    dg0 = np.asarray(dg)
+    keep = np.array([len(np.unique(x)) > 1 for x in dg0], dtype=bool)
+    P, gam, alpha, vg, vt = association_tests(dg0[keep], dt, dc, bsx=bs, bsy=bs,
+                                              return_dot=False, **ka)
+    ng, nt, nc = dg0.shape[0], dt.shape[0], dc.shape[0]
+    Pf = np.ones((ng, nt), dtype=dt.dtype)
+    Pf[keep] = P
+    gf = np.zeros((ng, nt), dtype=dt.dtype)
+    gf[keep] = gam
+    af = None
+    if alpha is not None:
+        af = np.zeros((ng, nt, nc), dtype=dt.dtype)
+        af[keep] = alpha
+    vgf = np.zeros(ng, dtype=dt.dtype)
+    vgf[keep] = vg
+    vtf = np.zeros((ng, nt), dtype=dt.dtype)
+    vtf[keep] = vt                                  # (nt,) broadcasts for single=0 (:120-121)
+    return Pf, gf, af, vgf, vtf
