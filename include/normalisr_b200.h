@@ -1,0 +1,118 @@
+/* normalisr_b200 -- C ABI of the B200-native association-testing hot path.
+ *
+ * The reference (lingfeiwang/normalisr v1.0.0) is pure Python and has no FFI; these
+ * entry points are what a ctypes binding for its hot path binds instead of the numpy /
+ * scipy calls cited per function (paths relative to the reference tree).  The Python
+ * side that mirrors the reference's functional API (normalisr_b200/association.py)
+ * calls exactly these; INTEGRATION.md shows the stub a maintainer would add upstream.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless named host_*; matrices are row-major
+ *     with rows = variables (genes / groupings) and columns = cells, like the reference;
+ *   - `stream` is a cudaStream_t passed as an integer (0 = legacy default stream); calls
+ *     are asynchronous with respect to the host unless stated otherwise;
+ *   - every function returns 0 on success, non-zero on error, and nsr_last_error()
+ *     then returns a message (thread-local);
+ *   - a context is bound to one device and must not be used from two threads at once.
+ */
+#ifndef NORMALISR_B200_H
+#define NORMALISR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nsr_ctx nsr_ctx;
+
+#define NSR_VERSION 100          /* 0.1.0 */
+#define NSR_TILE 128             /* output tiles are NSR_TILE x NSR_TILE            */
+#define NSR_KBLOCK 128           /* cells are padded to a multiple of this          */
+#define NSR_MAX_SLICES 4
+#define NSR_MAX_RANK 64          /* covariate rank handled by the projection kernels */
+
+/* contraction modes */
+#define NSR_MODE_COEX 0   /* A == B, symmetric: both triangles written, diagonal = 0,
+                             out2 = dot = sum(res_i res_j)/n   (association.py:1036-1057) */
+#define NSR_MODE_DE 1     /* rectangular: out2 = gamma = dot / var_x (association.py:234)  */
+#define NSR_MODE_RAW 2    /* rectangular: out2 = sum(res_i res_j) (Gram tile, prod1,
+                             association.py:393-418); P is not written                    */
+#define NSR_MODE_COEX_UPPER 3 /* like COEX but only the listed tiles are written (no mirrored
+                             copy): a rank that owns a strip of tile rows produces the upper
+                             triangle of its strip; the full matrix is U + U^T            */
+/* contraction engines */
+#define NSR_ENGINE_UMMA 0 /* tcgen05 int8 tensor-core kernel (the product path)           */
+#define NSR_ENGINE_SIMT 1 /* dp4a CUDA-core kernel, bit-identical integer sums; used by the
+                             tests to cross-check the tensor-core kernel on device         */
+
+int nsr_version(void);
+const char* nsr_last_error(void);
+
+int nsr_ctx_create(int device, nsr_ctx** ctx);
+int nsr_ctx_destroy(nsr_ctx* ctx);
+
+/* Number of int8 bytes one slice plane of a rows x n matrix occupies, and the padded
+ * cell count (multiple of NSR_KBLOCK). */
+int64_t nsr_padded_cells(int64_t n);
+
+/* Residualise `rows` variables against an orthonormal covariate basis and quantise.
+ *
+ * Replaces association.py:226-233 (dx1 = dx - (dci (dc dx^T))^T dc; var = mean(dx1^2),
+ * 0 -> 1).  Qt is the (rank x n) orthonormal basis of the row space of dc that the host
+ * derives from the same SVD-with-tolerance rule as inv_rank (association.py:66-80), so
+ * X - (X Qt^T) Qt is the same projection.
+ *
+ * Outputs
+ *   var[rows]        mean squared residual, 0 replaced by 1 (reference rule)
+ *   coef[rows*rank]  X Qt^T, row-major (needed for alpha when lowmem=False)
+ *   slices           int8 [n_slices][rows_alloc][n_pad]: balanced base-256 digits of
+ *                    round(z' / quantum[row]), z' = residual after a sign-randomised
+ *                    128-point Walsh-Hadamard transform along cells (orthonormal, so
+ *                    all inner products are unchanged; it only flattens outliers so
+ *                    that a fixed-point row scale loses no precision)
+ *   quantum[rows]    z' ~= quantum * integer
+ * rows_alloc >= rows is the plane pitch in rows; bytes beyond `rows` are not touched.
+ */
+int nsr_residualize(nsr_ctx* ctx, uintptr_t stream,
+                    const double* X, int64_t rows, int64_t n, int64_t ldx,
+                    const double* Qt, int rank, int64_t ldq,
+                    int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
+                    double* quantum, double* var, double* coef);
+
+/* All-pairs contraction over cells + P-value epilogue for a list of output tiles.
+ *
+ * Replaces association.py:234-249 (gamma = res_y res_x^T / (n var_x); R2; P =
+ * beta.cdf(1-R2, dof/2, 1/2)) and, in NSR_MODE_COEX, the assembly at :1036-1057.
+ * A (rows_a) indexes output rows, B (rows_b) output columns.  tiles = n_tiles pairs
+ * (tile_row, tile_col) of NSR_TILE-sized blocks, host_tiles is a HOST pointer.
+ * dof_a = (n - 1 - rank - dimreduce) / 2.  Sums over cells are exact integer sums
+ * (int8 digits, int32 accumulation), combined in float64.
+ */
+int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
+                 const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
+                 const double* quantum_a, const double* var_a,
+                 const int8_t* b_slices, int64_t rows_b, int64_t rows_alloc_b,
+                 const double* quantum_b, const double* var_b,
+                 int64_t n, int64_t n_pad, int n_slices, int n_products,
+                 const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                 double* P, double* out2, int64_t ld);
+
+/* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
+ * association.py:249, 563.  `a` holds one value per row of row_len entries. */
+int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,
+               int64_t row_len, int64_t count, double* P);
+
+/* Test hooks: "hadamard" (0/1, default 1), "umma_kblock" (64 or 128 cells per pipeline
+ * stage of the tcgen05 kernel, default 128). Process-wide. */
+int nsr_set_option(const char* name, int value);
+
+/* Debug / test helper: reconstruct z' (float64, rows x n_pad) from slices and quantum. */
+int nsr_unslice(nsr_ctx* ctx, uintptr_t stream, const int8_t* slices, int64_t rows,
+                int64_t rows_alloc, int64_t n_pad, int n_slices, const double* quantum,
+                double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+"""ctypes binding of libnsr_b200.so (the C ABI declared in include/normalisr_b200.h).
+
+The product path has no CPU fallback: if the library is missing or the device is not a
+B200-class (sm_100) GPU, calls raise."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnsr_b200.so")
+
+MODE_COEX, MODE_DE, MODE_RAW, MODE_COEX_UPPER = 0, 1, 2, 3
+ENGINE_UMMA, ENGINE_SIMT = 0, 1
+TILE = 128
+KBLOCK = 128
+MAX_RANK = 64
+
+_lib = None
+
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_vp = ctypes.c_void_p
+c_dbl = ctypes.c_double
+c_up = ctypes.c_size_t           # uintptr_t
+
+_SIGNATURES = {
+    "nsr_version": (c_int, []),
+    "nsr_last_error": (ctypes.c_char_p, []),
+    "nsr_ctx_create": (c_int, [c_int, ctypes.POINTER(c_vp)]),
+    "nsr_ctx_destroy": (c_int, [c_vp]),
+    "nsr_padded_cells": (c_i64, [c_i64]),
+    "nsr_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "nsr_residualize": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp,
+                                c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "nsr_contract": (c_int, [c_vp, c_up, c_int, c_int,
+                             c_vp, c_i64, c_i64, c_vp, c_vp,
+                             c_vp, c_i64, c_i64, c_vp, c_vp,
+                             c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64]),
+    "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
+}
+
+
+class NsrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building it first if sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NsrError(
+            "normalisr_b200: %s is missing. Build it with `python -m normalisr_b200._build` "
+            "(needs nvcc; sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().nsr_last_error()
+        raise NsrError("%s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

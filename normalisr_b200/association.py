@@ -1,0 +1,229 @@
+"""Host-side mirror of ``normalisr.association`` for the hot path (reference
+``src/normalisr/association.py``).  Same names, argument order, return tuples and
+exceptions as the reference, with the numerics running on the GPU:
+
+    association_tests(dx, dy, dc, bsx, bsy, nth, lowmem, return_dot, single, bs4, **ka)
+
+Inputs may be numpy arrays (results come back as numpy arrays, like the reference) or CUDA
+tensors (results stay on the device).  ``bsx/bsy/bs4/nth`` are accepted and ignored: tiling
+and parallelism are the GPU's business (reference ``_auto_batchsize``, association.py:731-758).
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import MODE_COEX, MODE_DE, MODE_RAW, ENGINE_UMMA, MAX_RANK
+
+_ROW_CHUNK_BYTES = 1 << 30       # host->device staging granularity for numpy inputs
+
+
+# --------------------------------------------------------------------------------------
+# covariates: inv_rank(dc dc^T) -> orthonormal basis              (association.py:4-134, 899-903)
+# --------------------------------------------------------------------------------------
+def inv_rank(m, tol=1E-8, method='auto', logger=None, mpc=0, qr=0, **ka):
+    """Pseudo-inverse and rank by SVD with the reference's tolerance rule
+    (singular values < tol * largest are dropped, association.py:77).  Only the exact
+    branch (``method`` auto/scipy with ``mpc == 0``) is on the accelerated path."""
+    m = np.asarray(m, dtype=np.float64)
+    if m.ndim <= 1 or m.shape[-1] != m.shape[-2]:
+        raise ValueError('Wrong shape for m.')
+    if tol <= 0:
+        raise ValueError('tol must be positive.')
+    if qr < 0 or int(qr) != qr:
+        raise ValueError('qr must be non-negative integer.')
+    if method not in ('auto', 'scipy') or mpc != 0:
+        raise NotImplementedError('normalisr_b200 implements the exact SVD branch of inv_rank only '
+                                  '(method auto/scipy, mpc=0).')
+    if m.ndim > 2:
+        flat = m.reshape((-1,) + m.shape[-2:])
+        res = [inv_rank(x, tol=tol) for x in flat]
+        return (np.array([r[0] for r in res]).reshape(m.shape),
+                np.array([r[1] for r in res]).reshape(m.shape[:-2]))
+    u, s, vt = np.linalg.svd(m)
+    n2 = m.shape[0] - int(np.searchsorted(s[::-1], tol * s[0]))
+    v = vt[:n2]
+    return (v.T / s[:n2]) @ v, n2
+
+
+def covariate_basis(dc, tol=1e-8):
+    """Return (Qt, rank, W): Qt (rank, n) has orthonormal rows spanning the part of the row
+    space of ``dc`` that the reference keeps (eigenvalues of dc dc^T >= tol * largest), so that
+    x - Qt^T (Qt x) equals the reference projection x - dc^T dci dc x.  W (rank, n_cov) maps
+    basis coefficients back to covariate coefficients: c = W^T (Qt x)  (needed for alpha)."""
+    dc = np.asarray(dc, dtype=np.float64)
+    nc, n = dc.shape
+    if nc == 0 or not (dc != 0).any():          # association.py:899-903
+        return None, 0, np.zeros((0, nc))
+    gram = dc @ dc.T
+    _, s, vt = np.linalg.svd(gram)
+    rank = nc - int(np.searchsorted(s[::-1], tol * s[0]))
+    w0 = vt[:rank] / np.sqrt(s[:rank])[:, None]            # (rank, nc):  Q0 = w0 dc
+    q0 = w0 @ dc
+    # re-orthonormalise (removes the 1/sqrt(s) amplification of rounding error)
+    qf, rr = np.linalg.qr(q0.T)                            # q0^T = qf rr
+    W = np.linalg.solve(rr.T, w0)                          # Qt = rr^-T q0 = W dc
+    return np.ascontiguousarray(qf.T), rank, W
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+def _is_dev(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _as_host_f64(x):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.asarray(x)
+
+
+def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef):
+    """Residualise a (rows, n) matrix that lives on the host (numpy, staged in row chunks so the
+    copy of chunk i+1 overlaps the kernels of chunk i) or on the device."""
+    dev = ctx.device
+    if _is_dev(x):
+        xd = x.to(torch.float64)
+        if xd.stride(1) != 1:
+            xd = xd.contiguous()
+        return engine.residualize(ctx, xd, Qt_dev, n_slices, keep_coef=keep_coef)
+    xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    if xh.dtype != torch.float64:
+        xh = xh.to(torch.float64)
+    rows, n = xh.shape
+    out = engine.Sliced(rows, n, n_slices, dev)
+    chunk = max(1, min(rows, _ROW_CHUNK_BYTES // max(1, n * 8)))
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    bufs = [torch.empty((chunk, n), dtype=torch.float64, device=dev) for _ in range(2)]
+    done = [None, None]
+    for i, r0 in enumerate(range(0, rows, chunk)):
+        r1 = min(r0 + chunk, rows)
+        b = bufs[i & 1]
+        with torch.cuda.stream(copy_stream):
+            if done[i & 1] is not None:
+                copy_stream.wait_event(done[i & 1])      # buffer free again
+            b[:r1 - r0].copy_(xh[r0:r1], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=out, row_offset=r0,
+                           keep_coef=keep_coef)
+        done[i & 1] = torch.cuda.Event()
+        done[i & 1].record(main)
+    main.synchronize()          # staging buffers are released after this
+    return out
+
+
+def _out(t, to_host, host_buf=None):
+    if t is None or not to_host:
+        return t
+    if host_buf is not None:
+        host_buf.copy_(t, non_blocking=False)
+        return host_buf.numpy()
+    return t.cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------
+# association_tests                                              (association.py:761-1093)
+# --------------------------------------------------------------------------------------
+def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=True, single=0,
+                      bs4=500, **ka):
+    """Association tests between all pairs of rows of dx and dy (or within dx when
+    ``dy is None``) given covariates dc.  See the reference docstring
+    (association.py:772-843) for the model; returns ``(P, dot|gamma, alpha|None, varx|None,
+    vary)`` with the reference's shapes.
+
+    Extra keyword arguments understood here (all optional, none changes results beyond the
+    stated tolerance): ``precision`` in {'fast','default','precise'}, ``device``,
+    ``engine`` (tests only)."""
+    precision = ka.pop('precision', 'default')
+    device = ka.pop('device', None)
+    eng = ka.pop('engine', ENGINE_UMMA)
+    dimreduce = ka.pop('dimreduce', 0)
+    if single not in (0, 1, 4, 5):
+        raise ValueError('Unknown value single={}'.format(single))
+    if single in (1, 5):
+        raise NotImplementedError('normalisr_b200 accelerates single=0 and single=4; single={} is '
+                                  'outside the hot path (SURVEY.md 8f).'.format(single))
+    if np.ndim(dimreduce) != 0:
+        # the reference's scalar comparison at association.py:213 raises for arrays as well
+        raise ValueError('dimreduce must be a scalar.')
+    dimreduce = int(dimreduce)
+    samexy = dy is None
+    if len(dx.shape) != 2 or (not samexy and len(dy.shape) != 2) or len(dc.shape) != 2:
+        raise ValueError('Incorrect dx/dy/dc size.')
+    n = dx.shape[1]
+    if (not samexy and dy.shape[1] != n) or dc.shape[1] != n:
+        raise ValueError('Unmatching dx/dy/dc dimensions.')
+    if single == 4:
+        from .single4 import association_tests_single4
+        if samexy:
+            raise NotImplementedError('single=4 with dy=None is not on the accelerated path.')
+        return association_tests_single4(dx, dy, dc, lowmem=lowmem, return_dot=return_dot,
+                                         dimreduce=dimreduce, precision=precision, device=device,
+                                         engine=eng, **ka)
+    if ka:
+        raise TypeError("association_test_1() got an unexpected keyword argument '{}'".format(
+            next(iter(ka))))
+    to_host = not _is_dev(dx)
+    ctx = engine.context(device if device is not None else (dx.device if _is_dev(dx) else None))
+    n_slices, n_products = engine.PRESETS[precision]
+    nc = dc.shape[0]
+    if nc == 0:
+        logging.warning('No covariate dc input.')
+    Qt, rank, W = covariate_basis(_as_host_f64(dc))
+    if rank > MAX_RANK:
+        raise NotImplementedError('covariate rank {} > {}'.format(rank, MAX_RANK))
+    if n <= rank + dimreduce + 1:
+        raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
+                         'removed + covariate + 1.')
+    dof_a = (n - 1 - rank - dimreduce) / 2
+    with torch.cuda.device(ctx.device):
+        Qt_dev = torch.from_numpy(Qt).to(ctx.device) if rank else None
+        keep_coef = not lowmem
+        A = _residualize_any(ctx, dx, Qt_dev, n_slices, keep_coef)
+        B = A if samexy else _residualize_any(ctx, dy, Qt_dev, n_slices, keep_coef)
+        nx, ny = A.rows, B.rows
+        P = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+        out2 = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+        if samexy:
+            engine.contract(ctx, MODE_COEX, A, A, engine.coex_tiles(nx), dof_a, P, out2, n_products, eng)
+            gamma = None
+            if not (lowmem and return_dot):
+                gamma = out2 / A.var[:, None]
+        else:
+            engine.contract(ctx, MODE_DE, A, B, engine.rect_tiles(nx, ny), dof_a, P, out2,
+                            n_products, eng)
+            gamma = out2
+        alpha = None if lowmem else _alpha(A, B, gamma, W, rank, nc, samexy)
+        if samexy and not return_dot:                      # association.py:1058-1061
+            out2 = gamma
+        elif not samexy and return_dot:                    # association.py:1044-1048
+            out2 = gamma * A.var[:, None]
+        varx = None if samexy else A.var
+        res = (P, out2, alpha, varx, B.var)
+        if to_host:
+            torch.cuda.current_stream().synchronize()
+            res = tuple(_out(t, True) for t in res)
+    return res
+
+
+def _alpha(A, B, gamma, W, rank, nc, samexy):
+    """alpha[x, y, :] = c_y - gamma[x, y] c_x   (association.py:238-245); for dy=None the
+    reference keeps the upper triangle and mirrors it (association.py:1062-1065), which leaves
+    a zero diagonal because gamma[x, x] = 1 there."""
+    dev = A.var.device
+    nx, ny = A.rows, B.rows
+    if rank == 0:
+        return torch.zeros((nx, ny, nc), dtype=torch.float64, device=dev)
+    Wd = torch.from_numpy(W).to(dev)                        # (rank, nc)
+    cx = A.coef @ Wd
+    cy = B.coef @ Wd
+    al = cy[None, :, :] - gamma[:, :, None] * cx[:, None, :]
+    if samexy:
+        al = torch.triu(al.permute(2, 0, 1), 1)
+        al = (al + al.transpose(1, 2)).permute(1, 2, 0).contiguous()
+    return al

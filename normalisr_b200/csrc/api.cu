@@ -1,0 +1,176 @@
+// C ABI of normalisr_b200 (see include/normalisr_b200.h for the contract of each entry).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "epilogue.cuh"
+
+int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, const int8_t* b,
+                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep);
+int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
+                             int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
+                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep);
+extern int nsr_use_hadamard;
+extern int nsr_umma_kblock;
+
+static thread_local char g_err[1024] = "";
+
+void nsr_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int nsr_scratch(nsr_ctx* ctx, size_t bytes, void** out) {
+    if (bytes > ctx->scratch_bytes) {
+        // grow-only; a synchronising free is fine here (size changes are rare)
+        if (ctx->scratch) NSR_CHECK(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        size_t want = bytes + bytes / 4;
+        NSR_CHECK(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return 0;
+}
+
+extern "C" int nsr_version(void) { return NSR_VERSION; }
+extern "C" const char* nsr_last_error(void) { return g_err; }
+
+extern "C" int nsr_ctx_create(int device, nsr_ctx** out) {
+    NSR_REQUIRE(out != nullptr, "nsr_ctx_create: null output pointer");
+    int count = 0;
+    NSR_CHECK(cudaGetDeviceCount(&count));
+    NSR_REQUIRE(device >= 0 && device < count, "nsr_ctx_create: device %d of %d", device, count);
+    NSR_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NSR_CHECK(cudaGetDeviceProperties(&prop, device));
+    NSR_REQUIRE(prop.major == 10, "normalisr_b200 is built for sm_100a only; device %d is sm_%d%d (%s)",
+                device, prop.major, prop.minor, prop.name);
+    nsr_ctx* ctx = new nsr_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
+    ctx->encode_tiled = fn;
+    *out = ctx;
+    return 0;
+}
+
+extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->tiles_dev) cudaFree(ctx->tiles_dev);
+    delete ctx;
+    return 0;
+}
+
+// test hooks: "hadamard" (0/1), "umma_kblock" (64/128)
+extern "C" int nsr_set_option(const char* name, int value) {
+    if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "umma_kblock")) {
+        NSR_REQUIRE(value == 64 || value == 128, "umma_kblock must be 64 or 128");
+        nsr_umma_kblock = value;
+        return 0;
+    }
+    nsr_set_error("nsr_set_option: unknown option %s", name);
+    return 2;
+}
+
+extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
+                            const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
+                            const double* quantum_a, const double* var_a, const int8_t* b_slices,
+                            int64_t rows_b, int64_t rows_alloc_b, const double* quantum_b,
+                            const double* var_b, int64_t n, int64_t n_pad, int n_slices,
+                            int n_products, const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                            double* P, double* out2, int64_t ld) {
+    NSR_REQUIRE(ctx != nullptr, "nsr_contract: null context");
+    NSR_REQUIRE(mode == NSR_MODE_COEX || mode == NSR_MODE_DE || mode == NSR_MODE_RAW ||
+                    mode == NSR_MODE_COEX_UPPER,
+                "nsr_contract: unknown mode %d", mode);
+    NSR_REQUIRE(engine == NSR_ENGINE_UMMA || engine == NSR_ENGINE_SIMT, "nsr_contract: unknown engine %d", engine);
+    NSR_REQUIRE(rows_a > 0 && rows_b > 0 && n > 0 && n_pad == nsr_padded_cells(n),
+                "nsr_contract: bad shape rows_a=%lld rows_b=%lld n=%lld n_pad=%lld", (long long)rows_a,
+                (long long)rows_b, (long long)n, (long long)n_pad);
+    const bool sym = mode == NSR_MODE_COEX || mode == NSR_MODE_COEX_UPPER;
+    NSR_REQUIRE(ld >= rows_b && (!sym || rows_a == rows_b),
+                "nsr_contract: bad leading dimension %lld", (long long)ld);
+    const int wmax = nsr_wmax(n_slices, n_products);
+    NSR_REQUIRE(wmax > 0, "nsr_contract: unsupported (n_slices=%d, n_products=%d)", n_slices, n_products);
+    NSR_REQUIRE(mode == NSR_MODE_RAW || (P != nullptr && var_a != nullptr && var_b != nullptr && dof_a > 0.0),
+                "nsr_contract: P / var / dof missing");
+    NSR_REQUIRE(out2 != nullptr && quantum_a && quantum_b && a_slices && b_slices, "nsr_contract: null buffer");
+    NSR_REQUIRE(((uintptr_t)a_slices & 15) == 0 && ((uintptr_t)b_slices & 15) == 0,
+                "nsr_contract: slice planes must be 16-byte aligned");
+    if (n_tiles == 0) return 0;
+    NSR_REQUIRE(host_tiles != nullptr && n_tiles > 0 && n_tiles < (1ll << 30), "nsr_contract: bad tile list");
+    const int64_t tr_max = (rows_a + NSR_TILE - 1) / NSR_TILE, tc_max = (rows_b + NSR_TILE - 1) / NSR_TILE;
+    for (int64_t t = 0; t < n_tiles; ++t) {
+        const int32_t tr = host_tiles[2 * t], tc = host_tiles[2 * t + 1];
+        NSR_REQUIRE(tr >= 0 && tr < tr_max && tc >= 0 && tc < tc_max, "nsr_contract: tile %lld = (%d,%d) out of range",
+                    (long long)t, tr, tc);
+        NSR_REQUIRE(!sym || tr <= tc, "nsr_contract: COEX tiles must have row <= col");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    if ((size_t)n_tiles > ctx->tiles_cap) {
+        if (ctx->tiles_dev) NSR_CHECK(cudaFree(ctx->tiles_dev));
+        ctx->tiles_dev = nullptr;
+        ctx->tiles_cap = 0;
+        NSR_CHECK(cudaMalloc(&ctx->tiles_dev, (size_t)n_tiles * 2 * sizeof(int32_t) * 2));
+        ctx->tiles_cap = (size_t)n_tiles * 2;
+    }
+    // pageable-host copy: synchronous with respect to the host for the staging part, ordered on `st`
+    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, host_tiles, (size_t)n_tiles * 2 * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, st));
+
+    ContractParams ep;
+    ep.mode = mode;
+    ep.n_groups = wmax - 1;
+    ep.rows_a = rows_a; ep.rows_b = rows_b; ep.ld = ld;
+    ep.qa = quantum_a; ep.va = var_a; ep.qb = quantum_b; ep.vb = var_b;
+    ep.P = P; ep.out2 = out2;
+    ep.inv_n = 1.0 / (double)n;
+    for (int g = 0; g < 4; ++g) ep.group_scale[g] = (g < ep.n_groups) ? ldexp(1.0, 8 * (ep.n_groups - 1 - g)) : 0.0;
+    ep.scale_all = ldexp(1.0, 8 * (2 * n_slices - wmax));
+    ep.pv = nsr_pval_params(mode == NSR_MODE_RAW ? 1.0 : dof_a);
+
+    if (engine == NSR_ENGINE_SIMT) {
+        if (nsr_launch_contract_simt(st, a_slices, rows_alloc_a, b_slices, rows_alloc_b, n_pad, n_slices, wmax,
+                                     ctx->tiles_dev, n_tiles, ep)) {
+            nsr_set_error("nsr_contract: SIMT launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        return 0;
+    }
+    return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
+                                    n_pad, n_slices, wmax, ctx->tiles_dev, n_tiles, ep);
+}
+
+namespace {
+__global__ void pvalue_kernel(const double* __restrict__ r2, const double* __restrict__ a, int64_t row_len,
+                              int64_t count, double* __restrict__ P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const NsrPvalParams p = nsr_pval_params(a[i / row_len]);
+    P[i] = nsr_pvalue_r2(r2[i], p);
+}
+}  // namespace
+
+extern "C" int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a, int64_t row_len,
+                          int64_t count, double* P) {
+    NSR_REQUIRE(ctx != nullptr && r2 && a && P && row_len > 0 && count >= 0, "nsr_pvalue: bad arguments");
+    if (count == 0) return 0;
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    pvalue_kernel<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(r2, a, row_len, count, P);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}

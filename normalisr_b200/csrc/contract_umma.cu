@@ -1,0 +1,327 @@
+// tcgen05 / TMEM / TMA contraction over cells for sm_100a: the product path.
+//
+// For an output tile (128 rows of A) x (128 rows of B) the kernel forms, for every kept pair
+// of digit planes (a, b), the exact integer sum over cells  sum_k dA_a[i,k] dB_b[j,k]  with
+// tcgen05.mma.kind::i8 (int8 x int8 -> int32 in TMEM; integer accumulation is exact, which a
+// float accumulator - round-toward-zero in the tensor pipe - is not).  Pairs with equal a + b
+// share one 128-column TMEM accumulator.  The epilogue warps read the accumulators with
+// tcgen05.ld, combine them in float64, scale by the row quanta and evaluate r^2 and the exact
+// P-value in registers, so P and dot are written once (reference association.py:234-249 and
+// the assembly at :1036-1057).
+//
+// Roles (192 threads, persistent over a tile list, one CTA per SM):
+//   warp 0 lane 0  TMA producer: 2S boxes (128 rows x KB bytes, swizzled) per k-block
+//   warp 1         TMEM allocator; lane 0 issues the MMAs and commits to mbarriers
+//   warps 2..5     epilogue, one TMEM lane quadrant each
+#include <cuda.h>
+
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+constexpr int kSmemBudget = 200 * 1024;       // operand ring; barriers live in static smem
+
+struct UmmaArgs {
+    const int32_t* tiles;
+    int n_tiles;
+    int num_kb;                   // k-blocks of KB cells
+    ContractParams ep;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the launch, never hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {       // ~2 s
+            printf("nsr umma: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
+                   threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst,
+                                            int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile, rows of KB bytes, swizzle width == KB (128B or 64B), 8-row groups dense
+template <int KB>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+    constexpr uint64_t layout = (KB == 128) ? 2ull : 4ull;       // SWIZZLE_128B / SWIZZLE_64B
+    constexpr uint64_t sbo = (8ull * KB) >> 4;                   // next 8-row group
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) |
+           (layout << 61);
+}
+// int8 x int8 -> int32, A and B K-major, M = 128, N = 128
+constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int S, int WMAX, int KB>
+struct Cfg {
+    static constexpr int kSliceBytes = NSR_TILE * KB;
+    static constexpr int kStageBytes = 2 * S * kSliceBytes;
+    static constexpr int kStages = kSmemBudget / kStageBytes;
+    static constexpr int kGroups = WMAX - 1;
+    static_assert(kStages >= 1, "stage does not fit");
+    static_assert(kGroups * NSR_TILE <= (int)kTmemCols, "TMEM overflow");
+};
+
+template <int S, int WMAX, int KB>
+__global__ void __launch_bounds__(kThreads, 1)
+contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, const UmmaArgs g) {
+    using C = Cfg<S, WMAX, KB>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_tmem_full), 1);
+        mbar_init(smem_u32(&bar_tmem_empty), 4);          // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+                const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = g.tiles[2 * t + 1] * NSR_TILE;
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+                    const uint32_t full = smem_u32(&bar_full[stage]);
+                    mbar_expect_tx(full, C::kStageBytes);
+                    const uint32_t base = ring_u32 + stage * C::kStageBytes;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        tma_load_3d(&map_a, full, base + s * C::kSliceBytes, kb * KB, row_a, s);
+                        tma_load_3d(&map_b, full, base + (S + s) * C::kSliceBytes, kb * KB, row_b, s);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+                mbar_wait(smem_u32(&bar_tmem_empty), tphase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t base = ring_u32 + stage * C::kStageBytes;
+#pragma unroll
+                    for (int ks = 0; ks < KB / 32; ++ks) {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+#pragma unroll
+                            for (int b = 0; b < S; ++b) {
+                                if (a + b + 2 <= WMAX) {
+                                    constexpr int dummy = 0; (void)dummy;
+                                    const int grp = a + b;
+                                    // first product of its group in this (a asc, b asc) order
+                                    const bool first = (a == (grp > S - 1 ? grp - (S - 1) : 0));
+                                    const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                    const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                    const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
+                                    tc_mma_i8(tmem_base + grp * NSR_TILE, da, db, kInstrDesc, acc);
+                                }
+                            }
+                        }
+                    }
+                    tc_commit(smem_u32(&bar_empty[stage]));      // frees the stage when MMAs retire
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(smem_u32(&bar_tmem_full));             // accumulators complete
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;                                // TMEM lane quadrant of this warp
+        uint32_t tphase = 0;
+        for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+            const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
+            mbar_wait(smem_u32(&bar_tmem_full), tphase);
+            tc_fence_after();
+            const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
+            const bool row_ok = i < g.ep.rows_a;
+            const double qi = row_ok ? g.ep.qa[i] : 0.0;
+            const double vi = (row_ok && g.ep.va) ? g.ep.va[i] : 1.0;
+            const bool mirror = g.ep.mode == NSR_MODE_COEX && tr != tc;
+            const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NSR_TILE; c0 += 16) {
+                uint32_t v[C::kGroups][16];
+#pragma unroll
+                for (int grp = 0; grp < C::kGroups; ++grp) tc_ld16(lane_base + grp * NSR_TILE + c0, v[grp]);
+                tc_ld_wait();
+                const int64_t j0 = (int64_t)tc * NSR_TILE + c0;
+                if (row_ok && j0 < g.ep.rows_b) {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) {
+                        const int64_t j = j0 + c;
+                        if (j < g.ep.rows_b) {
+                            int32_t a4[4] = {0, 0, 0, 0};
+#pragma unroll
+                            for (int grp = 0; grp < C::kGroups; ++grp) a4[grp] = (int32_t)v[grp][c];
+                            nsr_finish(g.ep, i, j, qi, vi, g.ep.qb[j], g.ep.vb ? g.ep.vb[j] : 1.0,
+                                       nsr_combine(g.ep, a4), mirror);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+            tphase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                     : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int make_map(nsr_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, int64_t rows_alloc,
+             int64_t n_pad, int n_slices, int kb) {
+    EncodeTiledFn fn = (EncodeTiledFn)ctx->encode_tiled;
+    NSR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
+    cuuint64_t dims[3] = {(cuuint64_t)n_pad, (cuuint64_t)rows, (cuuint64_t)n_slices};
+    cuuint64_t strides[2] = {(cuuint64_t)n_pad, (cuuint64_t)rows_alloc * (cuuint64_t)n_pad};
+    cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)NSR_TILE, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    kb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    NSR_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 0;
+}
+
+template <int S, int WMAX, int KB>
+int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
+    using C = Cfg<S, WMAX, KB>;
+    const int smem = C::kStages * C::kStageBytes + 1024;
+    auto kern = contract_umma_kernel<S, WMAX, KB>;
+    NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = g.n_tiles < ctx->sm_count ? g.n_tiles : ctx->sm_count;
+    kern<<<grid, kThreads, smem, st>>>(ma, mb, g);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
+
+int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
+                             int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
+                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep) {
+    const int kb = (n_slices == 4) ? 64 : nsr_umma_kblock;
+    CUtensorMap ma, mb;
+    if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices, kb)) return 1;
+    if (make_map(ctx, &mb, b, rows_b, rows_alloc_b, n_pad, n_slices, kb)) return 1;
+    UmmaArgs g;
+    g.tiles = tiles_dev;
+    g.n_tiles = (int)n_tiles;
+    g.num_kb = (int)(n_pad / kb);
+    g.ep = ep;
+    if (n_slices == 3 && wmax == 4 && kb == 128) return launch<3, 4, 128>(ctx, st, ma, mb, g);
+    if (n_slices == 3 && wmax == 5 && kb == 128) return launch<3, 5, 128>(ctx, st, ma, mb, g);
+    if (n_slices == 3 && wmax == 4 && kb == 64) return launch<3, 4, 64>(ctx, st, ma, mb, g);
+    if (n_slices == 3 && wmax == 5 && kb == 64) return launch<3, 5, 64>(ctx, st, ma, mb, g);
+    if (n_slices == 4 && wmax == 5) return launch<4, 5, 64>(ctx, st, ma, mb, g);
+    nsr_set_error("nsr_contract: unsupported (n_slices=%d, wmax=%d) for the tcgen05 engine", n_slices, wmax);
+    return 2;
+}

@@ -1,0 +1,53 @@
+// Shared epilogue of the contraction kernels: exact integer cell-sums -> dot, r^2, P.
+// Reference: association.py:234-249 (gamma, R2, beta.cdf) and :1036-1057 (dot, symmetry).
+#pragma once
+#include "nsr_common.cuh"
+#include "pvalue.cuh"
+
+struct ContractParams {
+    int mode;                    // NSR_MODE_*
+    int n_groups;                // weight groups kept (w = 2 .. n_groups + 1)
+    int64_t rows_a, rows_b, ld;
+    const double* qa; const double* va;
+    const double* qb; const double* vb;
+    double* P; double* out2;
+    double inv_n;
+    double group_scale[4];       // 256^(2S - w), relative to the least significant kept group
+    double scale_all;            // weight of the least significant kept group
+    NsrPvalParams pv;
+};
+
+// acc = exact sum_k V_ik V_jk restricted to the kept digit products, as a double
+__device__ __forceinline__ double nsr_combine(const ContractParams& p, const int32_t* acc_g) {
+    double s = 0.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+        if (g < p.n_groups) s = fma((double)acc_g[g], p.group_scale[g], s);
+    return s * p.scale_all;
+}
+
+// one output element (i = row in A, j = row in B); `mirror` also writes (j, i) (COEX, i != j tile)
+__device__ __forceinline__ void nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
+                                           double vi, double qj, double vj, double acc,
+                                           bool mirror) {
+    const double sum = (qi * qj) * acc;            // sum_k res_i res_j
+    if (p.mode == NSR_MODE_RAW) {
+        p.out2[i * p.ld + j] = sum;
+        return;
+    }
+    const double dot = sum * p.inv_n;
+    double P, o2;
+    if ((p.mode == NSR_MODE_COEX || p.mode == NSR_MODE_COEX_UPPER) && i == j) {
+        P = 0.0; o2 = 0.0;                         // triu(.,1) + transpose leaves a zero diagonal
+    } else {
+        const double r2 = (dot * dot) / (vi * vj);
+        P = nsr_pvalue_r2(r2, p.pv);
+        o2 = (p.mode == NSR_MODE_DE) ? dot / vi : dot;
+    }
+    p.P[i * p.ld + j] = P;
+    p.out2[i * p.ld + j] = o2;
+    if (mirror) {
+        p.P[j * p.ld + i] = P;
+        p.out2[j * p.ld + i] = o2;
+    }
+}

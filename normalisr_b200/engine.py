@@ -1,0 +1,174 @@
+"""Device-level operators of the hot path: thin Python over the C ABI.
+
+PyTorch is used for device memory, streams and (in ``parallel.py``) NCCL only; every
+numerical kernel on the path is in ``libnsr_b200.so``.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ENGINE_SIMT, ENGINE_UMMA, MODE_COEX, MODE_COEX_UPPER, MODE_DE, MODE_RAW,  # noqa: F401
+                   TILE)
+
+_ctx_lock = threading.Lock()
+_contexts = {}
+
+# precision presets: (digit planes, digit-pair products kept)
+PRESETS = {"fast": (3, 6), "default": (3, 8), "precise": (4, 10)}
+
+
+class Context:
+    """One per device.  Not for concurrent use from several threads."""
+
+    def __init__(self, device):
+        if not torch.cuda.is_available():
+            raise _lib.NsrError("normalisr_b200 needs a CUDA device (sm_100a); none is visible and "
+                                "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.nsr_ctx_create(device, ctypes.byref(h)), "nsr_ctx_create")
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.nsr_ctx_destroy(self.handle)
+        except Exception:
+            pass
+
+
+def context(device=None):
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    with _ctx_lock:
+        if device not in _contexts:
+            _contexts[device] = Context(device)
+        return _contexts[device]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def padded_cells(n):
+    return (n + _lib.KBLOCK - 1) // _lib.KBLOCK * _lib.KBLOCK
+
+
+class Sliced:
+    """Residualised rows as int8 digit planes + per-row quantum / variance (device)."""
+
+    def __init__(self, rows, n, n_slices, device):
+        self.rows, self.n, self.n_slices = rows, n, n_slices
+        self.n_pad = padded_cells(n)
+        self.slices = torch.empty((n_slices, rows, self.n_pad), dtype=torch.int8, device=device)
+        self.quantum = torch.empty(rows, dtype=torch.float64, device=device)
+        self.var = torch.empty(rows, dtype=torch.float64, device=device)
+        self.coef = None
+
+    @property
+    def rows_alloc(self):
+        return self.slices.shape[1]
+
+
+def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
+    """X: (rows, n) float64 CUDA tensor (row stride arbitrary, unit column stride);
+    Qt: (rank, n) float64 CUDA tensor with orthonormal rows, or None.
+    Writes rows [row_offset, row_offset+rows) of ``out`` (a Sliced) or a fresh one."""
+    assert X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.stride(1) == 1
+    rows, n = X.shape
+    rank = 0 if Qt is None else Qt.shape[0]
+    if rank:
+        assert Qt.is_cuda and Qt.dtype == torch.float64 and Qt.shape[1] == n and Qt.stride(1) == 1
+    if out is None:
+        out = Sliced(rows, n, n_slices, X.device)
+        row_offset = 0
+    assert out.n == n and out.n_slices == n_slices and row_offset + rows <= out.rows
+    coef = None
+    if keep_coef and rank:
+        if out.coef is None:
+            out.coef = torch.zeros((out.rows, rank), dtype=torch.float64, device=X.device)
+        coef = out.coef[row_offset:row_offset + rows]
+    slices = out.slices[:, row_offset:row_offset + rows]
+    # a dimension of extent 1 may carry any stride: use the row length for single-row operands
+    ldx = X.stride(0) if rows > 1 else n
+    ldq = Qt.stride(0) if rank > 1 else n
+    st = ctx.lib.nsr_residualize(
+        ctx.handle, _stream(), X.data_ptr(), rows, n, ldx,
+        Qt.data_ptr() if rank else None, rank, ldq,
+        n_slices, slices.data_ptr(), out.rows_alloc, out.n_pad,
+        out.quantum[row_offset:].data_ptr(), out.var[row_offset:].data_ptr(),
+        coef.data_ptr() if coef is not None else None)
+    _lib.check(st, "nsr_residualize")
+    return out
+
+
+def unslice(ctx, s):
+    out = torch.empty((s.rows, s.n_pad), dtype=torch.float64, device=s.slices.device)
+    _lib.check(ctx.lib.nsr_unslice(ctx.handle, _stream(), s.slices.data_ptr(), s.rows, s.rows_alloc,
+                                   s.n_pad, s.n_slices, s.quantum.data_ptr(), out.data_ptr()),
+               "nsr_unslice")
+    return out
+
+
+def coex_tiles(rows, strip=12):
+    """Upper-triangular 128x128 tile list (tile_row <= tile_col), ordered in column strips so
+    that the ~148 tiles in flight share few row blocks (L2 reuse of the operand planes)."""
+    t = (rows + TILE - 1) // TILE
+    out = []
+    for js in range(0, t, strip):
+        je = min(js + strip, t)
+        for i in range(0, je):
+            for j in range(max(i, js), je):
+                out.append((i, j))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
+def rect_tiles(rows_a, rows_b, strip=12):
+    ta, tb = (rows_a + TILE - 1) // TILE, (rows_b + TILE - 1) // TILE
+    out = []
+    for js in range(0, tb, strip):
+        for i in range(ta):
+            for j in range(js, min(js + strip, tb)):
+                out.append((i, j))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
+def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_UMMA):
+    """Run the contraction + epilogue for ``tiles`` ((k,2) int32 numpy array of tile coords)."""
+    assert A.n == B.n and A.n_slices == B.n_slices
+    tiles = np.ascontiguousarray(tiles, dtype=np.int32)
+    ld = out2.stride(0) if out2.shape[0] > 1 else out2.shape[1]
+    assert out2.stride(1) == 1 and (P is None or P.shape == out2.shape and P.stride(1) == 1)
+    assert P is None or out2.shape[0] == 1 or P.stride(0) == ld
+    st = ctx.lib.nsr_contract(
+        ctx.handle, _stream(), engine, mode,
+        A.slices.data_ptr(), A.rows, A.rows_alloc, A.quantum.data_ptr(), A.var.data_ptr(),
+        B.slices.data_ptr(), B.rows, B.rows_alloc, B.quantum.data_ptr(), B.var.data_ptr(),
+        A.n, A.n_pad, A.n_slices, n_products,
+        tiles.ctypes.data, tiles.shape[0], float(dof_a),
+        P.data_ptr() if P is not None else None, out2.data_ptr(), ld)
+    _lib.check(st, "nsr_contract")
+
+
+def pvalue(ctx, r2, a):
+    """P = I_{1-r2}(a, 1/2); r2 (rows, cols) CUDA float64, a scalar or (rows,) per-row."""
+    r2 = r2.contiguous()
+    rows, cols = (r2.shape[0], r2.shape[1]) if r2.dim() == 2 else (1, r2.numel())
+    a_t = torch.as_tensor(a, dtype=torch.float64, device=r2.device).reshape(-1)
+    if a_t.numel() == 1:
+        a_t = a_t.expand(rows).contiguous()
+    assert a_t.numel() == rows
+    P = torch.empty_like(r2)
+    _lib.check(ctx.lib.nsr_pvalue(ctx.handle, _stream(), r2.data_ptr(), a_t.data_ptr(), cols,
+                                  r2.numel(), P.data_ptr()), "nsr_pvalue")
+    return P
+
+
+def set_option(name, value):
+    _lib.check(_lib.load().nsr_set_option(name.encode(), int(value)), "nsr_set_option")

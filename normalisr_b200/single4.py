@@ -1,0 +1,148 @@
+"""single=4: test every grouping x against every gene y with all OTHER groupings and the
+covariates as nuisance regressors (reference ``association_test_4``, association.py:421-576,
+driven from ``association_tests`` :926-974).
+
+The reference forms the Gram matrices of A = [dx; dc] (``prod1`` tiles) and then, for every
+x, pseudo-inverts the (m-1)x(m-1) Gram matrix of everything but x.  Algebraically that is the
+multiple regression of y on all rows of A, so here:
+
+  1. dx and dy are residualised against dc by the projection kernel (exact in float64);
+  2. the two Gram blocks  Gxx = Rx Rx^T,  Gxy = Rx Ry^T  come from the tensor-core
+     contraction in NSR_MODE_RAW (exact integer sums);
+  3. one float64 factorisation of Gxx gives every leave-one-out quantity in closed form
+     (Schur complements), and the P-values come from nsr_pvalue.
+
+When Gxx is numerically rank deficient the closed form does not apply and step 3 falls back
+to the reference's per-x pseudo-inverse, on the same Gram matrices.
+"""
+import logging
+
+import numpy as np
+import torch
+
+from . import engine
+from ._lib import MODE_RAW, MAX_RANK
+
+
+def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduce=0,
+                              precision='default', device=None, engine_id=None, **ka):
+    from .association import covariate_basis, inv_rank, _residualize_any, _as_host_f64, _is_dev, _out
+    eng = ka.pop('engine', engine.ENGINE_UMMA) if engine_id is None else engine_id
+    tol = ka.pop('tol', 1e-8)
+    if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
+        raise NotImplementedError('normalisr_b200 implements the exact SVD branch of inv_rank only '
+                                  '(method auto/scipy, mpc=0).')
+    ka.pop('qr', None)
+    if ka:
+        raise TypeError("association_test_4() got an unexpected keyword argument '{}'".format(
+            next(iter(ka))))
+    if tol <= 0:
+        raise ValueError('tol must be positive.')
+    to_host = not _is_dev(dx)
+    ctx = engine.context(device if device is not None else (dx.device if _is_dev(dx) else None))
+    n_slices, n_products = engine.PRESETS[precision]
+    nx, n = dx.shape
+    ny, nc = dy.shape[0], dc.shape[0]
+    if nx == 0 or ny == 0 or n == 0:
+        raise ValueError('Dimensions in na==0 detected.')
+    if nc == 0:
+        logging.warning('No covariate dc input.')
+    Qt, rank_c, W = covariate_basis(_as_host_f64(dc), tol=tol)
+    if rank_c > MAX_RANK:
+        raise NotImplementedError('covariate rank {} > {}'.format(rank_c, MAX_RANK))
+    with torch.cuda.device(ctx.device):
+        dev = ctx.device
+        Qt_dev = torch.from_numpy(Qt).to(dev) if rank_c else None
+        Rx = _residualize_any(ctx, dx, Qt_dev, n_slices, not lowmem)
+        Ry = _residualize_any(ctx, dy, Qt_dev, n_slices, not lowmem)
+        Gxx = torch.empty((nx, nx), dtype=torch.float64, device=dev)
+        Gxy = torch.empty((nx, ny), dtype=torch.float64, device=dev)
+        engine.contract(ctx, MODE_RAW, Rx, Rx, engine.rect_tiles(nx, nx), 1.0, None, Gxx, n_products, eng)
+        engine.contract(ctx, MODE_RAW, Rx, Ry, engine.rect_tiles(nx, ny), 1.0, None, Gxy, n_products, eng)
+        Gxx = 0.5 * (Gxx + Gxx.T)
+        yy = _row_sumsq(Ry)
+
+        dxx, dxy, dyy, rank, w = loo_stats(Gxx, Gxy, yy, n, rank_c, tol)
+        dxx = torch.where(dxx == 0, torch.ones_like(dxx), dxx)               # :545-547
+        gamma = dxy / dxx[:, None]
+        r2 = dxy * dxy / (dxx[:, None] * dyy)
+        if not bool(((r2 >= 0) & (r2 <= 1 + 1e-8)).all()):                   # :557
+            raise AssertionError('R^2 outside [0, 1]: collinear groupings?')
+        dof = n - 1 - rank - dimreduce
+        if bool((dof <= 0).any()):
+            raise RuntimeError('Insufficient number of cells: must be greater than degrees of '
+                               'freedom removed + covariate + 1.')
+        P = engine.pvalue(ctx, r2, dof / 2)
+        alpha = None
+        if not lowmem:
+            if rank_c:
+                Wd = torch.from_numpy(W).to(dev)
+                al = Ry.coef @ Wd - w.T @ (Rx.coef @ Wd)                      # (ny, nc)
+            else:
+                al = torch.zeros((ny, nc), dtype=torch.float64, device=dev)
+            alpha = al[None, :, :].expand(nx, ny, nc).contiguous()
+        out2 = gamma * dxx[:, None] if return_dot else gamma
+        res = (P, out2, alpha, dxx, dyy)
+        if to_host:
+            torch.cuda.current_stream().synchronize()
+            res = tuple(_out(t, True) for t in res)
+    return res
+
+
+def loo_stats(Gxx, Gxy, yy, n, rank_c, tol=1e-8):
+    """Leave-one-out regression statistics of association_test_4 (association.py:521-544)
+    from Gram matrices of covariate-residualised rows: Gxx = Rx Rx^T (nx, nx),
+    Gxy = Rx Ry^T (nx, ny), yy = rowsum(Ry^2).  Returns (dxx, dxy, dyy, rank, w) where w are
+    the full multiple-regression coefficients.  float64 torch tensors on any device."""
+    from .association import inv_rank
+    nx = Gxx.shape[0]
+    ev = torch.linalg.eigvalsh(Gxx)
+    full_rank = bool(ev[0] > tol * ev[-1]) if nx > 1 else bool(ev[0] > 0)
+    if not full_rank:
+        return _loo_pinv(Gxx, Gxy, yy, n, rank_c, tol, inv_rank)
+    K = torch.linalg.inv(Gxx)
+    K = 0.5 * (K + K.T)
+    w = K @ Gxy                                   # full-regression coefficients (nx, ny)
+    kd = torch.diagonal(K)
+    dxx = 1.0 / (n * kd)                          # association.py:539-540 (Schur complement)
+    dxy = w / kd[:, None] / n                     # :543-544
+    qf = (Gxy * w).sum(dim=0)
+    dyy = (yy[None, :] - qf[None, :] + w * w / kd[:, None]) / n      # :541-542
+    rank = torch.full((nx,), float(nx - 1 + rank_c), dtype=torch.float64, device=Gxx.device)
+    return dxx, dxy, dyy, rank, w
+
+
+def _row_sumsq(R):
+    """sum_k res^2 per row from the stored variance (var = mean, with exact zeros mapped to 1)."""
+    return R.var * R.n
+
+
+def _loo_pinv(Gxx, Gxy, yy, n, rank_c, tol, inv_rank):
+    """Rank-deficient groupings: the reference's per-x pseudo-inverse (association.py:521-544)
+    on the residualised Gram matrices, in float64 on the host."""
+    G = Gxx.cpu().numpy()
+    Gy = Gxy.cpu().numpy()
+    y2 = yy.cpu().numpy()
+    nx, ny = Gy.shape
+    dxx = np.zeros(nx)
+    dxy = np.zeros((nx, ny))
+    dyy = np.zeros((nx, ny))
+    rank = np.zeros(nx)
+    for x in range(nx):
+        t0 = [k for k in range(nx) if k != x]
+        r = 0
+        if t0:
+            gi, r = inv_rank(G[np.ix_(t0, t0)], tol=tol)
+        if r == 0:
+            dxx[x], dyy[x], dxy[x] = G[x, x] / n, y2 / n, Gy[x] / n
+        else:
+            cx = G[x, t0] @ gi
+            dxx[x] = (G[x, x] - cx @ G[t0, x]) / n
+            cy = Gy[t0].T @ gi
+            dyy[x] = (y2 - np.sum(cy.T * Gy[t0], axis=0)) / n
+            dxy[x] = (Gy[x] - cy @ G[t0, x]) / n
+        rank[x] = r + rank_c
+    dev = Gxx.device
+    w = torch.from_numpy(np.linalg.pinv(G, rcond=tol) @ Gy).to(dev)
+    return (torch.from_numpy(dxx).to(dev), torch.from_numpy(dxy).to(dev), torch.from_numpy(dyy).to(dev),
+            torch.from_numpy(rank).to(dev), w)

@@ -1,0 +1,216 @@
+"""Parity of the CUDA path with the reference, through the public API / C ABI.
+
+Tolerances are the ones BASELINE.json states: |delta r| <= 1e-6 and relative error in P
+<= 1e-4 wherever P >= 1e-300 (r = dot / sqrt(var_i var_j), coex.py:34).  Three kinds of checks:
+  * against the committed golden vectors produced by the unmodified reference;
+  * against the CPU oracle on seeded synthetic inputs sized so the oracle takes seconds;
+  * size-independent properties at the BASELINE sizes (bit-identical integer sums between the
+    tcgen05 and the CUDA-core engines, symmetry, tile-subset invariance, linearity).
+"""
+import numpy as np
+import pytest
+import torch
+
+import normalisr_oracle as orc
+import nsr_testlib as tl
+from conftest import R_ATOL, assert_p_close, load_golden, pearson_from
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from normalisr_b200 import association, engine, synth
+    from normalisr_b200 import normalisr as norm
+
+
+def _check_coex(got, ref, p_rtol=1e-4):
+    P, dot, var = got
+    Pr, dotr, varr = ref
+    np.testing.assert_allclose(var, varr, rtol=1e-10)
+    r = pearson_from(dot, var, var)
+    rr = pearson_from(dotr, varr, varr)
+    assert np.abs(r - rr).max() <= R_ATOL, np.abs(r - rr).max()
+    assert_p_close(P, Pr, rtol=p_rtol)
+    assert (np.diag(P) == 0).all() and (np.diag(dot) == 0).all()
+    assert np.array_equal(P, P.T) and np.array_equal(dot, dot.T)
+
+
+@pytest.mark.parametrize("precision", ["default", "fast", "precise"])
+@pytest.mark.parametrize("case", ["coex_chain", "coex_tail", "coex_rankdef", "coex_nocov"])
+def test_coex_golden(case, precision):
+    g = load_golden(case)
+    ka = {"dimreduce": int(g["dimreduce"])} if "dimreduce" in g else {}
+    got = norm.coex(g["dt"], g["dc"], precision=precision, **ka)
+    assert all(isinstance(x, np.ndarray) and x.dtype == np.float64 for x in got)
+    _check_coex(got, (g["P"], g["dot"], g["var"]))
+
+
+def test_coex_golden_simt_engine():
+    g = load_golden("coex_tail")
+    got = norm.coex(g["dt"], g["dc"], engine=engine.ENGINE_SIMT)
+    _check_coex(got, (g["P"], g["dot"], g["var"]))
+
+
+@pytest.mark.parametrize("case,ka", [("de_single0", {}), ("de_single0_alpha", {"lowmem": False}),
+                                     ("de_single4", {"single": 4}), ("de_single4_rankdef", {"single": 4})])
+def test_de_golden(case, ka):
+    g = load_golden(case)
+    P, gamma, alpha, varg, vart = norm.de(g["dg"], g["dt"], g["dc"], **ka)
+    np.testing.assert_allclose(varg, g["varg"], rtol=1e-7)
+    np.testing.assert_allclose(vart, g["vart"], rtol=1e-7)
+    # gamma = r * sqrt(vart / varg): |delta r| <= 1e-6 translates to this absolute bound
+    scale = np.sqrt(g["vart"] / np.where(g["varg"] > 0, g["varg"], 1)[:, None])
+    assert (np.abs(gamma - g["gamma"]) <= R_ATOL * scale + 1e-12).all()
+    assert_p_close(P, g["P"])
+    if "alpha" in g:
+        np.testing.assert_allclose(alpha, g["alpha"], rtol=1e-5, atol=1e-5 * np.abs(g["alpha"]).max())
+    else:
+        assert alpha is None
+    assert (P[5] == 1).all() and (gamma[5] == 0).all() and varg[5] == 0 and (vart[5] == 0).all()
+
+
+def test_coex_config1_against_oracle():
+    """BASELINE configs[0] shape: 2,000 cells x 1,000 genes."""
+    p = synth.host_problem(1001, 1000, 2000)
+    ref = orc.coex(p["dt"], p["dc"])
+    got = norm.coex(p["dt"], p["dc"])
+    _check_coex(got, ref)
+    iu = np.triu_indices(1000, 1)
+    assert (ref[0][iu] < 1e-50).sum() > 10          # the tail is exercised
+
+
+def test_coex_lowmem_false_and_gamma():
+    g = load_golden("coex_chain")
+    ref = orc.association_tests(g["dt"], None, g["dc"], lowmem=False, return_dot=False)
+    got = association.association_tests(g["dt"], None, g["dc"], lowmem=False, return_dot=False)
+    np.testing.assert_allclose(got[1], ref[1], atol=1e-6 * np.abs(ref[1]).max())
+    np.testing.assert_allclose(got[2], ref[2], atol=1e-6 * np.abs(ref[2]).max())
+    assert got[3] is None
+    assert_p_close(got[0], ref[0])
+
+
+def test_de_config_like_against_oracle():
+    p = synth.host_problem(1003, 600, 3000, n_group=40, group_p=0.03)
+    for single in (0, 4):
+        ref = orc.de(p["dg"], p["dt"], p["dc"], single=single)
+        got = norm.de(p["dg"], p["dt"], p["dc"], single=single)
+        assert_p_close(got[0], ref[0])
+        np.testing.assert_allclose(got[3], ref[3], rtol=1e-7)
+        np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
+        scale = np.sqrt(ref[4] / ref[3][:, None])
+        assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+
+
+def test_device_tensors_in_device_tensors_out():
+    g = load_golden("coex_chain")
+    dt = torch.from_numpy(g["dt"]).cuda()
+    dc = torch.from_numpy(g["dc"]).cuda()
+    P, dot, var = norm.coex(dt, dc)
+    assert P.is_cuda and dot.is_cuda and var.is_cuda
+    _check_coex((P.cpu().numpy(), dot.cpu().numpy(), var.cpu().numpy()), (g["P"], g["dot"], g["var"]))
+
+
+def test_edge_shapes():
+    rng = np.random.default_rng(11)
+    for (gnum, n) in [(1, 50), (2, 129), (127, 128), (129, 257), (300, 1000)]:
+        dt = rng.normal(size=(gnum, n))
+        dc = np.concatenate([rng.normal(size=(2, n)), np.ones((1, n))])
+        _check_coex(norm.coex(dt, dc), orc.coex(dt, dc))
+
+
+def test_errors_match_reference():
+    x = np.random.default_rng(0).normal(size=(4, 5))
+    with pytest.raises(ValueError):
+        norm.coex(x, np.random.default_rng(1).normal(size=(4, 5)))     # n <= rank + 1
+    with pytest.raises(ValueError):
+        norm.coex(x, np.ones((1, 6)))
+    with pytest.raises(TypeError):
+        norm.coex(x, np.ones((1, 5)), nonsense=1)
+
+
+# ---- properties at BASELINE sizes -------------------------------------------------------
+def _sliced(rows, n, precision="default", seed=1002):
+    ctx = engine.context(0)
+    p = synth.device_problem(seed, rows, n, "cuda")
+    Qt, rank, _ = association.covariate_basis(p["dc"].cpu().numpy())
+    S, prods = engine.PRESETS[precision]
+    A = engine.residualize(ctx, p["dt"], torch.from_numpy(Qt).cuda(), S)
+    return ctx, p, A, rank, prods
+
+
+@pytest.mark.parametrize("precision", ["default", "fast", "precise"])
+def test_config2_engines_bit_identical(precision):
+    """10k cells x 5k genes (BASELINE configs[1]): the tensor-core kernel must reproduce the
+    CUDA-core kernel's integer sums exactly, hence identical P and dot bit patterns."""
+    rows, n = 5000, 10000
+    ctx, p, A, rank, prods = _sliced(rows, n, precision)
+    tiles = engine.coex_tiles(rows)
+    outs = []
+    for eng in (engine.ENGINE_UMMA, engine.ENGINE_SIMT):
+        P = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+        D = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+        engine.contract(ctx, engine.MODE_COEX, A, A, tiles, (n - 1 - rank) / 2, P, D, prods, eng)
+        outs.append((P, D))
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    P, D = outs[0]
+    assert torch.equal(P, P.T) and torch.equal(D, D.T)
+    assert bool((torch.diagonal(P) == 0).all()) and bool(((P >= 0) & (P <= 1)).all())
+    # a checksum of a random sample of entries against float64 inner products of the residuals
+    idx = torch.randint(0, rows, (200, 2), device="cuda")
+    z = p["dt"] - (p["dt"] @ torch.from_numpy(association.covariate_basis(p["dc"].cpu().numpy())[0]).cuda().T) @ \
+        torch.from_numpy(association.covariate_basis(p["dc"].cpu().numpy())[0]).cuda()
+    want = (z[idx[:, 0]] * z[idx[:, 1]]).sum(1) / n
+    want = torch.where(idx[:, 0] == idx[:, 1], torch.zeros_like(want), want)
+    got = D[idx[:, 0], idx[:, 1]]
+    r_err = (got - want).abs() / torch.sqrt(A.var[idx[:, 0]] * A.var[idx[:, 1]])
+    assert float(r_err.max()) < 1e-7
+
+
+def test_tile_subset_invariance_and_rect_vs_sym():
+    rows, n = 1500, 4096
+    ctx, p, A, rank, prods = _sliced(rows, n)
+    dof = (n - 1 - rank) / 2
+    tiles = engine.coex_tiles(rows)
+    full_P = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+    full_D = torch.zeros_like(full_P)
+    engine.contract(ctx, engine.MODE_COEX, A, A, tiles, dof, full_P, full_D, prods)
+    part_P = torch.zeros_like(full_P)
+    part_D = torch.zeros_like(full_P)
+    perm = np.random.default_rng(0).permutation(len(tiles))
+    for chunk in np.array_split(perm, 3):                       # any partition, any order
+        engine.contract(ctx, engine.MODE_COEX, A, A, tiles[chunk], dof, part_P, part_D, prods)
+    torch.cuda.synchronize()
+    assert torch.equal(full_P, part_P) and torch.equal(full_D, part_D)
+    # rectangular (DE) mode on the same planes: gamma * var_x == dot off the diagonal
+    gP = torch.zeros_like(full_P)
+    gG = torch.zeros_like(full_P)
+    engine.contract(ctx, engine.MODE_DE, A, A, engine.rect_tiles(rows, rows), dof, gP, gG, prods)
+    torch.cuda.synchronize()
+    off = ~torch.eye(rows, dtype=torch.bool, device="cuda")
+    assert torch.equal(gP[off], full_P[off])
+    torch.testing.assert_close((gG * A.var[:, None])[off], full_D[off], rtol=1e-14, atol=0)
+
+
+def test_residual_planes_reconstruct_projection():
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(77, 1000)) + 4
+    dc = np.concatenate([rng.normal(size=(3, 1000)), np.ones((1, 1000))])
+    Qt, rank, _ = association.covariate_basis(dc)
+    ctx = engine.context(0)
+    for S in (3, 4):
+        A = engine.residualize(ctx, torch.from_numpy(x).cuda(), torch.from_numpy(Qt).cuda(), S)
+        z = tl.residual(x, Qt)
+        want = tl.hadamard128(z)
+        got = engine.unslice(ctx, A).cpu().numpy()
+        q = A.quantum.cpu().numpy()
+        assert (np.abs(got - want) <= 0.5000001 * q[:, None]).all()
+        np.testing.assert_allclose(A.var.cpu().numpy(), (z ** 2).mean(1), rtol=1e-12)
+        sl = A.slices.cpu().numpy()
+        assert np.abs(sl[0].astype(int)).max() <= 127
+
+
+def test_pvalue_kernel_known_answers():
+    g = load_golden("pvalue_kat")
+    ctx = engine.context(0)
+    got = engine.pvalue(ctx, torch.from_numpy(g["r2"]).cuda(), g["a"][:, 0]).cpu().numpy()
+    assert_p_close(got, g["P"], rtol=1e-9)

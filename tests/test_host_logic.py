@@ -1,0 +1,140 @@
+"""Host-side logic that needs no GPU: covariate basis, tile lists, single=4 closed form,
+digit slicing arithmetic, argument validation, the C-ABI library's symbol table."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import normalisr_oracle as orc
+from conftest import ROOT, assert_p_close, load_golden
+from normalisr_b200 import _lib, association, engine, single4
+
+
+def test_covariate_basis_is_reference_projection():
+    g = load_golden("coex_rankdef")
+    dc, dt = g["dc"], g["dt"]
+    Qt, rank, W = association.covariate_basis(dc)
+    dci, dcr = orc.pinv_rank(dc @ dc.T)
+    assert rank == dcr == 4
+    np.testing.assert_allclose(Qt @ Qt.T, np.eye(rank), atol=1e-13)
+    ref = dt - (dci @ (dc @ dt.T)).T @ dc          # association.py:226-229
+    mine = dt - (dt @ Qt.T) @ Qt
+    np.testing.assert_allclose(mine, ref, atol=1e-10)
+    # W maps basis coefficients to covariate coefficients: same fitted values
+    np.testing.assert_allclose((dt @ Qt.T) @ W @ dc, (dt @ Qt.T) @ Qt, atol=1e-9)
+
+
+def test_covariate_basis_empty_and_zero():
+    assert association.covariate_basis(np.zeros((0, 10)))[1] == 0
+    assert association.covariate_basis(np.zeros((3, 10)))[1] == 0
+
+
+def test_inv_rank_matches_oracle():
+    rng = np.random.default_rng(3)
+    c = rng.normal(size=(6, 40))
+    c[5] = c[0] - c[1]
+    a, ra = association.inv_rank(c @ c.T)
+    b, rb = orc.pinv_rank(c @ c.T)
+    assert ra == rb == 5
+    np.testing.assert_allclose(a, b, atol=1e-12)
+    with pytest.raises(ValueError):
+        association.inv_rank(np.zeros((2, 3)))
+    with pytest.raises(NotImplementedError):
+        association.inv_rank(np.eye(3), mpc=2)
+
+
+def test_tile_lists_cover_exactly_once():
+    for rows in (1, 128, 129, 1000, 5000):
+        t = engine.coex_tiles(rows)
+        nt = (rows + 127) // 128
+        assert len(t) == nt * (nt + 1) // 2
+        assert len({tuple(x) for x in t}) == len(t) and (t[:, 0] <= t[:, 1]).all()
+    t = engine.rect_tiles(300, 1000)
+    assert len(t) == 3 * 8 and len({tuple(x) for x in t}) == 24
+
+
+@pytest.mark.parametrize("case", ["de_single4", "de_single4_rankdef"])
+def test_single4_closed_form_equals_reference(case):
+    """loo_stats on exact float64 Gram matrices reproduces the reference's single=4 numbers."""
+    g = load_golden(case)
+    dg, dt, dc = g["dg"], g["dt"], g["dc"]
+    keep = np.array([len(np.unique(x)) > 1 for x in dg])
+    dx = dg[keep]
+    n = dx.shape[1]
+    Qt, rank_c, _ = association.covariate_basis(dc)
+    rx = dx - (dx @ Qt.T) @ Qt
+    ry = dt - (dt @ Qt.T) @ Qt
+    dxx, dxy, dyy, rank, w = single4.loo_stats(torch.from_numpy(rx @ rx.T), torch.from_numpy(rx @ ry.T),
+                                               torch.from_numpy((ry ** 2).sum(1)), n, rank_c)
+    gamma = (dxy / dxx[:, None]).numpy()
+    np.testing.assert_allclose(gamma, g["gamma"][keep], rtol=1e-7, atol=1e-12)
+    np.testing.assert_allclose(dxx.numpy(), g["varg"][keep], rtol=1e-9)
+    np.testing.assert_allclose(dyy.numpy(), g["vart"][keep], rtol=1e-9)
+    r2 = (dxy * dxy / (dxx[:, None] * dyy)).numpy()
+    P = orc.beta_cdf(1 - r2, ((n - 1 - rank.numpy()) / 2)[:, None])
+    assert_p_close(P, g["P"][keep], rtol=1e-6)
+
+
+def test_single4_rank_deficient_groupings_fall_back():
+    rng = np.random.default_rng(5)
+    n = 300
+    dx = (rng.random((5, n)) < 0.2).astype(float)
+    dx[4] = dx[0] + dx[1]                       # exactly collinear grouping
+    ry = rng.normal(size=(7, n))
+    G = torch.from_numpy(dx @ dx.T)
+    out = single4.loo_stats(G, torch.from_numpy(dx @ ry.T), torch.from_numpy((ry ** 2).sum(1)), n, 0)
+    assert out[3].max() < 4 + 1e-9              # per-x rank is reduced, as inv_rank reports
+
+
+def test_digit_slicing_roundtrip():
+    """Balanced base-256 digits (nsr_common.cuh nsr_digits) restated in numpy."""
+    rng = np.random.default_rng(0)
+    for s in (2, 3, 4):
+        vmax = 127 * 256 ** (s - 1)
+        v = np.concatenate([rng.integers(-vmax, vmax + 1, size=5000), [vmax, -vmax, 0, 127, 128, -128, -129]])
+        digits = []
+        w = v.copy()
+        for _ in range(s - 1):
+            d = ((w + 128) % 256) - 128
+            digits.append(d)
+            w = (w - d) // 256
+        digits.append(w)
+        digits = digits[::-1]
+        assert all(np.abs(d).max() <= 128 for d in digits) and np.abs(digits[0]).max() <= 127
+        back = sum(d * 256 ** (s - 1 - i) for i, d in enumerate(digits))
+        np.testing.assert_array_equal(back, v)
+
+
+def test_argument_validation_needs_no_gpu():
+    x = np.zeros((3, 10))
+    with pytest.raises(ValueError):
+        association.association_tests(x, None, np.ones((1, 9)))
+    with pytest.raises(ValueError):
+        association.association_tests(x, None, np.ones((1, 10)), single=7)
+    with pytest.raises(NotImplementedError):
+        association.association_tests(x, x, np.ones((1, 10)), single=1)
+    with pytest.raises(ValueError):
+        association.association_tests(x, None, np.ones((1, 10)), dimreduce=np.zeros(3))
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads (no compute without a GPU) and exports what include/*.h declares."""
+    header = open(os.path.join(ROOT, "include", "normalisr_b200.h")).read()
+    declared = set(re.findall(r"\b(nsr_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_lib.exported_symbols()), declared ^ set(_lib.exported_symbols())
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.nsr_version() == 100
+    assert lib.nsr_padded_cells(1) == 128 and lib.nsr_padded_cells(128) == 128 and lib.nsr_padded_cells(129) == 256
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    g = load_golden("coex_nocov")
+    with pytest.raises(Exception) as e:
+        association.association_tests(g["dt"], None, g["dc"])
+    assert "CUDA" in str(e.value) or "cuda" in str(e.value)

@@ -1,0 +1,81 @@
+"""Host-side logic of the multi-GPU path on CPU: strip partition, tile lists, and the
+all-gather of digit planes over a world_size-2 gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from normalisr_b200 import engine, parallel
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("rows", [100, 1000, 5000, 20000])
+def test_strips_partition_upper_triangle(rows, world):
+    t = (rows + 127) // 128
+    strips = parallel.strip_bounds(t, world)
+    assert len(strips) == world and strips[0][0] == 0 and strips[-1][1] == t
+    seen = set()
+    counts = []
+    for a, b in strips:
+        tl = parallel.strip_tiles(t, a, b)
+        counts.append(len(tl))
+        for x in map(tuple, tl):
+            assert x not in seen and a <= x[0] < b and x[0] <= x[1]
+            seen.add(x)
+    assert len(seen) == t * (t + 1) // 2
+    if t >= 8 * world:
+        assert max(counts) <= 1.25 * (sum(counts) / world) + t      # balanced up to one tile row
+
+
+def test_row_split():
+    assert parallel.row_split(20000, 8) == 2500 and parallel.row_split(10, 4) == 3
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, rows_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        blk = parallel.row_split(rows_total, world)
+        local = engine.Sliced(blk, 200, 3, "cpu")
+        g = torch.Generator().manual_seed(100 + rank)
+        local.slices.copy_(torch.randint(-128, 128, local.slices.shape, generator=g, dtype=torch.int8))
+        local.quantum.fill_(rank + 1.0)
+        local.var.fill_(10.0 * (rank + 1))
+        full = parallel.gather_sliced(local, rows_total)
+        ok = full.rows == rows_total and full.rows_alloc == blk * world
+        for k in range(world):
+            gk = torch.Generator().manual_seed(100 + k)
+            want = torch.randint(-128, 128, local.slices.shape, generator=gk, dtype=torch.int8)
+            ok = ok and torch.equal(full.slices[:, k * blk:(k + 1) * blk], want)
+            ok = ok and bool((full.quantum[k * blk:(k + 1) * blk] == k + 1.0).all())
+            ok = ok and bool((full.var[k * blk:(k + 1) * blk] == 10.0 * (k + 1)).all())
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_sliced_gloo_world2():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 37, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
