@@ -1,0 +1,387 @@
+#!/usr/bin/env python3
+"""Headline benchmark: norm.coex on 100k cells x 20k genes (BASELINE.json metric), one process
+per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over the synthetic matrix: residualise + quantise, (N > 1:
+all-gather of the digit planes), tensor-core contraction with the fused r / P epilogue.
+  value  unique gene pairs per second with inputs and outputs resident in HBM;
+  e2e    the same pairs through the public API with HOST buffers: pinned host -> device copy of
+         the expression matrix and device -> pinned host copy of P and dot inside the timed region.
+The reference arm (--impl reference) times the CPU port of the reference (oracle/) on the box's
+host cores on a bounded sample of the same workload and extrapolates by the reference's own
+tile count (association.py:854-894).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (genes, cells, description)
+    "coex_100k_x_20k": (20000, 100000, "large co-expression: 100k cells x 20k genes norm.coex (BASELINE configs[3], the "
+                                       "size the metric is quoted on; fits one B200)"),
+    "coex_10k_x_5k": (5000, 10000, "GSE123139-shaped: 10k cells x 5k genes norm.coex (BASELINE configs[1])"),
+    "coex_2k_x_1k": (1000, 2000, "2,000 cells x 1,000 genes (BASELINE configs[0])"),
+}
+METRIC = "coex gene-pairs/s (r+P)"
+UNIT = "pairs/s"
+SEED = 1004
+CPU_SAMPLE_GENES = 3000
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load": samples drawing more than half of the peak power seen
+            load = [s for s, p_ in zip(sm, pw) if p_ >= 0.5 * max(pw)] or sm
+            out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference)
+# --------------------------------------------------------------------------------------
+def reference_tiles(n_gene, bs=500):
+    nb = (n_gene + bs - 1) // bs
+    return nb * (nb + 1) // 2
+
+
+def cpu_sample_problem(n_gene, n_cell):
+    from normalisr_b200 import synth
+    g = min(CPU_SAMPLE_GENES, n_gene)
+    p = synth.host_problem(SEED, g, n_cell, n_module=2, module_size=20)
+    return p["dt"], p["dc"]
+
+
+def cpu_time_once(dt, dc, setting):
+    """One pass of the oracle over the sample.  setting 'A' = the reference CLI's configuration
+    (BLAS pinned to one thread, bin/normalisr:3, thread pool over tiles with nth = all cores);
+    'B' = nth=1 with BLAS using all cores."""
+    import normalisr_oracle as orc
+    cores = os.cpu_count()
+    t0 = time.perf_counter()
+    if setting == "A":
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):
+                orc.coex(dt, dc, nth=cores)
+        except ImportError:
+            orc.coex(dt, dc, nth=cores)
+    else:
+        orc.coex(dt, dc, nth=1)
+    return time.perf_counter() - t0
+
+
+def cpu_extrapolate(seconds, sample_genes, n_gene):
+    """The reference executes reference_tiles(n_gene) tiles of <=500x500 genes; the sample is a
+    whole number of such tiles, all over the full cell count, so time scales by the tile ratio."""
+    per_tile = seconds / reference_tiles(sample_genes)
+    total = per_tile * reference_tiles(n_gene)
+    return (n_gene * (n_gene - 1) / 2) / total
+
+
+def run_reference(args, n_gene, n_cell, wl_name, wl_desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dt, dc = cpu_sample_problem(n_gene, n_cell)
+    sg = dt.shape[0]
+    best = {}
+    for setting in ("B", "A"):
+        best[setting] = cpu_time_once(dt, dc, setting)          # also serves as warm-up
+    setting = min(best, key=best.get)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_time_once(dt, dc, setting)
+    ts = [cpu_time_once(dt, dc, setting) for _ in range(args.steps)]
+    total = sum(ts)
+    value = cpu_extrapolate(total / args.steps, sg, n_gene)
+    sample = ("%d of %d genes x all %d cells = %d of the reference's %d 500x500 tiles per step, extrapolated by tile "
+              "count; thread setting %s (%s)" % (sg, n_gene, n_cell, reference_tiles(sg), reference_tiles(n_gene), setting,
+                                                 "BLAS=1 thread, nth=cores" if setting == "A" else "nth=1, BLAS=all cores"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "genes": n_gene, "cells": n_cell, "covariates": int(dc.shape[0]), "note": wl_desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
+    import torch
+    import torch.distributed as dist
+    from normalisr_b200 import association, engine, parallel, synth
+    from normalisr_b200 import normalisr as norm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = engine.context(local)
+    precision = args.precision
+    n_slices, n_products = engine.PRESETS[precision]
+
+    # ---- synthetic inputs: this rank's block of genes, covariates identical on all ranks
+    blk = parallel.row_split(n_gene, world)
+    g0, g1 = rank * blk, min((rank + 1) * blk, n_gene)
+    prob = synth.device_problem(SEED, g1 - g0, n_cell, dev, gene_seed=SEED * 1000 + rank)
+    dt_dev, dc_dev = prob["dt"], prob["dc"]
+    dc_np = dc_dev.cpu().numpy()
+    Qt, crank, _ = association.covariate_basis(dc_np)
+    Qt_dev = torch.from_numpy(Qt).to(dev)
+    dof_a = (n_cell - 1 - crank) / 2
+    pairs = n_gene * (n_gene - 1) / 2
+
+    t_tiles = (n_gene + 127) // 128
+    a, b = parallel.strip_bounds(t_tiles, world)[rank]
+    r0, r1 = a * 128, min(b * 128, n_gene)
+    tiles = parallel.strip_tiles(t_tiles, a, b)
+    single = world == 1
+    if single:
+        P = torch.empty((n_gene, n_gene), dtype=torch.float64, device=dev)
+        D = torch.empty_like(P)
+        tiles_full = engine.coex_tiles(n_gene)
+    else:
+        P = torch.zeros((max(r1 - r0, 1), n_gene), dtype=torch.float64, device=dev)
+        D = torch.zeros_like(P)
+    local_sl = engine.Sliced(blk, n_cell, n_slices, dev)
+    if g1 - g0 < blk:
+        local_sl.slices.zero_(); local_sl.quantum.fill_(1.0); local_sl.var.fill_(1.0)
+    contract_ms = []
+
+    def step_device(record=False):
+        engine.residualize(ctx, dt_dev, Qt_dev, n_slices, out=local_sl, row_offset=0)
+        full = parallel.gather_sliced(local_sl, n_gene) if world > 1 else local_sl
+        full.rows = n_gene
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        if single:
+            engine.contract(ctx, engine.MODE_COEX, full, full, tiles_full, dof_a, P, D, n_products)
+        elif len(tiles):
+            parallel._contract_strip(ctx, engine.MODE_COEX_UPPER, full, full, tiles, dof_a, P, D, r0, n_products)
+        if record:
+            e1.record()
+            contract_ms.append((e0, e1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = engine.LAUNCHES
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device(record=True)
+    ev1.record()
+    barrier()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = engine.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = pairs / (ms_step * 1e-3)
+    k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in contract_ms])) if contract_ms else None
+
+    # ---- end to end through the public API, host buffers
+    e2e = None
+    if not args.no_e2e:
+        dt_host = torch.empty((g1 - g0, n_cell), dtype=torch.float64, pin_memory=True)
+        dt_host.copy_(dt_dev)
+        if single:
+            P_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
+            D_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
+        else:
+            P_host = torch.empty((max(r1 - r0, 1), n_gene), dtype=torch.float64, pin_memory=True)
+            D_host = torch.empty((max(r1 - r0, 1), n_gene), dtype=torch.float64, pin_memory=True)
+        del dt_dev, prob
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            if single:
+                norm.coex(dt_host, dc_np, precision=precision, out=(P_host, D_host))
+            else:
+                parallel.coex_host(dt_host, dc_np, n_gene, precision=precision, out_dev=(P, D), out_host=(P_host, D_host))
+
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(min(args.warmup, 3)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        barrier()
+        sec = max_over_ranks(time.perf_counter() - t0)
+        h2d_t = torch.tensor([float(dt_host.numel() * 8), float(P_host.numel() * 16)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(h2d_t)
+        e2e = {"value": pairs / (sec / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
+               "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": e2e_steps, "ms_per_step": 1e3 * sec / e2e_steps,
+               "api": "normalisr_b200.normalisr.coex(dt_host, dc, out=pinned)" if single else
+                      "normalisr_b200.parallel.coex_host(dt_block_host, dc, n_gene)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tcgen05 contraction)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    my_pairs = len(tiles_full if single else tiles) * 128 * 128 / 2.0        # ~unique pairs in this rank's tiles
+    alg_flops = 2.0 * n_cell * (pairs if single else my_pairs)
+    roof = None
+    if k_ms:
+        ach = alg_flops / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "kernel": "contract_umma_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                "executed_int8_tops": 2.0 * n_products * len(tiles_full if single else tiles) * 128 * 128 *
+                                      engine.padded_cells(n_cell) / (k_ms * 1e-3) / 1e12,
+                "note": "algorithmic flop = 2*cells per unique pair; the kernel executes %d int8 digit-plane products per "
+                        "pair so its ceiling on this scale is 2/%d of the bf16 peak" % (n_products, n_products)}
+
+    # ---- CPU baseline on a bounded sample (N = 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        dt_s, dc_s = cpu_sample_problem(n_gene, n_cell)
+        tb = {s: cpu_time_once(dt_s, dc_s, s) for s in ("B", "A")}
+        s_best = min(tb, key=tb.get)
+        cpu = {"value": cpu_extrapolate(tb[s_best], dt_s.shape[0], n_gene), "unit": UNIT, "cores": os.cpu_count(),
+               "kind": "port",
+               "sample": "%d of %d genes x all %d cells (%d of the reference's %d 500x500 tiles), one pass per thread setting, "
+                         "faster one (%s) extrapolated by tile count; A=%.2fs B=%.2fs" % (
+                             dt_s.shape[0], n_gene, n_cell, reference_tiles(dt_s.shape[0]), reference_tiles(n_gene), s_best,
+                             tb["A"], tb["B"])}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl_name, "genes": n_gene, "cells": n_cell, "covariates": int(dc_np.shape[0]),
+                   "precision": precision, "digit_planes": n_slices, "digit_products": n_products,
+                   "arithmetic": "f64 projection and epilogue; int8 x int8 -> int32 exact tensor-core sums",
+                   "l2": "inputs (%.1f GB per rank) are larger than L2, no explicit flush" % ((g1 - g0) * n_cell * 8 / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else "%d GPUs: gene-block projection, one all-gather of digit planes, "
+                                                              "tile-row strips" % world,
+                   "note": wl_desc},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="coex_100k_x_20k", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="default", choices=["fast", "default", "precise"])
+    ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: same as --steps)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    n_gene, n_cell, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, n_gene, n_cell, args.workload, desc)
+    else:
+        run_ours(args, n_gene, n_cell, args.workload, desc)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,12 @@ int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,
                int64_t row_len, int64_t count, double* P);
 
+/* Strided device<->host copy on `stream` (cudaMemcpy2DAsync): lets the host layer return
+ * finished blocks of P / dot while later tiles are still being computed.  kind: 0 = device to
+ * host, 1 = host to device.  Pitches and width in bytes. */
+int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
+               int64_t src_pitch, int64_t width_bytes, int64_t height, int kind);
+
 /* Test hooks: "hadamard" (0/1, default 1), "umma_kblock" (64 or 128 cells per pipeline
  * stage of the tcgen05 kernel, default 128). Process-wide. */
 int nsr_set_option(const char* name, int value);

@@ -36,6 +36,7 @@ _SIGNATURES = {
                              c_vp, c_i64, c_i64, c_vp, c_vp,
                              c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64]),
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
 }
 

@@ -80,20 +80,24 @@ def _as_host_f64(x):
     return np.asarray(x)
 
 
-def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef):
-    """Residualise a (rows, n) matrix that lives on the host (numpy, staged in row chunks so the
-    copy of chunk i+1 overlaps the kernels of chunk i) or on the device."""
+def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef, out=None, row_offset=0):
+    """Residualise a (rows, n) matrix that lives on the host (numpy array or CPU tensor, staged
+    in row chunks so the copy of chunk i+1 overlaps the kernels of chunk i; pinned memory makes
+    the copies asynchronous) or on the device."""
     dev = ctx.device
     if _is_dev(x):
         xd = x.to(torch.float64)
         if xd.stride(1) != 1:
             xd = xd.contiguous()
-        return engine.residualize(ctx, xd, Qt_dev, n_slices, keep_coef=keep_coef)
+        return engine.residualize(ctx, xd, Qt_dev, n_slices, out=out, row_offset=row_offset,
+                                  keep_coef=keep_coef)
     xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
     if xh.dtype != torch.float64:
         xh = xh.to(torch.float64)
     rows, n = xh.shape
-    out = engine.Sliced(rows, n, n_slices, dev)
+    if out is None:
+        out = engine.Sliced(rows, n, n_slices, dev)
+        row_offset = 0
     chunk = max(1, min(rows, _ROW_CHUNK_BYTES // max(1, n * 8)))
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
@@ -109,7 +113,7 @@ def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef):
             ready = torch.cuda.Event()
             ready.record(copy_stream)
         main.wait_event(ready)
-        engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=out, row_offset=r0,
+        engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=out, row_offset=row_offset + r0,
                            keep_coef=keep_coef)
         done[i & 1] = torch.cuda.Event()
         done[i & 1].record(main)
@@ -117,11 +121,60 @@ def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef):
     return out
 
 
+def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef, out_host):
+    """Co-expression of a HOST matrix with the three legs overlapped:
+      copy stream : chunk c+1 of the expression matrix, host -> device
+      main stream : projection of chunk c, then every output tile whose columns lie in chunk c
+                    (such a tile only needs rows <= its column, i.e. chunks 0..c)
+      d2h stream  : the blocks of P / dot that became final with chunk c, device -> host
+    After strip c the square [0, end_c)^2 is complete (mirrored entries included), so the newly
+    final part is the column block [0:end_c, begin_c:end_c] plus the row block
+    [begin_c:end_c, 0:begin_c].  Returns (A, P_dev, dot_dev, P_host|None, dot_host|None)."""
+    dev = ctx.device
+    rows, n = xh.shape
+    A = engine.Sliced(rows, n, n_slices, dev)
+    P = torch.empty((rows, rows), dtype=torch.float64, device=dev)
+    D = torch.empty((rows, rows), dtype=torch.float64, device=dev)
+    strip_rows = 12 * engine.TILE
+    chunk = max(strip_rows, (_ROW_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
+    chunk = min(chunk, (rows + engine.TILE - 1) // engine.TILE * engine.TILE)
+    copy_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    bufs = [torch.empty((min(chunk, rows), n), dtype=torch.float64, device=dev) for _ in range(2)]
+    done = [None, None]
+    for i, r0 in enumerate(range(0, rows, chunk)):
+        r1 = min(r0 + chunk, rows)
+        b = bufs[i & 1]
+        with torch.cuda.stream(copy_stream):
+            if done[i & 1] is not None:
+                copy_stream.wait_event(done[i & 1])
+            b[:r1 - r0].copy_(xh[r0:r1], non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        main.wait_event(ready)
+        engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=A, row_offset=r0, keep_coef=keep_coef)
+        done[i & 1] = torch.cuda.Event()
+        done[i & 1].record(main)
+        tiles = engine.coex_strip_tiles(r0 // engine.TILE, (r1 + engine.TILE - 1) // engine.TILE)
+        engine.contract(ctx, MODE_COEX, A, A, tiles, dof_a, P, D, n_products, eng)
+        if out_host is not None:
+            fin = torch.cuda.Event()
+            fin.record(main)
+            d2h_stream.wait_event(fin)
+            for dst, src in zip(out_host, (P, D)):
+                engine.copy_block_to_host(ctx, dst, src, 0, r1, r0, r1, d2h_stream)
+                engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
+    main.synchronize()
+    d2h_stream.synchronize()
+    return A, P, D
+
+
 def _out(t, to_host, host_buf=None):
     if t is None or not to_host:
         return t
     if host_buf is not None:
-        host_buf.copy_(t, non_blocking=False)
+        host_buf.copy_(t, non_blocking=True)       # synchronised by the caller
         return host_buf.numpy()
     return t.cpu().numpy()
 
@@ -138,10 +191,12 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
 
     Extra keyword arguments understood here (all optional, none changes results beyond the
     stated tolerance): ``precision`` in {'fast','default','precise'}, ``device``,
+    ``out`` = (P, dot) preallocated (pinned) CPU tensors that receive the two matrices,
     ``engine`` (tests only)."""
     precision = ka.pop('precision', 'default')
     device = ka.pop('device', None)
     eng = ka.pop('engine', ENGINE_UMMA)
+    out_host = ka.pop('out', None)          # optional (P, dot|gamma) host tensors to fill
     dimreduce = ka.pop('dimreduce', 0)
     if single not in (0, 1, 4, 5):
         raise ValueError('Unknown value single={}'.format(single))
@@ -184,13 +239,28 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     with torch.cuda.device(ctx.device):
         Qt_dev = torch.from_numpy(Qt).to(ctx.device) if rank else None
         keep_coef = not lowmem
-        A = _residualize_any(ctx, dx, Qt_dev, n_slices, keep_coef)
-        B = A if samexy else _residualize_any(ctx, dy, Qt_dev, n_slices, keep_coef)
+        piped = samexy and to_host
+        if piped:
+            xh = dx if isinstance(dx, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dx))
+            if xh.dtype != torch.float64:
+                xh = xh.to(torch.float64)
+            direct = out_host if (out_host is not None and lowmem and return_dot) else None
+            A, P, out2 = _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef,
+                                             direct)
+            B = A
+            if direct is not None:       # P and dot are already in the caller's host buffers
+                var_h = A.var.cpu().numpy()
+                return (direct[0].numpy(), direct[1].numpy(), None, None, var_h)
+        else:
+            A = _residualize_any(ctx, dx, Qt_dev, n_slices, keep_coef)
+            B = A if samexy else _residualize_any(ctx, dy, Qt_dev, n_slices, keep_coef)
         nx, ny = A.rows, B.rows
-        P = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
-        out2 = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+        if not piped:
+            P = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+            out2 = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
         if samexy:
-            engine.contract(ctx, MODE_COEX, A, A, engine.coex_tiles(nx), dof_a, P, out2, n_products, eng)
+            if not piped:
+                engine.contract(ctx, MODE_COEX, A, A, engine.coex_tiles(nx), dof_a, P, out2, n_products, eng)
             gamma = None
             if not (lowmem and return_dot):
                 gamma = out2 / A.var[:, None]
@@ -206,8 +276,9 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
         varx = None if samexy else A.var
         res = (P, out2, alpha, varx, B.var)
         if to_host:
+            bufs = list(out_host) + [None] * 3 if out_host is not None else [None] * 5
+            res = tuple(_out(t, True, hb) for t, hb in zip(res, bufs))
             torch.cuda.current_stream().synchronize()
-            res = tuple(_out(t, True) for t in res)
     return res
 
 

@@ -155,6 +155,18 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
                                     n_pad, n_slices, wmax, ctx->tiles_dev, n_tiles, ep);
 }
 
+extern "C" int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
+                          int64_t src_pitch, int64_t width_bytes, int64_t height, int kind) {
+    NSR_REQUIRE(ctx != nullptr && dst && src && width_bytes >= 0 && height >= 0 && dst_pitch >= width_bytes &&
+                    src_pitch >= width_bytes && (kind == 0 || kind == 1),
+                "nsr_copy2d: bad arguments");
+    if (width_bytes == 0 || height == 0) return 0;
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    NSR_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes, (size_t)height,
+                                kind == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 namespace {
 __global__ void pvalue_kernel(const double* __restrict__ r2, const double* __restrict__ a, int64_t row_len,
                               int64_t count, double* __restrict__ P) {

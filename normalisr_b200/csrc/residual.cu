@@ -3,264 +3,330 @@
 // Reference: association.py:226-233
 //     ccx = dci @ (dc @ dx.T);  dx1 = dx - ccx.T @ dc;  var = mean(dx1**2), 0 -> 1
 // Here the host supplies Qt, an orthonormal basis (rank x n) of the row space of dc, so
-//     coef = X Qt^T  (pass A),   z = X - coef Qt  (passes B1/B2).
-// B1 measures var and max|z'| per row, B2 re-derives z' and writes the int8 digit planes
-// the tensor-core contraction reads.  z' is z after a sign-randomised 128-point
-// Walsh-Hadamard transform along cells; it is orthonormal, so every inner product over
-// cells is unchanged, but rows become near-Gaussian and a per-row fixed-point scale then
-// costs no precision even for genes expressed in a handful of cells.
+//     coef = X Qt^T (pass A),   z = X - coef Qt (pass B).
+// Pass B also applies a sign-randomised orthonormal 128-point Walsh-Hadamard transform along
+// cells (z' = z D H: inner products over cells are unchanged, rows become near-Gaussian so a
+// fixed-point row scale wastes no bits on outliers) and writes round(z'/quantum) as balanced
+// base-256 int8 digit planes - the operand format of the tensor-core contraction.
 //
-// Layout: each warp owns one 128-cell block at a time; lane l holds cells l, l+32, l+64,
-// l+96 of the block, so every global load is a fully coalesced 256 B row segment.
-// The covariate block (Qt) is held in registers and reused across the CTA's rows.
+// Two passes over X (algorithmic traffic 8 B read + S B written per element, actual 16 + S):
+//   A  coef and sum(x^2) per row -> rms estimate sqrt((sum x^2 - |coef|^2)/n) (Qt orthonormal)
+//   B  z, z', exact var = mean(z^2), exact max|z'|, digits with quantum = kKappa*rms_est/vmax
+// A row whose max|z'| exceeds kKappa*rms_est (probability ~2e-9 per element for Gaussianised
+// rows, certain for degenerate ones) is re-quantised by a third, sparse pass with
+// quantum = max|z'|/vmax.
+//
+// Layout: all 8 warps of a CTA walk the same 128-cell blocks (so the covariate block is an L1
+// hit for 7 of them) and own different rows.  Lane l holds cells l, l+32, l+64, l+96 of the
+// block: every global load is a fully coalesced 256 B row segment.  For the transform each warp
+// transposes its 8 rows x 128 cells through shared memory so that a lane owns 32 consecutive
+// cells of one row: 5 butterfly stages in registers, 2 by shuffle, and 32-byte digit stores.
 #include "nsr_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRowsA = 4;   // rows per CTA in the coefficient kernel
-constexpr int kRowsB = 8;   // rows per CTA in the residual kernels
+constexpr int kRowsA = 4;                  // rows per warp, pass A
+constexpr int kRowsB = 8;                  // rows per warp, pass B
+constexpr int kSegPitch = 33;              // doubles per 32-cell segment in smem (+1: bank spread)
 constexpr double kHadScale = 0.088388347648318440550;   // 1/sqrt(128)
+constexpr double kKappa = 6.0;
 
 __device__ __forceinline__ bool cell_flip(uint64_t k) {
     uint32_t h = (uint32_t)k ^ (uint32_t)(k >> 32) * 0x9e3779b9u;
     h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
     return h & 1u;
 }
-
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
 }
-__device__ __forceinline__ double warp_max(double v) {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
-    return v;
-}
 
-// ---- pass A: partial[ks][row][c] = sum over the CTA's cells of X[row][k] Qt[c][k] ------
+// ---- pass A ------------------------------------------------------------------------------
+// partial[ks][row][c] = sum over the CTA's cells of X[row][k] Qt[c0+c][k];  psq[ks][row] = sum x^2
 template <int CB>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 coef_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
             const double* __restrict__ Qt, int rank, int64_t ldq, int c0, int nblk, int ksplit,
-            double* __restrict__ partial) {
+            double* __restrict__ partial, double* __restrict__ psq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * kRowsA;
+    const int64_t row0 = ((int64_t)blockIdx.x * kWarps + warp) * kRowsA;
     const int ks = blockIdx.y;
     const int b_begin = (int)((int64_t)nblk * ks / ksplit);
     const int b_end = (int)((int64_t)nblk * (ks + 1) / ksplit);
+    if (row0 >= rows) return;
 
-    double acc[kRowsA][CB];
+    double acc[kRowsA][CB], sq[kRowsA];
 #pragma unroll
-    for (int r = 0; r < kRowsA; ++r)
+    for (int r = 0; r < kRowsA; ++r) {
+        sq[r] = 0.0;
 #pragma unroll
         for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
-
-    for (int blk = b_begin + warp; blk < b_end; blk += kWarps) {
+    }
+    for (int blk = b_begin; blk < b_end; ++blk) {
         const int64_t k0 = (int64_t)blk * 128 + lane;
-        double q[CB][4];
+        double x[kRowsA][4];
 #pragma unroll
-        for (int c = 0; c < CB; ++c)
+        for (int r = 0; r < kRowsA; ++r) {
+            const bool rv = row0 + r < rows;
+            const double* xr = X + (rv ? row0 + r : row0) * ldx;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int64_t k = k0 + 32 * j;
-                q[c][j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
-            }
-#pragma unroll
-        for (int r = 0; r < kRowsA; ++r) {
-            if (row0 + r < rows) {
-                const double* xr = X + (row0 + r) * ldx;
-                double x[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t k = k0 + 32 * j;
-                    x[j] = (k < n) ? __ldg(xr + k) : 0.0;
-                }
-#pragma unroll
-                for (int c = 0; c < CB; ++c)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[r][c] = fma(x[j], q[c][j], acc[r][c]);
+                x[r][j] = (rv && k < n) ? __ldg(xr + k) : 0.0;
             }
         }
-    }
-    __shared__ double red[kWarps][kRowsA][CB];
 #pragma unroll
-    for (int r = 0; r < kRowsA; ++r)
+        for (int c = 0; c < CB; ++c) {
+            double q[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + 32 * j;
+                q[j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < kRowsA; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][c] = fma(x[r][j], q[j], acc[r][c]);
+        }
+        if (c0 == 0) {
+#pragma unroll
+            for (int r = 0; r < kRowsA; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) sq[r] = fma(x[r][j], x[r][j], sq[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsA; ++r) {
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
             const double v = warp_sum(acc[r][c]);
-            if (lane == 0) red[warp][r][c] = v;
+            if (lane == 0 && row0 + r < rows && c0 + c < rank)
+                partial[((int64_t)ks * rows + row0 + r) * rank + c0 + c] = v;
         }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kRowsA * CB; i += kThreads) {
-        const int r = i / CB, c = i % CB;
-        double s = 0.0;
-        for (int w = 0; w < kWarps; ++w) s += red[w][r][c];
-        if (row0 + r < rows && c0 + c < rank)
-            partial[((int64_t)ks * rows + row0 + r) * rank + c0 + c] = s;
+        if (c0 == 0) {
+            const double v = warp_sum(sq[r]);
+            if (lane == 0 && row0 + r < rows) psq[(int64_t)ks * rows + row0 + r] = v;
+        }
     }
 }
 
-__global__ void coef_reduce_kernel(const double* __restrict__ partial, int64_t count, int ksplit,
-                                   double* __restrict__ coef) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+// rank == 0: only sum x^2 is needed
+__global__ void __launch_bounds__(kThreads, 2)
+sumsq_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx, int nblk, int ksplit,
+             double* __restrict__ psq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
+    const int ks = blockIdx.y;
+    if (row >= rows) return;
+    const int64_t k_begin = (int64_t)nblk * ks / ksplit * 128, k_end = (int64_t)nblk * (ks + 1) / ksplit * 128;
     double s = 0.0;
-    for (int ks = 0; ks < ksplit; ++ks) s += partial[(int64_t)ks * count + i];   // fixed order
-    coef[i] = s;
+    for (int64_t k = k_begin + lane; k < k_end && k < n; k += 32) {
+        const double x = __ldg(X + row * ldx + k);
+        s = fma(x, x, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) psq[(int64_t)ks * rows + row] = s;
 }
 
-// ---- passes B1 / B2 ---------------------------------------------------------------------
-template <bool WRITE, bool HAD>
-__global__ void __launch_bounds__(kThreads)
+// coef[row][c] = sum_ks partial; inv_quantum estimate from rms_est = sqrt((sum x^2 - |coef|^2)/n)
+__global__ void coef_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ psq,
+                                     int64_t rows, int rank, int ksplit, int64_t n, double vmax,
+                                     double* __restrict__ coef, double* __restrict__ invq_est) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    double c2 = 0.0;
+    for (int c = 0; c < rank; ++c) {
+        double s = 0.0;
+        for (int ks = 0; ks < ksplit; ++ks) s += partial[((int64_t)ks * rows + row) * rank + c];   // fixed order
+        coef[row * rank + c] = s;
+        c2 = fma(s, s, c2);
+    }
+    double sq = 0.0;
+    for (int ks = 0; ks < ksplit; ++ks) sq += psq[(int64_t)ks * rows + row];
+    const double ms = (sq - c2) / (double)n;
+    const double est = (ms > 0.0 && isfinite(ms)) ? kKappa * sqrt(ms) : 0.0;
+    invq_est[row] = est > 0.0 ? vmax / est : 0.0;          // 0 -> digits 0, row goes to the fix-up pass
+}
+
+// ---- pass B ------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void store_digits(const double (&v)[32], double invq, double vmax,
+                                             int8_t* __restrict__ dst, int64_t plane_stride) {
+    uint32_t w[S][8];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[s][i] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const double t = fmin(fmax(v[i] * invq, -vmax), vmax);
+        int32_t q = __double2int_rn(t);
+#pragma unroll
+        for (int s = S - 1; s >= 1; --s) {
+            const int32_t d = (int32_t)(int8_t)(q & 0xFF);           // balanced low digit
+            w[s][i >> 2] |= (uint32_t)(d & 0xFF) << (8 * (i & 3));
+            q = (q - d) >> 8;
+        }
+        w[0][i >> 2] |= (uint32_t)(q & 0xFF) << (8 * (i & 3));
+    }
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        uint4* p = reinterpret_cast<uint4*>(dst + (int64_t)s * plane_stride);
+        p[0] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
+        p[1] = make_uint4(w[s][4], w[s][5], w[s][6], w[s][7]);
+    }
+}
+
+// row_list == nullptr: logical row == row.  Otherwise the kernel handles rows row_list[0..*row_count).
+template <int S, bool HAD>
+__global__ void __launch_bounds__(kThreads, 2)
 residual_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
-                const double* __restrict__ Qt, int rank, int64_t ldq,
-                const double* __restrict__ coef, int nblk, int ksplit, uint64_t cell_offset,
-                double* __restrict__ part_sumsq, double* __restrict__ part_amax,
-                const double* __restrict__ inv_quantum, int n_slices, double vmax,
+                const double* __restrict__ Qt, int rank, int64_t ldq, const double* __restrict__ coef,
+                const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
+                int nblk, int ksplit, uint64_t cell_offset, const double* __restrict__ inv_quantum,
+                double vmax, double* __restrict__ part_sumsq, double* __restrict__ part_amax,
                 int8_t* __restrict__ slices, int64_t rows_alloc, int64_t n_pad) {
+    extern __shared__ double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * kRowsB;
+    const int64_t n_logical = row_list ? (int64_t)*row_count : rows;
+    const int64_t l0 = ((int64_t)blockIdx.x * kWarps + warp) * kRowsB;    // first logical row of this warp
     const int ks = blockIdx.y;
     const int b_begin = (int)((int64_t)nblk * ks / ksplit);
     const int b_end = (int)((int64_t)nblk * (ks + 1) / ksplit);
+    if ((int64_t)blockIdx.x * kWarps * kRowsB >= n_logical) return;        // whole CTA idle
     const int rank4 = (rank + 3) & ~3;
 
-    __shared__ double s_coef[kRowsB][NSR_MAX_RANK];
-    __shared__ double s_red[2][kWarps][kRowsB];
-    for (int i = threadIdx.x; i < kRowsB * NSR_MAX_RANK; i += kThreads) {
-        const int r = i / NSR_MAX_RANK, c = i % NSR_MAX_RANK;
-        s_coef[r][c] = (row0 + r < rows && c < rank) ? coef[(row0 + r) * rank + c] : 0.0;
-    }
-    __syncthreads();
-
-    double sumsq[kRowsB], amax[kRowsB], invq[kRowsB];
+    double* s_coef = smem + warp * (kRowsB * NSR_MAX_RANK + 32 * kSegPitch);   // [kRowsB][NSR_MAX_RANK]
+    double* s_z = s_coef + kRowsB * NSR_MAX_RANK;                               // [32 segments][kSegPitch]
+    int64_t row_of[kRowsB];
 #pragma unroll
     for (int r = 0; r < kRowsB; ++r) {
-        sumsq[r] = 0.0;
-        amax[r] = 0.0;
-        invq[r] = (WRITE && row0 + r < rows) ? inv_quantum[row0 + r] : 0.0;
+        const int64_t l = l0 + r;
+        row_of[r] = (l < n_logical) ? (row_list ? (int64_t)row_list[l] : l) : -1;
     }
+    for (int i = lane; i < kRowsB * NSR_MAX_RANK; i += 32) {
+        const int r = i / NSR_MAX_RANK, c = i % NSR_MAX_RANK;
+        const int64_t l = l0 + r;
+        const int64_t row = (l < n_logical) ? (row_list ? (int64_t)row_list[l] : l) : -1;
+        s_coef[i] = (row >= 0 && c < rank) ? coef[row * rank + c] : 0.0;
+    }
+    __syncwarp();
 
-    for (int blk = b_begin + warp; blk < b_end; blk += kWarps) {
+    // phase-2 ownership: lane -> (row slot lane>>2, cells 32*(lane&3) .. +32 of the block)
+    const int my_slot = lane >> 2, my_quarter = lane & 3;
+    int64_t my_row = -1;
+#pragma unroll
+    for (int r = 0; r < kRowsB; ++r)
+        if (r == my_slot) my_row = row_of[r];
+    const double my_invq = (my_row >= 0 && inv_quantum) ? inv_quantum[my_row] : 0.0;
+    double my_amax = 0.0;
+    double sumsq[kRowsB];
+#pragma unroll
+    for (int r = 0; r < kRowsB; ++r) sumsq[r] = 0.0;
+
+    for (int blk = b_begin; blk < b_end; ++blk) {
         const int64_t k0 = (int64_t)blk * 128 + lane;
-        double z[kRowsB][4];
+        bool flip[4];
 #pragma unroll
-        for (int r = 0; r < kRowsB; ++r) {
-            const bool rv = row0 + r < rows;
-            const double* xr = X + (rv ? row0 + r : 0) * ldx;
+        for (int j = 0; j < 4; ++j) flip[j] = HAD && cell_flip(cell_offset + (uint64_t)(k0 + 32 * j));
+        // ---- phase 1: residuals of 8 rows (two halves of 4 to bound registers) -> smem
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t k = k0 + 32 * j;
-                z[r][j] = (rv && k < n) ? __ldg(xr + k) : 0.0;
-            }
-        }
-        for (int c0 = 0; c0 < rank4; c0 += 4) {
-            double q[4][4];
+        for (int half = 0; half < 2; ++half) {
+            double z[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int r = 0; r < 4; ++r) {
+                const int64_t row = row_of[4 * half + r];
+                const double* xr = X + (row >= 0 ? row : 0) * ldx;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int64_t k = k0 + 32 * j;
-                    q[c][j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
+                    z[r][j] = (row >= 0 && k < n) ? __ldg(xr + k) : 0.0;
                 }
-#pragma unroll
-            for (int r = 0; r < kRowsB; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double b = s_coef[r][c0 + c];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) z[r][j] = fma(-b, q[c][j], z[r][j]);
-                }
-        }
-        bool flip[4];
-        if (HAD) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) flip[j] = cell_flip(cell_offset + (uint64_t)(k0 + 32 * j));
-        }
-#pragma unroll
-        for (int r = 0; r < kRowsB; ++r) {
-            double a = z[r][0], b = z[r][1], c = z[r][2], d = z[r][3];
-            sumsq[r] += a * a + b * b + c * c + d * d;
-            if (HAD) {
-                if (flip[0]) a = -a;
-                if (flip[1]) b = -b;
-                if (flip[2]) c = -c;
-                if (flip[3]) d = -d;
-                // element index e = 32 j + lane: bits 5,6 are in-thread, bits 0..4 across lanes
-                double t0 = a + b, t1 = a - b, t2 = c + d, t3 = c - d;
-                a = t0 + t2; b = t1 + t3; c = t0 - t2; d = t1 - t3;
-#pragma unroll
-                for (int m = 1; m < 32; m <<= 1) {
-                    const bool up = lane & m;
-                    double p;
-                    p = __shfl_xor_sync(0xffffffffu, a, m); a = up ? p - a : a + p;
-                    p = __shfl_xor_sync(0xffffffffu, b, m); b = up ? p - b : b + p;
-                    p = __shfl_xor_sync(0xffffffffu, c, m); c = up ? p - c : c + p;
-                    p = __shfl_xor_sync(0xffffffffu, d, m); d = up ? p - d : d + p;
-                }
-                a *= kHadScale; b *= kHadScale; c *= kHadScale; d *= kHadScale;
             }
-            amax[r] = fmax(amax[r], fmax(fmax(fabs(a), fabs(b)), fmax(fabs(c), fabs(d))));
-            if (WRITE) {
-                const double zz[4] = {a, b, c, d};
-                uint32_t word[NSR_MAX_SLICES] = {0, 0, 0, 0};
+            for (int c0 = 0; c0 < rank4; c0 += 4) {
+                double q[4][4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int64_t k = k0 + 32 * j;
+                        q[c][j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
+                    }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double b = s_coef[(4 * half + r) * NSR_MAX_RANK + c0 + c];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) z[r][j] = fma(-b, q[c][j], z[r][j]);
+                    }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    double t = fmin(fmax(zz[j] * invq[r], -vmax), vmax);
-                    int8_t dg[NSR_MAX_SLICES];
-                    nsr_digits(__double2int_rn(t), n_slices, dg);
-#pragma unroll
-                    for (int s = 0; s < NSR_MAX_SLICES; ++s)
-                        if (s < n_slices) word[s] |= (uint32_t)(uint8_t)dg[s] << (8 * j);
+                    const double v = z[r][j];
+                    sumsq[4 * half + r] = fma(v, v, sumsq[4 * half + r]);
+                    s_z[(4 * (4 * half + r) + j) * kSegPitch + lane] = flip[j] ? -v : v;
                 }
-                // lane l holds bytes of cells l+32j; regroup so lane l owns cells 4l..4l+3
-                if (row0 + r < rows) {
+        }
+        __syncwarp();
+        // ---- phase 2: 32 consecutive cells of one row per lane
+        double v[32];
 #pragma unroll
-                    for (int s = 0; s < NSR_MAX_SLICES; ++s) {
-                        if (s < n_slices) {
-                            uint32_t out = 0;
+        for (int i = 0; i < 32; ++i) v[i] = s_z[lane * kSegPitch + i];
+        __syncwarp();
+        if (HAD) {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const uint32_t w = __shfl_sync(0xffffffffu, word[s], (4 * lane + i) & 31);
-                                out |= ((w >> (8 * (lane >> 3))) & 0xFFu) << (8 * i);
-                            }
-                            int8_t* dst = slices + ((int64_t)s * rows_alloc + row0 + r) * n_pad +
-                                          (int64_t)blk * 128 + 4 * lane;
-                            *reinterpret_cast<uint32_t*>(dst) = out;
-                        }
+            for (int h = 1; h < 32; h <<= 1)
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if ((i & h) == 0) {
+                        const double a = v[i], b = v[i + h];
+                        v[i] = a + b;
+                        v[i + h] = a - b;
                     }
+#pragma unroll
+            for (int m = 1; m <= 2; m <<= 1) {
+                const bool up = lane & m;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const double p = __shfl_xor_sync(0xffffffffu, v[i], m);
+                    v[i] = up ? p - v[i] : v[i] + p;
                 }
             }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] *= kHadScale;
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) my_amax = fmax(my_amax, fabs(v[i]));
+        if (slices != nullptr && my_row >= 0)
+            store_digits<S>(v, my_invq, vmax,
+                            slices + my_row * n_pad + (int64_t)blk * 128 + 32 * my_quarter,
+                            rows_alloc * n_pad);
     }
-    if (!WRITE) {
+    if (part_sumsq != nullptr) {
 #pragma unroll
         for (int r = 0; r < kRowsB; ++r) {
             const double s = warp_sum(sumsq[r]);
-            const double m = warp_max(amax[r]);
-            if (lane == 0) { s_red[0][warp][r] = s; s_red[1][warp][r] = m; }
+            if (lane == 0 && row_of[r] >= 0) part_sumsq[(int64_t)ks * rows + row_of[r]] = s;
         }
-        __syncthreads();
-        if (threadIdx.x < kRowsB && row0 + threadIdx.x < rows) {
-            double s = 0.0, m = 0.0;
-            for (int w = 0; w < kWarps; ++w) {
-                s += s_red[0][w][threadIdx.x];
-                m = fmax(m, s_red[1][w][threadIdx.x]);
-            }
-            part_sumsq[(int64_t)ks * rows + row0 + threadIdx.x] = s;
-            part_amax[(int64_t)ks * rows + row0 + threadIdx.x] = m;
-        }
+        my_amax = fmax(my_amax, __shfl_xor_sync(0xffffffffu, my_amax, 1));
+        my_amax = fmax(my_amax, __shfl_xor_sync(0xffffffffu, my_amax, 2));
+        if (my_quarter == 0 && my_row >= 0) part_amax[(int64_t)ks * rows + my_row] = my_amax;
     }
 }
 
+// var, final quantum, and the list of rows whose digits overflowed the estimated scale
 __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
                                       const double* __restrict__ part_amax, int64_t rows,
                                       int ksplit, int64_t n, double vmax,
                                       double* __restrict__ var, double* __restrict__ quantum,
-                                      double* __restrict__ inv_quantum) {
+                                      double* __restrict__ inv_quantum, int32_t* __restrict__ fix_list,
+                                      int32_t* __restrict__ fix_count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     double s = 0.0, m = 0.0;
@@ -271,9 +337,15 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
     double v = s / (double)n;
     if (v == 0.0) v = 1.0;                       // association.py:231,233
     var[i] = v;
-    const double q = (m > 0.0 && isfinite(m)) ? m / vmax : 1.0;
-    quantum[i] = q;
-    inv_quantum[i] = 1.0 / q;
+    const double iq = inv_quantum[i];
+    if (m > 0.0 && isfinite(m) && (iq == 0.0 || !(m * iq <= vmax))) {     // iq == 0: no usable estimate
+        const double q = m / vmax;
+        quantum[i] = q;
+        inv_quantum[i] = 1.0 / q;
+        fix_list[atomicAdd(fix_count, 1)] = (int32_t)i;
+    } else {
+        quantum[i] = iq > 0.0 ? 1.0 / iq : 1.0;
+    }
 }
 
 __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, int64_t rows_alloc,
@@ -287,12 +359,22 @@ __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, 
     out[i] = (double)v * quantum[r];
 }
 
-template <int CB>
-void launch_coef(cudaStream_t st, dim3 grid, const double* X, int64_t rows, int64_t n, int64_t ldx,
-                 const double* Qt, int rank, int64_t ldq, int c0, int nblk, int ksplit,
-                 double* partial) {
-    coef_kernel<CB><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ksplit,
-                                               partial);
+constexpr int kSmemB = kWarps * (kRowsB * NSR_MAX_RANK + 32 * kSegPitch) * (int)sizeof(double);
+
+template <int S, bool HAD>
+int launch_residual(cudaStream_t st, dim3 grid, const double* X, int64_t rows, int64_t n, int64_t ldx,
+                    const double* Qt, int rank, int64_t ldq, const double* coef, const int32_t* row_list,
+                    const int32_t* row_count, int nblk, int ksplit, const double* invq, double vmax,
+                    double* p_sumsq, double* p_amax, int8_t* slices, int64_t rows_alloc, int64_t n_pad) {
+    auto kern = residual_kernel<S, HAD>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemB));
+        attr_done = true;
+    }
+    kern<<<grid, kThreads, kSmemB, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef, row_list, row_count, nblk, ksplit,
+                                         0, invq, vmax, p_sumsq, p_amax, slices, rows_alloc, n_pad);
+    return 0;
 }
 
 }  // namespace
@@ -306,12 +388,13 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
                                int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
                                double* quantum, double* var, double* coef) {
     NSR_REQUIRE(ctx != nullptr, "nsr_residualize: null context");
-    NSR_REQUIRE(rows > 0 && n > 0 && ldx >= n, "nsr_residualize: bad shape rows=%lld n=%lld ldx=%lld",
-                (long long)rows, (long long)n, (long long)ldx);
+    NSR_REQUIRE(rows > 0 && rows < (1ll << 31) && n > 0 && ldx >= n,
+                "nsr_residualize: bad shape rows=%lld n=%lld ldx=%lld", (long long)rows, (long long)n,
+                (long long)ldx);
     NSR_REQUIRE(rank >= 0 && rank <= NSR_MAX_RANK, "nsr_residualize: rank %d outside [0,%d]", rank,
                 NSR_MAX_RANK);
     NSR_REQUIRE(rank == 0 || (Qt != nullptr && ldq >= n), "nsr_residualize: bad covariate basis");
-    NSR_REQUIRE(n_slices >= 2 && n_slices <= NSR_MAX_SLICES, "nsr_residualize: n_slices %d", n_slices);
+    NSR_REQUIRE(n_slices == 3 || n_slices == 4, "nsr_residualize: n_slices %d (3 or 4)", n_slices);
     NSR_REQUIRE(n_pad == nsr_padded_cells(n) && rows_alloc >= rows,
                 "nsr_residualize: n_pad/rows_alloc inconsistent");
     NSR_REQUIRE(((uintptr_t)slices & 15) == 0, "nsr_residualize: slices must be 16-byte aligned");
@@ -320,50 +403,65 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
 
     const int nblk = (int)(n_pad / 128);
     auto pick_split = [&](int64_t groups) {
-        int64_t ks = (2 * (int64_t)ctx->sm_count + groups - 1) / groups;
+        int64_t ks = (4 * (int64_t)ctx->sm_count + groups - 1) / groups;
         if (ks < 1) ks = 1;
         if (ks > nblk) ks = nblk;
         if (ks > 64) ks = 64;
         return (int)ks;
     };
-    const int64_t groups_a = (rows + kRowsA - 1) / kRowsA;
-    const int64_t groups_b = (rows + kRowsB - 1) / kRowsB;
-    const int ks_a = pick_split(groups_a), ks_b = pick_split(groups_b);
+    const int64_t groups_a = (rows + kWarps * kRowsA - 1) / (kWarps * kRowsA);
+    const int64_t groups_s = (rows + kWarps - 1) / kWarps;
+    const int64_t groups_b = (rows + kWarps * kRowsB - 1) / (kWarps * kRowsB);
+    const int ks_a = pick_split(rank ? groups_a : groups_s), ks_b = pick_split(groups_b);
+    const int rk = rank > 0 ? rank : 1;
 
-    // scratch: coef partials | sumsq partials | amax partials | inv_quantum | coef (if caller passed none)
-    const size_t n_part = (size_t)ks_a * rows * (rank > 0 ? rank : 1);
-    const size_t n_coef = (size_t)rows * (rank > 0 ? rank : 1);
-    const size_t total = n_part + 2 * (size_t)ks_b * rows + rows + n_coef;
+    // scratch (doubles): coef partials | sum-x^2 partials | sumsq partials | amax partials | inv_quantum
+    //                    | coef (if the caller passed none) ; then int32: fix_count(+pad) | fix_list
+    const size_t n_part = (size_t)ks_a * rows * rk, n_psq = (size_t)ks_a * rows;
+    const size_t n_stat = (size_t)ks_b * rows, n_coef = (size_t)rows * rk;
+    const size_t n_dbl = n_part + n_psq + 2 * n_stat + rows + n_coef;
     void* scratch = nullptr;
-    if (nsr_scratch(ctx, total * sizeof(double), &scratch)) return 1;
+    if (nsr_scratch(ctx, n_dbl * sizeof(double) + (size_t)(rows + 4) * sizeof(int32_t), &scratch)) return 1;
     double* partial = (double*)scratch;
-    double* p_sumsq = partial + n_part;
-    double* p_amax = p_sumsq + (size_t)ks_b * rows;
-    double* invq = p_amax + (size_t)ks_b * rows;
+    double* psq = partial + n_part;
+    double* p_sumsq = psq + n_psq;
+    double* p_amax = p_sumsq + n_stat;
+    double* invq = p_amax + n_stat;
     double* coef_buf = coef ? coef : invq + rows;
+    int32_t* fix_count = (int32_t*)((double*)scratch + n_dbl);
+    int32_t* fix_list = fix_count + 4;
+    const double vmax = nsr_vmax(n_slices);
 
+    NSR_CHECK(cudaMemsetAsync(fix_count, 0, sizeof(int32_t), st));
     if (rank > 0) {
         const dim3 grid((unsigned)groups_a, (unsigned)ks_a);
-        for (int c0 = 0; c0 < rank; c0 += 12) {
-            const int left = rank - c0;
-            if (left <= 4) launch_coef<4>(st, grid, X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial);
-            else if (left <= 8) launch_coef<8>(st, grid, X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial);
-            else launch_coef<12>(st, grid, X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial);
+        for (int c0 = 0; c0 < rank; c0 += 8) {
+            if (rank - c0 <= 4)
+                coef_kernel<4><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial, psq);
+            else
+                coef_kernel<8><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial, psq);
         }
-        const int64_t count = rows * rank;
-        coef_reduce_kernel<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(partial, count, ks_a, coef_buf);
+    } else {
+        sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ks_a), kThreads, 0, st>>>(X, rows, n, ldx, nblk, ks_a, psq);
     }
-    const double vmax = nsr_vmax(n_slices);
+    coef_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial, psq, rows, rank, ks_a, n, vmax,
+                                                                       coef_buf, invq);
     const dim3 gridb((unsigned)groups_b, (unsigned)ks_b);
-    if (nsr_use_hadamard)
-        residual_kernel<false, true><<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, nblk, ks_b, 0, p_sumsq, p_amax, nullptr, n_slices, vmax, nullptr, rows_alloc, n_pad);
-    else
-        residual_kernel<false, false><<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, nblk, ks_b, 0, p_sumsq, p_amax, nullptr, n_slices, vmax, nullptr, rows_alloc, n_pad);
-    stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var, quantum, invq);
-    if (nsr_use_hadamard)
-        residual_kernel<true, true><<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, nblk, ks_b, 0, nullptr, nullptr, invq, n_slices, vmax, slices, rows_alloc, n_pad);
-    else
-        residual_kernel<true, false><<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, nblk, ks_b, 0, nullptr, nullptr, invq, n_slices, vmax, slices, rows_alloc, n_pad);
+    const bool had = nsr_use_hadamard != 0;
+    int rc;
+#define NSR_LAUNCH_B(GRID, LIST, COUNT, KS, PS, PA)                                                          \
+    (n_slices == 3 ? (had ? launch_residual<3, true>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)   \
+                          : launch_residual<3, false>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)) \
+                   : (had ? launch_residual<4, true>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)   \
+                          : launch_residual<4, false>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)))
+    rc = NSR_LAUNCH_B(gridb, nullptr, nullptr, ks_b, p_sumsq, p_amax);
+    if (rc) return rc;
+    stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
+                                                                        quantum, invq, fix_list, fix_count);
+    // sparse fix-up: CTAs beyond the (device-side) count exit at once
+    rc = NSR_LAUNCH_B(gridb, fix_list, fix_count, ks_b, nullptr, nullptr);
+#undef NSR_LAUNCH_B
+    if (rc) return rc;
     NSR_CHECK(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@ from ._lib import (ENGINE_SIMT, ENGINE_UMMA, MODE_COEX, MODE_COEX_UPPER, MODE_DE
 
 _ctx_lock = threading.Lock()
 _contexts = {}
+LAUNCHES = 0          # kernels of libnsr_b200.so launched by this process (bench bookkeeping)
 
 # precision presets: (digit planes, digit-pair products kept)
 PRESETS = {"fast": (3, 6), "default": (3, 8), "precise": (4, 10)}
@@ -105,6 +106,10 @@ def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
         out.quantum[row_offset:].data_ptr(), out.var[row_offset:].data_ptr(),
         coef.data_ptr() if coef is not None else None)
     _lib.check(st, "nsr_residualize")
+    global LAUNCHES
+    # pass A (8 covariates per launch, or the sum-of-squares kernel), its finalize, pass B,
+    # stats finalize, sparse fix-up pass
+    LAUNCHES += ((rank + 7) // 8 if rank else 1) + 4
     return out
 
 
@@ -154,6 +159,8 @@ def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_U
         tiles.ctypes.data, tiles.shape[0], float(dof_a),
         P.data_ptr() if P is not None else None, out2.data_ptr(), ld)
     _lib.check(st, "nsr_contract")
+    global LAUNCHES
+    LAUNCHES += 1
 
 
 def pvalue(ctx, r2, a):
@@ -168,6 +175,30 @@ def pvalue(ctx, r2, a):
     _lib.check(ctx.lib.nsr_pvalue(ctx.handle, _stream(), r2.data_ptr(), a_t.data_ptr(), cols,
                                   r2.numel(), P.data_ptr()), "nsr_pvalue")
     return P
+
+
+def copy_block_to_host(ctx, dst_host, src_dev, r0, r1, c0, c1, stream=None):
+    """dst_host[r0:r1, c0:c1] <- src_dev[r0:r1, c0:c1] (both 2-D float64, unit column stride),
+    asynchronously on ``stream`` (default: current).  dst_host should be pinned."""
+    if r1 <= r0 or c1 <= c0:
+        return
+    es = 8
+    st = stream.cuda_stream if stream is not None else _stream()
+    _lib.check(ctx.lib.nsr_copy2d(ctx.handle, st,
+                                  dst_host.data_ptr() + (r0 * dst_host.stride(0) + c0) * es, dst_host.stride(0) * es,
+                                  src_dev.data_ptr() + (r0 * src_dev.stride(0) + c0) * es, src_dev.stride(0) * es,
+                                  (c1 - c0) * es, r1 - r0, 0), "nsr_copy2d")
+
+
+def coex_strip_tiles(t_begin, t_end, strip=12):
+    """Upper-triangular tiles whose tile column lies in [t_begin, t_end), in column sub-strips."""
+    out = []
+    for js in range(t_begin, t_end, strip):
+        je = min(js + strip, t_end)
+        for i in range(0, je):
+            for j in range(max(i, js), je):
+                out.append((i, j))
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
 
 
 def set_option(name, value):

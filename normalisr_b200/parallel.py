@@ -117,6 +117,55 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
     return P, D, full.var[:n_gene], (r0, r1)
 
 
+def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimreduce=0, out_dev=None,
+              out_host=None):
+    """``coex_sharded`` for HOST inputs and outputs: this rank's gene block is a CPU tensor / numpy
+    array (pinned memory makes the staged copies asynchronous and overlapped with the projection
+    kernels); P and dot strips are copied back into ``out_host`` (CPU tensors) if given.
+    Returns (P_strip, dot_strip, var, (row_begin, row_end)) as numpy arrays."""
+    from .association import _residualize_any
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ctx = engine.context(None)
+    n_slices, n_products = engine.PRESETS[precision]
+    xh = dt_block_host if isinstance(dt_block_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt_block_host))
+    n = xh.shape[1]
+    dc_h = dc.detach().cpu().numpy() if isinstance(dc, torch.Tensor) else np.asarray(dc)
+    Qt, crank, _ = covariate_basis(dc_h)
+    if n <= crank + dimreduce + 1:
+        raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
+                         'removed + covariate + 1.')
+    with torch.cuda.device(ctx.device):
+        Qt_dev = torch.from_numpy(Qt).to(ctx.device) if crank else None
+        blk = row_split(n_gene, world)
+        local = engine.Sliced(blk, n, n_slices, ctx.device)
+        if xh.shape[0] < blk:
+            local.slices.zero_(); local.quantum.fill_(1.0); local.var.fill_(1.0)
+        if xh.shape[0]:
+            _residualize_any(ctx, xh, Qt_dev, n_slices, False, out=local, row_offset=0)
+        full = gather_sliced(local, n_gene, group) if world > 1 else local
+        full.rows = n_gene
+        t = (n_gene + TILE - 1) // TILE
+        a, b = strip_bounds(t, world)[rank]
+        r0, r1 = a * TILE, min(b * TILE, n_gene)
+        if out_dev is None:
+            P = torch.zeros((max(r1 - r0, 1), n_gene), dtype=torch.float64, device=ctx.device)
+            D = torch.zeros_like(P)
+        else:
+            P, D = out_dev
+        if r1 > r0:
+            _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b),
+                            (n - 1 - crank - dimreduce) / 2, P, D, r0, n_products)
+        if out_host is not None:
+            out_host[0].copy_(P, non_blocking=True)
+            out_host[1].copy_(D, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            Ph, Dh = out_host[0].numpy(), out_host[1].numpy()
+        else:
+            Ph, Dh = P.cpu().numpy(), D.cpu().numpy()
+        return Ph, Dh, full.var[:n_gene].cpu().numpy(), (r0, r1)
+
+
 def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products):
     """Contract with outputs stored from global row ``row0``: hand the C ABI a base pointer that
     is row0 rows before the strip buffers (it only dereferences rows of the listed tiles)."""
@@ -131,6 +180,7 @@ def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products):
         A.n, A.n_pad, A.n_slices, n_products, tiles.ctypes.data, tiles.shape[0], float(dof_a),
         P.data_ptr() - off, D.data_ptr() - off, ld)
     _lib.check(st, "nsr_contract")
+    engine.LAUNCHES += 1
 
 
 def gather_dense(P_strip, D_strip, bounds, n_gene, group=None, dst=0):

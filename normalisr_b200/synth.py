@@ -20,11 +20,11 @@ def host_counts(rng, n_gene, n_cell, n_module=0, module_size=30):
     return rng.negative_binomial(2, 2.0 / (2.0 + m)), depth
 
 
-def host_problem(seed, n_gene, n_cell, n_batch=6, n_module=4, n_group=0, group_p=0.02):
+def host_problem(seed, n_gene, n_cell, n_batch=6, n_module=4, n_group=0, group_p=0.02, module_size=30):
     """Return dict(dt, dc[, dg]): float64, rows = variables, columns = cells.  dc = one-hot
     batches minus one + log depth + detection rate + a constant row (like normcov's output)."""
     rng = np.random.default_rng(seed)
-    reads, depth = host_counts(rng, n_gene, n_cell, n_module)
+    reads, depth = host_counts(rng, n_gene, n_cell, n_module, module_size)
     tot = reads.sum(axis=0) + 1.0
     dt = np.log((reads + 0.5) / tot[None, :] * 1e4 + 1.0)
     b = rng.integers(0, n_batch, size=n_cell)
@@ -43,22 +43,31 @@ def host_problem(seed, n_gene, n_cell, n_batch=6, n_module=4, n_group=0, group_p
 
 
 def device_problem(seed, n_gene, n_cell, device, n_batch=6, n_module=8, module_size=200,
-                   n_group=0, group_p=0.02, gene_chunk=2048):
-    """Same recipe generated on the GPU with torch (plumbing only), chunked over genes."""
+                   n_group=0, group_p=0.02, gene_chunk=2048, gene_seed=None):
+    """Same recipe generated on the GPU with torch (plumbing only), chunked over genes.
+    Everything per cell (depth, batches, covariates, groupings) depends on ``seed`` only, so
+    ranks that pass different ``gene_seed`` values get different genes of the same cells."""
     import torch
-    g = torch.Generator(device=device)
-    g.manual_seed(seed)
     f64 = torch.float64
-    depth = torch.exp(0.4 * torch.randn(n_cell, generator=g, device=device, dtype=f64))
-    mu = torch.distributions.Gamma(torch.tensor(0.5, device=device, dtype=f64),
-                                   torch.tensor(0.5, device=device, dtype=f64))
-    torch.manual_seed(seed)
-    mu = mu.sample((n_gene,)) + 0.05
-    factors = [torch.exp(torch.randn(n_cell, generator=g, device=device, dtype=f64) * (0.3 + 0.7 * k / max(1, n_module)))
-               for k in range(n_module)]
+    gc = torch.Generator(device=device)
+    gc.manual_seed(seed)
+    gg = torch.Generator(device=device)
+    gg.manual_seed(seed * 7919 + 13 if gene_seed is None else gene_seed)
+    depth = torch.exp(0.4 * torch.randn(n_cell, generator=gc, device=device, dtype=f64))
+    b = torch.randint(0, n_batch, (n_cell,), generator=gc, device=device)
+    noise = torch.randn(n_cell, generator=gc, device=device, dtype=f64)
+    cov = [(b == i).to(f64) for i in range(1, n_batch)]
+    ld = torch.log(depth)
+    c2 = 0.6 * ld + 0.8 * noise
+    cov += [(ld - ld.mean()) / ld.std(), (c2 - c2.mean()) / c2.std(),
+            torch.ones(n_cell, dtype=f64, device=device)]
+    dc = torch.stack(cov)
+    # gene means ~ Gamma(0.5, scale 2) + 0.05 via the square of a normal (chi2_1 = Gamma(1/2, 2))
+    mu = torch.randn(n_gene, generator=gg, device=device, dtype=f64) ** 2 + 0.05
+    factors = [torch.exp(torch.randn(n_cell, generator=gg, device=device, dtype=f64) *
+                         (0.3 + 0.7 * k / max(1, n_module))) for k in range(n_module)]
     dt = torch.empty((n_gene, n_cell), dtype=f64, device=device)
-    tot = torch.zeros(n_cell, dtype=f64, device=device)
-    det = torch.zeros(n_cell, dtype=f64, device=device)
+    scale = 1e4 / (depth * (mu.sum() + 1.0))
     for g0 in range(0, n_gene, gene_chunk):
         g1 = min(g0 + gene_chunk, n_gene)
         m = mu[g0:g1, None] * depth[None, :]
@@ -66,26 +75,17 @@ def device_problem(seed, n_gene, n_cell, device, n_batch=6, n_module=8, module_s
             lo = (k * module_size) % max(1, n_gene)
             a, b_ = max(lo, g0), min(lo + module_size, g1)
             if a < b_:
-                lvl = 3.0 + 12.0 * torch.rand(b_ - a, generator=g, device=device, dtype=f64)
+                lvl = 3.0 + 12.0 * torch.rand(b_ - a, generator=gg, device=device, dtype=f64)
                 m[a - g0:b_ - g0] = lvl[:, None] * depth[None, :] * f[None, :]
-        # NB(size=2) as a Gamma-Poisson mixture
-        lam = torch.distributions.Gamma(torch.full_like(m, 2.0), 2.0 / m).sample()
-        reads = torch.poisson(lam, generator=g)
-        dt[g0:g1] = reads
-        tot += reads.sum(dim=0)
-        det += (reads > 0).sum(dim=0)
-    tot += 1.0
-    for g0 in range(0, n_gene, gene_chunk):
-        g1 = min(g0 + gene_chunk, n_gene)
-        dt[g0:g1] = torch.log((dt[g0:g1] + 0.5) / tot[None, :] * 1e4 + 1.0)
-    b = torch.randint(0, n_batch, (n_cell,), generator=g, device=device)
-    cov = [(b == i).to(f64) for i in range(1, n_batch)]
-    ld = torch.log(tot)
-    dr = det / n_gene
-    cov += [(ld - ld.mean()) / ld.std(), (dr - dr.mean()) / dr.std(), torch.ones(n_cell, dtype=f64, device=device)]
-    out = {"dt": dt, "dc": torch.stack(cov)}
+        # NB(size=2) = Poisson with Gamma(2, m/2) rate; Gamma(2) = sum of two exponentials
+        u = torch.rand((2,) + m.shape, generator=gg, device=device, dtype=f64).clamp_min_(1e-300)
+        lam = -(torch.log(u[0]) + torch.log(u[1])) * (m * 0.5)
+        reads = torch.poisson(lam, generator=gg)
+        dt[g0:g1] = torch.log((reads + 0.5) * scale[None, :] + 1.0)
+        del m, u, lam, reads
+    out = {"dt": dt, "dc": dc}
     if n_group:
-        dg = (torch.rand((n_group, n_cell), generator=g, device=device) < group_p).to(f64)
+        dg = (torch.rand((n_group, n_cell), generator=gc, device=device) < group_p).to(f64)
         k = min(n_group, n_gene, 8)
         dt[:k] += 0.5 * dg[:k]
         out["dg"] = dg
