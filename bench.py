@@ -191,6 +191,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = engine.context(local)
+    if args.umma_pair is not None:
+        engine.set_option("umma_pair", args.umma_pair)
     precision = args.precision
     n_slices, n_products = engine.PRESETS[precision]
 
@@ -269,7 +271,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = pairs / (ms_step * 1e-3)
-    k_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in contract_ms])) if contract_ms else None
+    k_list = [e0.elapsed_time(e1) for e0, e1 in contract_ms]
+    k_ms = float(np.mean(k_list)) if k_list else None
 
     # ---- end to end through the public API, host buffers
     e2e = None
@@ -327,7 +330,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     if k_ms:
         ach = alg_flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "contract_umma_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                "traffic": None, "kernel": "contract_umma_kernel", "kernel_ms": k_ms,
+                "kernel_ms_per_step": [round(x, 2) for x in k_list], "peak_source": peak_src,
                 "executed_int8_tops": 2.0 * n_products * len(tiles_full if single else tiles) * 128 * 128 *
                                       engine.padded_cells(n_cell) / (k_ms * 1e-3) / 1e12,
                 "note": "algorithmic flop = 2*cells per unique pair; the kernel executes %d int8 digit-plane products per "
@@ -375,6 +379,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: same as --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--umma-pair", type=int, default=None, help="test hook: 1 = cta_group::2 kernel, 0 = single-CTA")
     args = ap.parse_args()
     n_gene, n_cell, desc = WORKLOADS[args.workload]
     if args.impl == "reference":

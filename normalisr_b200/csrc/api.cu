@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <unordered_map>
 #include <vector>
 
 #include "epilogue.cuh"
@@ -15,6 +16,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep);
 extern int nsr_use_hadamard;
 extern int nsr_umma_kblock;
+extern int nsr_umma_pair;
 
 static thread_local char g_err[1024] = "";
 
@@ -76,6 +78,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
 // test hooks: "hadamard" (0/1), "umma_kblock" (64/128)
 extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_kblock")) {
         NSR_REQUIRE(value == 64 || value == 128, "umma_kblock must be 64 or 128");
         nsr_umma_kblock = value;
@@ -121,15 +124,43 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
     }
     cudaStream_t st = (cudaStream_t)stream;
     NSR_CHECK(cudaSetDevice(ctx->device));
-    if ((size_t)n_tiles > ctx->tiles_cap) {
+    // the cta_group::2 kernel works on 256 x 128 pair tiles: fold (tr, tc) into (tr/2, tc, half mask),
+    // keeping first-appearance order (the caller's order carries the L2-locality plan)
+    const bool pair = engine == NSR_ENGINE_UMMA && nsr_umma_pair != 0;
+    std::vector<int32_t> folded;
+    int64_t n_upload = n_tiles * 2;
+    const int32_t* upload = host_tiles;
+    int64_t n_entries = n_tiles;
+    if (pair) {
+        std::unordered_map<uint64_t, int64_t> seen;
+        seen.reserve((size_t)n_tiles * 2);
+        folded.reserve((size_t)n_tiles * 3);
+        for (int64_t t = 0; t < n_tiles; ++t) {
+            const int32_t tr = host_tiles[2 * t], tc = host_tiles[2 * t + 1];
+            const uint64_t key = ((uint64_t)(uint32_t)(tr >> 1) << 32) | (uint32_t)tc;
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                seen.emplace(key, (int64_t)folded.size() / 3);
+                folded.push_back(tr >> 1);
+                folded.push_back(tc);
+                folded.push_back(1 << (tr & 1));
+            } else {
+                folded[(size_t)it->second * 3 + 2] |= 1 << (tr & 1);
+            }
+        }
+        n_entries = (int64_t)folded.size() / 3;
+        n_upload = n_entries * 3;
+        upload = folded.data();
+    }
+    if ((size_t)n_upload > ctx->tiles_cap) {
         if (ctx->tiles_dev) NSR_CHECK(cudaFree(ctx->tiles_dev));
         ctx->tiles_dev = nullptr;
         ctx->tiles_cap = 0;
-        NSR_CHECK(cudaMalloc(&ctx->tiles_dev, (size_t)n_tiles * 2 * sizeof(int32_t) * 2));
-        ctx->tiles_cap = (size_t)n_tiles * 2;
+        NSR_CHECK(cudaMalloc(&ctx->tiles_dev, (size_t)n_upload * sizeof(int32_t) * 2));
+        ctx->tiles_cap = (size_t)n_upload * 2;
     }
-    // pageable-host copy: synchronous with respect to the host for the staging part, ordered on `st`
-    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, host_tiles, (size_t)n_tiles * 2 * sizeof(int32_t),
+    // pageable-host copy: staged synchronously with respect to the host, ordered on `st`
+    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, upload, (size_t)n_upload * sizeof(int32_t),
                               cudaMemcpyHostToDevice, st));
 
     ContractParams ep;
@@ -152,7 +183,7 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
         return 0;
     }
     return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
-                                    n_pad, n_slices, wmax, ctx->tiles_dev, n_tiles, ep);
+                                    n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep);
 }
 
 extern "C" int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,

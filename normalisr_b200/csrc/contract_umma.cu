@@ -9,17 +9,21 @@
 // P-value in registers, so P and dot are written once (reference association.py:234-249 and
 // the assembly at :1036-1057).
 //
-// Roles (192 threads, persistent over a tile list, one CTA per SM):
+// Roles (320 threads, persistent over a tile list, one CTA per SM):
 //   warp 0 lane 0  TMA producer: 2S boxes (128 rows x KB bytes, swizzled) per k-block
 //   warp 1         TMEM allocator; lane 0 issues the MMAs and commits to mbarriers
-//   warps 2..5     epilogue, one TMEM lane quadrant each
+//   warps 2..9     epilogue: warp w reads TMEM lane quadrant w%4, columns 64*((w-2)/4)..+64.
+// The epilogue first DRAINS its 64 accumulators per thread into float64 registers and releases
+// TMEM, so the next tile's MMAs run underneath the P-value arithmetic (which is latency-bound
+// float64: ~330 us per tile when it was serialised with the MMAs, as long as 40 % of a tile).
 #include <cuda.h>
 
 #include "epilogue.cuh"
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr uint32_t kTmemCols = 512;
 constexpr int kSmemBudget = 200 * 1024;       // operand ring; barriers live in static smem
 
@@ -113,6 +117,56 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
 // int8 x int8 -> int32, A and B K-major, M = 128, N = 128
 constexpr uint32_t kInstrDesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// One 128 x 128 sub-tile for the 8 epilogue warps of a CTA.  empty_bar: the barrier the MMA issuer
+// waits on before reusing TMEM (a shared::cta address, or a shared::cluster one if `remote`).
+template <int GROUPS>
+__device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t tmem_base, int warp, int lane,
+                                              int tr, int tc, bool wanted, uint32_t empty_bar, bool remote) {
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    double acc[64];
+    if (wanted) {
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 64;
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[GROUPS][16];
+#pragma unroll
+            for (int grp = 0; grp < GROUPS; ++grp) tc_ld16(lane_base + grp * NSR_TILE + c0, v[grp]);
+            tc_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                int32_t a4[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int grp = 0; grp < GROUPS; ++grp) a4[grp] = (int32_t)v[grp][c];
+                acc[c0 + c] = nsr_combine(ep, a4);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (remote) mbar_arrive_cluster_addr(empty_bar);
+        else mbar_arrive(empty_bar);
+    }
+    const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
+    if (wanted && i < ep.rows_a) {
+        const double qi = ep.qa[i];
+        const double vi = ep.va ? ep.va[i] : 1.0;
+        const bool mirror = ep.mode == NSR_MODE_COEX && tr != tc;
+        const int64_t j_base = (int64_t)tc * NSR_TILE + half * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+            const int64_t j = j_base + c;
+            if (j < ep.rows_b) nsr_finish2(ep, i, j, qi, vi, acc[c], acc[c + 1], j + 1 < ep.rows_b, mirror);
+        }
+    }
+}
+
 template <int S, int WMAX, int KB>
 struct Cfg {
     static constexpr int kSliceBytes = NSR_TILE * KB;
@@ -142,7 +196,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         mbar_init(smem_u32(&bar_tmem_full), 1);
-        mbar_init(smem_u32(&bar_tmem_empty), 4);          // one arrival per epilogue warp
+        mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps);  // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -218,43 +272,13 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue (warps 2..5)
-        const int quad = warp & 3;                                // TMEM lane quadrant of this warp
+        // ------------------------------------------------------------ epilogue (warps 2..9)
         uint32_t tphase = 0;
         for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
             const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
             mbar_wait(smem_u32(&bar_tmem_full), tphase);
             tc_fence_after();
-            const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
-            const bool row_ok = i < g.ep.rows_a;
-            const double qi = row_ok ? g.ep.qa[i] : 0.0;
-            const double vi = (row_ok && g.ep.va) ? g.ep.va[i] : 1.0;
-            const bool mirror = g.ep.mode == NSR_MODE_COEX && tr != tc;
-            const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-            for (int c0 = 0; c0 < NSR_TILE; c0 += 16) {
-                uint32_t v[C::kGroups][16];
-#pragma unroll
-                for (int grp = 0; grp < C::kGroups; ++grp) tc_ld16(lane_base + grp * NSR_TILE + c0, v[grp]);
-                tc_ld_wait();
-                const int64_t j0 = (int64_t)tc * NSR_TILE + c0;
-                if (row_ok && j0 < g.ep.rows_b) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) {
-                        const int64_t j = j0 + c;
-                        if (j < g.ep.rows_b) {
-                            int32_t a4[4] = {0, 0, 0, 0};
-#pragma unroll
-                            for (int grp = 0; grp < C::kGroups; ++grp) a4[grp] = (int32_t)v[grp][c];
-                            nsr_finish(g.ep, i, j, qi, vi, g.ep.qb[j], g.ep.vb ? g.ep.vb[j] : 1.0,
-                                       nsr_combine(g.ep, a4), mirror);
-                        }
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bar_tmem_empty));
+            epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false);
             tphase ^= 1;
         }
     }
@@ -267,18 +291,198 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     }
 }
 
+
+// =============================================================================================
+// cta_group::2 variant: a CTA pair (one cluster) computes a 256 x 128 output tile.  CTA r of the
+// pair stages its own 128 rows of A and half (64 rows) of B, so per MMA each SM reads 6 KB of
+// operands from shared memory instead of 8 KB and fills 72 KB instead of 96 KB per k-block: the
+// 1-CTA kernel is bound by exactly that traffic (128 B/clk operand reads + 64 B/clk TMA fill
+// against the 128 B/clk the SM can move; ncu: tensor pipe 68 % active).  The leader CTA issues
+// tcgen05.mma.cta_group::2; both CTAs' TMA loads complete on the leader's full barrier;
+// tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers.
+// Tile list entries are (tile_row/2, tile_col, mask): mask bit r = half r is wanted.
+// =============================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* map, uint32_t leader_bar, uint32_t dst,
+                                                int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// int8 x int8 -> int32, K-major, M = 256 (pair), N = 128
+constexpr uint32_t kInstrDesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+
+template <int S, int WMAX>
+struct Cfg2 {
+    static constexpr int kSliceA = NSR_TILE * 128;          // 128 rows x 128 B
+    static constexpr int kSliceB = (NSR_TILE / 2) * 128;    // 64 rows x 128 B
+    static constexpr int kStageBytes = S * (kSliceA + kSliceB);
+    static constexpr int kStages = (216 * 1024) / kStageBytes;
+    static constexpr int kGroups = WMAX - 1;
+    static_assert(kStages >= 2 && kStages <= 8, "bad stage count");
+};
+
+template <int S, int WMAX>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
+                      const __grid_constant__ CUtensorMap map_b, const UmmaArgs g) {
+    using C = Cfg2<S, WMAX>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty;
+    __shared__ uint32_t tmem_base_slot;
+
+    uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t ring_u32 = smem_u32(ring);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_tmem_full), 1);
+        mbar_init(smem_u32(&bar_tmem_empty), 2 * kEpiWarps);   // epilogue warps of both CTAs of the pair
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < g.n_tiles; t += n_clusters) {
+                const int row_a = g.tiles[3 * t] * (2 * NSR_TILE) + (int)rank * NSR_TILE;
+                const int row_b = g.tiles[3 * t + 1] * NSR_TILE + (int)rank * (NSR_TILE / 2);
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
+                    const uint32_t full_local = smem_u32(&bar_full[stage]);
+                    const uint32_t full_leader = map_to_cta(full_local, 0);
+                    if (leader) mbar_expect_tx(full_local, 2 * C::kStageBytes);
+                    const uint32_t base = ring_u32 + stage * C::kStageBytes;
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        tma_load_3d_2sm(&map_a, full_leader, base + s * C::kSliceA, kb * 128, row_a, s);
+                        tma_load_3d_2sm(&map_b, full_leader, base + S * C::kSliceA + s * C::kSliceB, kb * 128, row_b, s);
+                    }
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int t = cluster_id; t < g.n_tiles; t += n_clusters) {
+                mbar_wait(smem_u32(&bar_tmem_empty), tphase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < g.num_kb; ++kb) {
+                    mbar_wait(smem_u32(&bar_full[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t base = ring_u32 + stage * C::kStageBytes;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (int a = 0; a < S; ++a) {
+#pragma unroll
+                            for (int b = 0; b < S; ++b) {
+                                if (a + b + 2 <= WMAX) {
+                                    const int grp = a + b;
+                                    const bool first = (a == (grp > S - 1 ? grp - (S - 1) : 0));
+                                    const uint64_t da = make_smem_desc<128>(base + a * C::kSliceA) + (uint64_t)(2 * ks);
+                                    const uint64_t db = make_smem_desc<128>(base + S * C::kSliceA + b * C::kSliceB) + (uint64_t)(2 * ks);
+                                    const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
+                                    tc_mma_i8_2sm(tmem_base + grp * NSR_TILE, da, db, kInstrDesc2, acc);
+                                }
+                            }
+                        }
+                    }
+                    tc_commit_2sm(smem_u32(&bar_empty[stage]));
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm(smem_u32(&bar_tmem_full));
+                tphase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+        uint32_t tphase = 0;
+        const uint32_t empty_leader = map_to_cta(smem_u32(&bar_tmem_empty), 0);
+        for (int t = cluster_id; t < g.n_tiles; t += n_clusters) {
+            const int tr = g.tiles[3 * t] * 2 + (int)rank, tc = g.tiles[3 * t + 1];
+            const bool wanted = (g.tiles[3 * t + 2] >> rank) & 1;
+            mbar_wait(smem_u32(&bar_tmem_full), tphase);
+            tc_fence_after();
+            epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
+            tphase ^= 1;
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols)
+                     : "memory");
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
 int make_map(nsr_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, int64_t rows_alloc,
-             int64_t n_pad, int n_slices, int kb) {
+             int64_t n_pad, int n_slices, int kb, int box_rows = NSR_TILE) {
     EncodeTiledFn fn = (EncodeTiledFn)ctx->encode_tiled;
     NSR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
     cuuint64_t dims[3] = {(cuuint64_t)n_pad, (cuuint64_t)rows, (cuuint64_t)n_slices};
     cuuint64_t strides[2] = {(cuuint64_t)n_pad, (cuuint64_t)rows_alloc * (cuuint64_t)n_pad};
-    cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)NSR_TILE, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -300,14 +504,44 @@ int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorM
     return 0;
 }
 
+template <int S, int WMAX>
+int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
+    using C = Cfg2<S, WMAX>;
+    const int smem = C::kStages * C::kStageBytes + 1024;
+    auto kern = contract_umma2_kernel<S, WMAX>;
+    NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int pairs = ctx->sm_count / 2;
+    if (g.n_tiles < pairs) pairs = g.n_tiles;
+    kern<<<2 * pairs, kThreads, smem, st>>>(ma, mb, g);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
+int nsr_umma_pair = 1;       // test hook: 1 -> cta_group::2 kernel (default), 0 -> 1-CTA kernel
 int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
 
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep) {
+    if (n_tiles < 0) {
+        // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
+        CUtensorMap ma, mb;
+        if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices, 128, NSR_TILE)) return 1;
+        if (make_map(ctx, &mb, b, rows_b, rows_alloc_b, n_pad, n_slices, 128, NSR_TILE / 2)) return 1;
+        UmmaArgs g;
+        g.tiles = tiles_dev;
+        g.n_tiles = (int)(-n_tiles);
+        g.num_kb = (int)(n_pad / 128);
+        g.ep = ep;
+        if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
+        if (n_slices == 3 && wmax == 5) return launch2<3, 5>(ctx, st, ma, mb, g);
+        if (n_slices == 4 && wmax == 5) return launch2<4, 5>(ctx, st, ma, mb, g);
+        nsr_set_error("nsr_contract: unsupported (n_slices=%d, wmax=%d) for the tcgen05 pair engine", n_slices, wmax);
+        return 2;
+    }
     const int kb = (n_slices == 4) ? 64 : nsr_umma_kblock;
     CUtensorMap ma, mb;
     if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices, kb)) return 1;

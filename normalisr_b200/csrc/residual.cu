@@ -46,6 +46,35 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ---- pass A ------------------------------------------------------------------------------
 // partial[ks][row][c] = sum over the CTA's cells of X[row][k] Qt[c0+c][k];  psq[ks][row] = sum x^2
+template <int CB, bool FULL>
+__device__ __forceinline__ void coef_block(const double* const (&xp)[kRowsA], const double* qp, int64_t ldq, int nq,
+                                           int64_t k0, int64_t n, bool first_chunk, double (&acc)[kRowsA][CB],
+                                           double (&sq)[kRowsA]) {
+    double x[kRowsA][4];
+#pragma unroll
+    for (int r = 0; r < kRowsA; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[r][j] = (FULL || k0 + 32 * j < n) ? __ldg(xp[r] + k0 + 32 * j) : 0.0;
+    const double* qc = qp + k0;
+#pragma unroll
+    for (int c = 0; c < CB; ++c) {
+        double q[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) q[j] = (c < nq && (FULL || k0 + 32 * j < n)) ? __ldg(qc + 32 * j) : 0.0;
+        qc += ldq;
+#pragma unroll
+        for (int r = 0; r < kRowsA; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][c] = fma(x[r][j], q[j], acc[r][c]);
+    }
+    if (first_chunk) {
+#pragma unroll
+        for (int r = 0; r < kRowsA; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sq[r] = fma(x[r][j], x[r][j], sq[r]);
+    }
+}
+
 template <int CB>
 __global__ void __launch_bounds__(kThreads, 2)
 coef_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
@@ -57,7 +86,13 @@ coef_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
     const int b_begin = (int)((int64_t)nblk * ks / ksplit);
     const int b_end = (int)((int64_t)nblk * (ks + 1) / ksplit);
     if (row0 >= rows) return;
+    const int nblk_full = (int)(n / 128);
+    const int nq = rank - c0 < CB ? rank - c0 : CB;
 
+    const double* xp[kRowsA];
+#pragma unroll
+    for (int r = 0; r < kRowsA; ++r) xp[r] = X + (row0 + r < rows ? row0 + r : row0) * ldx + lane;
+    const double* qp = Qt + (int64_t)c0 * ldq + lane;
     double acc[kRowsA][CB], sq[kRowsA];
 #pragma unroll
     for (int r = 0; r < kRowsA; ++r) {
@@ -65,45 +100,16 @@ coef_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
 #pragma unroll
         for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
     }
-    for (int blk = b_begin; blk < b_end; ++blk) {
-        const int64_t k0 = (int64_t)blk * 128 + lane;
-        double x[kRowsA][4];
-#pragma unroll
-        for (int r = 0; r < kRowsA; ++r) {
-            const bool rv = row0 + r < rows;
-            const double* xr = X + (rv ? row0 + r : row0) * ldx;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t k = k0 + 32 * j;
-                x[r][j] = (rv && k < n) ? __ldg(xr + k) : 0.0;
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < CB; ++c) {
-            double q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int64_t k = k0 + 32 * j;
-                q[j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < kRowsA; ++r)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[r][c] = fma(x[r][j], q[j], acc[r][c]);
-        }
-        if (c0 == 0) {
-#pragma unroll
-            for (int r = 0; r < kRowsA; ++r)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sq[r] = fma(x[r][j], x[r][j], sq[r]);
-        }
-    }
+    int blk = b_begin;
+    const int fast_end = b_end < nblk_full ? b_end : nblk_full;
+    for (; blk < fast_end; ++blk) coef_block<CB, true>(xp, qp, ldq, nq, (int64_t)blk * 128, n, c0 == 0, acc, sq);
+    for (; blk < b_end; ++blk) coef_block<CB, false>(xp, qp, ldq, nq, (int64_t)blk * 128, n - lane, c0 == 0, acc, sq);
 #pragma unroll
     for (int r = 0; r < kRowsA; ++r) {
 #pragma unroll
         for (int c = 0; c < CB; ++c) {
             const double v = warp_sum(acc[r][c]);
-            if (lane == 0 && row0 + r < rows && c0 + c < rank)
+            if (lane == 0 && row0 + r < rows && c < nq)
                 partial[((int64_t)ks * rows + row0 + r) * rank + c0 + c] = v;
         }
         if (c0 == 0) {
@@ -166,9 +172,9 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
         int32_t q = __double2int_rn(t);
 #pragma unroll
         for (int s = S - 1; s >= 1; --s) {
-            const int32_t d = (int32_t)(int8_t)(q & 0xFF);           // balanced low digit
-            w[s][i >> 2] |= (uint32_t)(d & 0xFF) << (8 * (i & 3));
-            q = (q - d) >> 8;
+            // balanced low digit d = sext8(q & 0xFF); (q - d) >> 8 == (q + 128) >> 8
+            w[s][i >> 2] |= (uint32_t)(q & 0xFF) << (8 * (i & 3));
+            q = (q + 128) >> 8;
         }
         w[0][i >> 2] |= (uint32_t)(q & 0xFF) << (8 * (i & 3));
     }
@@ -227,34 +233,50 @@ residual_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t l
 #pragma unroll
     for (int r = 0; r < kRowsB; ++r) sumsq[r] = 0.0;
 
+    const int nblk_full = (int)(n / 128);
+    const double* xp[kRowsB];
+#pragma unroll
+    for (int r = 0; r < kRowsB; ++r) xp[r] = X + (row_of[r] >= 0 ? row_of[r] : 0) * ldx + lane;
+    const double* qbase = Qt + lane;
     for (int blk = b_begin; blk < b_end; ++blk) {
-        const int64_t k0 = (int64_t)blk * 128 + lane;
+        const int64_t k0 = (int64_t)blk * 128;
+        const bool full = blk < nblk_full;
+        const int64_t n_lane = n - lane;                 // cell (k0 + 32 j + lane) < n  <=>  k0 + 32 j < n_lane
         bool flip[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) flip[j] = HAD && cell_flip(cell_offset + (uint64_t)(k0 + 32 * j));
+        for (int j = 0; j < 4; ++j) flip[j] = HAD && cell_flip(cell_offset + (uint64_t)(k0 + lane + 32 * j));
         // ---- phase 1: residuals of 8 rows (two halves of 4 to bound registers) -> smem
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             double z[4][4];
+            if (full) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int64_t row = row_of[4 * half + r];
-                const double* xr = X + (row >= 0 ? row : 0) * ldx;
+                for (int r = 0; r < 4; ++r)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t k = k0 + 32 * j;
-                    z[r][j] = (row >= 0 && k < n) ? __ldg(xr + k) : 0.0;
-                }
+                    for (int j = 0; j < 4; ++j) z[r][j] = __ldg(xp[4 * half + r] + k0 + 32 * j);
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        z[r][j] = (k0 + 32 * j < n_lane) ? __ldg(xp[4 * half + r] + k0 + 32 * j) : 0.0;
             }
+            const double* qc = qbase + k0;
             for (int c0 = 0; c0 < rank4; c0 += 4) {
                 double q[4][4];
+                if (full && c0 + 4 <= rank) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                    for (int c = 0; c < 4; ++c)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int64_t k = k0 + 32 * j;
-                        q[c][j] = (c0 + c < rank && k < n) ? __ldg(Qt + (int64_t)(c0 + c) * ldq + k) : 0.0;
-                    }
+                        for (int j = 0; j < 4; ++j) q[c][j] = __ldg(qc + (int64_t)c * ldq + 32 * j);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            q[c][j] = (c0 + c < rank && k0 + 32 * j < n_lane) ? __ldg(qc + (int64_t)c * ldq + 32 * j) : 0.0;
+                }
+                qc += 4 * ldq;
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
 #pragma unroll

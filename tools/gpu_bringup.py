@@ -117,11 +117,12 @@ def stage_umma_golden(precision="default", kblock="128"):
     _golden_coex("umma", precision)
 
 
-def stage_umma_vs_simt(precision="default", kblock="128", rows="700", n="5000"):
+def stage_umma_vs_simt(precision="default", kblock="128", rows="700", n="5000", pair="1"):
     """bit-identical outputs from the two engines on identical digit planes"""
     torch, orc, tl, association, engine, synth = _imports()
     rows, n = int(rows), int(n)
     engine.set_option("umma_kblock", int(kblock))
+    engine.set_option("umma_pair", int(pair))
     ctx = engine.context(0)
     p = synth.host_problem(7, rows, n)
     Qt, rank, W = association.covariate_basis(p["dc"])
@@ -136,8 +137,8 @@ def stage_umma_vs_simt(precision="default", kblock="128", rows="700", n="5000"):
         outs.append((P.cpu().numpy(), D.cpu().numpy()))
     same_p = np.array_equal(outs[0][0], outs[1][0])
     same_d = np.array_equal(outs[0][1], outs[1][1])
-    print("precision %s kblock %s rows %d n %d: P identical %s, dot identical %s, max|dP| %.3e max|dD| %.3e" % (
-        precision, kblock, rows, n, same_p, same_d, np.abs(outs[0][0] - outs[1][0]).max(),
+    print("pair %s precision %s kblock %s rows %d n %d: P identical %s, dot identical %s, max|dP| %.3e max|dD| %.3e" % (
+        pair, precision, kblock, rows, n, same_p, same_d, np.abs(outs[0][0] - outs[1][0]).max(),
         np.abs(outs[0][1] - outs[1][1]).max()))
     # exact integer check of the SIMT engine against numpy int64
     sl = A.slices.cpu().numpy()[:, :64]
@@ -163,10 +164,11 @@ def _time_ms(torch, fn, reps=3):
     return min(ts), sorted(ts)[len(ts) // 2]
 
 
-def stage_perf(rows="5000", n="10000", precision="default", kblock="128", check="1"):
+def stage_perf(rows="5000", n="10000", precision="default", kblock="128", check="1", pair="1"):
     torch, orc, tl, association, engine, synth = _imports()
     rows, n = int(rows), int(n)
     engine.set_option("umma_kblock", int(kblock))
+    engine.set_option("umma_pair", int(pair))
     ctx = engine.context(0)
     t0 = time.time()
     p = synth.device_problem(1002, rows, n, "cuda")
@@ -184,7 +186,7 @@ def stage_perf(rows="5000", n="10000", precision="default", kblock="128", check=
     tc = _time_ms(torch, lambda: engine.contract(ctx, engine.MODE_COEX, out, out, tiles, dof, P, D, prods, engine.ENGINE_UMMA))
     pairs = rows * (rows - 1) / 2
     ops = 2.0 * prods * len(tiles) * 128 * 128 * out.n_pad
-    print(json.dumps(dict(rows=rows, n=n, precision=precision, kblock=int(kblock), residualize_ms=tr, contract_ms=tc,
+    print(json.dumps(dict(rows=rows, n=n, precision=precision, kblock=int(kblock), pair=int(pair), residualize_ms=tr, contract_ms=tc,
                           pairs_per_s=pairs / ((tr[0] + tc[0]) * 1e-3), int8_tops=ops / (tc[0] * 1e-3) / 1e12,
                           alg_tflops=2.0 * n * pairs / (tc[0] * 1e-3) / 1e12,
                           resid_GBs=16.0 * rows * n / (tr[0] * 1e-3) / 1e9)))
@@ -222,12 +224,20 @@ STAGES = [
 
 QUICK = [
     ("residual", [], 300),
+    ("umma_vs_simt", ["default", "128", "700", "5000", "1"], 120),
+    ("umma_vs_simt", ["default", "128", "300", "1000", "1"], 120),
+    ("umma_vs_simt", ["fast", "128", "700", "5000", "1"], 120),
+    ("umma_vs_simt", ["precise", "128", "700", "5000", "1"], 120),
+    ("umma_vs_simt", ["default", "128", "1333", "3001", "1"], 120),
     ("umma_golden", ["default", "128"], 180),
-    ("umma_vs_simt", ["default", "128"], 240),
-    ("perf", ["5000", "10000", "default", "128"], 300),
-    ("perf", ["5000", "10000", "fast", "128"], 300),
-    ("perf", ["8192", "65536", "default", "128", "0"], 400),
-    ("perf", ["8192", "65536", "fast", "128", "0"], 400),
+    ("umma_vs_simt", ["default", "128", "700", "5000", "0"], 120),
+    ("umma_vs_simt", ["precise", "64", "700", "5000", "0"], 120),
+    ("perf", ["5000", "10000", "default", "128", "1", "1"], 300),
+    ("perf", ["5000", "10000", "default", "128", "1", "0"], 300),
+    ("perf", ["8192", "65536", "default", "128", "0", "1"], 400),
+    ("perf", ["8192", "65536", "default", "128", "0", "0"], 400),
+    ("perf", ["8192", "65536", "fast", "128", "0", "1"], 400),
+    ("perf", ["8192", "65536", "precise", "128", "0", "1"], 400),
 ]
 
 
