@@ -193,6 +193,9 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     ctx = engine.context(local)
     if args.umma_pair is not None:
         engine.set_option("umma_pair", args.umma_pair)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        engine.set_option(k, int(v))
     precision = args.precision
     n_slices, n_products = engine.PRESETS[precision]
 
@@ -350,6 +353,14 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                              dt_s.shape[0], n_gene, n_cell, reference_tiles(dt_s.shape[0]), reference_tiles(n_gene), s_best,
                              tb["A"], tb["B"])}
 
+    # ---- secondary metric of BASELINE.json: DE tests/s (config 3 shape), N = 1 only
+    de = None
+    if world == 1 and not args.no_de:
+        try:
+            de = bench_de(torch, dev, args)
+        except Exception as e:          # the headline line must still be printed
+            de = {"error": repr(e)[:300]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -362,10 +373,36 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                                                               "tile-row strips" % world,
                    "note": wl_desc},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "de": de,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
+    """DE tests/s on the GSE120861-shaped config (50k cells x 10k genes x 300 gRNAs), inputs resident
+    in HBM, through the public API: single=0 and single=4 ("untested gRNAs as covariates")."""
+    from normalisr_b200 import normalisr as norm, synth
+    torch.cuda.empty_cache()
+    p = synth.device_problem(1003, n_gene, n_cell, dev, n_group=n_group, group_p=0.02)
+    out = {"workload": "de_50k_x_10k_x_300", "genes": n_gene, "cells": n_cell, "groupings": n_group, "unit": "tests/s"}
+    for single in (0, 4):
+        for _ in range(2):
+            norm.de(p["dg"], p["dt"], p["dc"], single=single)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record()
+        for _ in range(reps):
+            norm.de(p["dg"], p["dt"], p["dc"], single=single)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out["single%d" % single] = {"value": n_group * n_gene / (ms * 1e-3), "ms": ms}
+    del p
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -379,7 +416,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: same as --steps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-de", action="store_true", help="skip the secondary DE tests/s measurement")
     ap.add_argument("--umma-pair", type=int, default=None, help="test hook: 1 = cta_group::2 kernel, 0 = single-CTA")
+    ap.add_argument("--opt", action="append", default=[], help="test hook: name=value for nsr_set_option")
     args = ap.parse_args()
     n_gene, n_cell, desc = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -109,8 +109,8 @@ int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a
 int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
                int64_t src_pitch, int64_t width_bytes, int64_t height, int kind);
 
-/* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel, default;
- * 0 = single-CTA kernel), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
+/* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
+ * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
  * kernel, default 128). Process-wide. */
 int nsr_set_option(const char* name, int value);
 

@@ -13,9 +13,8 @@
 //   warp 0 lane 0  TMA producer: 2S boxes (128 rows x KB bytes, swizzled) per k-block
 //   warp 1         TMEM allocator; lane 0 issues the MMAs and commits to mbarriers
 //   warps 2..9     epilogue: warp w reads TMEM lane quadrant w%4, columns 64*((w-2)/4)..+64.
-// The epilogue first DRAINS its 64 accumulators per thread into float64 registers and releases
-// TMEM, so the next tile's MMAs run underneath the P-value arithmetic (which is latency-bound
-// float64: ~330 us per tile when it was serialised with the MMAs, as long as 40 % of a tile).
+// The P-value arithmetic is latency-bound float64 (~330 us per tile with 4 epilogue warps, as long
+// as 40 % of a 100k-cell tile), hence 8 epilogue warps, two per scheduler.
 #include <cuda.h>
 
 #include "epilogue.cuh"
@@ -31,6 +30,8 @@ struct UmmaArgs {
     const int32_t* tiles;
     int n_tiles;
     int num_kb;                   // k-blocks of KB cells
+    int epi_overlap;              // 1: release TMEM before the P-value math (overlap with next tile)
+    int epi_sleep_ns;             // back-off of the epilogue warps while they wait for a tile
     ContractParams ep;
 };
 
@@ -67,6 +68,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) {       // ~2 s
             printf("nsr umma: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
                    threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+// Waiting epilogue warps must not spin on the issue ports (they wait most of a tile's duration).
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity, int sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (sleep_ns > 0) __nanosleep(sleep_ns);
+        if (clock64() - t0 > 8000000000ll) {
+            printf("nsr umma: epilogue mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
@@ -122,28 +135,44 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
-// One 128 x 128 sub-tile for the 8 epilogue warps of a CTA.  empty_bar: the barrier the MMA issuer
-// waits on before reusing TMEM (a shared::cta address, or a shared::cluster one if `remote`).
+// One 128 x 128 sub-tile for the 8 epilogue warps of a CTA: warp w owns TMEM lane quadrant w%4
+// (a hardware rule) and columns 64*((w-2)/4) .. +64, 16 at a time.  empty_bar: the barrier the
+// MMA issuer waits on before reusing TMEM (shared::cta address, or shared::cluster if `remote`).
+//
+// Measured alternatives (profiles/r01_epilogue_ab.md, 100k x 20k, 12 steps under the 1 kW cap):
+// draining all accumulators into registers first and releasing TMEM early (so the next tile's
+// MMAs overlap the P-value arithmetic) is 13 % faster in a short burst but 25 % SLOWER sustained:
+// the chip is power-bound here, and that variant costs more energy per tile than it saves time.
 template <int GROUPS>
 __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t tmem_base, int warp, int lane,
                                               int tr, int tc, bool wanted, uint32_t empty_bar, bool remote) {
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
-    double acc[64];
+    const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
+    const bool row_ok = wanted && i < ep.rows_a;
+    const double qi = row_ok ? ep.qa[i] : 0.0;
+    const double vi = (row_ok && ep.va) ? ep.va[i] : 1.0;
+    const bool mirror = ep.mode == NSR_MODE_COEX && tr != tc;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     if (wanted) {
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + half * 64;
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
+#pragma unroll 1
+        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
             uint32_t v[GROUPS][16];
 #pragma unroll
             for (int grp = 0; grp < GROUPS; ++grp) tc_ld16(lane_base + grp * NSR_TILE + c0, v[grp]);
             tc_ld_wait();
+            const int64_t j0 = (int64_t)tc * NSR_TILE + c0;
+            if (row_ok && j0 < ep.rows_b) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                int32_t a4[4] = {0, 0, 0, 0};
+                for (int c = 0; c < 16; ++c) {
+                    const int64_t j = j0 + c;
+                    if (j < ep.rows_b) {
+                        int32_t a4[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int grp = 0; grp < GROUPS; ++grp) a4[grp] = (int32_t)v[grp][c];
-                acc[c0 + c] = nsr_combine(ep, a4);
+                        for (int grp = 0; grp < GROUPS; ++grp) a4[grp] = (int32_t)v[grp][c];
+                        nsr_finish(ep, i, j, qi, vi, ep.qb[j], ep.vb ? ep.vb[j] : 1.0, nsr_combine(ep, a4), mirror);
+                    }
+                }
             }
         }
     }
@@ -152,18 +181,6 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     if (lane == 0) {
         if (remote) mbar_arrive_cluster_addr(empty_bar);
         else mbar_arrive(empty_bar);
-    }
-    const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
-    if (wanted && i < ep.rows_a) {
-        const double qi = ep.qa[i];
-        const double vi = ep.va ? ep.va[i] : 1.0;
-        const bool mirror = ep.mode == NSR_MODE_COEX && tr != tc;
-        const int64_t j_base = (int64_t)tc * NSR_TILE + half * 64;
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-            const int64_t j = j_base + c;
-            if (j < ep.rows_b) nsr_finish2(ep, i, j, qi, vi, acc[c], acc[c + 1], j + 1 < ep.rows_b, mirror);
-        }
     }
 }
 
@@ -180,7 +197,7 @@ struct Cfg {
 template <int S, int WMAX, int KB>
 __global__ void __launch_bounds__(kThreads, 1)
 contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
-                     const __grid_constant__ CUtensorMap map_b, const UmmaArgs g) {
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ UmmaArgs g) {
     using C = Cfg<S, WMAX, KB>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty;
@@ -276,7 +293,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         uint32_t tphase = 0;
         for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
             const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
-            mbar_wait(smem_u32(&bar_tmem_full), tphase);
+            mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
             epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false);
             tphase ^= 1;
@@ -354,7 +371,7 @@ struct Cfg2 {
 template <int S, int WMAX>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
-                      const __grid_constant__ CUtensorMap map_b, const UmmaArgs g) {
+                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ UmmaArgs g) {
     using C = Cfg2<S, WMAX>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty;
@@ -455,7 +472,7 @@ contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
         for (int t = cluster_id; t < g.n_tiles; t += n_clusters) {
             const int tr = g.tiles[3 * t] * 2 + (int)rank, tc = g.tiles[3 * t + 1];
             const bool wanted = (g.tiles[3 * t + 2] >> rank) & 1;
-            mbar_wait(smem_u32(&bar_tmem_full), tphase);
+            mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
             epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
             tphase ^= 1;
@@ -519,7 +536,9 @@ int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensor
 
 }  // namespace
 
-int nsr_umma_pair = 1;       // test hook: 1 -> cta_group::2 kernel (default), 0 -> 1-CTA kernel
+int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sustained), 1 -> cta_group::2 kernel
+int nsr_epi_overlap = 1;     // test hook: release TMEM before (1) or after (0) the P-value math
+int nsr_epi_sleep_ns = 500;  // test hook: epilogue wait back-off
 int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
 
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
@@ -535,6 +554,8 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.tiles = tiles_dev;
         g.n_tiles = (int)(-n_tiles);
         g.num_kb = (int)(n_pad / 128);
+        g.epi_overlap = nsr_epi_overlap;
+        g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
         if (n_slices == 3 && wmax == 5) return launch2<3, 5>(ctx, st, ma, mb, g);
@@ -550,6 +571,8 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     g.tiles = tiles_dev;
     g.n_tiles = (int)n_tiles;
     g.num_kb = (int)(n_pad / kb);
+    g.epi_overlap = nsr_epi_overlap;
+    g.epi_sleep_ns = nsr_epi_sleep_ns;
     g.ep = ep;
     if (n_slices == 3 && wmax == 4 && kb == 128) return launch<3, 4, 128>(ctx, st, ma, mb, g);
     if (n_slices == 3 && wmax == 5 && kb == 128) return launch<3, 5, 128>(ctx, st, ma, mb, g);

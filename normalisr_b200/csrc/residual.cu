@@ -16,22 +16,30 @@
 // rows, certain for degenerate ones) is re-quantised by a third, sparse pass with
 // quantum = max|z'|/vmax.
 //
-// Layout: all 8 warps of a CTA walk the same 128-cell blocks (so the covariate block is an L1
-// hit for 7 of them) and own different rows.  Lane l holds cells l, l+32, l+64, l+96 of the
-// block: every global load is a fully coalesced 256 B row segment.  For the transform each warp
-// transposes its 8 rows x 128 cells through shared memory so that a lane owns 32 consecutive
-// cells of one row: 5 butterfly stages in registers, 2 by shuffle, and 32-byte digit stores.
+// Both passes put the skinny float64 products on the FP64 tensor cores (mma.sync m8n8k4, "DMMA"):
+// one warp instruction does 256 FMAs, so the kernels issue ~0.1 (A) / ~30 (B, mostly the
+// butterflies and the digit extraction) instructions per element instead of ~60-110 with scalar
+// FMAs, which left them issue-bound at a quarter of the HBM rate (profiles/r01c_project_ncu.md).
+//   fragment layouts (g = lane/4, t = lane%4):  A[8x4]: (row g, k t)   B[4x8]: (k t, col g)
+//                                               C[8x8]: (row g, cols 2t, 2t+1)
+//   pass A: M = 8 rows, N = 8 covariates, K = cells.  Lane (g,t) loads 4 consecutive cells of row g
+//           (a quad reads a full 128 B line) and uses them as the K index of 4 successive MMAs.
+//   pass B: M = 8 rows, N = 8 cells, K = 4 covariates: C = X tile, A = -coef, B = Qt tile, so the
+//           residual comes out in the accumulator layout: after 16 tiles lane (g,t) owns the 32
+//           cells {8u + 2t + e} of row g.  5 butterfly stages are then in registers, 2 by shuffle.
+// Cells are stored in that (fixed, row-independent) order: position 32t + 2u + e of the 128-cell
+// block holds transformed index 8u + 2t + e.  The contraction sums over all positions, so any
+// fixed permutation is as good as the natural order, and every lane stores 32 contiguous bytes.
 #include "nsr_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kRowsA = 4;                  // rows per warp, pass A
-constexpr int kRowsB = 8;                  // rows per warp, pass B
-constexpr int kSegPitch = 33;              // doubles per 32-cell segment in smem (+1: bank spread)
+constexpr int kRowsW = 8;                  // rows per warp (one MMA row tile)
 constexpr double kHadScale = 0.088388347648318440550;   // 1/sqrt(128)
 constexpr double kKappa = 6.0;
+constexpr int kQPitch = 132;
 
 __device__ __forceinline__ bool cell_flip(uint64_t k) {
     uint32_t h = (uint32_t)k ^ (uint32_t)(k >> 32) * 0x9e3779b9u;
@@ -43,91 +51,114 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
     return v;
 }
-
-// ---- pass A ------------------------------------------------------------------------------
-// partial[ks][row][c] = sum over the CTA's cells of X[row][k] Qt[c0+c][k];  psq[ks][row] = sum x^2
-template <int CB, bool FULL>
-__device__ __forceinline__ void coef_block(const double* const (&xp)[kRowsA], const double* qp, int64_t ldq, int nq,
-                                           int64_t k0, int64_t n, bool first_chunk, double (&acc)[kRowsA][CB],
-                                           double (&sq)[kRowsA]) {
-    double x[kRowsA][4];
+// D(8x8) += A(8x4) B(4x8), float64, one warp
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void load4(const double* p, bool vec, double (&v)[4]) {
+    if (vec) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(p + 2));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
 #pragma unroll
-    for (int r = 0; r < kRowsA; ++r)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x[r][j] = (FULL || k0 + 32 * j < n) ? __ldg(xp[r] + k0 + 32 * j) : 0.0;
-    const double* qc = qp + k0;
-#pragma unroll
-    for (int c = 0; c < CB; ++c) {
-        double q[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = (c < nq && (FULL || k0 + 32 * j < n)) ? __ldg(qc + 32 * j) : 0.0;
-        qc += ldq;
-#pragma unroll
-        for (int r = 0; r < kRowsA; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[r][c] = fma(x[r][j], q[j], acc[r][c]);
-    }
-    if (first_chunk) {
-#pragma unroll
-        for (int r = 0; r < kRowsA; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sq[r] = fma(x[r][j], x[r][j], sq[r]);
+        for (int e = 0; e < 4; ++e) v[e] = __ldg(p + e);
     }
 }
+__device__ __forceinline__ void load4_tail(const double* p, int64_t k, int64_t n, double (&v)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (k + e < n) ? __ldg(p + e) : 0.0;
+}
 
-template <int CB>
-__global__ void __launch_bounds__(kThreads, 2)
-coef_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
-            const double* __restrict__ Qt, int rank, int64_t ldq, int c0, int nblk, int ksplit,
-            double* __restrict__ partial, double* __restrict__ psq) {
+// ---- pass A ------------------------------------------------------------------------------
+// partial[ks][row][c0 .. c0+8*NQ) = sum over this CTA's cells of X[row][k] Qt[c][k];  psq = sum x^2
+template <int NQ>
+__global__ void __launch_bounds__(kThreads, 3)
+coef_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
+                const double* __restrict__ Qt, int rank, int64_t ldq, int c0, int ksplit, int vec,
+                double* __restrict__ partial, double* __restrict__ psq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = ((int64_t)blockIdx.x * kWarps + warp) * kRowsA;
-    const int ks = blockIdx.y;
-    const int b_begin = (int)((int64_t)nblk * ks / ksplit);
-    const int b_end = (int)((int64_t)nblk * (ks + 1) / ksplit);
-    if (row0 >= rows) return;
-    const int nblk_full = (int)(n / 128);
-    const int nq = rank - c0 < CB ? rank - c0 : CB;
-
-    const double* xp[kRowsA];
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t row_w = ((int64_t)blockIdx.x * kWarps + warp) * kRowsW;
+    if (row_w >= rows) return;
+    const int64_t row = row_w + g;
+    const bool valid = row < rows;
+    const double* xr = X + (valid ? row : row_w) * ldx + 4 * t;
+    const double* qr[NQ];
+    bool qok[NQ];
 #pragma unroll
-    for (int r = 0; r < kRowsA; ++r) xp[r] = X + (row0 + r < rows ? row0 + r : row0) * ldx + lane;
-    const double* qp = Qt + (int64_t)c0 * ldq + lane;
-    double acc[kRowsA][CB], sq[kRowsA];
-#pragma unroll
-    for (int r = 0; r < kRowsA; ++r) {
-        sq[r] = 0.0;
-#pragma unroll
-        for (int c = 0; c < CB; ++c) acc[r][c] = 0.0;
+    for (int q = 0; q < NQ; ++q) {
+        const int c = c0 + 8 * q + g;
+        qok[q] = c < rank;
+        qr[q] = Qt + (int64_t)(qok[q] ? c : 0) * ldq + 4 * t;
     }
-    int blk = b_begin;
-    const int fast_end = b_end < nblk_full ? b_end : nblk_full;
-    for (; blk < fast_end; ++blk) coef_block<CB, true>(xp, qp, ldq, nq, (int64_t)blk * 128, n, c0 == 0, acc, sq);
-    for (; blk < b_end; ++blk) coef_block<CB, false>(xp, qp, ldq, nq, (int64_t)blk * 128, n - lane, c0 == 0, acc, sq);
+    const int64_t n16 = (n + 15) / 16, n16_full = n / 16;
+    const int64_t kb = n16 * blockIdx.y / ksplit, ke = n16 * (blockIdx.y + 1) / ksplit;
+    const int64_t ke_fast = ke < n16_full ? ke : n16_full;
+
+    double acc[NQ][2], sq = 0.0;
 #pragma unroll
-    for (int r = 0; r < kRowsA; ++r) {
+    for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = 0.0;
+    int64_t kk = kb;
+#pragma unroll 2
+    for (; kk < ke_fast; ++kk) {
+        double xv[4], qv[NQ][4];
+        load4(xr + kk * 16, vec, xv);
 #pragma unroll
-        for (int c = 0; c < CB; ++c) {
-            const double v = warp_sum(acc[r][c]);
-            if (lane == 0 && row0 + r < rows && c < nq)
-                partial[((int64_t)ks * rows + row0 + r) * rank + c0 + c] = v;
+        for (int q = 0; q < NQ; ++q) {
+            if (qok[q]) load4(qr[q] + kk * 16, vec, qv[q]);
+            else qv[q][0] = qv[q][1] = qv[q][2] = qv[q][3] = 0.0;
         }
-        if (c0 == 0) {
-            const double v = warp_sum(sq[r]);
-            if (lane == 0 && row0 + r < rows) psq[(int64_t)ks * rows + row0 + r] = v;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) dmma(acc[q][0], acc[q][1], xv[e], qv[q][e]);
+            sq = fma(xv[e], xv[e], sq);
         }
+    }
+    for (; kk < ke; ++kk) {                                // ragged last group of 16 cells
+        double xv[4], qv[NQ][4];
+        const int64_t k = kk * 16 + 4 * t;
+        load4_tail(xr + kk * 16, k, n, xv);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (qok[q]) load4_tail(qr[q] + kk * 16, k, n, qv[q]);
+            else qv[q][0] = qv[q][1] = qv[q][2] = qv[q][3] = 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) dmma(acc[q][0], acc[q][1], xv[e], qv[q][e]);
+            sq = fma(xv[e], xv[e], sq);
+        }
+    }
+    // accumulator: row g, covariates c0 + 8q + 2t, +1
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int c = c0 + 8 * q + 2 * t + e;
+            if (valid && c < rank) partial[((int64_t)blockIdx.y * rows + row) * rank + c] = acc[q][e];
+        }
+    if (c0 == 0) {
+        sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+        sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+        if (t == 0 && valid) psq[(int64_t)blockIdx.y * rows + row] = sq;
     }
 }
 
 // rank == 0: only sum x^2 is needed
 __global__ void __launch_bounds__(kThreads, 2)
-sumsq_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx, int nblk, int ksplit,
+sumsq_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx, int ksplit,
              double* __restrict__ psq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * kWarps + warp;
     const int ks = blockIdx.y;
     if (row >= rows) return;
-    const int64_t k_begin = (int64_t)nblk * ks / ksplit * 128, k_end = (int64_t)nblk * (ks + 1) / ksplit * 128;
+    const int64_t nblk = (n + 127) / 128;
+    const int64_t k_begin = nblk * ks / ksplit * 128, k_end = nblk * (ks + 1) / ksplit * 128;
     double s = 0.0;
     for (int64_t k = k_begin + lane; k < k_end && k < n; k += 32) {
         const double x = __ldg(X + row * ldx + k);
@@ -159,8 +190,8 @@ __global__ void coef_finalize_kernel(const double* __restrict__ partial, const d
 
 // ---- pass B ------------------------------------------------------------------------------
 template <int S>
-__device__ __forceinline__ void store_digits(const double (&v)[32], double invq, double vmax,
-                                             int8_t* __restrict__ dst, int64_t plane_stride) {
+__device__ __forceinline__ void store_digits(const double (&v)[32], double invq, int8_t* __restrict__ dst,
+                                             int64_t plane_stride) {
     uint32_t w[S][8];
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -168,8 +199,9 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
         for (int i = 0; i < 8; ++i) w[s][i] = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-        const double t = fmin(fmax(v[i] * invq, -vmax), vmax);
-        int32_t q = __double2int_rn(t);
+        // no clamp: a row that overflows here is flagged (exact max|z'| vs quantum) and rewritten by
+        // the fix-up pass; the conversion saturates, it cannot trap
+        int32_t q = __double2int_rn(v[i] * invq);
 #pragma unroll
         for (int s = S - 1; s >= 1; --s) {
             // balanced low digit d = sext8(q & 0xFF); (q - d) >> 8 == (q + 128) >> 8
@@ -189,118 +221,119 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
 // row_list == nullptr: logical row == row.  Otherwise the kernel handles rows row_list[0..*row_count).
 template <int S, bool HAD>
 __global__ void __launch_bounds__(kThreads, 2)
-residual_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
-                const double* __restrict__ Qt, int rank, int64_t ldq, const double* __restrict__ coef,
-                const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
-                int nblk, int ksplit, uint64_t cell_offset, const double* __restrict__ inv_quantum,
-                double vmax, double* __restrict__ part_sumsq, double* __restrict__ part_amax,
-                int8_t* __restrict__ slices, int64_t rows_alloc, int64_t n_pad) {
-    extern __shared__ double smem[];
+residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
+                    const double* __restrict__ Qt, int rank, int64_t ldq, const double* __restrict__ coef,
+                    const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
+                    int nblk, int ksplit, int vec, uint64_t cell_offset,
+                    const double* __restrict__ inv_quantum, double* __restrict__ part_sumsq,
+                    double* __restrict__ part_amax, int8_t* __restrict__ slices, int64_t rows_alloc,
+                    int64_t n_pad) {
+    // covariate block of the current 128 cells, shared by the CTA's 8 warps (they walk the same
+    // cells): [buffer][covariate][cell], pitch 132 so that a B-fragment read (4 covariates x 8 cells
+    // per half-warp) touches 16 distinct banks
+    __shared__ double s_q[2][16][kQPitch];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
     const int64_t n_logical = row_list ? (int64_t)*row_count : rows;
-    const int64_t l0 = ((int64_t)blockIdx.x * kWarps + warp) * kRowsB;    // first logical row of this warp
-    const int ks = blockIdx.y;
-    const int b_begin = (int)((int64_t)nblk * ks / ksplit);
-    const int b_end = (int)((int64_t)nblk * (ks + 1) / ksplit);
-    if ((int64_t)blockIdx.x * kWarps * kRowsB >= n_logical) return;        // whole CTA idle
-    const int rank4 = (rank + 3) & ~3;
-
-    double* s_coef = smem + warp * (kRowsB * NSR_MAX_RANK + 32 * kSegPitch);   // [kRowsB][NSR_MAX_RANK]
-    double* s_z = s_coef + kRowsB * NSR_MAX_RANK;                               // [32 segments][kSegPitch]
-    int64_t row_of[kRowsB];
-#pragma unroll
-    for (int r = 0; r < kRowsB; ++r) {
-        const int64_t l = l0 + r;
-        row_of[r] = (l < n_logical) ? (row_list ? (int64_t)row_list[l] : l) : -1;
-    }
-    for (int i = lane; i < kRowsB * NSR_MAX_RANK; i += 32) {
-        const int r = i / NSR_MAX_RANK, c = i % NSR_MAX_RANK;
-        const int64_t l = l0 + r;
-        const int64_t row = (l < n_logical) ? (row_list ? (int64_t)row_list[l] : l) : -1;
-        s_coef[i] = (row >= 0 && c < rank) ? coef[row * rank + c] : 0.0;
-    }
-    __syncwarp();
-
-    // phase-2 ownership: lane -> (row slot lane>>2, cells 32*(lane&3) .. +32 of the block)
-    const int my_slot = lane >> 2, my_quarter = lane & 3;
-    int64_t my_row = -1;
-#pragma unroll
-    for (int r = 0; r < kRowsB; ++r)
-        if (r == my_slot) my_row = row_of[r];
-    const double my_invq = (my_row >= 0 && inv_quantum) ? inv_quantum[my_row] : 0.0;
-    double my_amax = 0.0;
-    double sumsq[kRowsB];
-#pragma unroll
-    for (int r = 0; r < kRowsB; ++r) sumsq[r] = 0.0;
-
+    if ((int64_t)blockIdx.x * kWarps * kRowsW >= n_logical) return;        // whole CTA idle
+    const int64_t l0 = ((int64_t)blockIdx.x * kWarps + warp) * kRowsW;
+    const int64_t lrow = l0 + g;
+    const int64_t my_row = lrow < n_logical ? (row_list ? (int64_t)row_list[lrow] : lrow) : -1;
+    const double* xr = X + (my_row >= 0 ? my_row : 0) * ldx + 2 * t;
+    const double* cf = coef + (my_row >= 0 ? my_row : 0) * rank;
+    const int b_begin = (int)((int64_t)nblk * blockIdx.y / ksplit);
+    const int b_end = (int)((int64_t)nblk * (blockIdx.y + 1) / ksplit);
     const int nblk_full = (int)(n / 128);
-    const double* xp[kRowsB];
+    const int ngroup = (rank + 15) / 16;                 // covariates in groups of 16 = 4 MMA k-chunks
+    const double my_invq = (my_row >= 0 && inv_quantum) ? inv_quantum[my_row] * (HAD ? kHadScale : 1.0) : 0.0;
+
+    // A fragments (-coef[row g][4 ch + t]) of the first covariate group stay in registers
+    double ca[4];
 #pragma unroll
-    for (int r = 0; r < kRowsB; ++r) xp[r] = X + (row_of[r] >= 0 ? row_of[r] : 0) * ldx + lane;
-    const double* qbase = Qt + lane;
+    for (int ch = 0; ch < 4; ++ch) {
+        const int c = 4 * ch + t;
+        ca[ch] = (my_row >= 0 && c < rank) ? -cf[c] : 0.0;
+    }
+    double sumsq = 0.0, amax = 0.0;
+
     for (int blk = b_begin; blk < b_end; ++blk) {
         const int64_t k0 = (int64_t)blk * 128;
         const bool full = blk < nblk_full;
-        const int64_t n_lane = n - lane;                 // cell (k0 + 32 j + lane) < n  <=>  k0 + 32 j < n_lane
-        bool flip[4];
+        // sign pattern of the block: lane l evaluates cells 4l .. 4l+3, ballots share them
+        uint32_t ma = 0, mb = 0;
+        if (HAD) {
+            uint32_t m[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) flip[j] = HAD && cell_flip(cell_offset + (uint64_t)(k0 + lane + 32 * j));
-        // ---- phase 1: residuals of 8 rows (two halves of 4 to bound registers) -> smem
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            double z[4][4];
-            if (full) {
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) z[r][j] = __ldg(xp[4 * half + r] + k0 + 32 * j);
-            } else {
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        z[r][j] = (k0 + 32 * j < n_lane) ? __ldg(xp[4 * half + r] + k0 + 32 * j) : 0.0;
-            }
-            const double* qc = qbase + k0;
-            for (int c0 = 0; c0 < rank4; c0 += 4) {
-                double q[4][4];
-                if (full && c0 + 4 <= rank) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) q[c][j] = __ldg(qc + (int64_t)c * ldq + 32 * j);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            q[c][j] = (c0 + c < rank && k0 + 32 * j < n_lane) ? __ldg(qc + (int64_t)c * ldq + 32 * j) : 0.0;
-                }
-                qc += 4 * ldq;
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double b = s_coef[(4 * half + r) * NSR_MAX_RANK + c0 + c];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) z[r][j] = fma(-b, q[c][j], z[r][j]);
-                    }
-            }
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const double v = z[r][j];
-                    sumsq[4 * half + r] = fma(v, v, sumsq[4 * half + r]);
-                    s_z[(4 * (4 * half + r) + j) * kSegPitch + lane] = flip[j] ? -v : v;
-                }
+            for (int e = 0; e < 4; ++e)
+                m[e] = __ballot_sync(0xffffffffu, cell_flip(cell_offset + (uint64_t)(k0 + 4 * lane + e)));
+            // my cells 8u + 2t + e' = 4 (2u + t/2) + (2 (t%2) + e')  ->  mask 2(t%2)+e', bit 2u + t/2
+            ma = ((t & 1) ? m[2] : m[0]) >> (t >> 1);
+            mb = ((t & 1) ? m[3] : m[1]) >> (t >> 1);
         }
-        __syncwarp();
-        // ---- phase 2: 32 consecutive cells of one row per lane
         double v[32];
+        // ---- all X loads of the block first (independent, 8 KB per warp in flight)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = s_z[lane * kSegPitch + i];
-        __syncwarp();
+        for (int u = 0; u < 16; ++u) {
+            const int64_t k = k0 + 8 * u + 2 * t;
+            if (full) {
+                if (vec) {
+                    const double2 c2 = __ldg(reinterpret_cast<const double2*>(xr + k0 + 8 * u));
+                    v[2 * u] = c2.x; v[2 * u + 1] = c2.y;
+                } else {
+                    v[2 * u] = __ldg(xr + k0 + 8 * u);
+                    v[2 * u + 1] = __ldg(xr + k0 + 8 * u + 1);
+                }
+            } else {
+                v[2 * u] = (k < n) ? __ldg(xr + k0 + 8 * u) : 0.0;
+                v[2 * u + 1] = (k + 1 < n) ? __ldg(xr + k0 + 8 * u + 1) : 0.0;
+            }
+        }
+        // ---- stage the first 16 covariates of this block in shared memory (coalesced rows)
+        const int buf = blk & 1;
+        const int nq0 = rank < 16 ? rank : 16;
+        for (int i = threadIdx.x; i < nq0 * 128; i += kThreads) {
+            const int c = i >> 7, cell = i & 127;
+            s_q[buf][c][cell] = (full || k0 + cell < n) ? __ldg(Qt + (int64_t)c * ldq + k0 + cell) : 0.0;
+        }
+        __syncthreads();          // one barrier per block is enough with two buffers
+        // ---- residual tiles: C = X (8 rows x 8 cells), A = -coef, B = Qt
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            double c0v = v[2 * u], c1v = v[2 * u + 1];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                if (4 * ch < rank) {                       // warp-uniform
+                    const int c = 4 * ch + t;              // rows >= rank of s_q are never read as non-zero:
+                    const double b = (c < rank) ? s_q[buf][c][8 * u + g] : 0.0;
+                    dmma(c0v, c1v, ca[ch], b);
+                }
+            }
+            if (ngroup > 1) {                              // rank > 16: further groups straight from L1/L2
+                const int64_t kq = k0 + 8 * u + g;
+                const bool qin = full || kq < n;
+                for (int gq = 1; gq < ngroup; ++gq) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const int cbase = 16 * gq + 4 * ch;
+                        if (cbase < rank) {
+                            const int c = cbase + t;
+                            const double a = (my_row >= 0 && c < rank) ? -cf[c] : 0.0;
+                            const double b = (qin && c < rank) ? __ldg(Qt + (int64_t)c * ldq + kq) : 0.0;
+                            dmma(c0v, c1v, a, b);
+                        }
+                    }
+                }
+            }
+            sumsq = fma(c0v, c0v, sumsq);
+            sumsq = fma(c1v, c1v, sumsq);
+            if (HAD) {
+                c0v = __hiloint2double(__double2hiint(c0v) ^ (int)(((ma >> (2 * u)) & 1u) << 31), __double2loint(c0v));
+                c1v = __hiloint2double(__double2hiint(c1v) ^ (int)(((mb >> (2 * u)) & 1u) << 31), __double2loint(c1v));
+            }
+            v[2 * u] = c0v;
+            v[2 * u + 1] = c1v;
+        }
+        // ---- Walsh-Hadamard over the 128 cells: local index bits 0..4 in registers, t by shuffle
         if (HAD) {
 #pragma unroll
             for (int h = 1; h < 32; h <<= 1)
@@ -313,32 +346,29 @@ residual_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t l
                     }
 #pragma unroll
             for (int m = 1; m <= 2; m <<= 1) {
-                const bool up = lane & m;
+                const bool up = t & m;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     const double p = __shfl_xor_sync(0xffffffffu, v[i], m);
                     v[i] = up ? p - v[i] : v[i] + p;
                 }
             }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= kHadScale;
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) my_amax = fmax(my_amax, fabs(v[i]));
+        for (int i = 0; i < 32; ++i) amax = fmax(amax, fabs(v[i]));          // unscaled; scaled at the end
         if (slices != nullptr && my_row >= 0)
-            store_digits<S>(v, my_invq, vmax,
-                            slices + my_row * n_pad + (int64_t)blk * 128 + 32 * my_quarter,
-                            rows_alloc * n_pad);
+            store_digits<S>(v, my_invq, slices + my_row * n_pad + k0 + 32 * t, rows_alloc * n_pad);
     }
     if (part_sumsq != nullptr) {
-#pragma unroll
-        for (int r = 0; r < kRowsB; ++r) {
-            const double s = warp_sum(sumsq[r]);
-            if (lane == 0 && row_of[r] >= 0) part_sumsq[(int64_t)ks * rows + row_of[r]] = s;
+        sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 1);
+        sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 2);
+        amax *= (HAD ? kHadScale : 1.0);
+        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        if (t == 0 && my_row >= 0) {
+            part_sumsq[(int64_t)blockIdx.y * rows + my_row] = sumsq;
+            part_amax[(int64_t)blockIdx.y * rows + my_row] = amax;
         }
-        my_amax = fmax(my_amax, __shfl_xor_sync(0xffffffffu, my_amax, 1));
-        my_amax = fmax(my_amax, __shfl_xor_sync(0xffffffffu, my_amax, 2));
-        if (my_quarter == 0 && my_row >= 0) part_amax[(int64_t)ks * rows + my_row] = my_amax;
     }
 }
 
@@ -370,33 +400,18 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
     }
 }
 
+// position p of a 128-cell block holds transformed index 8u + 2t + e with p = 32t + 2u + e
 __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, int64_t rows_alloc,
                                int64_t n_pad, int n_slices, const double* __restrict__ quantum,
                                double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * n_pad) return;
     const int64_t r = i / n_pad, k = i % n_pad;
+    const int p = (int)(k & 127);
+    const int m = 8 * ((p & 31) >> 1) + 2 * (p >> 5) + (p & 1);
     int64_t v = 0;
     for (int s = 0; s < n_slices; ++s) v = v * 256 + slices[((int64_t)s * rows_alloc + r) * n_pad + k];
-    out[i] = (double)v * quantum[r];
-}
-
-constexpr int kSmemB = kWarps * (kRowsB * NSR_MAX_RANK + 32 * kSegPitch) * (int)sizeof(double);
-
-template <int S, bool HAD>
-int launch_residual(cudaStream_t st, dim3 grid, const double* X, int64_t rows, int64_t n, int64_t ldx,
-                    const double* Qt, int rank, int64_t ldq, const double* coef, const int32_t* row_list,
-                    const int32_t* row_count, int nblk, int ksplit, const double* invq, double vmax,
-                    double* p_sumsq, double* p_amax, int8_t* slices, int64_t rows_alloc, int64_t n_pad) {
-    auto kern = residual_kernel<S, HAD>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemB));
-        attr_done = true;
-    }
-    kern<<<grid, kThreads, kSmemB, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef, row_list, row_count, nblk, ksplit,
-                                         0, invq, vmax, p_sumsq, p_amax, slices, rows_alloc, n_pad);
-    return 0;
+    out[r * n_pad + (k - p) + m] = (double)v * quantum[r];     // natural (transformed-index) order
 }
 
 }  // namespace
@@ -420,21 +435,23 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     NSR_REQUIRE(n_pad == nsr_padded_cells(n) && rows_alloc >= rows,
                 "nsr_residualize: n_pad/rows_alloc inconsistent");
     NSR_REQUIRE(((uintptr_t)slices & 15) == 0, "nsr_residualize: slices must be 16-byte aligned");
+    NSR_REQUIRE(((uintptr_t)X & 7) == 0 && ((uintptr_t)Qt & 7) == 0, "nsr_residualize: inputs must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     NSR_CHECK(cudaSetDevice(ctx->device));
 
+    // 16-byte vector loads need even leading dimensions and 16-byte aligned bases
+    const int vec = ((uintptr_t)X % 16 == 0) && (ldx % 2 == 0) &&
+                    (rank == 0 || (((uintptr_t)Qt % 16 == 0) && (ldq % 2 == 0)));
     const int nblk = (int)(n_pad / 128);
-    auto pick_split = [&](int64_t groups) {
-        int64_t ks = (4 * (int64_t)ctx->sm_count + groups - 1) / groups;
-        if (ks < 1) ks = 1;
-        if (ks > nblk) ks = nblk;
-        if (ks > 64) ks = 64;
-        return (int)ks;
-    };
-    const int64_t groups_a = (rows + kWarps * kRowsA - 1) / (kWarps * kRowsA);
+    // The split of the cell axis depends on n only (2048 cells per CTA, at most 64 splits), never on
+    // the number of rows in the call: partial sums are then combined in the same order whether a
+    // matrix is residualised whole, in row chunks, or sharded over GPUs - results stay bit-identical.
+    int ksplit = (nblk + 15) / 16;
+    if (ksplit > 64) ksplit = 64;
+    if (ksplit < 1) ksplit = 1;
+    const int64_t groups_w = (rows + kWarps * kRowsW - 1) / (kWarps * kRowsW);   // CTAs of 8 warps x 8 rows
     const int64_t groups_s = (rows + kWarps - 1) / kWarps;
-    const int64_t groups_b = (rows + kWarps * kRowsB - 1) / (kWarps * kRowsB);
-    const int ks_a = pick_split(rank ? groups_a : groups_s), ks_b = pick_split(groups_b);
+    const int ks_a = ksplit, ks_b = ksplit;
     const int rk = rank > 0 ? rank : 1;
 
     // scratch (doubles): coef partials | sum-x^2 partials | sumsq partials | amax partials | inv_quantum
@@ -456,34 +473,37 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
 
     NSR_CHECK(cudaMemsetAsync(fix_count, 0, sizeof(int32_t), st));
     if (rank > 0) {
-        const dim3 grid((unsigned)groups_a, (unsigned)ks_a);
-        for (int c0 = 0; c0 < rank; c0 += 8) {
-            if (rank - c0 <= 4)
-                coef_kernel<4><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial, psq);
+        const dim3 grid((unsigned)groups_w, (unsigned)ks_a);
+        for (int c0 = 0; c0 < rank; c0 += 16) {          // 16 covariates per launch
+            if (rank - c0 <= 8)
+                coef_mma_kernel<1><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, ks_a, vec, partial, psq);
             else
-                coef_kernel<8><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, nblk, ks_a, partial, psq);
+                coef_mma_kernel<2><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, ks_a, vec, partial, psq);
         }
     } else {
-        sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ks_a), kThreads, 0, st>>>(X, rows, n, ldx, nblk, ks_a, psq);
+        sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ks_a), kThreads, 0, st>>>(X, rows, n, ldx, ks_a, psq);
     }
     coef_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial, psq, rows, rank, ks_a, n, vmax,
                                                                        coef_buf, invq);
-    const dim3 gridb((unsigned)groups_b, (unsigned)ks_b);
+    const dim3 gridb((unsigned)groups_w, (unsigned)ks_b);
     const bool had = nsr_use_hadamard != 0;
-    int rc;
-#define NSR_LAUNCH_B(GRID, LIST, COUNT, KS, PS, PA)                                                          \
-    (n_slices == 3 ? (had ? launch_residual<3, true>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)   \
-                          : launch_residual<3, false>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)) \
-                   : (had ? launch_residual<4, true>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)   \
-                          : launch_residual<4, false>(st, GRID, X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, KS, invq, vmax, PS, PA, slices, rows_alloc, n_pad)))
-    rc = NSR_LAUNCH_B(gridb, nullptr, nullptr, ks_b, p_sumsq, p_amax);
-    if (rc) return rc;
+#define NSR_LAUNCH_B(KERN, LIST, COUNT, PS, PA)                                                              \
+    KERN<<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, vec, \
+                                     (uint64_t)0, invq, PS, PA, slices, rows_alloc, n_pad)
+#define NSR_LAUNCH_B_ALL(LIST, COUNT, PS, PA)                                                                \
+    do {                                                                                                     \
+        if (n_slices == 3 && had) NSR_LAUNCH_B((residual_mma_kernel<3, true>), LIST, COUNT, PS, PA);          \
+        else if (n_slices == 3) NSR_LAUNCH_B((residual_mma_kernel<3, false>), LIST, COUNT, PS, PA);           \
+        else if (had) NSR_LAUNCH_B((residual_mma_kernel<4, true>), LIST, COUNT, PS, PA);                      \
+        else NSR_LAUNCH_B((residual_mma_kernel<4, false>), LIST, COUNT, PS, PA);                              \
+    } while (0)
+    NSR_LAUNCH_B_ALL(nullptr, nullptr, p_sumsq, p_amax);
     stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
                                                                         quantum, invq, fix_list, fix_count);
-    // sparse fix-up: CTAs beyond the (device-side) count exit at once
-    rc = NSR_LAUNCH_B(gridb, fix_list, fix_count, ks_b, nullptr, nullptr);
+    // sparse fix-up: warps beyond the (device-side) count exit at once
+    NSR_LAUNCH_B_ALL(fix_list, fix_count, nullptr, nullptr);
+#undef NSR_LAUNCH_B_ALL
 #undef NSR_LAUNCH_B
-    if (rc) return rc;
     NSR_CHECK(cudaGetLastError());
     return 0;
 }

@@ -22,7 +22,8 @@ def host_counts(rng, n_gene, n_cell, n_module=0, module_size=30):
 
 def host_problem(seed, n_gene, n_cell, n_batch=6, n_module=4, n_group=0, group_p=0.02, module_size=30):
     """Return dict(dt, dc[, dg]): float64, rows = variables, columns = cells.  dc = one-hot
-    batches minus one + log depth + detection rate + a constant row (like normcov's output)."""
+    batches minus one + 3 continuous summaries + a constant row: 9 covariates, like the
+    reference chain's 5 batch indicators + lcpm's 3 covariates + normcov's constant row."""
     rng = np.random.default_rng(seed)
     reads, depth = host_counts(rng, n_gene, n_cell, n_module, module_size)
     tot = reads.sum(axis=0) + 1.0
@@ -31,7 +32,8 @@ def host_problem(seed, n_gene, n_cell, n_batch=6, n_module=4, n_group=0, group_p
     cov = [(b == i).astype(float) for i in range(1, n_batch)]
     ld = np.log(tot)
     det = (reads > 0).mean(axis=0)
-    cov += [(ld - ld.mean()) / ld.std(), (det - det.mean()) / det.std()]
+    dv = np.log1p(reads).var(axis=0)
+    cov += [(ld - ld.mean()) / ld.std(), (det - det.mean()) / det.std(), (dv - dv.mean()) / dv.std()]
     dc = np.array(cov + [np.ones(n_cell)])
     out = {"dt": np.ascontiguousarray(dt), "dc": np.ascontiguousarray(dc)}
     if n_group:
@@ -58,8 +60,10 @@ def device_problem(seed, n_gene, n_cell, device, n_batch=6, n_module=8, module_s
     noise = torch.randn(n_cell, generator=gc, device=device, dtype=f64)
     cov = [(b == i).to(f64) for i in range(1, n_batch)]
     ld = torch.log(depth)
+    noise2 = torch.randn(n_cell, generator=gc, device=device, dtype=f64)
     c2 = 0.6 * ld + 0.8 * noise
-    cov += [(ld - ld.mean()) / ld.std(), (c2 - c2.mean()) / c2.std(),
+    c3 = 0.3 * ld - 0.5 * noise + 0.8 * noise2
+    cov += [(ld - ld.mean()) / ld.std(), (c2 - c2.mean()) / c2.std(), (c3 - c3.mean()) / c3.std(),
             torch.ones(n_cell, dtype=f64, device=device)]
     dc = torch.stack(cov)
     # gene means ~ Gamma(0.5, scale 2) + 0.05 via the square of a normal (chi2_1 = Gamma(1/2, 2))

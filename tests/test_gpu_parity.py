@@ -128,6 +128,32 @@ def test_edge_shapes():
         _check_coex(norm.coex(dt, dc), orc.coex(dt, dc))
 
 
+def test_outlier_and_degenerate_rows():
+    """Rows that defeat the rms-based scale estimate: one giant spike, an all-zero row, a row that
+    is an exact linear combination of covariates (residual = rounding noise in the reference,
+    so only its var is compared loosely) and a very sparse gene."""
+    rng = np.random.default_rng(21)
+    n, g = 3000, 40
+    dc = np.concatenate([rng.normal(size=(3, n)), np.ones((1, n))])
+    dt = rng.normal(size=(g, n)) + 3.0
+    dt[3, 777] += 5e4                       # spike: max|z'| >> 6 rms -> re-quantisation pass
+    dt[5] = 0.0                             # exact zero residual: var 0 -> 1, P = 1
+    dt[9] = (rng.random(n) < 0.002) * 7.0   # expressed in ~6 cells
+    ref = orc.coex(dt, dc)
+    got = norm.coex(dt, dc)
+    _check_coex(got, ref)
+    assert got[2][5] == 1.0 and (np.delete(got[0][5], 5) == 1.0).all()
+
+
+def test_many_covariates():
+    """rank 20 > 16: the coefficient pass needs two launches."""
+    rng = np.random.default_rng(22)
+    n, g = 1500, 50
+    dc = np.concatenate([rng.normal(size=(19, n)), np.ones((1, n))])
+    dt = rng.normal(size=(g, n)) + 0.3 * dc[:5].sum(0)
+    _check_coex(norm.coex(dt, dc), orc.coex(dt, dc))
+
+
 def test_errors_match_reference():
     x = np.random.default_rng(0).normal(size=(4, 5))
     with pytest.raises(ValueError):

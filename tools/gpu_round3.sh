@@ -7,8 +7,8 @@ echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | ta
 echo "== bench ours"; timeout 900 python bench.py --steps 5 --warmup 3 2>&1 | tail -2 | cut -c1-3000 | tee $OUT/bench_ours.txt
 echo "== ncu full: projection"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"residual_kernel|coef_kernel" -s 3 -c 3 -f -o $OUT/prof_project \
-   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_project_stdout.txt 2>&1
+   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-de > $OUT/ncu_project_stdout.txt 2>&1
 echo "== ncu full: contraction"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:contract_umma -s 1 -c 1 -f -o $OUT/prof_contract \
-   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > $OUT/ncu_contract_stdout.txt 2>&1
+   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-de > $OUT/ncu_contract_stdout.txt 2>&1
 ls -la $OUT

@@ -4,7 +4,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 echo "== bringup residual + perf"; timeout 900 python tools/gpu_bringup.py residual > $OUT/residual.txt 2>&1; tail -3 $OUT/residual.txt | cut -c1-300
 for v in "default 0" "default 1" "fast 0" "fast 1"; do set -- $v
-  echo "== bench $1 pair=$2 (12 steps)"; timeout 600 python bench.py --steps 12 --warmup 3 --no-e2e --no-cpu --precision $1 --umma-pair $2 2>&1 | tail -1 > $OUT/bench_$1_$2.txt
+  echo "== bench $1 pair=$2 (12 steps)"; timeout 600 python bench.py --steps 12 --warmup 3 --no-e2e --no-cpu --no-de --precision $1 --umma-pair $2 2>&1 | tail -1 > $OUT/bench_$1_$2.txt
   python - <<PY
 import json
 d=json.loads(open("$OUT/bench_$1_$2.txt").read())
