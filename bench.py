@@ -329,11 +329,17 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
     my_pairs = len(tiles_full if single else tiles) * 128 * 128 / 2.0        # ~unique pairs in this rank's tiles
     alg_flops = 2.0 * n_cell * (pairs if single else my_pairs)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            "%s/%s/%d" % (wl_name, precision, world))
+    except Exception:
+        pass
     roof = None
     if k_ms:
         ach = alg_flops / (k_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": None, "kernel": "contract_umma_kernel", "kernel_ms": k_ms,
+                "traffic": traffic, "kernel": "contract_umma_kernel", "kernel_ms": k_ms,
                 "kernel_ms_per_step": [round(x, 2) for x in k_list], "peak_source": peak_src,
                 "executed_int8_tops": 2.0 * n_products * len(tiles_full if single else tiles) * 128 * 128 *
                                       engine.padded_cells(n_cell) / (k_ms * 1e-3) / 1e12,

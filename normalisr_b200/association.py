@@ -136,15 +136,22 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
     P = torch.empty((rows, rows), dtype=torch.float64, device=dev)
     D = torch.empty((rows, rows), dtype=torch.float64, device=dev)
     strip_rows = 12 * engine.TILE
-    chunk = max(strip_rows, (_ROW_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
-    chunk = min(chunk, (rows + engine.TILE - 1) // engine.TILE * engine.TILE)
+    base = max(strip_rows, (_ROW_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
+    # row chunks: `base` rows while plenty remain, then geometrically smaller ones, so that the work
+    # left after the last host->device copy (the last strip's tiles and its device->host copy) is small
+    bounds = [0]
+    while bounds[-1] < rows:
+        left = rows - bounds[-1]
+        step = base if left > 3 * base else max(2 * engine.TILE, (left // 3) // engine.TILE * engine.TILE)
+        bounds.append(min(rows, bounds[-1] + step))
+    chunk = min(base, (rows + engine.TILE - 1) // engine.TILE * engine.TILE)
     copy_stream = torch.cuda.Stream(device=dev)
     d2h_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     bufs = [torch.empty((min(chunk, rows), n), dtype=torch.float64, device=dev) for _ in range(2)]
     done = [None, None]
-    for i, r0 in enumerate(range(0, rows, chunk)):
-        r1 = min(r0 + chunk, rows)
+    for i in range(len(bounds) - 1):
+        r0, r1 = bounds[i], bounds[i + 1]
         b = bufs[i & 1]
         with torch.cuda.stream(copy_stream):
             if done[i & 1] is not None:

@@ -17,6 +17,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
 extern int nsr_use_hadamard;
 extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
+extern int nsr_epi_warps;
 extern int nsr_epi_overlap;
 extern int nsr_epi_sleep_ns;
 
@@ -81,6 +82,11 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
 extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "epi_warps")) {
+        NSR_REQUIRE(value == 8 || value == 16, "epi_warps must be 8 or 16");
+        nsr_epi_warps = value;
+        return 0;
+    }
     if (!strcmp(name, "epi_overlap")) { nsr_epi_overlap = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_sleep_ns")) { nsr_epi_sleep_ns = value < 0 ? 0 : value; return 0; }
     if (!strcmp(name, "umma_kblock")) {

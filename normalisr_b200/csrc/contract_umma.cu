@@ -19,6 +19,8 @@
 
 #include "epilogue.cuh"
 
+extern int nsr_epi_warps;
+
 namespace {
 
 constexpr int kEpiWarps = 8;
@@ -117,6 +119,19 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tc_ldN(uint32_t taddr, uint32_t (&v)[N]);
+template <>
+__device__ __forceinline__ void tc_ldN<16>(uint32_t taddr, uint32_t (&v)[16]) { tc_ld16(taddr, v); }
+template <>
+__device__ __forceinline__ void tc_ldN<8>(uint32_t taddr, uint32_t (&v)[8]) { tc_ld8(taddr, v); }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, rows of KB bytes, swizzle width == KB (128B or 64B), 8-row groups dense
@@ -143,11 +158,13 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
 // draining all accumulators into registers first and releasing TMEM early (so the next tile's
 // MMAs overlap the P-value arithmetic) is 13 % faster in a short burst but 25 % SLOWER sustained:
 // the chip is power-bound here, and that variant costs more energy per tile than it saves time.
-template <int GROUPS>
+template <int GROUPS, int EW>
 __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t tmem_base, int warp, int lane,
                                               int tr, int tc, bool wanted, uint32_t empty_bar, bool remote) {
+    constexpr int kCols = NSR_TILE / (EW / 4);          // columns per epilogue warp
+    constexpr int CH = EW > 8 ? 8 : 16;                 // columns per TMEM read (register budget)
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;                   // column group of this warp
     const int64_t i = (int64_t)tr * NSR_TILE + quad * 32 + lane;
     const bool row_ok = wanted && i < ep.rows_a;
     const double qi = row_ok ? ep.qa[i] : 0.0;
@@ -156,15 +173,15 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     if (wanted) {
 #pragma unroll 1
-        for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 16) {
-            uint32_t v[GROUPS][16];
+        for (int c0 = half * kCols; c0 < half * kCols + kCols; c0 += CH) {
+            uint32_t v[GROUPS][CH];
 #pragma unroll
-            for (int grp = 0; grp < GROUPS; ++grp) tc_ld16(lane_base + grp * NSR_TILE + c0, v[grp]);
+            for (int grp = 0; grp < GROUPS; ++grp) tc_ldN<CH>(lane_base + grp * NSR_TILE + c0, v[grp]);
             tc_ld_wait();
             const int64_t j0 = (int64_t)tc * NSR_TILE + c0;
             if (row_ok && j0 < ep.rows_b) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
+                for (int c = 0; c < CH; ++c) {
                     const int64_t j = j0 + c;
                     if (j < ep.rows_b) {
                         int32_t a4[4] = {0, 0, 0, 0};
@@ -194,8 +211,8 @@ struct Cfg {
     static_assert(kGroups * NSR_TILE <= (int)kTmemCols, "TMEM overflow");
 };
 
-template <int S, int WMAX, int KB>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int S, int WMAX, int KB, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ UmmaArgs g) {
     using C = Cfg<S, WMAX, KB>;
@@ -213,7 +230,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
         mbar_init(smem_u32(&bar_tmem_full), 1);
-        mbar_init(smem_u32(&bar_tmem_empty), kEpiWarps);  // one arrival per epilogue warp
+        mbar_init(smem_u32(&bar_tmem_empty), EW);         // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -295,7 +312,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
-            epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false);
+            epilogue_tile<C::kGroups, EW>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false);
             tphase ^= 1;
         }
     }
@@ -474,7 +491,7 @@ contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             const bool wanted = (g.tiles[3 * t + 2] >> rank) & 1;
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
-            epilogue_tile<C::kGroups>(g.ep, tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
+            epilogue_tile<C::kGroups, kEpiWarps>(g.ep, tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
             tphase ^= 1;
         }
     }
@@ -509,16 +526,22 @@ int make_map(nsr_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, i
     return 0;
 }
 
-template <int S, int WMAX, int KB>
-int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
+template <int S, int WMAX, int KB, int EW>
+int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
     using C = Cfg<S, WMAX, KB>;
     const int smem = C::kStages * C::kStageBytes + 1024;
-    auto kern = contract_umma_kernel<S, WMAX, KB>;
+    auto kern = contract_umma_kernel<S, WMAX, KB, EW>;
     NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = g.n_tiles < ctx->sm_count ? g.n_tiles : ctx->sm_count;
-    kern<<<grid, kThreads, smem, st>>>(ma, mb, g);
+    kern<<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, g);
     NSR_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int S, int WMAX, int KB>
+int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
+    if (nsr_epi_warps == 16) return launch_ew<S, WMAX, KB, 16>(ctx, st, ma, mb, g);
+    return launch_ew<S, WMAX, KB, 8>(ctx, st, ma, mb, g);
 }
 
 template <int S, int WMAX>
@@ -536,6 +559,7 @@ int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensor
 
 }  // namespace
 
+int nsr_epi_warps = 8;       // test hook: epilogue warps of the single-CTA kernel (8 or 16)
 int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sustained), 1 -> cta_group::2 kernel
 int nsr_epi_overlap = 1;     // test hook: release TMEM before (1) or after (0) the P-value math
 int nsr_epi_sleep_ns = 500;  // test hook: epilogue wait back-off

@@ -57,8 +57,9 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void load4(const double* p, bool vec, double (&v)[4]) {
-    if (vec) {
+template <bool VEC>
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+    if (VEC) {
         const double2 a = __ldg(reinterpret_cast<const double2*>(p));
         const double2 b = __ldg(reinterpret_cast<const double2*>(p + 2));
         v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
@@ -74,10 +75,10 @@ __device__ __forceinline__ void load4_tail(const double* p, int64_t k, int64_t n
 
 // ---- pass A ------------------------------------------------------------------------------
 // partial[ks][row][c0 .. c0+8*NQ) = sum over this CTA's cells of X[row][k] Qt[c][k];  psq = sum x^2
-template <int NQ>
+template <int NQ, bool VEC>
 __global__ void __launch_bounds__(kThreads, 3)
 coef_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
-                const double* __restrict__ Qt, int rank, int64_t ldq, int c0, int ksplit, int vec,
+                const double* __restrict__ Qt, int rank, int64_t ldq, int c0, int ksplit,
                 double* __restrict__ partial, double* __restrict__ psq) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
@@ -102,13 +103,13 @@ coef_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t l
 #pragma unroll
     for (int q = 0; q < NQ; ++q) acc[q][0] = acc[q][1] = 0.0;
     int64_t kk = kb;
-#pragma unroll 2
+#pragma unroll 4
     for (; kk < ke_fast; ++kk) {
         double xv[4], qv[NQ][4];
-        load4(xr + kk * 16, vec, xv);
+        load4<VEC>(xr + kk * 16, xv);
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            if (qok[q]) load4(qr[q] + kk * 16, vec, qv[q]);
+            if (qok[q]) load4<VEC>(qr[q] + kk * 16, qv[q]);
             else qv[q][0] = qv[q][1] = qv[q][2] = qv[q][3] = 0.0;
         }
 #pragma unroll
@@ -194,21 +195,21 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
                                              int64_t plane_stride) {
     uint32_t w[S][8];
 #pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[s][i] = 0;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i4 = 0; i4 < 8; ++i4) {
         // no clamp: a row that overflows here is flagged (exact max|z'| vs quantum) and rewritten by
         // the fix-up pass; the conversion saturates, it cannot trap
-        int32_t q = __double2int_rn(v[i] * invq);
+        int32_t q[4];
 #pragma unroll
-        for (int s = S - 1; s >= 1; --s) {
-            // balanced low digit d = sext8(q & 0xFF); (q - d) >> 8 == (q + 128) >> 8
-            w[s][i >> 2] |= (uint32_t)(q & 0xFF) << (8 * (i & 3));
-            q = (q + 128) >> 8;
+        for (int j = 0; j < 4; ++j) q[j] = __double2int_rn(v[4 * i4 + j] * invq);
+#pragma unroll
+        for (int s = S - 1; s >= 0; --s) {
+            // low bytes of q[0..3] -> one word; balanced digit: (q - sext8(q)) >> 8 == (q + 128) >> 8
+            w[s][i4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+            if (s > 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q[j] = (q[j] + 128) >> 8;
+            }
         }
-        w[0][i >> 2] |= (uint32_t)(q & 0xFF) << (8 * (i & 3));
     }
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -219,12 +220,14 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
 }
 
 // row_list == nullptr: logical row == row.  Otherwise the kernel handles rows row_list[0..*row_count).
-template <int S, bool HAD>
+// NCH = covariate chunks of 4 handled from shared memory (rank <= 16 -> ceil(rank/4); larger ranks
+// use NCH = 4 plus the global-memory groups).
+template <int S, bool HAD, bool VEC, int NCH>
 __global__ void __launch_bounds__(kThreads, 2)
 residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
                     const double* __restrict__ Qt, int rank, int64_t ldq, const double* __restrict__ coef,
                     const int32_t* __restrict__ row_list, const int32_t* __restrict__ row_count,
-                    int nblk, int ksplit, int vec, uint64_t cell_offset,
+                    int nblk, int ksplit, uint64_t cell_offset,
                     const double* __restrict__ inv_quantum, double* __restrict__ part_sumsq,
                     double* __restrict__ part_amax, int8_t* __restrict__ slices, int64_t rows_alloc,
                     int64_t n_pad) {
@@ -254,7 +257,9 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         const int c = 4 * ch + t;
         ca[ch] = (my_row >= 0 && c < rank) ? -cf[c] : 0.0;
     }
-    double sumsq = 0.0, amax = 0.0;
+    double sumsq = 0.0;
+    int amax_hi = 0;                                     // max over the high words of |z'| (monotone)
+    const double sgn1 = (t & 1) ? -1.0 : 1.0, sgn2 = (t & 2) ? -1.0 : 1.0;
 
     for (int blk = b_begin; blk < b_end; ++blk) {
         const int64_t k0 = (int64_t)blk * 128;
@@ -276,7 +281,7 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         for (int u = 0; u < 16; ++u) {
             const int64_t k = k0 + 8 * u + 2 * t;
             if (full) {
-                if (vec) {
+                if (VEC) {
                     const double2 c2 = __ldg(reinterpret_cast<const double2*>(xr + k0 + 8 * u));
                     v[2 * u] = c2.x; v[2 * u + 1] = c2.y;
                 } else {
@@ -290,10 +295,9 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         }
         // ---- stage the first 16 covariates of this block in shared memory (coalesced rows)
         const int buf = blk & 1;
-        const int nq0 = rank < 16 ? rank : 16;
-        for (int i = threadIdx.x; i < nq0 * 128; i += kThreads) {
+        for (int i = threadIdx.x; i < 4 * NCH * 128; i += kThreads) {
             const int c = i >> 7, cell = i & 127;
-            s_q[buf][c][cell] = (full || k0 + cell < n) ? __ldg(Qt + (int64_t)c * ldq + k0 + cell) : 0.0;
+            s_q[buf][c][cell] = (c < rank && (full || k0 + cell < n)) ? __ldg(Qt + (int64_t)c * ldq + k0 + cell) : 0.0;
         }
         __syncthreads();          // one barrier per block is enough with two buffers
         // ---- residual tiles: C = X (8 rows x 8 cells), A = -coef, B = Qt
@@ -301,14 +305,9 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         for (int u = 0; u < 16; ++u) {
             double c0v = v[2 * u], c1v = v[2 * u + 1];
 #pragma unroll
-            for (int ch = 0; ch < 4; ++ch) {
-                if (4 * ch < rank) {                       // warp-uniform
-                    const int c = 4 * ch + t;              // rows >= rank of s_q are never read as non-zero:
-                    const double b = (c < rank) ? s_q[buf][c][8 * u + g] : 0.0;
-                    dmma(c0v, c1v, ca[ch], b);
-                }
-            }
-            if (ngroup > 1) {                              // rank > 16: further groups straight from L1/L2
+            for (int ch = 0; ch < NCH; ++ch)               // rows >= rank of s_q hold zeros
+                dmma(c0v, c1v, ca[ch], s_q[buf][4 * ch + t][8 * u + g]);
+            if (NCH == 4 && ngroup > 1) {                              // rank > 16: further groups straight from L1/L2
                 const int64_t kq = k0 + 8 * u + g;
                 const bool qin = full || kq < n;
                 for (int gq = 1; gq < ngroup; ++gq) {
@@ -345,23 +344,23 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
                         v[i + h] = a - b;
                     }
 #pragma unroll
-            for (int m = 1; m <= 2; m <<= 1) {
-                const bool up = t & m;
+            for (int i = 0; i < 32; ++i)                  // lower lane: v + p, upper lane: p - v
+                v[i] = fma(sgn1, v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const double p = __shfl_xor_sync(0xffffffffu, v[i], m);
-                    v[i] = up ? p - v[i] : v[i] + p;
-                }
-            }
+            for (int i = 0; i < 32; ++i)
+                v[i] = fma(sgn2, v[i], __shfl_xor_sync(0xffffffffu, v[i], 2));
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) amax = fmax(amax, fabs(v[i]));          // unscaled; scaled at the end
+        for (int i = 0; i < 32; ++i) amax_hi = max(amax_hi, __double2hiint(v[i]) & 0x7fffffff);
         if (slices != nullptr && my_row >= 0)
             store_digits<S>(v, my_invq, slices + my_row * n_pad + k0 + 32 * t, rows_alloc * n_pad);
     }
     if (part_sumsq != nullptr) {
         sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 1);
         sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 2);
+        // upper bound of max|z'| from its high word (relative slack 2^-20): conservative for the
+        // overflow test and costs the re-quantised rows one millionth of their scale
+        double amax = amax_hi ? __hiloint2double(amax_hi + 1, 0) : 0.0;
         amax *= (HAD ? kHadScale : 1.0);
         amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
         amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
@@ -475,10 +474,10 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     if (rank > 0) {
         const dim3 grid((unsigned)groups_w, (unsigned)ks_a);
         for (int c0 = 0; c0 < rank; c0 += 16) {          // 16 covariates per launch
-            if (rank - c0 <= 8)
-                coef_mma_kernel<1><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, ks_a, vec, partial, psq);
-            else
-                coef_mma_kernel<2><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, ks_a, vec, partial, psq);
+#define NSR_LAUNCH_A(NQ, V) coef_mma_kernel<NQ, V><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, c0, ks_a, partial, psq)
+            if (rank - c0 <= 8) { if (vec) NSR_LAUNCH_A(1, true); else NSR_LAUNCH_A(1, false); }
+            else { if (vec) NSR_LAUNCH_A(2, true); else NSR_LAUNCH_A(2, false); }
+#undef NSR_LAUNCH_A
         }
     } else {
         sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ks_a), kThreads, 0, st>>>(X, rows, n, ldx, ks_a, psq);
@@ -487,15 +486,30 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
                                                                        coef_buf, invq);
     const dim3 gridb((unsigned)groups_w, (unsigned)ks_b);
     const bool had = nsr_use_hadamard != 0;
-#define NSR_LAUNCH_B(KERN, LIST, COUNT, PS, PA)                                                              \
-    KERN<<<gridb, kThreads, 0, st>>>(X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, vec, \
-                                     (uint64_t)0, invq, PS, PA, slices, rows_alloc, n_pad)
+    const int nch = rank >= 16 ? 4 : (rank + 3) / 4;
+#define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
+    residual_mma_kernel<S_, H_, V_, N_><<<gridb, kThreads, 0, st>>>(                                         \
+        X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
+        rows_alloc, n_pad)
+#define NSR_LAUNCH_B_N(S_, H_, V_, LIST, COUNT, PS, PA)                                                      \
+    do {                                                                                                     \
+        switch (nch) {                                                                                       \
+            case 0: NSR_LAUNCH_B(S_, H_, V_, 0, LIST, COUNT, PS, PA); break;                                  \
+            case 1: NSR_LAUNCH_B(S_, H_, V_, 1, LIST, COUNT, PS, PA); break;                                  \
+            case 2: NSR_LAUNCH_B(S_, H_, V_, 2, LIST, COUNT, PS, PA); break;                                  \
+            case 3: NSR_LAUNCH_B(S_, H_, V_, 3, LIST, COUNT, PS, PA); break;                                  \
+            default: NSR_LAUNCH_B(S_, H_, V_, 4, LIST, COUNT, PS, PA); break;                                 \
+        }                                                                                                    \
+    } while (0)
 #define NSR_LAUNCH_B_ALL(LIST, COUNT, PS, PA)                                                                \
     do {                                                                                                     \
-        if (n_slices == 3 && had) NSR_LAUNCH_B((residual_mma_kernel<3, true>), LIST, COUNT, PS, PA);          \
-        else if (n_slices == 3) NSR_LAUNCH_B((residual_mma_kernel<3, false>), LIST, COUNT, PS, PA);           \
-        else if (had) NSR_LAUNCH_B((residual_mma_kernel<4, true>), LIST, COUNT, PS, PA);                      \
-        else NSR_LAUNCH_B((residual_mma_kernel<4, false>), LIST, COUNT, PS, PA);                              \
+        if (n_slices == 3) {                                                                                 \
+            if (had) { if (vec) NSR_LAUNCH_B_N(3, true, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(3, true, false, LIST, COUNT, PS, PA); }     \
+            else { if (vec) NSR_LAUNCH_B_N(3, false, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(3, false, false, LIST, COUNT, PS, PA); }        \
+        } else {                                                                                             \
+            if (had) { if (vec) NSR_LAUNCH_B_N(4, true, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(4, true, false, LIST, COUNT, PS, PA); }     \
+            else { if (vec) NSR_LAUNCH_B_N(4, false, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(4, false, false, LIST, COUNT, PS, PA); }        \
+        }                                                                                                    \
     } while (0)
     NSR_LAUNCH_B_ALL(nullptr, nullptr, p_sumsq, p_amax);
     stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
@@ -503,6 +517,7 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     // sparse fix-up: warps beyond the (device-side) count exit at once
     NSR_LAUNCH_B_ALL(fix_list, fix_count, nullptr, nullptr);
 #undef NSR_LAUNCH_B_ALL
+#undef NSR_LAUNCH_B_N
 #undef NSR_LAUNCH_B
     NSR_CHECK(cudaGetLastError());
     return 0;

@@ -123,6 +123,8 @@ def stage_umma_vs_simt(precision="default", kblock="128", rows="700", n="5000", 
     rows, n = int(rows), int(n)
     engine.set_option("umma_kblock", int(kblock))
     engine.set_option("umma_pair", int(pair))
+    if os.environ.get("NSR_EPI_WARPS"):
+        engine.set_option("epi_warps", int(os.environ["NSR_EPI_WARPS"]))
     ctx = engine.context(0)
     p = synth.host_problem(7, rows, n)
     Qt, rank, W = association.covariate_basis(p["dc"])
