@@ -36,6 +36,9 @@ WORKLOADS = {
                                        "size the metric is quoted on; fits one B200)"),
     "coex_10k_x_5k": (5000, 10000, "GSE123139-shaped: 10k cells x 5k genes norm.coex (BASELINE configs[1])"),
     "coex_2k_x_1k": (1000, 2000, "2,000 cells x 1,000 genes (BASELINE configs[0])"),
+    # extra (not the headline): gene-block sharded DE sweep, 2,500 genes per GPU (20k genes on 8 GPUs)
+    "de_1m_x_20k_x_1000": (20000, 1000000, "atlas-scale DE sweep: 1M cells x 20k genes x 1,000 perturbations, gene blocks "
+                                           "sharded over the GPUs (BASELINE configs[4]); 2,500 genes per GPU"),
 }
 METRIC = "coex gene-pairs/s (r+P)"
 UNIT = "pairs/s"
@@ -226,6 +229,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     if g1 - g0 < blk:
         local_sl.slices.zero_(); local_sl.quantum.fill_(1.0); local_sl.var.fill_(1.0)
     contract_ms = []
+    k_plan = {}
 
     def step_device(record=False):
         engine.residualize(ctx, dt_dev, Qt_dev, n_slices, out=local_sl, row_offset=0)
@@ -234,10 +238,13 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        if "k" not in k_plan:          # int32-overflow bound from the digit energies: planned once (tiny D2H)
+            k_plan["k"] = engine.plan_k_chunk(full, full, n_products)
         if single:
-            engine.contract(ctx, engine.MODE_COEX, full, full, tiles_full, dof_a, P, D, n_products)
+            engine.contract(ctx, engine.MODE_COEX, full, full, tiles_full, dof_a, P, D, n_products, k_chunk=k_plan["k"])
         elif len(tiles):
-            parallel._contract_strip(ctx, engine.MODE_COEX_UPPER, full, full, tiles, dof_a, P, D, r0, n_products)
+            parallel._contract_strip(ctx, engine.MODE_COEX_UPPER, full, full, tiles, dof_a, P, D, r0, n_products,
+                                     k_chunk=k_plan["k"])
         if record:
             e1.record()
             contract_ms.append((e0, e1))
@@ -373,6 +380,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         "data": "synthetic",
         "config": {"workload": wl_name, "genes": n_gene, "cells": n_cell, "covariates": int(dc_np.shape[0]),
                    "precision": precision, "digit_planes": n_slices, "digit_products": n_products,
+                   "cell_chunk": k_plan.get("k", 0),
                    "arithmetic": "f64 projection and epilogue; int8 x int8 -> int32 exact tensor-core sums",
                    "l2": "inputs (%.1f GB per rank) are larger than L2, no explicit flush" % ((g1 - g0) * n_cell * 8 / 1e9),
                    "parallelism": "1 GPU" if world == 1 else "%d GPUs: gene-block projection, one all-gather of digit planes, "
@@ -382,6 +390,57 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         "de": de,
     }
     print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_de_sweep(args, n_gene, n_cell, wl_name, wl_desc, n_group=1000, genes_per_gpu=2500):
+    """DE tests/s, genes sharded over ranks, no exchange step (weak scaling: 2,500 genes per GPU)."""
+    import torch
+    import torch.distributed as dist
+    from normalisr_b200 import engine, parallel, synth
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    p = synth.device_problem(SEED + 1, genes_per_gpu, n_cell, dev, n_group=n_group, group_p=0.002,
+                             gene_seed=SEED * 77 + rank, n_module=0)
+    total_genes = genes_per_gpu * world
+
+    def step():
+        return parallel.de_sharded(p["dg"], p["dt"], p["dc"], total_genes)
+
+    for _ in range(args.warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = engine.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        ms_step = ms / args.steps
+        print(json.dumps({
+            "metric": "DE tests/s (single=0)", "value": n_group * total_genes / (ms_step * 1e-3), "unit": "tests/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl_name, "genes": total_genes, "cells": n_cell, "groupings": n_group,
+                       "genes_per_gpu": genes_per_gpu, "note": wl_desc},
+            "gpu_launches": engine.LAUNCHES - launches0, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -427,7 +486,12 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="test hook: name=value for nsr_set_option")
     args = ap.parse_args()
     n_gene, n_cell, desc = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if args.workload.startswith("de_"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the DE sweep is an extra workload without a CPU arm"}))
+        else:
+            run_de_sweep(args, n_gene, n_cell, args.workload, desc)
+    elif args.impl == "reference":
         run_reference(args, n_gene, n_cell, args.workload, desc)
     else:
         run_ours(args, n_gene, n_cell, args.workload, desc)

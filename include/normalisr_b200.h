@@ -31,6 +31,7 @@ typedef struct nsr_ctx nsr_ctx;
 #define NSR_KBLOCK 128           /* cells are padded to a multiple of this          */
 #define NSR_MAX_SLICES 4
 #define NSR_MAX_RANK 64          /* covariate rank handled by the projection kernels */
+#define NSR_MAX_SPLITS 64        /* cell splits of the projection kernels (depends on n only) */
 
 /* contraction modes */
 #define NSR_MODE_COEX 0   /* A == B, symmetric: both triangles written, diagonal = 0,
@@ -55,6 +56,7 @@ int nsr_ctx_destroy(nsr_ctx* ctx);
 /* Number of int8 bytes one slice plane of a rows x n matrix occupies, and the padded
  * cell count (multiple of NSR_KBLOCK). */
 int64_t nsr_padded_cells(int64_t n);
+int nsr_cell_splits(int64_t n);
 
 /* Residualise `rows` variables against an orthonormal covariate basis and quantise.
  *
@@ -72,13 +74,19 @@ int64_t nsr_padded_cells(int64_t n);
  *                    all inner products are unchanged; it only flattens outliers so
  *                    that a fixed-point row scale loses no precision)
  *   quantum[rows]    z' ~= quantum * integer
+ *   energy_max       optional [NSR_MAX_SPLITS][NSR_MAX_SLICES] doubles, zeroed by the caller before
+ *                    the first call for an operand: entry (k, a) is raised to the largest
+ *                    sum of squared digits of plane a that any row has within cell split k
+ *                    (split k = 128-cell blocks [nblk k / ks, nblk (k+1) / ks), nblk = n_pad/128,
+ *                    ks = nsr_cell_splits(n)).  With it the caller bounds the contraction's
+ *                    int32 partial sums (Cauchy-Schwarz) and picks nsr_contract's k_chunk.
  * rows_alloc >= rows is the plane pitch in rows; bytes beyond `rows` are not touched.
  */
 int nsr_residualize(nsr_ctx* ctx, uintptr_t stream,
                     const double* X, int64_t rows, int64_t n, int64_t ldx,
                     const double* Qt, int rank, int64_t ldq,
                     int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
-                    double* quantum, double* var, double* coef);
+                    double* quantum, double* var, double* coef, double* energy_max);
 
 /* All-pairs contraction over cells + P-value epilogue for a list of output tiles.
  *
@@ -87,7 +95,10 @@ int nsr_residualize(nsr_ctx* ctx, uintptr_t stream,
  * A (rows_a) indexes output rows, B (rows_b) output columns.  tiles = n_tiles pairs
  * (tile_row, tile_col) of NSR_TILE-sized blocks, host_tiles is a HOST pointer.
  * dof_a = (n - 1 - rank - dimreduce) / 2.  Sums over cells are exact integer sums
- * (int8 digits, int32 accumulation), combined in float64.
+ * (int8 digits, int32 accumulation), combined in float64.  k_chunk = 0 contracts all cells in
+ * one pass; k_chunk > 0 (a multiple of NSR_KBLOCK) processes the cells in chunks of that length,
+ * keeping the float64 running sum in out2 between chunks - required when the int32 partial sums
+ * could overflow (see nsr_residualize `energy`).
  */
 int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
                  const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
@@ -96,7 +107,7 @@ int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
                  const double* quantum_b, const double* var_b,
                  int64_t n, int64_t n_pad, int n_slices, int n_products,
                  const int32_t* host_tiles, int64_t n_tiles, double dof_a,
-                 double* P, double* out2, int64_t ld);
+                 double* P, double* out2, int64_t ld, int64_t k_chunk);
 
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */

@@ -13,6 +13,8 @@ ENGINE_UMMA, ENGINE_SIMT = 0, 1
 TILE = 128
 KBLOCK = 128
 MAX_RANK = 64
+MAX_SPLITS = 64
+MAX_SLICES = 4
 
 _lib = None
 
@@ -29,12 +31,13 @@ _SIGNATURES = {
     "nsr_ctx_destroy": (c_int, [c_vp]),
     "nsr_padded_cells": (c_i64, [c_i64]),
     "nsr_set_option": (c_int, [ctypes.c_char_p, c_int]),
+    "nsr_cell_splits": (c_int, [c_i64]),
     "nsr_residualize": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_int, c_vp,
-                                c_i64, c_i64, c_vp, c_vp, c_vp]),
+                                c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "nsr_contract": (c_int, [c_vp, c_up, c_int, c_int,
                              c_vp, c_i64, c_i64, c_vp, c_vp,
                              c_vp, c_i64, c_i64, c_vp, c_vp,
-                             c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64]),
+                             c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64, c_i64]),
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),

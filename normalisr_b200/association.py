@@ -164,7 +164,9 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
         done[i & 1] = torch.cuda.Event()
         done[i & 1].record(main)
         tiles = engine.coex_strip_tiles(r0 // engine.TILE, (r1 + engine.TILE - 1) // engine.TILE)
-        engine.contract(ctx, MODE_COEX, A, A, tiles, dof_a, P, D, n_products, eng)
+        # optimistic single pass over the cells (planning would need a device->host sync per chunk
+        # and stall the copy stream); the int32 bound is verified once at the end
+        engine.contract(ctx, MODE_COEX, A, A, tiles, dof_a, P, D, n_products, eng, k_chunk=0)
         if out_host is not None:
             fin = torch.cuda.Event()
             fin.record(main)
@@ -174,6 +176,14 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
                 engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
     main.synchronize()
     d2h_stream.synchronize()
+    k_chunk = engine.plan_k_chunk(A, A, n_products)
+    if k_chunk:
+        # some int32 partial sum was not provably exact: redo the contraction in cell chunks
+        engine.contract(ctx, MODE_COEX, A, A, engine.coex_tiles(rows), dof_a, P, D, n_products, eng, k_chunk=k_chunk)
+        if out_host is not None:
+            for dst, src in zip(out_host, (P, D)):
+                dst.copy_(src, non_blocking=True)
+        main.synchronize()
     return A, P, D
 
 

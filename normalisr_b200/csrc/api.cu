@@ -9,15 +9,18 @@
 
 int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, const int8_t* b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
-                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep);
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                             int64_t cell_begin, int64_t cell_end);
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
-                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep);
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                             int64_t cell_begin, int64_t cell_end);
 extern int nsr_use_hadamard;
 extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
 extern int nsr_epi_warps;
+extern int nsr_umma_stack;
 extern int nsr_epi_overlap;
 extern int nsr_epi_sleep_ns;
 
@@ -82,6 +85,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
 extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "umma_stack")) { nsr_umma_stack = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_warps")) {
         NSR_REQUIRE(value == 8 || value == 16, "epi_warps must be 8 or 16");
         nsr_epi_warps = value;
@@ -104,7 +108,7 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
                             int64_t rows_b, int64_t rows_alloc_b, const double* quantum_b,
                             const double* var_b, int64_t n, int64_t n_pad, int n_slices,
                             int n_products, const int32_t* host_tiles, int64_t n_tiles, double dof_a,
-                            double* P, double* out2, int64_t ld) {
+                            double* P, double* out2, int64_t ld, int64_t k_chunk) {
     NSR_REQUIRE(ctx != nullptr, "nsr_contract: null context");
     NSR_REQUIRE(mode == NSR_MODE_COEX || mode == NSR_MODE_DE || mode == NSR_MODE_RAW ||
                     mode == NSR_MODE_COEX_UPPER,
@@ -180,20 +184,36 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
     ep.qa = quantum_a; ep.va = var_a; ep.qb = quantum_b; ep.vb = var_b;
     ep.P = P; ep.out2 = out2;
     ep.inv_n = 1.0 / (double)n;
+    ep.acc_in = 0;
+    ep.raw_out = 0;
     for (int g = 0; g < 4; ++g) ep.group_scale[g] = (g < ep.n_groups) ? ldexp(1.0, 8 * (ep.n_groups - 1 - g)) : 0.0;
     ep.scale_all = ldexp(1.0, 8 * (2 * n_slices - wmax));
     ep.pv = nsr_pval_params(mode == NSR_MODE_RAW ? 1.0 : dof_a);
 
-    if (engine == NSR_ENGINE_SIMT) {
-        if (nsr_launch_contract_simt(st, a_slices, rows_alloc_a, b_slices, rows_alloc_b, n_pad, n_slices, wmax,
-                                     ctx->tiles_dev, n_tiles, ep)) {
-            nsr_set_error("nsr_contract: SIMT launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            return 1;
+    // Cell chunking: int32 accumulators are exact only while no partial sum can overflow; the caller
+    // bounds that (Cauchy-Schwarz on the digit-plane energies) and passes the chunk length.  Chunks
+    // but the last leave the float64 running sum in out2; the last one adds it and finishes.
+    NSR_REQUIRE(k_chunk >= 0 && k_chunk % NSR_KBLOCK == 0, "nsr_contract: k_chunk must be a multiple of %d", NSR_KBLOCK);
+    const int64_t chunk = (k_chunk == 0 || k_chunk >= n_pad) ? n_pad : k_chunk;
+    for (int64_t c0 = 0; c0 < n_pad; c0 += chunk) {
+        const int64_t c1 = c0 + chunk < n_pad ? c0 + chunk : n_pad;
+        ep.acc_in = c0 > 0;
+        ep.raw_out = c1 < n_pad;
+        int rc;
+        if (engine == NSR_ENGINE_SIMT) {
+            rc = nsr_launch_contract_simt(st, a_slices, rows_alloc_a, b_slices, rows_alloc_b, n_pad, n_slices, wmax,
+                                          ctx->tiles_dev, n_tiles, ep, c0, c1);
+            if (rc) {
+                nsr_set_error("nsr_contract: SIMT launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return 1;
+            }
+        } else {
+            rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
+                                          n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep, c0, c1);
+            if (rc) return rc;
         }
-        return 0;
     }
-    return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
-                                    n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep);
+    return 0;
 }
 
 extern "C" int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,

@@ -11,7 +11,7 @@ constexpr int kPitchW = kKc / 4 + 1;   // smem row pitch in 32-bit words (+1: ba
 
 struct SimtArgs {
     const int8_t* a; const int8_t* b;
-    int64_t rows_alloc_a, rows_alloc_b, n_pad;
+    int64_t rows_alloc_a, rows_alloc_b, n_pad, cell_begin, cell_end;
     int n_slices, wmax;
     const int32_t* tiles;
     ContractParams ep;
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
             for (int c = 0; c < 4; ++c) acc[w][r][c] = 0;
 
     const int lrow = threadIdx.x >> 2, lchunk = threadIdx.x & 3;    // 64 rows x 4 x 16 B
-    for (int64_t k0 = 0; k0 < g.n_pad; k0 += kKc) {
+    for (int64_t k0 = g.cell_begin; k0 < g.cell_end; k0 += kKc) {
         for (int s = 0; s < S; ++s) {
             uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
             if (row0 + lrow < g.ep.rows_a)
@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
 
 int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, const int8_t* b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
-                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep) {
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                             int64_t cell_begin, int64_t cell_end) {
     SimtArgs g;
+    g.cell_begin = cell_begin; g.cell_end = cell_end;
     g.a = a; g.b = b; g.rows_alloc_a = rows_alloc_a; g.rows_alloc_b = rows_alloc_b; g.n_pad = n_pad;
     g.n_slices = n_slices; g.wmax = wmax; g.tiles = tiles_dev; g.ep = ep;
     contract_simt_kernel<<<dim3((unsigned)n_tiles, 4), 256, 0, st>>>(g);

@@ -20,6 +20,7 @@
 #include "epilogue.cuh"
 
 extern int nsr_epi_warps;
+extern int nsr_umma_stack;
 
 namespace {
 
@@ -31,7 +32,9 @@ constexpr int kSmemBudget = 200 * 1024;       // operand ring; barriers live in 
 struct UmmaArgs {
     const int32_t* tiles;
     int n_tiles;
-    int num_kb;                   // k-blocks of KB cells
+    int num_kb;                   // k-blocks of KB cells in this launch
+    int kb_begin;                 // first k-block (cell chunking)
+    int stack_b;                  // 1: N = 256 MMAs over two stacked B planes (single-CTA kernel)
     int epi_overlap;              // 1: release TMEM before the P-value math (overlap with next tile)
     int epi_sleep_ns;             // back-off of the epilogue warps while they wait for a tile
     ContractParams ep;
@@ -201,6 +204,28 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     }
 }
 
+// int8 x int8 -> int32, M = 128, N = 256 (two stacked B planes)
+constexpr uint32_t kInstrDescN256 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+// MMA schedule with stacked B planes: entries (a, b, wide, first): A plane a times B plane b
+// (wide: planes b and b+1 as one N = 256 operand); `first` = the entry initialises its group(s).
+template <int S, int WMAX> struct Sched;
+template <> struct Sched<3, 5> {      // products (0,0)(0,1) | (0,2) | (1,0)(1,1) | (1,2) | (2,0)(2,1)
+    static constexpr int kCount = 5;
+    int a[5] = {0, 0, 1, 1, 2}, b[5] = {0, 2, 0, 2, 0};
+    bool wide[5] = {true, false, true, false, true}, first[5] = {true, true, false, true, false};
+};
+template <> struct Sched<3, 4> {      // (0,0)(0,1) | (0,2) | (1,0)(1,1) | (2,0)
+    static constexpr int kCount = 4;
+    int a[4] = {0, 0, 1, 2}, b[4] = {0, 2, 0, 0};
+    bool wide[4] = {true, false, true, false}, first[4] = {true, true, false, false};
+};
+template <> struct Sched<4, 5> {      // (0,0)(0,1) | (0,2)(0,3) | (1,0)(1,1) | (1,2) | (2,0)(2,1) | (3,0)
+    static constexpr int kCount = 6;
+    int a[6] = {0, 0, 1, 1, 2, 3}, b[6] = {0, 2, 0, 2, 0, 0};
+    bool wide[6] = {true, true, true, false, true, false}, first[6] = {true, true, false, false, false, false};
+};
+
 template <int S, int WMAX, int KB>
 struct Cfg {
     static constexpr int kSliceBytes = NSR_TILE * KB;
@@ -260,8 +285,8 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     const uint32_t base = ring_u32 + stage * C::kStageBytes;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        tma_load_3d(&map_a, full, base + s * C::kSliceBytes, kb * KB, row_a, s);
-                        tma_load_3d(&map_b, full, base + (S + s) * C::kSliceBytes, kb * KB, row_b, s);
+                        tma_load_3d(&map_a, full, base + s * C::kSliceBytes, (g.kb_begin + kb) * KB, row_a, s);
+                        tma_load_3d(&map_b, full, base + (S + s) * C::kSliceBytes, (g.kb_begin + kb) * KB, row_b, s);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -281,19 +306,35 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     const uint32_t base = ring_u32 + stage * C::kStageBytes;
 #pragma unroll
                     for (int ks = 0; ks < KB / 32; ++ks) {
+                        if (g.stack_b) {
+                            // Two adjacent B planes are contiguous in the stage, i.e. one 256-row
+                            // K-major tile: A(a) x [B(b); B(b+1)] with N = 256 accumulates product
+                            // (a,b) into group a+b and (a,b+1) into group a+b+1 (adjacent TMEM
+                            // columns) while reading the A tile once: 52 KB instead of 64 KB of
+                            // operands per k-step, and 5 instructions instead of 8 (S=3, 8 products).
 #pragma unroll
-                        for (int a = 0; a < S; ++a) {
+                            for (int e = 0; e < Sched<S, WMAX>::kCount; ++e) {
+                                constexpr Sched<S, WMAX> sc{};
+                                const int a = sc.a[e], b = sc.b[e];
+                                const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                const uint32_t acc = (kb > 0 || ks > 0 || !sc.first[e]) ? 1u : 0u;
+                                tc_mma_i8(tmem_base + (a + b) * NSR_TILE, da, db, sc.wide[e] ? kInstrDescN256 : kInstrDesc, acc);
+                            }
+                        } else {
 #pragma unroll
-                            for (int b = 0; b < S; ++b) {
-                                if (a + b + 2 <= WMAX) {
-                                    constexpr int dummy = 0; (void)dummy;
-                                    const int grp = a + b;
-                                    // first product of its group in this (a asc, b asc) order
-                                    const bool first = (a == (grp > S - 1 ? grp - (S - 1) : 0));
-                                    const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                    const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                    const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
-                                    tc_mma_i8(tmem_base + grp * NSR_TILE, da, db, kInstrDesc, acc);
+                            for (int a = 0; a < S; ++a) {
+#pragma unroll
+                                for (int b = 0; b < S; ++b) {
+                                    if (a + b + 2 <= WMAX) {
+                                        const int grp = a + b;
+                                        // first product of its group in this (a asc, b asc) order
+                                        const bool first = (a == (grp > S - 1 ? grp - (S - 1) : 0));
+                                        const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                        const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                        const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
+                                        tc_mma_i8(tmem_base + grp * NSR_TILE, da, db, kInstrDesc, acc);
+                                    }
                                 }
                             }
                         }
@@ -439,8 +480,8 @@ contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
                     const uint32_t base = ring_u32 + stage * C::kStageBytes;
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
-                        tma_load_3d_2sm(&map_a, full_leader, base + s * C::kSliceA, kb * 128, row_a, s);
-                        tma_load_3d_2sm(&map_b, full_leader, base + S * C::kSliceA + s * C::kSliceB, kb * 128, row_b, s);
+                        tma_load_3d_2sm(&map_a, full_leader, base + s * C::kSliceA, (g.kb_begin + kb) * 128, row_a, s);
+                        tma_load_3d_2sm(&map_b, full_leader, base + S * C::kSliceA + s * C::kSliceB, (g.kb_begin + kb) * 128, row_b, s);
                     }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
@@ -559,6 +600,7 @@ int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensor
 
 }  // namespace
 
+int nsr_umma_stack = 1;      // test hook: stacked-B N = 256 MMAs in the single-CTA kernel
 int nsr_epi_warps = 8;       // test hook: epilogue warps of the single-CTA kernel (8 or 16)
 int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sustained), 1 -> cta_group::2 kernel
 int nsr_epi_overlap = 1;     // test hook: release TMEM before (1) or after (0) the P-value math
@@ -568,7 +610,8 @@ int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B 
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
-                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep) {
+                             const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                             int64_t cell_begin, int64_t cell_end) {
     if (n_tiles < 0) {
         // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
         CUtensorMap ma, mb;
@@ -577,7 +620,9 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         UmmaArgs g;
         g.tiles = tiles_dev;
         g.n_tiles = (int)(-n_tiles);
-        g.num_kb = (int)(n_pad / 128);
+        g.num_kb = (int)((cell_end - cell_begin) / 128);
+        g.kb_begin = (int)(cell_begin / 128);
+        g.stack_b = 0;
         g.epi_overlap = nsr_epi_overlap;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.ep = ep;
@@ -594,7 +639,9 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     UmmaArgs g;
     g.tiles = tiles_dev;
     g.n_tiles = (int)n_tiles;
-    g.num_kb = (int)(n_pad / kb);
+    g.num_kb = (int)((cell_end - cell_begin) / kb);
+    g.kb_begin = (int)(cell_begin / kb);
+    g.stack_b = (nsr_umma_stack != 0 && kb == 128) ? 1 : 0;
     g.epi_overlap = nsr_epi_overlap;
     g.epi_sleep_ns = nsr_epi_sleep_ns;
     g.ep = ep;

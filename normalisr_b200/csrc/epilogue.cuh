@@ -12,6 +12,8 @@ struct ContractParams {
     const double* qb; const double* vb;
     double* P; double* out2;
     double inv_n;
+    int acc_in;                  // add the float64 partial already stored at out2[i][j] (cell chunking)
+    int raw_out;                 // store the running sum instead of finishing (not the last chunk)
     double group_scale[4];       // 256^(2S - w), relative to the least significant kept group
     double scale_all;            // weight of the least significant kept group
     NsrPvalParams pv;
@@ -30,8 +32,9 @@ __device__ __forceinline__ double nsr_combine(const ContractParams& p, const int
 __device__ __forceinline__ void nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
                                            double vi, double qj, double vj, double acc,
                                            bool mirror) {
-    const double sum = (qi * qj) * acc;            // sum_k res_i res_j
-    if (p.mode == NSR_MODE_RAW) {
+    double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
+    if (p.acc_in) sum += p.out2[i * p.ld + j];     // earlier cell chunks
+    if (p.mode == NSR_MODE_RAW || p.raw_out) {
         p.out2[i * p.ld + j] = sum;
         return;
     }

@@ -192,7 +192,7 @@ __global__ void coef_finalize_kernel(const double* __restrict__ partial, const d
 // ---- pass B ------------------------------------------------------------------------------
 template <int S>
 __device__ __forceinline__ void store_digits(const double (&v)[32], double invq, int8_t* __restrict__ dst,
-                                             int64_t plane_stride) {
+                                             int64_t plane_stride, uint32_t (&energy)[S]) {
     uint32_t w[S][8];
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
@@ -216,6 +216,8 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
         uint4* p = reinterpret_cast<uint4*>(dst + (int64_t)s * plane_stride);
         p[0] = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
         p[1] = make_uint4(w[s][4], w[s][5], w[s][6], w[s][7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) energy[s] = (uint32_t)__dp4a((int)w[s][i], (int)w[s][i], (int)energy[s]);   // sum d^2
     }
 }
 
@@ -230,7 +232,7 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
                     int nblk, int ksplit, uint64_t cell_offset,
                     const double* __restrict__ inv_quantum, double* __restrict__ part_sumsq,
                     double* __restrict__ part_amax, int8_t* __restrict__ slices, int64_t rows_alloc,
-                    int64_t n_pad) {
+                    int64_t n_pad, unsigned long long* __restrict__ energy_max) {
     // covariate block of the current 128 cells, shared by the CTA's 8 warps (they walk the same
     // cells): [buffer][covariate][cell], pitch 132 so that a B-fragment read (4 covariates x 8 cells
     // per half-warp) touches 16 distinct banks
@@ -258,6 +260,9 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         ca[ch] = (my_row >= 0 && c < rank) ? -cf[c] : 0.0;
     }
     double sumsq = 0.0;
+    uint32_t energy[S];                                  // sum of squared digits per plane (this lane's cells)
+#pragma unroll
+    for (int sidx = 0; sidx < S; ++sidx) energy[sidx] = 0;
     int amax_hi = 0;                                     // max over the high words of |z'| (monotone)
     const double sgn1 = (t & 1) ? -1.0 : 1.0, sgn2 = (t & 2) ? -1.0 : 1.0;
 
@@ -353,7 +358,20 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
 #pragma unroll
         for (int i = 0; i < 32; ++i) amax_hi = max(amax_hi, __double2hiint(v[i]) & 0x7fffffff);
         if (slices != nullptr && my_row >= 0)
-            store_digits<S>(v, my_invq, slices + my_row * n_pad + k0 + 32 * t, rows_alloc * n_pad);
+            store_digits<S>(v, my_invq, slices + my_row * n_pad + k0 + 32 * t, rows_alloc * n_pad, energy);
+    }
+    if (energy_max != nullptr && slices != nullptr) {
+        // per-plane digit energy of each row over this CTA's cells -> maximum over rows, kept per
+        // cell split: the host bounds every int32 partial sum of the contraction with Cauchy-Schwarz
+#pragma unroll
+        for (int sidx = 0; sidx < S; ++sidx) {
+            double e = my_row >= 0 ? (double)energy[sidx] : 0.0;
+            e += __shfl_xor_sync(0xffffffffu, e, 1);
+            e += __shfl_xor_sync(0xffffffffu, e, 2);                         // row total (quad)
+#pragma unroll
+            for (int m = 4; m < 32; m <<= 1) e = fmax(e, __shfl_xor_sync(0xffffffffu, e, m));   // max over the 8 rows
+            if (lane == 0) atomicMax(energy_max + blockIdx.y * NSR_MAX_SLICES + sidx, (unsigned long long)__double_as_longlong(e));
+        }
     }
     if (part_sumsq != nullptr) {
         sumsq += __shfl_xor_sync(0xffffffffu, sumsq, 1);
@@ -419,10 +437,19 @@ int nsr_use_hadamard = 1;   // test hook (nsr_set_option)
 
 extern "C" int64_t nsr_padded_cells(int64_t n) { return (n + NSR_KBLOCK - 1) / NSR_KBLOCK * NSR_KBLOCK; }
 
+// number of contiguous cell ranges the projection kernels split a row into: a function of n only
+extern "C" int nsr_cell_splits(int64_t n) {
+    const int64_t nblk = (n + NSR_KBLOCK - 1) / NSR_KBLOCK;
+    int64_t ks = (nblk + 15) / 16;
+    if (ks > NSR_MAX_SPLITS) ks = NSR_MAX_SPLITS;
+    if (ks < 1) ks = 1;
+    return (int)ks;
+}
+
 extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows,
                                int64_t n, int64_t ldx, const double* Qt, int rank, int64_t ldq,
                                int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
-                               double* quantum, double* var, double* coef) {
+                               double* quantum, double* var, double* coef, double* energy_max) {
     NSR_REQUIRE(ctx != nullptr, "nsr_residualize: null context");
     NSR_REQUIRE(rows > 0 && rows < (1ll << 31) && n > 0 && ldx >= n,
                 "nsr_residualize: bad shape rows=%lld n=%lld ldx=%lld", (long long)rows, (long long)n,
@@ -445,9 +472,7 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     // The split of the cell axis depends on n only (2048 cells per CTA, at most 64 splits), never on
     // the number of rows in the call: partial sums are then combined in the same order whether a
     // matrix is residualised whole, in row chunks, or sharded over GPUs - results stay bit-identical.
-    int ksplit = (nblk + 15) / 16;
-    if (ksplit > 64) ksplit = 64;
-    if (ksplit < 1) ksplit = 1;
+    const int ksplit = nsr_cell_splits(n);
     const int64_t groups_w = (rows + kWarps * kRowsW - 1) / (kWarps * kRowsW);   // CTAs of 8 warps x 8 rows
     const int64_t groups_s = (rows + kWarps - 1) / kWarps;
     const int ks_a = ksplit, ks_b = ksplit;
@@ -490,7 +515,7 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
 #define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
     residual_mma_kernel<S_, H_, V_, N_><<<gridb, kThreads, 0, st>>>(                                         \
         X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
-        rows_alloc, n_pad)
+        rows_alloc, n_pad, (unsigned long long*)energy_max)
 #define NSR_LAUNCH_B_N(S_, H_, V_, LIST, COUNT, PS, PA)                                                      \
     do {                                                                                                     \
         switch (nch) {                                                                                       \

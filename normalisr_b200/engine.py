@@ -71,6 +71,8 @@ class Sliced:
         self.quantum = torch.empty(rows, dtype=torch.float64, device=device)
         self.var = torch.empty(rows, dtype=torch.float64, device=device)
         self.coef = None
+        # [cell split][plane]: largest per-row sum of squared digits (see nsr_residualize)
+        self.energy_max = torch.zeros((_lib.MAX_SPLITS, _lib.MAX_SLICES), dtype=torch.float64, device=device)
 
     @property
     def rows_alloc(self):
@@ -104,7 +106,7 @@ def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
         Qt.data_ptr() if rank else None, rank, ldq,
         n_slices, slices.data_ptr(), out.rows_alloc, out.n_pad,
         out.quantum[row_offset:].data_ptr(), out.var[row_offset:].data_ptr(),
-        coef.data_ptr() if coef is not None else None)
+        coef.data_ptr() if coef is not None else None, out.energy_max.data_ptr())
     _lib.check(st, "nsr_residualize")
     global LAUNCHES
     # pass A (8 covariates per launch, or the sum-of-squares kernel), its finalize, pass B,
@@ -144,9 +146,55 @@ def rect_tiles(rows_a, rows_b, strip=12):
     return np.asarray(out, dtype=np.int32).reshape(-1, 2)
 
 
-def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_UMMA):
+_INT32_LIMIT = float(2 ** 31 - 1)
+
+
+def products_of(n_slices, n_products):
+    """Kept digit pairs (a, b), 0-based, grouped by weight a + b."""
+    wmax = {(3, 6): 4, (3, 8): 5, (4, 10): 5}[(n_slices, n_products)]
+    groups = {}
+    for a in range(n_slices):
+        for b in range(n_slices):
+            if a + b + 2 <= wmax:
+                groups.setdefault(a + b, []).append((a, b))
+    return groups
+
+
+def plan_k_chunk(A, B, n_products, energies=None):
+    """Cells per contraction chunk such that no int32 partial sum can overflow, 0 = one pass.
+
+    For a weight group with products (a, b) and any cell range K, Cauchy-Schwarz gives
+    |sum_{k in K} sum_(a,b) dA_a[i,k] dB_b[j,k]| <= sum_(a,b) sqrt(EA_a(K) EB_b(K)), E = sum of squared
+    digits over K, which the projection reports as maxima over rows per cell split.  Chunks are
+    unions of consecutive splits (+1 split of slack because chunk and split borders differ)."""
+    if energies is None:
+        ea, eb = A.energy_max.cpu().numpy(), (A if B is A else B).energy_max.cpu().numpy()   # one small sync
+    else:
+        ea, eb = energies
+    ks = _lib.load().nsr_cell_splits(A.n)
+    nblk = A.n_pad // _lib.KBLOCK
+    groups = products_of(A.n_slices, n_products)
+
+    def bound(lo, hi):
+        sa, sb = ea[lo:hi].sum(axis=0), eb[lo:hi].sum(axis=0)
+        return max(sum(np.sqrt(sa[a] * sb[b]) for a, b in prods) for prods in groups.values())
+
+    if bound(0, ks) <= _INT32_LIMIT:
+        return 0
+    blocks_per_split = max(1, nblk // ks)
+    for m in range(ks - 1, 0, -1):                       # largest window of splits that is always safe
+        if all(bound(lo, min(ks, lo + m + 1)) <= _INT32_LIMIT for lo in range(0, ks)):
+            return m * blocks_per_split * _lib.KBLOCK
+    # even a single split (+ slack) is not provably safe: fall back to the unconditional bound
+    # (every digit -128, 4 products per group: 4 * 2^14 * cells < 2^31): 32768 - 128 cells
+    return 32768 - _lib.KBLOCK
+
+
+def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_UMMA, k_chunk=None):
     """Run the contraction + epilogue for ``tiles`` ((k,2) int32 numpy array of tile coords)."""
     assert A.n == B.n and A.n_slices == B.n_slices
+    if k_chunk is None:
+        k_chunk = plan_k_chunk(A, B, n_products)
     tiles = np.ascontiguousarray(tiles, dtype=np.int32)
     ld = out2.stride(0) if out2.shape[0] > 1 else out2.shape[1]
     assert out2.stride(1) == 1 and (P is None or P.shape == out2.shape and P.stride(1) == 1)
@@ -157,10 +205,10 @@ def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_U
         B.slices.data_ptr(), B.rows, B.rows_alloc, B.quantum.data_ptr(), B.var.data_ptr(),
         A.n, A.n_pad, A.n_slices, n_products,
         tiles.ctypes.data, tiles.shape[0], float(dof_a),
-        P.data_ptr() if P is not None else None, out2.data_ptr(), ld)
+        P.data_ptr() if P is not None else None, out2.data_ptr(), ld, int(k_chunk))
     _lib.check(st, "nsr_contract")
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
 
 
 def pvalue(ctx, r2, a):

@@ -61,6 +61,8 @@ def gather_sliced(local, rows_total, group=None):
         dist.all_gather_into_tensor(full.slices[s], local.slices[s].contiguous(), group=group)
     dist.all_gather_into_tensor(full.quantum, local.quantum, group=group)
     dist.all_gather_into_tensor(full.var, local.var, group=group)
+    full.energy_max.copy_(local.energy_max)
+    dist.all_reduce(full.energy_max, op=dist.ReduceOp.MAX, group=group)   # maxima over all ranks' rows
     full.rows = rows_total            # rows beyond rows_total are padding of the last block
     return full
 
@@ -166,21 +168,23 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         return Ph, Dh, full.var[:n_gene].cpu().numpy(), (r0, r1)
 
 
-def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products):
+def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products, k_chunk=None):
     """Contract with outputs stored from global row ``row0``: hand the C ABI a base pointer that
     is row0 rows before the strip buffers (it only dereferences rows of the listed tiles)."""
     from . import _lib
     ld = D.stride(0)
     tiles = np.ascontiguousarray(tiles, dtype=np.int32)
     off = row0 * ld * 8
+    if k_chunk is None:
+        k_chunk = engine.plan_k_chunk(A, B, n_products)
     st = ctx.lib.nsr_contract(
         ctx.handle, engine._stream(), engine.ENGINE_UMMA, mode,
         A.slices.data_ptr(), A.rows, A.rows_alloc, A.quantum.data_ptr(), A.var.data_ptr(),
         B.slices.data_ptr(), B.rows, B.rows_alloc, B.quantum.data_ptr(), B.var.data_ptr(),
         A.n, A.n_pad, A.n_slices, n_products, tiles.ctypes.data, tiles.shape[0], float(dof_a),
-        P.data_ptr() - off, D.data_ptr() - off, ld)
+        P.data_ptr() - off, D.data_ptr() - off, ld, int(k_chunk))
     _lib.check(st, "nsr_contract")
-    engine.LAUNCHES += 1
+    engine.LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
 
 
 def gather_dense(P_strip, D_strip, bounds, n_gene, group=None, dst=0):

@@ -111,6 +111,29 @@ def test_de_config_like_against_oracle():
         assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
 
 
+def test_de_million_cells_uses_cell_chunks():
+    """Config-5 cell count (1M): the int32 bound forces the contraction into cell chunks; the
+    result still matches the float64 oracle."""
+    rng = np.random.default_rng(31)
+    n, g, k = 1_000_000, 24, 6
+    dc = np.concatenate([rng.normal(size=(2, n)), np.ones((1, n))])
+    dg = (rng.random((k, n)) < 0.002).astype(np.float64)
+    dt = rng.normal(size=(g, n)) + 2.0
+    dt[:k] += 0.05 * dg                                    # effects: P spans ~1 .. 1e-50
+    ref = orc.de(dg, dt, dc)
+    got = norm.de(dg, dt, dc)
+    assert_p_close(got[0], ref[0])
+    np.testing.assert_allclose(got[3], ref[3], rtol=1e-7)
+    np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
+    scale = np.sqrt(ref[4] / ref[3][:, None])
+    assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+    # and the planner did ask for chunks at this size
+    ctx = engine.context(0)
+    Qt, rank, _ = association.covariate_basis(dc)
+    A = engine.residualize(ctx, torch.from_numpy(dt).cuda(), torch.from_numpy(Qt).cuda(), 3)
+    assert engine.plan_k_chunk(A, A, 8) > 0
+
+
 def test_device_tensors_in_device_tensors_out():
     g = load_golden("coex_chain")
     dt = torch.from_numpy(g["dt"]).cuda()
@@ -226,6 +249,48 @@ def test_tile_subset_invariance_and_rect_vs_sym():
     off = ~torch.eye(rows, dtype=torch.bool, device="cuda")
     assert torch.equal(gP[off], full_P[off])
     torch.testing.assert_close((gG * A.var[:, None])[off], full_D[off], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("eng", ["umma", "simt"])
+def test_cell_chunking_is_exact(eng):
+    """Contracting the cells in chunks (float64 running sum between chunks) reproduces the
+    single-pass result to float64 rounding, in every mode."""
+    rows, n = 700, 5000
+    ctx, p, A, rank, prods = _sliced(rows, n)
+    e = engine.ENGINE_UMMA if eng == "umma" else engine.ENGINE_SIMT
+    dof = (n - 1 - rank) / 2
+    for mode, tiles in ((engine.MODE_COEX, engine.coex_tiles(rows)), (engine.MODE_DE, engine.rect_tiles(rows, rows)),
+                        (engine.MODE_RAW, engine.rect_tiles(rows, rows))):
+        outs = []
+        for kc in (0, 128, 1024, 4096):
+            P = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+            D = torch.zeros_like(P)
+            engine.contract(ctx, mode, A, A, tiles, dof, None if mode == engine.MODE_RAW else P, D, prods, e, k_chunk=kc)
+            outs.append((P, D))
+        torch.cuda.synchronize()
+        for P, D in outs[1:]:
+            # every chunk's integer sum is exact; only the float64 additions of the scaled chunk
+            # sums are ordered differently, so results agree to rounding of the largest partial sum
+            scale = float(outs[0][1].abs().max())
+            torch.testing.assert_close(D, outs[0][1], rtol=1e-14, atol=1e-14 * scale)
+            torch.testing.assert_close(P, outs[0][0], rtol=1e-9, atol=0)
+
+
+def test_overflow_plan_from_energies():
+    rows, n = 300, 3000
+    ctx, p, A, rank, prods = _sliced(rows, n)
+    assert engine.plan_k_chunk(A, A, prods) == 0
+    em = A.energy_max.cpu().numpy()
+    ks = engine._lib.load().nsr_cell_splits(n)
+    assert (em[:ks, :3] > 0).all() and (em[ks:] == 0).all()
+    # exact per-row digit energies can only be below the reported maxima
+    sl = A.slices.cpu().numpy().astype(np.int64)
+    true_total = (sl ** 2).sum(axis=2).max(axis=1)          # per plane: max over rows of the full-row energy
+    assert (true_total <= em.sum(axis=0)[:3] + 1e-6).all()
+    # inflate the energies: the planner must fall back to chunks that are provably safe
+    big = em * 1e6
+    kc = engine.plan_k_chunk(A, A, prods, energies=(big, big))
+    assert kc > 0 and kc % 128 == 0
 
 
 def test_residual_planes_reconstruct_projection():

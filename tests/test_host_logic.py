@@ -89,6 +89,25 @@ def test_single4_rank_deficient_groupings_fall_back():
     assert out[3].max() < 4 + 1e-9              # per-x rank is reduced, as inv_rank reports
 
 
+def test_products_and_chunk_planner_arithmetic():
+    assert sorted(len(v) for v in engine.products_of(3, 8).values()) == [1, 2, 2, 3]
+    assert sum(len(v) for v in engine.products_of(3, 6).values()) == 6
+    assert sum(len(v) for v in engine.products_of(4, 10).values()) == 10
+
+    class Fake:                      # just the attributes plan_k_chunk reads
+        n, n_pad, n_slices = 100000, 100096, 3
+    ks = engine._lib.load().nsr_cell_splits(100000)
+    assert ks == 49
+    e = np.zeros((64, 4))
+    e[:ks, 0] = 450 * 2048          # plane 0: small digits after Hadamard mixing
+    e[:ks, 1:3] = 5461 * 2048       # lower planes: uniform digits
+    assert engine.plan_k_chunk(Fake, Fake, 8, energies=(e, e)) == 0
+    worst = np.zeros((64, 4))
+    worst[:ks, :3] = 128 * 128 * 2048      # every digit +-128: 3 products * 16384 * 100096 > 2^31
+    kc = engine.plan_k_chunk(Fake, Fake, 8, energies=(worst, worst))
+    assert 0 < kc <= 43690 and kc % 128 == 0
+
+
 def test_digit_slicing_roundtrip():
     """Balanced base-256 digits (nsr_common.cuh nsr_digits) restated in numpy."""
     rng = np.random.default_rng(0)
