@@ -208,9 +208,6 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     prob = synth.device_problem(SEED, g1 - g0, n_cell, dev, gene_seed=SEED * 1000 + rank)
     dt_dev, dc_dev = prob["dt"], prob["dc"]
     dc_np = dc_dev.cpu().numpy()
-    Qt, crank, _ = association.covariate_basis(dc_np)
-    Qt_dev = torch.from_numpy(Qt).to(dev)
-    dof_a = (n_cell - 1 - crank) / 2
     pairs = n_gene * (n_gene - 1) / 2
 
     t_tiles = (n_gene + 127) // 128
@@ -232,6 +229,10 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     k_plan = {}
 
     def step_device(record=False):
+        # the whole path, every step: covariate basis (Gram matrix + small factorisation), projection,
+        # (all-gather,) contraction + P-values
+        Qt_dev, crank, _ = association.covariate_basis_device(ctx, dc_dev)
+        dof_a = (n_cell - 1 - crank) / 2
         engine.residualize(ctx, dt_dev, Qt_dev, n_slices, out=local_sl, row_offset=0)
         full = parallel.gather_sliced(local_sl, n_gene) if world > 1 else local_sl
         full.rows = n_gene

@@ -42,6 +42,10 @@ typedef struct nsr_ctx nsr_ctx;
 #define NSR_MODE_COEX_UPPER 3 /* like COEX but only the listed tiles are written (no mirrored
                              copy): a rank that owns a strip of tile rows produces the upper
                              triangle of its strip; the full matrix is U + U^T            */
+#define NSR_MODE_COEX_RECT 4 /* rectangular block of a co-expression matrix between two DISJOINT
+                             gene blocks A (rows) and B (columns): out2 = dot like COEX, no diagonal
+                             rule, no mirrored copy.  The multi-GPU path computes the off-diagonal
+                             block pairs with it while the planes of later blocks are in flight  */
 /* contraction engines */
 #define NSR_ENGINE_UMMA 0 /* tcgen05 int8 tensor-core kernel (the product path)           */
 #define NSR_ENGINE_SIMT 1 /* dp4a CUDA-core kernel, bit-identical integer sums; used by the
@@ -108,6 +112,17 @@ int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
                  int64_t n, int64_t n_pad, int n_slices, int n_products,
                  const int32_t* host_tiles, int64_t n_tiles, double dof_a,
                  double* P, double* out2, int64_t ld, int64_t k_chunk);
+
+/* Covariate basis: the two products with the (nc x n) covariate matrix C that turn `dc` into the
+ * orthonormal basis Qt of nsr_residualize.  Replaces np.matmul(dc, dc.T) feeding inv_rank at
+ * association.py:899-903: the host factorises the nc x nc Gram matrix G = C C^T (SVD with the
+ * reference's tolerance rule, association.py:66-80) and the device applies the resulting small
+ * matrix, Q = M C (M: rank x nc, row-major, device).  nc, rank <= NSR_MAX_RANK.  Sums over
+ * cells are combined in a fixed order: results do not depend on the launch. */
+int nsr_cov_gram(nsr_ctx* ctx, uintptr_t stream, const double* C, int nc, int64_t n, int64_t ldc,
+                 double* G);
+int nsr_cov_apply(nsr_ctx* ctx, uintptr_t stream, const double* M, int rank, int nc,
+                  const double* C, int64_t n, int64_t ldc, double* Q, int64_t ldq);
 
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */

@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnsr_b200.so")
 
-MODE_COEX, MODE_DE, MODE_RAW, MODE_COEX_UPPER = 0, 1, 2, 3
+MODE_COEX, MODE_DE, MODE_RAW, MODE_COEX_UPPER, MODE_COEX_RECT = 0, 1, 2, 3, 4
 ENGINE_UMMA, ENGINE_SIMT = 0, 1
 TILE = 128
 KBLOCK = 128
@@ -41,6 +41,8 @@ _SIGNATURES = {
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
+    "nsr_cov_gram": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_vp]),
+    "nsr_cov_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64]),
 }
 
 

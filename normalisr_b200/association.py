@@ -11,6 +11,7 @@ and parallelism are the GPU's business (reference ``_auto_batchsize``, associati
 import logging
 
 import numpy as np
+import scipy.linalg
 import torch
 
 from . import engine
@@ -47,24 +48,63 @@ def inv_rank(m, tol=1E-8, method='auto', logger=None, mpc=0, qr=0, **ka):
     return (v.T / s[:n2]) @ v, n2
 
 
+def _basis_weights(gram, tol):
+    """(w0, rank): rows of w0 dc are the eigen-directions of the Gram matrix that the reference's
+    inv_rank keeps (singular values >= tol * largest, association.py:77), scaled to unit norm."""
+    nc = gram.shape[0]
+    _, s, vt = np.linalg.svd(gram)
+    rank = nc - int(np.searchsorted(s[::-1], tol * s[0]))
+    return vt[:rank] / np.sqrt(s[:rank])[:, None], rank
+
+
+def _reorthonormalise(g2, w0):
+    """q0 = w0 dc is orthonormal up to the 1/sqrt(s) amplification of rounding error; with
+    g2 = q0 q0^T = L L^T, Qt = L^-1 q0 is orthonormal to rounding.  Returns (L^-1, W = L^-1 w0)."""
+    L = np.linalg.cholesky(g2)
+    Linv = scipy.linalg.solve_triangular(L, np.eye(L.shape[0]), lower=True)
+    return Linv, Linv @ w0
+
+
 def covariate_basis(dc, tol=1e-8):
     """Return (Qt, rank, W): Qt (rank, n) has orthonormal rows spanning the part of the row
     space of ``dc`` that the reference keeps (eigenvalues of dc dc^T >= tol * largest), so that
     x - Qt^T (Qt x) equals the reference projection x - dc^T dci dc x.  W (rank, n_cov) maps
-    basis coefficients back to covariate coefficients: c = W^T (Qt x)  (needed for alpha)."""
+    basis coefficients back to covariate coefficients: c = W^T (Qt x)  (needed for alpha).
+    Host (numpy) version; the product path uses covariate_basis_device (same factorisation,
+    the two products over cells on the GPU)."""
     dc = np.asarray(dc, dtype=np.float64)
     nc, n = dc.shape
     if nc == 0 or not (dc != 0).any():          # association.py:899-903
         return None, 0, np.zeros((0, nc))
-    gram = dc @ dc.T
-    _, s, vt = np.linalg.svd(gram)
-    rank = nc - int(np.searchsorted(s[::-1], tol * s[0]))
-    w0 = vt[:rank] / np.sqrt(s[:rank])[:, None]            # (rank, nc):  Q0 = w0 dc
+    w0, rank = _basis_weights(dc @ dc.T, tol)
     q0 = w0 @ dc
-    # re-orthonormalise (removes the 1/sqrt(s) amplification of rounding error)
-    qf, rr = np.linalg.qr(q0.T)                            # q0^T = qf rr
-    W = np.linalg.solve(rr.T, w0)                          # Qt = rr^-T q0 = W dc
-    return np.ascontiguousarray(qf.T), rank, W
+    Linv, W = _reorthonormalise(q0 @ q0.T, w0)
+    return np.ascontiguousarray(Linv @ q0), rank, W
+
+
+def covariate_basis_device(ctx, dc, tol=1e-8):
+    """covariate_basis with the O(nc^2 n) products on the device: returns (Qt_dev, rank, W) with
+    Qt_dev a (rank, n) CUDA float64 tensor (None when rank == 0)."""
+    nc, n = dc.shape
+    if nc == 0:
+        return None, 0, np.zeros((0, 0))
+    if nc > MAX_RANK:                            # wider than the kernels take: host products
+        Qt, rank, W = covariate_basis(_as_host_f64(dc), tol)
+        return (torch.from_numpy(Qt).to(ctx.device) if rank else None), rank, W
+    if _is_dev(dc):
+        dc_d = dc.to(ctx.device, torch.float64)
+    else:
+        dc_d = torch.from_numpy(np.ascontiguousarray(_as_host_f64(dc), dtype=np.float64)).to(ctx.device)
+    if dc_d.stride(1) != 1:
+        dc_d = dc_d.contiguous()
+    with torch.cuda.device(ctx.device):
+        gram = engine.cov_gram(ctx, dc_d).cpu().numpy()
+        if not gram.any():                       # all-zero covariates, association.py:899-903
+            return None, 0, np.zeros((0, nc))
+        w0, rank = _basis_weights(gram, tol)
+        q0 = engine.cov_apply(ctx, w0, dc_d)
+        Linv, W = _reorthonormalise(engine.cov_gram(ctx, q0).cpu().numpy(), w0)
+        return engine.cov_apply(ctx, Linv, q0), rank, W
 
 
 # --------------------------------------------------------------------------------------
@@ -246,7 +286,7 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     nc = dc.shape[0]
     if nc == 0:
         logging.warning('No covariate dc input.')
-    Qt, rank, W = covariate_basis(_as_host_f64(dc))
+    Qt_dev, rank, W = covariate_basis_device(ctx, dc)
     if rank > MAX_RANK:
         raise NotImplementedError('covariate rank {} > {}'.format(rank, MAX_RANK))
     if n <= rank + dimreduce + 1:
@@ -254,7 +294,6 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
                          'removed + covariate + 1.')
     dof_a = (n - 1 - rank - dimreduce) / 2
     with torch.cuda.device(ctx.device):
-        Qt_dev = torch.from_numpy(Qt).to(ctx.device) if rank else None
         keep_coef = not lowmem
         piped = samexy and to_host
         if piped:

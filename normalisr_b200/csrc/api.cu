@@ -111,7 +111,7 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
                             double* P, double* out2, int64_t ld, int64_t k_chunk) {
     NSR_REQUIRE(ctx != nullptr, "nsr_contract: null context");
     NSR_REQUIRE(mode == NSR_MODE_COEX || mode == NSR_MODE_DE || mode == NSR_MODE_RAW ||
-                    mode == NSR_MODE_COEX_UPPER,
+                    mode == NSR_MODE_COEX_UPPER || mode == NSR_MODE_COEX_RECT,
                 "nsr_contract: unknown mode %d", mode);
     NSR_REQUIRE(engine == NSR_ENGINE_UMMA || engine == NSR_ENGINE_SIMT, "nsr_contract: unknown engine %d", engine);
     NSR_REQUIRE(rows_a > 0 && rows_b > 0 && n > 0 && n_pad == nsr_padded_cells(n),

@@ -123,6 +123,32 @@ def unslice(ctx, s):
     return out
 
 
+def cov_gram(ctx, C):
+    """G = C C^T for a (nc, n) CUDA float64 matrix with unit column stride (nsr_cov_gram)."""
+    nc, n = C.shape
+    G = torch.empty((nc, nc), dtype=torch.float64, device=C.device)
+    ldc = C.stride(0) if nc > 1 else n
+    _lib.check(ctx.lib.nsr_cov_gram(ctx.handle, _stream(), C.data_ptr(), nc, n, ldc, G.data_ptr()), "nsr_cov_gram")
+    global LAUNCHES
+    LAUNCHES += 2
+    return G
+
+
+def cov_apply(ctx, M, C):
+    """Q = M C, M (rank, nc) numpy or tensor, C (nc, n) CUDA float64 (nsr_cov_apply)."""
+    M_d = torch.as_tensor(np.ascontiguousarray(M), dtype=torch.float64).to(C.device) if not isinstance(M, torch.Tensor) \
+        else M.to(C.device, torch.float64).contiguous()
+    rank, nc = M_d.shape
+    n = C.shape[1]
+    Q = torch.empty((rank, n), dtype=torch.float64, device=C.device)
+    ldc = C.stride(0) if nc > 1 else n
+    _lib.check(ctx.lib.nsr_cov_apply(ctx.handle, _stream(), M_d.data_ptr(), rank, nc, C.data_ptr(), n, ldc,
+                                     Q.data_ptr(), n), "nsr_cov_apply")
+    global LAUNCHES
+    LAUNCHES += 1
+    return Q
+
+
 def coex_tiles(rows, strip=12):
     """Upper-triangular 128x128 tile list (tile_row <= tile_col), ordered in column strips so
     that the ~148 tiles in flight share few row blocks (L2 reuse of the operand planes)."""
@@ -175,16 +201,29 @@ def plan_k_chunk(A, B, n_products, energies=None):
     nblk = A.n_pad // _lib.KBLOCK
     groups = products_of(A.n_slices, n_products)
 
-    def bound(lo, hi):
-        sa, sb = ea[lo:hi].sum(axis=0), eb[lo:hi].sum(axis=0)
-        return max(sum(np.sqrt(sa[a] * sb[b]) for a, b in prods) for prods in groups.values())
+    ca = np.concatenate([np.zeros((1, ea.shape[1])), np.cumsum(ea[:ks], axis=0)])
+    cb = np.concatenate([np.zeros((1, eb.shape[1])), np.cumsum(eb[:ks], axis=0)])
 
-    if bound(0, ks) <= _INT32_LIMIT:
+    def worst(width):
+        """Largest bound over all windows of ``width`` consecutive splits (clipped at the end)."""
+        lo = np.arange(0, max(1, ks - width + 1))
+        hi = np.minimum(ks, lo + width)
+        sa, sb = ca[hi] - ca[lo], cb[hi] - cb[lo]
+        return max(float(sum(np.sqrt(sa[:, a] * sb[:, b]) for a, b in prods).max()) for prods in groups.values())
+
+    if worst(ks) <= _INT32_LIMIT:
         return 0
     blocks_per_split = max(1, nblk // ks)
-    for m in range(ks - 1, 0, -1):                       # largest window of splits that is always safe
-        if all(bound(lo, min(ks, lo + m + 1)) <= _INT32_LIMIT for lo in range(0, ks)):
-            return m * blocks_per_split * _lib.KBLOCK
+    # worst(width) grows with width: bisect for the largest m whose windows of m + 1 splits are safe
+    lo_m, hi_m = 0, ks - 1
+    while lo_m < hi_m:
+        mid = (lo_m + hi_m + 1) // 2
+        if worst(mid + 1) <= _INT32_LIMIT:
+            lo_m = mid
+        else:
+            hi_m = mid - 1
+    if lo_m >= 1:
+        return lo_m * blocks_per_split * _lib.KBLOCK
     # even a single split (+ slack) is not provably safe: fall back to the unconditional bound
     # (every digit -128, 4 products per group: 4 * 2^14 * cells < 2^31): 32768 - 128 cells
     return 32768 - _lib.KBLOCK

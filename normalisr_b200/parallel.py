@@ -4,24 +4,103 @@ parallel.py:12-74, used at association.py:997).
 
 The path shards naturally:
   * every rank residualises and quantises its own block of genes (covariates are tiny and
-    replicated);
-  * ONE all-gather of the int8 digit planes (+ per-row quantum and variance);
-  * each rank then owns a strip of 128-row output tile rows, balanced by tile count, and
-    computes the upper triangle of that strip with no further communication.
-The full matrices are U + U^T over the ranks' strips (``gather_dense`` assembles them).
+    replicated); blocks are equal multiples of the 128-row tile;
+  * the int8 digit planes (+ per-row quantum and variance) are exchanged ONCE.  Default schedule
+    ("pairs"): the unordered block pairs {i, j} are dealt out on a circulant - rank r computes its
+    diagonal block and the pairs (r, r+d mod W) for d = 1 .. W/2 (for even W the pairs at distance
+    W/2 are split between their two owners on a checkerboard of tiles).  Every rank therefore
+    needs only W/2 remote blocks instead of W-1, receives them in W/2 point-to-point rounds in
+    which all ranks send and receive at once, and contracts block pair d while round d+1 is in
+    flight.  The older schedule ("allgather": one all-gather, then a strip of tile rows per rank)
+    is kept for comparison;
+  * no further communication: rank r ends with the rows of its block of P / dot for the column
+    blocks it owns; ``gather_dense`` mirrors them into the full symmetric matrices.
+Because the sums over cells are exact integers, every schedule gives bit-identical results.
 """
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import engine
-from ._lib import MODE_COEX_UPPER, MODE_DE, TILE
-from .association import covariate_basis
+from ._lib import MODE_COEX_RECT, MODE_COEX_UPPER, MODE_DE, TILE
+from .association import covariate_basis_device
 
 
 def row_split(rows, world):
-    """Contiguous, equally sized row blocks (last one short): block size."""
-    return (rows + world - 1) // world
+    """Contiguous, equally sized row blocks (last one short or empty): block size, a multiple of
+    the tile so that no output tile straddles two blocks."""
+    t = (rows + TILE - 1) // TILE
+    return ((t + world - 1) // world) * TILE
+
+
+def block_rows(rows, world, k):
+    """Number of valid rows in block k."""
+    blk = row_split(rows, world)
+    return int(min(max(rows - k * blk, 0), blk))
+
+
+def exchange_plan(world, rank):
+    """Rounds of the block exchange for ``rank``: [(send_to, recv_from, parity)], round d-1 brings
+    block (rank + d) mod world.  parity is None for a pair this rank computes in full, or 0 / 1 when
+    the pair is shared with its other owner (even world, distance world/2): this rank takes the
+    tiles with (tile_row + tile_col) % 2 == parity."""
+    plan = []
+    for d in range(1, world // 2 + 1):
+        src = (rank + d) % world
+        parity = None
+        if world % 2 == 0 and d == world // 2:
+            parity = 0 if rank < src else 1
+        plan.append(((rank - d) % world, src, parity))
+    return plan
+
+
+def pair_tiles(rows_a, rows_b, parity=None):
+    """Tiles of the (rows_a x rows_b) block pair this rank computes."""
+    tl = engine.rect_tiles(rows_a, rows_b)
+    if parity is not None and len(tl):
+        tl = tl[(tl[:, 0] + tl[:, 1]) % 2 == parity]
+    return np.ascontiguousarray(tl, dtype=np.int32).reshape(-1, 2)
+
+
+def owned_tile_mask(n_gene, world, rank):
+    """Boolean (tile rows of block ``rank``, all tile columns): which output tiles the pairs
+    schedule computes on ``rank`` (diagonal block: upper triangle including diagonal tiles)."""
+    blk = row_split(n_gene, world)
+    tb = blk // TILE
+    t = (n_gene + TILE - 1) // TILE
+    ta = (block_rows(n_gene, world, rank) + TILE - 1) // TILE
+    m = np.zeros((ta, t), dtype=bool)
+    for i in range(ta):
+        m[i, rank * tb + i: rank * tb + ta] = True
+    for _, src, parity in exchange_plan(world, rank):
+        for ti, tj in pair_tiles(block_rows(n_gene, world, rank), block_rows(n_gene, world, src), parity):
+            m[ti, src * tb + tj] = True
+    return m
+
+
+def start_exchange(local, group=None):
+    """Post every round of the block exchange (non-blocking).  Returns [(src, parity, Sliced, works)]
+    in round order; ``wait_block`` makes the current stream wait for one round."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+
+    def peer(r):
+        return dist.get_global_rank(group, r) if group is not None else r
+
+    rounds = []
+    for dst, src, parity in exchange_plan(world, rank):
+        buf = engine.Sliced(local.rows_alloc, local.n, local.n_slices, local.slices.device)
+        ops = []
+        for t_send, t_recv in ((local.slices, buf.slices), (local.quantum, buf.quantum), (local.var, buf.var)):
+            ops.append(dist.P2POp(dist.isend, t_send, peer(dst), group))
+            ops.append(dist.P2POp(dist.irecv, t_recv, peer(src), group))
+        rounds.append((src, parity, buf, dist.batch_isend_irecv(ops)))
+    return rounds
+
+
+def wait_block(works):
+    for w in works:
+        w.wait()
 
 
 def strip_bounds(n_tile_rows, world):
@@ -81,50 +160,99 @@ def residualize_block(ctx, x_block, Qt_dev, n_slices, blk):
     return out
 
 
-def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduce=0, out=None):
-    """Co-expression over all ranks of ``group``.
+def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out):
+    """Pairs schedule on an already residualised block: post the exchange, contract the diagonal
+    block, then each block pair as soon as its round has arrived.  Returns (P, dot, var_all)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    blk = local.rows_alloc
+    rows_a = block_rows(n_gene, world, rank)
+    em = local.energy_max
+    var_all = local.var
+    rounds = []
+    if world > 1:
+        em = em.clone()
+        dist.all_reduce(em, op=dist.ReduceOp.MAX, group=group)       # int32 bound over every rank's rows
+        rounds = start_exchange(local, group)
+        var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
+        dist.all_gather_into_tensor(var_all, local.var, group=group)
+    em_h = em.cpu().numpy()
+    k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_h, em_h))
+    if out is None:
+        P = torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=local.slices.device)
+        D = torch.zeros_like(P)
+    else:
+        P, D = out
+    local.rows = max(rows_a, 1)
+    if rows_a:
+        c0 = rank * blk
+        engine.contract(ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
+                        P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk)
+    for src, parity, buf, works in rounds:
+        wait_block(works)
+        rows_b = block_rows(n_gene, world, src)
+        if rows_a and rows_b:
+            buf.rows = rows_b
+            c0 = src * blk
+            engine.contract(ctx, MODE_COEX_RECT, local, buf, pair_tiles(rows_a, rows_b, parity), dof_a,
+                            P[:rows_a, c0:c0 + rows_b], D[:rows_a, c0:c0 + rows_b], n_products, k_chunk=k_chunk)
+    return P, D, var_all[:n_gene]
 
-    dt_block: this rank's genes, rows [rank*blk, min((rank+1)*blk, n_gene)) of the expression
-              matrix, blk = row_split(n_gene, world); CUDA float64 (rows_local, n_cell).
-    dc:       full covariate matrix (numpy or tensor), identical on all ranks.
-    Returns (P_strip, dot_strip, var, (row_begin, row_end)): the upper triangle of this rank's
-    strip of rows (entries left of the diagonal tile are not written), var for all genes.
-    """
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    ctx = engine.context(dt_block.device)
-    n_slices, n_products = engine.PRESETS[precision]
-    n = dt_block.shape[1]
-    dc_h = dc.detach().cpu().numpy() if isinstance(dc, torch.Tensor) else np.asarray(dc)
-    Qt, crank, _ = covariate_basis(dc_h)
-    if n <= crank + dimreduce + 1:
-        raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
-                         'removed + covariate + 1.')
-    Qt_dev = torch.from_numpy(Qt).to(ctx.device) if crank else None
-    blk = row_split(n_gene, world)
-    local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk)
+
+def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out):
+    """All-gather schedule: every rank gets all planes, then computes a strip of tile rows."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
     full = gather_sliced(local, n_gene, group) if world > 1 else local
     full.rows = n_gene
     t = (n_gene + TILE - 1) // TILE
     a, b = strip_bounds(t, world)[rank]
     r0, r1 = a * TILE, min(b * TILE, n_gene)
     if out is None:
-        P = torch.zeros((max(r1 - r0, 0), n_gene), dtype=torch.float64, device=ctx.device)
+        P = torch.zeros((max(r1 - r0, 1), n_gene), dtype=torch.float64, device=local.slices.device)
         D = torch.zeros_like(P)
     else:
         P, D = out
     if r1 > r0:
-        _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b), (n - 1 - crank - dimreduce) / 2,
-                        P, D, r0, n_products)
+        _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b), dof_a, P, D, r0, n_products)
     return P, D, full.var[:n_gene], (r0, r1)
 
 
+def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduce=0, out=None,
+                 schedule="pairs"):
+    """Co-expression over all ranks of ``group``.
+
+    dt_block: this rank's genes, rows [rank*blk, min((rank+1)*blk, n_gene)) of the expression
+              matrix, blk = row_split(n_gene, world); CUDA float64 (rows_local, n_cell).
+    dc:       full covariate matrix (numpy or tensor), identical on all ranks.
+    Returns (P_rows, dot_rows, var, (row_begin, row_end)): rows [row_begin, row_end) of P / dot with
+    the tiles this rank owns filled in and zeros elsewhere (``owned_tile_mask`` for "pairs"; the
+    upper triangle of a strip of tile rows for "allgather"), and var for all genes.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ctx = engine.context(dt_block.device)
+    n_slices, n_products = engine.PRESETS[precision]
+    n = dt_block.shape[1]
+    Qt_dev, crank, _ = covariate_basis_device(ctx, dc)
+    if n <= crank + dimreduce + 1:
+        raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
+                         'removed + covariate + 1.')
+    dof_a = (n - 1 - crank - dimreduce) / 2
+    blk = row_split(n_gene, world)
+    local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk)
+    if schedule == "allgather":
+        return _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out)
+    P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out)
+    return P, D, var, (rank * blk, rank * blk + block_rows(n_gene, world, rank))
+
+
 def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimreduce=0, out_dev=None,
-              out_host=None):
+              out_host=None, schedule="pairs"):
     """``coex_sharded`` for HOST inputs and outputs: this rank's gene block is a CPU tensor / numpy
     array (pinned memory makes the staged copies asynchronous and overlapped with the projection
-    kernels); P and dot strips are copied back into ``out_host`` (CPU tensors) if given.
-    Returns (P_strip, dot_strip, var, (row_begin, row_end)) as numpy arrays."""
+    kernels); the rows of P and dot are copied back into ``out_host`` (CPU tensors) if given.
+    Returns (P_rows, dot_rows, var, (row_begin, row_end)) as numpy arrays."""
     from .association import _residualize_any
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -132,32 +260,23 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
     n_slices, n_products = engine.PRESETS[precision]
     xh = dt_block_host if isinstance(dt_block_host, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt_block_host))
     n = xh.shape[1]
-    dc_h = dc.detach().cpu().numpy() if isinstance(dc, torch.Tensor) else np.asarray(dc)
-    Qt, crank, _ = covariate_basis(dc_h)
+    Qt_dev, crank, _ = covariate_basis_device(ctx, dc)
     if n <= crank + dimreduce + 1:
         raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
                          'removed + covariate + 1.')
+    dof_a = (n - 1 - crank - dimreduce) / 2
     with torch.cuda.device(ctx.device):
-        Qt_dev = torch.from_numpy(Qt).to(ctx.device) if crank else None
         blk = row_split(n_gene, world)
         local = engine.Sliced(blk, n, n_slices, ctx.device)
         if xh.shape[0] < blk:
             local.slices.zero_(); local.quantum.fill_(1.0); local.var.fill_(1.0)
         if xh.shape[0]:
             _residualize_any(ctx, xh, Qt_dev, n_slices, False, out=local, row_offset=0)
-        full = gather_sliced(local, n_gene, group) if world > 1 else local
-        full.rows = n_gene
-        t = (n_gene + TILE - 1) // TILE
-        a, b = strip_bounds(t, world)[rank]
-        r0, r1 = a * TILE, min(b * TILE, n_gene)
-        if out_dev is None:
-            P = torch.zeros((max(r1 - r0, 1), n_gene), dtype=torch.float64, device=ctx.device)
-            D = torch.zeros_like(P)
+        if schedule == "allgather":
+            P, D, var, (r0, r1) = _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out_dev)
         else:
-            P, D = out_dev
-        if r1 > r0:
-            _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b),
-                            (n - 1 - crank - dimreduce) / 2, P, D, r0, n_products)
+            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev)
+            r0, r1 = rank * blk, rank * blk + block_rows(n_gene, world, rank)
         if out_host is not None:
             out_host[0].copy_(P, non_blocking=True)
             out_host[1].copy_(D, non_blocking=True)
@@ -165,7 +284,7 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
             Ph, Dh = out_host[0].numpy(), out_host[1].numpy()
         else:
             Ph, Dh = P.cpu().numpy(), D.cpu().numpy()
-        return Ph, Dh, full.var[:n_gene].cpu().numpy(), (r0, r1)
+        return Ph, Dh, var.cpu().numpy(), (r0, r1)
 
 
 def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products, k_chunk=None):
@@ -187,32 +306,47 @@ def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products, k_chu
     engine.LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
 
 
-def gather_dense(P_strip, D_strip, bounds, n_gene, group=None, dst=0):
-    """Assemble the full symmetric (n_gene, n_gene) P and dot on rank ``dst`` (None elsewhere)."""
+def gather_dense(P_rows, D_rows, bounds, n_gene, group=None, dst=0, schedule="pairs"):
+    """Assemble the full symmetric (n_gene, n_gene) P and dot on rank ``dst`` (None elsewhere)
+    from the per-rank outputs of ``coex_sharded`` (same ``schedule``)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    dev = P_strip.device
+    dev = P_rows.device
     t = (n_gene + TILE - 1) // TILE
-    strips = strip_bounds(t, world)
+    if schedule == "allgather":
+        spans = [(a * TILE, min(b * TILE, n_gene)) for a, b in strip_bounds(t, world)]
+    else:
+        blk = row_split(n_gene, world)
+        spans = [(k * blk, k * blk + block_rows(n_gene, world, k)) for k in range(world)]
     outs = []
-    for src_t in (P_strip, D_strip):
+    for src_t in (P_rows, D_rows):
         full = torch.zeros((n_gene, n_gene), dtype=torch.float64, device=dev) if rank == dst else None
-        for k, (a, b) in enumerate(strips):
-            r0, r1 = a * TILE, min(b * TILE, n_gene)
+        for k, (r0, r1) in enumerate(spans):
             if r1 <= r0:
                 continue
             if k == dst:
                 if rank == dst:
-                    full[r0:r1] = src_t
+                    full[r0:r1] = src_t[:r1 - r0]
             elif rank == dst:
                 buf = torch.empty((r1 - r0, n_gene), dtype=torch.float64, device=dev)
                 dist.recv(buf, src=k, group=group)
                 full[r0:r1] = buf
             elif rank == k:
-                dist.send(src_t.contiguous(), dst=dst, group=group)
+                dist.send(src_t[:r1 - r0].contiguous(), dst=dst, group=group)
         if rank == dst:
-            up = torch.triu(full, 1)
-            full = up + up.T
+            if schedule == "allgather":
+                up = torch.triu(full, 1)
+                full = up + up.T
+            else:
+                # entry (i, j) was computed by the owner of tile (i, j) or, mirrored, of tile (j, i)
+                res = torch.empty_like(full)
+                for k, (r0, r1) in enumerate(spans):
+                    if r1 <= r0:
+                        continue
+                    m = torch.from_numpy(owned_tile_mask(n_gene, world, k)).to(dev)
+                    m = m.repeat_interleave(TILE, 0)[:r1 - r0].repeat_interleave(TILE, 1)[:, :n_gene]
+                    res[r0:r1] = torch.where(m, full[r0:r1], full[:, r0:r1].T)
+                full = res
         outs.append(full)
     return outs[0], outs[1]
 
@@ -223,9 +357,7 @@ def de_sharded(dg, dt_block, dc, n_gene, group=None, precision="default", dimred
     ctx = engine.context(dt_block.device)
     n_slices, n_products = engine.PRESETS[precision]
     n = dt_block.shape[1]
-    dc_h = dc.detach().cpu().numpy() if isinstance(dc, torch.Tensor) else np.asarray(dc)
-    Qt, crank, _ = covariate_basis(dc_h)
-    Qt_dev = torch.from_numpy(Qt).to(ctx.device) if crank else None
+    Qt_dev, crank, _ = covariate_basis_device(ctx, dc)
     A = engine.residualize(ctx, dg.to(ctx.device, torch.float64), Qt_dev, n_slices)
     B = engine.residualize(ctx, dt_block, Qt_dev, n_slices)
     P = torch.empty((A.rows, B.rows), dtype=torch.float64, device=ctx.device)

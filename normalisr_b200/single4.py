@@ -26,7 +26,7 @@ from ._lib import MODE_RAW, MAX_RANK
 
 def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduce=0,
                               precision='default', device=None, engine_id=None, **ka):
-    from .association import covariate_basis, inv_rank, _residualize_any, _as_host_f64, _is_dev, _out
+    from .association import covariate_basis_device, inv_rank, _residualize_any, _as_host_f64, _is_dev, _out
     eng = ka.pop('engine', engine.ENGINE_UMMA) if engine_id is None else engine_id
     tol = ka.pop('tol', 1e-8)
     if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
@@ -47,12 +47,11 @@ def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
         raise ValueError('Dimensions in na==0 detected.')
     if nc == 0:
         logging.warning('No covariate dc input.')
-    Qt, rank_c, W = covariate_basis(_as_host_f64(dc), tol=tol)
+    Qt_dev, rank_c, W = covariate_basis_device(ctx, dc, tol=tol)
     if rank_c > MAX_RANK:
         raise NotImplementedError('covariate rank {} > {}'.format(rank_c, MAX_RANK))
     with torch.cuda.device(ctx.device):
         dev = ctx.device
-        Qt_dev = torch.from_numpy(Qt).to(dev) if rank_c else None
         Rx = _residualize_any(ctx, dx, Qt_dev, n_slices, not lowmem)
         Ry = _residualize_any(ctx, dy, Qt_dev, n_slices, not lowmem)
         Gxx = torch.empty((nx, nx), dtype=torch.float64, device=dev)

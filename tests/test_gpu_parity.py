@@ -293,6 +293,29 @@ def test_overflow_plan_from_energies():
     assert kc > 0 and kc % 128 == 0
 
 
+def test_covariate_basis_device_matches_host():
+    """nsr_cov_gram / nsr_cov_apply: same basis as the numpy restatement, orthonormal to rounding,
+    rank rule of inv_rank (association.py:77), also for rank-deficient and single-row covariates."""
+    rng = np.random.default_rng(17)
+    ctx = engine.context(0)
+    for nc, n, dup in [(1, 77, False), (4, 1000, False), (9, 100_003, True), (40, 5000, True)]:
+        dc = rng.normal(size=(nc, n)) * rng.uniform(0.1, 30, size=(nc, 1))
+        dc[-1] = 1.0
+        if dup and nc > 2:
+            dc[1] = 2 * dc[0] - 3 * dc[-1]                 # exact linear dependence
+        Qh, rh, Wh = association.covariate_basis(dc)
+        Qd, rd, Wd = association.covariate_basis_device(ctx, dc)
+        assert rd == rh == (nc - 1 if dup and nc > 2 else nc)
+        Qd = Qd.cpu().numpy()
+        np.testing.assert_allclose(Qd @ Qd.T, np.eye(rd), atol=1e-13)
+        # same subspace: the projectors agree (individual rows may differ by a rotation)
+        x = rng.normal(size=(5, n))
+        np.testing.assert_allclose((x @ Qd.T) @ Qd, (x @ Qh.T) @ Qh, atol=1e-9)
+        np.testing.assert_allclose(Wd @ dc, Qd, atol=1e-8)
+    Qd, rd, _ = association.covariate_basis_device(ctx, np.zeros((3, 50)))
+    assert Qd is None and rd == 0
+
+
 def test_residual_planes_reconstruct_projection():
     rng = np.random.default_rng(5)
     x = rng.normal(size=(77, 1000)) + 4
