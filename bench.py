@@ -210,45 +210,51 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     dc_np = dc_dev.cpu().numpy()
     pairs = n_gene * (n_gene - 1) / 2
 
-    t_tiles = (n_gene + 127) // 128
-    a, b = parallel.strip_bounds(t_tiles, world)[rank]
-    r0, r1 = a * 128, min(b * 128, n_gene)
-    tiles = parallel.strip_tiles(t_tiles, a, b)
     single = world == 1
+    schedule = args.schedule
     if single:
         P = torch.empty((n_gene, n_gene), dtype=torch.float64, device=dev)
         D = torch.empty_like(P)
         tiles_full = engine.coex_tiles(n_gene)
+        n_my_tiles = len(tiles_full)
+        local_sl = engine.Sliced(n_gene, n_cell, n_slices, dev)
     else:
-        P = torch.zeros((max(r1 - r0, 1), n_gene), dtype=torch.float64, device=dev)
+        if schedule == "pairs":
+            my_rows = parallel.block_rows(n_gene, world, rank)
+            n_my_tiles = int(parallel.owned_tile_mask(n_gene, world, rank).sum())
+        else:
+            t_tiles = (n_gene + 127) // 128
+            a, b = parallel.strip_bounds(t_tiles, world)[rank]
+            my_rows = min(b * 128, n_gene) - a * 128
+            n_my_tiles = len(parallel.strip_tiles(t_tiles, a, b))
+        P = torch.zeros((max(my_rows, 1), n_gene), dtype=torch.float64, device=dev)
         D = torch.zeros_like(P)
-    local_sl = engine.Sliced(blk, n_cell, n_slices, dev)
-    if g1 - g0 < blk:
-        local_sl.slices.zero_(); local_sl.quantum.fill_(1.0); local_sl.var.fill_(1.0)
     contract_ms = []
     k_plan = {}
 
     def step_device(record=False):
         # the whole path, every step: covariate basis (Gram matrix + small factorisation), projection,
-        # (all-gather,) contraction + P-values
+        # (block exchange,) contraction + P-values
+        if not single:
+            ev = [] if record else None
+            parallel.coex_sharded(dt_dev, dc_dev, n_gene, precision=precision, out=(P, D), schedule=schedule, events=ev)
+            if record:
+                contract_ms.append(ev)
+            return
         Qt_dev, crank, _ = association.covariate_basis_device(ctx, dc_dev)
         dof_a = (n_cell - 1 - crank) / 2
         engine.residualize(ctx, dt_dev, Qt_dev, n_slices, out=local_sl, row_offset=0)
-        full = parallel.gather_sliced(local_sl, n_gene) if world > 1 else local_sl
+        full = local_sl
         full.rows = n_gene
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         if "k" not in k_plan:          # int32-overflow bound from the digit energies: planned once (tiny D2H)
             k_plan["k"] = engine.plan_k_chunk(full, full, n_products)
-        if single:
-            engine.contract(ctx, engine.MODE_COEX, full, full, tiles_full, dof_a, P, D, n_products, k_chunk=k_plan["k"])
-        elif len(tiles):
-            parallel._contract_strip(ctx, engine.MODE_COEX_UPPER, full, full, tiles, dof_a, P, D, r0, n_products,
-                                     k_chunk=k_plan["k"])
+        engine.contract(ctx, engine.MODE_COEX, full, full, tiles_full, dof_a, P, D, n_products, k_chunk=k_plan["k"])
         if record:
             e1.record()
-            contract_ms.append((e0, e1))
+            contract_ms.append([(e0, e1)])
 
     def barrier():
         if world > 1:
@@ -282,8 +288,16 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = pairs / (ms_step * 1e-3)
-    k_list = [e0.elapsed_time(e1) for e0, e1 in contract_ms]
+    k_list = [sum(e0.elapsed_time(e1) for e0, e1 in evs) for evs in contract_ms]
     k_ms = float(np.mean(k_list)) if k_list else None
+
+    # ---- the consumer of P: per-row BH + threshold on the device-resident matrix
+    binnet_info = None
+    if single and not args.no_de:
+        try:
+            binnet_info = bench_binnet(torch, ctx, P, n_gene)
+        except Exception as e:
+            binnet_info = {"error": repr(e)[:300]}
 
     # ---- end to end through the public API, host buffers
     e2e = None
@@ -294,8 +308,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             P_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
             D_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
         else:
-            P_host = torch.empty((max(r1 - r0, 1), n_gene), dtype=torch.float64, pin_memory=True)
-            D_host = torch.empty((max(r1 - r0, 1), n_gene), dtype=torch.float64, pin_memory=True)
+            P_host = torch.empty((max(my_rows, 1), n_gene), dtype=torch.float64, pin_memory=True)
+            D_host = torch.empty((max(my_rows, 1), n_gene), dtype=torch.float64, pin_memory=True)
         del dt_dev, prob
         torch.cuda.empty_cache()
 
@@ -303,7 +317,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             if single:
                 norm.coex(dt_host, dc_np, precision=precision, out=(P_host, D_host))
             else:
-                parallel.coex_host(dt_host, dc_np, n_gene, precision=precision, out_dev=(P, D), out_host=(P_host, D_host))
+                parallel.coex_host(dt_host, dc_np, n_gene, precision=precision, out_dev=(P, D), out_host=(P_host, D_host),
+                                   schedule=schedule)
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         for _ in range(min(args.warmup, 3)):
@@ -314,7 +329,11 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             step_e2e()
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
-        h2d_t = torch.tensor([float(dt_host.numel() * 8), float(P_host.numel() * 16)], dtype=torch.float64, device=dev)
+        d2h_cols = P_host.shape[1]
+        if not single and schedule == "pairs":      # only the column blocks this rank owns travel back
+            d2h_cols = my_rows + sum(parallel.block_rows(n_gene, world, src) for _, src, _ in parallel.exchange_plan(world, rank))
+        h2d_t = torch.tensor([float(dt_host.numel() * 8), float(P_host.shape[0] * d2h_cols * 16)], dtype=torch.float64,
+                             device=dev)
         if world > 1:
             dist.all_reduce(h2d_t)
         e2e = {"value": pairs / (sec / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
@@ -335,7 +354,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         pass
     peak_tf = peaks.get("bf16_tflops_sustained") or 1400.0
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-    my_pairs = len(tiles_full if single else tiles) * 128 * 128 / 2.0        # ~unique pairs in this rank's tiles
+    my_pairs = n_my_tiles * 128 * 128.0          # ~unique pairs in this rank's tiles (each tile pair is computed once)
     alg_flops = 2.0 * n_cell * (pairs if single else my_pairs)
     traffic = None
     try:
@@ -349,7 +368,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         roof = {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": traffic, "kernel": "contract_umma_kernel", "kernel_ms": k_ms,
                 "kernel_ms_per_step": [round(x, 2) for x in k_list], "peak_source": peak_src,
-                "executed_int8_tops": 2.0 * n_products * len(tiles_full if single else tiles) * 128 * 128 *
+                "executed_int8_tops": 2.0 * n_products * n_my_tiles * 128 * 128 *
                                       engine.padded_cells(n_cell) / (k_ms * 1e-3) / 1e12,
                 "note": "algorithmic flop = 2*cells per unique pair; the kernel executes %d int8 digit-plane products per "
                         "pair so its ceiling on this scale is 2/%d of the bf16 peak" % (n_products, n_products)}
@@ -384,11 +403,13 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                    "cell_chunk": k_plan.get("k", 0),
                    "arithmetic": "f64 projection and epilogue; int8 x int8 -> int32 exact tensor-core sums",
                    "l2": "inputs (%.1f GB per rank) are larger than L2, no explicit flush" % ((g1 - g0) * n_cell * 8 / 1e9),
-                   "parallelism": "1 GPU" if world == 1 else "%d GPUs: gene-block projection, one all-gather of digit planes, "
-                                                              "tile-row strips" % world,
+                   "parallelism": "1 GPU" if world == 1 else ("%d GPUs: gene-block projection, one all-gather of digit planes, tile-row strips" % world
+                                   if schedule == "allgather" else
+                                   "%d GPUs: gene-block projection, circulant block-pair schedule (%d point-to-point rounds "
+                                   "of digit planes overlapped with the contraction)" % (world, world // 2)),
                    "note": wl_desc},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-        "de": de,
+        "de": de, "binnet": binnet_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -446,6 +467,35 @@ def run_de_sweep(args, n_gene, n_cell, wl_name, wl_desc, n_group=1000, genes_per
         dist.destroy_process_group()
 
 
+def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):
+    """normalisr_b200.binnet on the (n_gene, n_gene) P left on the device by coex: HBM-bound,
+    9 B per entry (8 read + 1 written)."""
+    from normalisr_b200 import binnet as bn
+    out = torch.empty((n_gene, n_gene), dtype=torch.uint8, device=P.device)
+    stats = torch.zeros(2, dtype=torch.int64, device=P.device)
+    for _ in range(2):
+        bn.binnet_rows(ctx, P, qcut, 0, out=out, stats=stats)
+    stats.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        bn.binnet_rows(ctx, P, qcut, 0, out=out, stats=stats)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs") or peaks.get("hbm_GBs") or 6545.0
+    gbs = 9.0 * n_gene * n_gene / (ms * 1e-3) / 1e9
+    return {"workload": "binnet_%dk" % (n_gene // 1000), "qcut": qcut, "ms": ms, "edges": int(stats[0].item()) // reps,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": 9 * n_gene * n_gene}}
+
+
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
     """DE tests/s on the GSE120861-shaped config (50k cells x 10k genes x 300 gRNAs), inputs resident
     in HBM, through the public API: single=0 and single=4 ("untested gRNAs as covariates")."""
@@ -480,6 +530,8 @@ def main():
     ap.add_argument("--workload", default="coex_100k_x_20k", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="default", choices=["fast", "default", "precise"])
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: same as --steps)")
+    ap.add_argument("--schedule", default="pairs", choices=["pairs", "allgather"],
+                    help="multi-GPU exchange schedule (normalisr_b200.parallel)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-de", action="store_true", help="skip the secondary DE tests/s measurement")

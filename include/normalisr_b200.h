@@ -129,6 +129,20 @@ int nsr_cov_apply(nsr_ctx* ctx, uintptr_t stream, const double* M, int rank, int
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,
                int64_t row_len, int64_t count, double* P);
 
+/* P-value network -> binary network (the consumer of NSR_MODE_COEX output).
+ *
+ * Replaces binnet.binnet (src/normalisr/binnet.py:134-170), i.e. bh() (:77-131) on every row
+ * with its diagonal entry removed, followed by Q <= qcut: net[i][j] = 1 iff the Benjamini-
+ * Hochberg Q-value of P[i][j] among row i's off-diagonal entries is <= qcut; diagonal = 0.
+ * The booleans are bit-identical to the reference's (same floating-point test p / (c / n0) <= qcut
+ * at the BH rank, found without sorting).  P is rows x cols (rows of a possibly larger matrix:
+ * the diagonal entry of row i is column i + diag0, outside [0, cols) = none).  stats (device,
+ * 2 x uint64, accumulated): [0] += number of edges, [1] += rows holding a value outside [0, 1]
+ * or NaN (the reference asserts on those, binnet.py:152-153). */
+int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64_t rows, int64_t cols,
+               int64_t ld, int64_t diag0, double qcut, uint8_t* net, int64_t ld_net,
+               unsigned long long* stats);
+
 /* Strided device<->host copy on `stream` (cudaMemcpy2DAsync): lets the host layer return
  * finished blocks of P / dot while later tiles are still being computed.  kind: 0 = device to
  * host, 1 = host to device.  Pitches and width in bytes. */
@@ -137,7 +151,8 @@ int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, con
 
 /* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
  * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
- * kernel, default 128). Process-wide. */
+ * kernel, default 128), "umma_dynamic" (1 = tiles claimed from a global counter, default; 0 = static
+ * round-robin). Process-wide. */
 int nsr_set_option(const char* name, int value);
 
 /* Debug / test helper: reconstruct z' (float64, rows x n_pad) from slices and quantum. */

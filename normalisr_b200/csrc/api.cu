@@ -21,6 +21,7 @@ extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
 extern int nsr_epi_warps;
 extern int nsr_umma_stack;
+extern int nsr_umma_dynamic;
 extern int nsr_epi_overlap;
 extern int nsr_epi_sleep_ns;
 
@@ -68,6 +69,11 @@ extern "C" int nsr_ctx_create(int device, nsr_ctx** out) {
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess) fn = nullptr;
     ctx->encode_tiled = fn;
+    if (cudaMalloc(&ctx->tile_counters, NSR_TILE_COUNTERS * sizeof(int)) != cudaSuccess) {
+        delete ctx;
+        nsr_set_error("nsr_ctx_create: cudaMalloc failed");
+        return 1;
+    }
     *out = ctx;
     return 0;
 }
@@ -77,6 +83,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tiles_dev) cudaFree(ctx->tiles_dev);
+    if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     delete ctx;
     return 0;
 }
@@ -85,6 +92,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
 extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "umma_dynamic")) { nsr_umma_dynamic = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_stack")) { nsr_umma_stack = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_warps")) {
         NSR_REQUIRE(value == 8 || value == 16, "epi_warps must be 8 or 16");

@@ -21,6 +21,7 @@
 
 extern int nsr_epi_warps;
 extern int nsr_umma_stack;
+extern int nsr_umma_dynamic;
 
 namespace {
 
@@ -37,8 +38,12 @@ struct UmmaArgs {
     int stack_b;                  // 1: N = 256 MMAs over two stacked B planes (single-CTA kernel)
     int epi_overlap;              // 1: release TMEM before the P-value math (overlap with next tile)
     int epi_sleep_ns;             // back-off of the epilogue warps while they wait for a tile
+    int* tile_counter;            // dynamic tile scheduler (single-CTA kernel): next unclaimed list index,
+                                  // zeroed before the launch; nullptr = static round-robin
     ContractParams ep;
 };
+
+constexpr int kTileRing = 8;      // tile-index hand-off ring; the producer leads the epilogue by <= 3 tiles
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -242,8 +247,9 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ UmmaArgs g) {
     using C = Cfg<S, WMAX, KB>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty;
+    __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty, bar_tile[kTileRing];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ int s_tile[kTileRing];
 
     uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t ring_u32 = smem_u32(ring);
@@ -254,6 +260,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_init(smem_u32(&bar_full[s]), 1);
             mbar_init(smem_u32(&bar_empty[s]), 1);
         }
+        for (int s = 0; s < kTileRing; ++s) mbar_init(smem_u32(&bar_tile[s]), 1);
         mbar_init(smem_u32(&bar_tmem_full), 1);
         mbar_init(smem_u32(&bar_tmem_empty), EW);         // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -273,10 +280,17 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
+        // Tiles are claimed from a global counter (CTAs that start late or run on a slower SM simply
+        // take fewer) and handed to the MMA and epilogue warps through a small shared-memory ring.
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+            for (int it = 0;; ++it) {
+                int t = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
+                if (t >= g.n_tiles) t = -1;
+                s_tile[it % kTileRing] = t;
+                mbar_arrive(smem_u32(&bar_tile[it % kTileRing]));
+                if (t < 0) break;
                 const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = g.tiles[2 * t + 1] * NSR_TILE;
                 for (int kb = 0; kb < g.num_kb; ++kb) {
                     mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
@@ -297,7 +311,9 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, tphase = 0;
-            for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+            for (int it = 0;; ++it) {
+                mbar_wait(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1);
+                if (s_tile[it % kTileRing] < 0) break;
                 mbar_wait(smem_u32(&bar_tmem_empty), tphase ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < g.num_kb; ++kb) {
@@ -349,7 +365,10 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..9)
         uint32_t tphase = 0;
-        for (int t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
+        for (int it = 0;; ++it) {
+            mbar_wait_backoff(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1, g.epi_sleep_ns);
+            const int t = s_tile[it % kTileRing];
+            if (t < 0) break;
             const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
@@ -606,6 +625,7 @@ int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sust
 int nsr_epi_overlap = 1;     // test hook: release TMEM before (1) or after (0) the P-value math
 int nsr_epi_sleep_ns = 500;  // test hook: epilogue wait back-off
 int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
+int nsr_umma_dynamic = 1;    // 1: tiles claimed from a global counter, 0: static round-robin (single-CTA kernel)
 
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
@@ -623,6 +643,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.num_kb = (int)((cell_end - cell_begin) / 128);
         g.kb_begin = (int)(cell_begin / 128);
         g.stack_b = 0;
+        g.tile_counter = nullptr;
         g.epi_overlap = nsr_epi_overlap;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.ep = ep;
@@ -642,6 +663,11 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     g.num_kb = (int)((cell_end - cell_begin) / kb);
     g.kb_begin = (int)(cell_begin / kb);
     g.stack_b = (nsr_umma_stack != 0 && kb == 128) ? 1 : 0;
+    g.tile_counter = nullptr;
+    if (nsr_umma_dynamic && ctx->tile_counters) {
+        g.tile_counter = ctx->tile_counters + (ctx->launch_seq++ % NSR_TILE_COUNTERS);
+        NSR_CHECK(cudaMemsetAsync(g.tile_counter, 0, sizeof(int), st));
+    }
     g.epi_overlap = nsr_epi_overlap;
     g.epi_sleep_ns = nsr_epi_sleep_ns;
     g.ep = ep;

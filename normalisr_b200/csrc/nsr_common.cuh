@@ -1,5 +1,6 @@
 // Shared declarations for the normalisr_b200 CUDA library (internal).
 #pragma once
+#define NSR_TILE_COUNTERS 64
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -16,6 +17,10 @@ struct nsr_ctx {
     int32_t* tiles_dev = nullptr;
     size_t tiles_cap = 0;
     void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled, resolved at create
+    // dynamic tile scheduler of the tcgen05 kernel: one counter per launch, used round-robin so
+    // launches in flight on different streams never share one
+    int* tile_counters = nullptr;
+    unsigned launch_seq = 0;
 };
 
 void nsr_set_error(const char* fmt, ...);

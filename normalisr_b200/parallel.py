@@ -160,9 +160,24 @@ def residualize_block(ctx, x_block, Qt_dev, n_slices, blk):
     return out
 
 
-def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out):
+def _timed(events, fn):
+    """Run fn(); with ``events`` a list, bracket it with CUDA events on the current stream."""
+    if events is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    events.append((e0, e1))
+
+
+def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None):
     """Pairs schedule on an already residualised block: post the exchange, contract the diagonal
-    block, then each block pair as soon as its round has arrived.  Returns (P, dot, var_all)."""
+    block, then each block pair as soon as its round has arrived.  Returns (P, dot, var_all).
+    ``events`` (a list) receives one CUDA event pair per contraction launch (bench bookkeeping).
+    ``out_host`` = (P, dot) pinned CPU tensors: every finished column block is copied back on a
+    side stream while the next block pair is contracted (column blocks this rank does not own are
+    not written)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     blk = local.rows_alloc
@@ -173,9 +188,11 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out):
     if world > 1:
         em = em.clone()
         dist.all_reduce(em, op=dist.ReduceOp.MAX, group=group)       # int32 bound over every rank's rows
-        rounds = start_exchange(local, group)
+        # small collectives first: the compute stream waits for them, and they must not queue
+        # behind the plane exchange on the communication stream
         var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
         dist.all_gather_into_tensor(var_all, local.var, group=group)
+        rounds = start_exchange(local, group)
     em_h = em.cpu().numpy()
     k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_h, em_h))
     if out is None:
@@ -184,22 +201,37 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out):
     else:
         P, D = out
     local.rows = max(rows_a, 1)
+    copy_stream = torch.cuda.Stream(device=local.slices.device) if out_host is not None else None
+
+    def send_home(c0, c1):
+        if out_host is None:
+            return
+        copy_stream.wait_stream(torch.cuda.current_stream())
+        for src_t, dst_t in ((P, out_host[0]), (D, out_host[1])):
+            engine.copy_block_to_host(ctx, dst_t, src_t, 0, rows_a, c0, c1, stream=copy_stream)
+
     if rows_a:
         c0 = rank * blk
-        engine.contract(ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
-                        P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk)
+        _timed(events, lambda: engine.contract(
+            ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
+            P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk))
+        send_home(c0, c0 + rows_a)
     for src, parity, buf, works in rounds:
         wait_block(works)
         rows_b = block_rows(n_gene, world, src)
         if rows_a and rows_b:
             buf.rows = rows_b
             c0 = src * blk
-            engine.contract(ctx, MODE_COEX_RECT, local, buf, pair_tiles(rows_a, rows_b, parity), dof_a,
-                            P[:rows_a, c0:c0 + rows_b], D[:rows_a, c0:c0 + rows_b], n_products, k_chunk=k_chunk)
+            _timed(events, lambda: engine.contract(
+                ctx, MODE_COEX_RECT, local, buf, pair_tiles(rows_a, rows_b, parity), dof_a,
+                P[:rows_a, c0:c0 + rows_b], D[:rows_a, c0:c0 + rows_b], n_products, k_chunk=k_chunk))
+            send_home(c0, c0 + rows_b)
+    if copy_stream is not None:
+        torch.cuda.current_stream().wait_stream(copy_stream)
     return P, D, var_all[:n_gene]
 
 
-def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out):
+def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events=None):
     """All-gather schedule: every rank gets all planes, then computes a strip of tile rows."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -214,12 +246,13 @@ def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out):
     else:
         P, D = out
     if r1 > r0:
-        _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b), dof_a, P, D, r0, n_products)
+        _timed(events, lambda: _contract_strip(ctx, MODE_COEX_UPPER, full, full, strip_tiles(t, a, b), dof_a, P, D,
+                                               r0, n_products))
     return P, D, full.var[:n_gene], (r0, r1)
 
 
 def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduce=0, out=None,
-                 schedule="pairs"):
+                 schedule="pairs", events=None):
     """Co-expression over all ranks of ``group``.
 
     dt_block: this rank's genes, rows [rank*blk, min((rank+1)*blk, n_gene)) of the expression
@@ -242,8 +275,8 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
     blk = row_split(n_gene, world)
     local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk)
     if schedule == "allgather":
-        return _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out)
-    P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out)
+        return _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events)
+    P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events)
     return P, D, var, (rank * blk, rank * blk + block_rows(n_gene, world, rank))
 
 
@@ -275,11 +308,12 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         if schedule == "allgather":
             P, D, var, (r0, r1) = _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out_dev)
         else:
-            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev)
+            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host)
             r0, r1 = rank * blk, rank * blk + block_rows(n_gene, world, rank)
         if out_host is not None:
-            out_host[0].copy_(P, non_blocking=True)
-            out_host[1].copy_(D, non_blocking=True)
+            if schedule == "allgather":
+                out_host[0].copy_(P, non_blocking=True)
+                out_host[1].copy_(D, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             Ph, Dh = out_host[0].numpy(), out_host[1].numpy()
         else:

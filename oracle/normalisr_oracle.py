@@ -312,3 +312,48 @@ def de(dg, dt, dc, bs=0, **ka):
     vtf = np.zeros((ng, nt), dtype=dt.dtype)
     vtf[keep] = vt                                  # (nt,) broadcasts for single=0 (:120-121)
     return Pf, gf, af, vgf, vtf
+
+
+# --------------------------------------------------------------------------------------
+# next row of SURVEY 8(f): P-value network -> per-row BH Q-values -> binary network
+# (reference src/normalisr/binnet.py:77-173)
+# --------------------------------------------------------------------------------------
+def bh(pv, weight=None):
+    """Benjamini-Hochberg Q-values, binnet.py:77-131: unique P-values, cumulative (weighted)
+    counts normalised to 1, q = p / w clipped to [0, 1], running minimum from the largest P."""
+    pv = np.asarray(pv)
+    assert pv.ndim == 1 and pv.size > 0
+    assert np.isfinite(pv).all() and pv.min() >= 0 and pv.max() <= 1
+    weight = np.ones(pv.size) if weight is None else np.asarray(weight)
+    assert weight.shape == pv.shape
+    vals, inv = np.unique(pv, return_inverse=True)                 # :113
+    w = np.zeros(vals.size, dtype=pv.dtype)
+    np.add.at(w, inv, weight)                                      # :117-119 (same order of additions)
+    w = np.cumsum(w)                                               # :122
+    w /= w[-1]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        q = vals / w                                               # :124
+    q[~np.isfinite(q)] = 1
+    q = np.minimum(q, 1)
+    q = np.maximum(q, 0)
+    q = np.minimum.accumulate(q[::-1])[::-1]                       # :128-129
+    return q[inv].astype(pv.dtype, copy=False)
+
+
+def binnet(net, qcut):
+    """binnet.py:134-170: BH per row over the off-diagonal entries, diagonal Q = 1, threshold."""
+    net = np.asarray(net)
+    assert net.ndim == 2 and np.isfinite(net).all() and net.min() >= 0 and net.max() <= 1
+    nt = net.shape[0]
+    if net.shape[1] != nt or nt <= 1:
+        raise ValueError('Wrong shape of net or namet.')
+    if qcut <= 0 or qcut >= 1:
+        raise ValueError('Q-value cutoff must be between 0 and 1.')
+    q = np.ones_like(net)
+    off = ~np.eye(nt, dtype=bool)
+    for i in range(nt):
+        q[i, off[i]] = bh(net[i, off[i]])                          # nodiag / rediag, :156-157
+    ans = q <= qcut
+    if ans.sum() == 0:
+        raise RuntimeError("Empty binary network.")
+    return ans

@@ -276,6 +276,27 @@ def test_cell_chunking_is_exact(eng):
             torch.testing.assert_close(P, outs[0][0], rtol=1e-9, atol=0)
 
 
+def test_dynamic_and_static_tile_schedulers_agree():
+    """The tcgen05 kernel claims tiles from a global counter by default; the static round-robin
+    order gives the same bits (few tiles, many tiles, and a tile count below the SM count)."""
+    for rows, n in ((300, 700), (2500, 2048), (5000, 256)):
+        ctx, p, A, rank, prods = _sliced(rows, n)
+        dof = (n - 1 - rank) / 2
+        outs = []
+        try:
+            for dyn in (1, 0, 1):
+                engine.set_option("umma_dynamic", dyn)
+                P = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+                D = torch.zeros_like(P)
+                engine.contract(ctx, engine.MODE_COEX, A, A, engine.coex_tiles(rows), dof, P, D, prods)
+                outs.append((P, D))
+        finally:
+            engine.set_option("umma_dynamic", 1)
+        torch.cuda.synchronize()
+        for P, D in outs[1:]:
+            assert torch.equal(P, outs[0][0]) and torch.equal(D, outs[0][1])
+
+
 def test_overflow_plan_from_energies():
     rows, n = 300, 3000
     ctx, p, A, rank, prods = _sliced(rows, n)

@@ -32,7 +32,40 @@ def test_strips_partition_upper_triangle(rows, world):
 
 
 def test_row_split():
-    assert parallel.row_split(20000, 8) == 2500 and parallel.row_split(10, 4) == 3
+    # equal blocks, multiples of the 128-row tile
+    assert parallel.row_split(20000, 8) == 2560 and parallel.row_split(10, 4) == 128
+    assert parallel.row_split(20000, 1) == 20096
+    assert [parallel.block_rows(20000, 8, k) for k in (0, 6, 7)] == [2560, 2560, 2080]
+    assert [parallel.block_rows(300, 4, k) for k in range(4)] == [128, 128, 44, 0]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+@pytest.mark.parametrize("rows", [100, 300, 1000, 5000, 20000])
+def test_pairs_schedule_covers_every_tile_pair_once(rows, world):
+    """Circulant block-pair schedule: every unordered tile pair is computed by exactly one rank,
+    each rank receives world // 2 blocks, work is balanced, rounds are mutually consistent."""
+    t = (rows + 127) // 128
+    tb = parallel.row_split(rows, world) // 128
+    cnt = np.zeros((t, t), dtype=int)
+    work = []
+    for r in range(world):
+        plan = parallel.exchange_plan(world, r)
+        assert len(plan) == world // 2
+        for d, (dst, src, parity) in enumerate(plan, 1):
+            assert src == (r + d) % world and dst == (r - d) % world
+            # my round-d receive is my source's round-d send
+            assert parallel.exchange_plan(world, src)[d - 1][0] == r
+            if parity is not None:
+                other = [p for (_, s2, p) in parallel.exchange_plan(world, src) if s2 == r]
+                assert other == [1 - parity]
+        m = parallel.owned_tile_mask(rows, world, r)
+        work.append(int(m.sum()))
+        for i, j in zip(*np.nonzero(m)):
+            gi = r * tb + i
+            cnt[min(gi, j), max(gi, j)] += 1
+    assert (cnt[np.triu_indices(t)] == 1).all()
+    if t >= 16 * world:
+        assert max(work) <= 1.06 * sum(work) / world
 
 
 def _free_port():
@@ -54,6 +87,15 @@ def _worker(rank, world, port, rows_total, q):
         local.slices.copy_(torch.randint(-128, 128, local.slices.shape, generator=g, dtype=torch.int8))
         local.quantum.fill_(rank + 1.0)
         local.var.fill_(10.0 * (rank + 1))
+        # block exchange of the pairs schedule: round d brings block (rank + d) % world
+        for src, parity, buf, works in parallel.start_exchange(local):
+            parallel.wait_block(works)
+            gk = torch.Generator().manual_seed(100 + src)
+            want = torch.randint(-128, 128, local.slices.shape, generator=gk, dtype=torch.int8)
+            if not (torch.equal(buf.slices, want) and bool((buf.quantum == src + 1.0).all())
+                    and bool((buf.var == 10.0 * (src + 1)).all())):
+                q.put((rank, False))
+                return
         full = parallel.gather_sliced(local, rows_total)
         ok = full.rows == rows_total and full.rows_alloc == blk * world
         for k in range(world):

@@ -27,19 +27,26 @@ def main():
     p = synth.device_problem(77, genes, cells, dev)          # same seed -> same full matrix on every rank
     dt, dc = p["dt"], p["dc"]
     blk = parallel.row_split(genes, world)
-    P_s, D_s, var, (r0, r1) = parallel.coex_sharded(dt[rank * blk:(rank + 1) * blk], dc, genes)
-    P, D = parallel.gather_dense(P_s, D_s, None, genes)
-    ok = True
+    mine = dt[rank * blk:(rank + 1) * blk]
+    ok = same = True
     if rank == 0:
         res = association.association_tests(dt, None, dc)
         P1, D1, var1 = res[0], res[1], res[4]
-        ok = bool(torch.equal(P, P1) and torch.equal(D, D1) and torch.equal(var, var1))
-        print("multi-GPU check: world %d genes %d cells %d: identical to single GPU: %s (max|dP| %.3e)" % (
-            world, genes, cells, ok, float((P - P1).abs().max())), flush=True)
-    # host-buffer API
-    Ph, Dh, varh, (a0, a1) = parallel.coex_host(dt[rank * blk:(rank + 1) * blk].cpu(), dc.cpu().numpy(), genes)
-    same = bool(torch.equal(torch.from_numpy(Ph).to(dev), P_s) and torch.equal(torch.from_numpy(Dh).to(dev), D_s))
-    print("rank %d: strip rows [%d,%d) host-API strips identical to device-API strips: %s" % (rank, r0, r1, same), flush=True)
+    for schedule in ("pairs", "allgather"):
+        P_s, D_s, var, (r0, r1) = parallel.coex_sharded(mine, dc, genes, schedule=schedule)
+        P, D = parallel.gather_dense(P_s, D_s, None, genes, schedule=schedule)
+        if rank == 0:
+            good = bool(torch.equal(P, P1) and torch.equal(D, D1) and torch.equal(var, var1))
+            ok = ok and good
+            print("multi-GPU check [%s]: world %d genes %d cells %d: identical to single GPU: %s (max|dP| %.3e)" % (
+                schedule, world, genes, cells, good, float((P - P1).abs().max())), flush=True)
+        # host-buffer API
+        Ph, Dh, varh, (a0, a1) = parallel.coex_host(mine.cpu(), dc.cpu().numpy(), genes, schedule=schedule)
+        s_ok = bool(torch.equal(torch.from_numpy(Ph).to(dev), P_s) and torch.equal(torch.from_numpy(Dh).to(dev), D_s)
+                    and (a0, a1) == (r0, r1))
+        same = same and s_ok
+        print("rank %d [%s]: rows [%d,%d) host-API output identical to device-API output: %s" % (
+            rank, schedule, r0, r1, s_ok), flush=True)
     flag = torch.tensor([1.0 if (ok and same) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
