@@ -124,6 +124,28 @@ int nsr_cov_gram(nsr_ctx* ctx, uintptr_t stream, const double* C, int nc, int64_
 int nsr_cov_apply(nsr_ctx* ctx, uintptr_t stream, const double* M, int rank, int nc,
                   const double* C, int64_t n, int64_t ldc, double* Q, int64_t ldq);
 
+/* de(single=1) building blocks (association_test_2, association.py:263-390: every grouping x is
+ * tested on its own subset of cells S_x = U + T_x; U = cells without any gRNA, T_x = cells that
+ * carry only x, association.py:913-916).  All statistics of that test are sums over S_x of
+ * products of covariates, x and y, and sum_{S_x} = sum_U + sum_{T_x} with disjoint T_x:
+ *   nsr_project_coef  coef = X Q^T (rows x rank) and sumsq[row] = sum_k X^2 for any (rank x n) Q:
+ *                     with Q = covariates masked to U it yields every U-part in one pass over dy
+ *                     (it is pass A of nsr_residualize: FP64 tensor cores, fixed summation order);
+ *   nsr_group_stats   Y (genes x m) holds the non-U columns of dy gathered in group order, C
+ *                     (nc1 x m) the covariates (+ a row of ones) gathered alike, goff[n_groups+1]
+ *                     (device, int64) the group boundaries:
+ *                       out[g][y][j] = sum_{k in g} C[j][k] Y[y][k]  (j < nc1),
+ *                       out[g][y][nc1] = sum_{k in g} Y[y][k]^2,   out is [n_groups][genes][nc1+1].
+ * The per-(x, y) closed form (pseudo-inverse of the nc x nc Gram matrix of S_x with the reference's
+ * rank rule, gamma, R2, d.o.f.) is host-side logic in normalisr_b200/single1.py; P-values come from
+ * nsr_pvalue with one `a` per grouping. */
+int nsr_project_coef(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows, int64_t n,
+                     int64_t ldx, const double* Q, int rank, int64_t ldq, double* coef,
+                     double* sumsq);
+int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, int64_t genes, int64_t ldy,
+                    const double* C, int nc1, int64_t ldc, const int64_t* goff, int n_groups,
+                    double* out);
+
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,

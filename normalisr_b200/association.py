@@ -257,9 +257,9 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     dimreduce = ka.pop('dimreduce', 0)
     if single not in (0, 1, 4, 5):
         raise ValueError('Unknown value single={}'.format(single))
-    if single in (1, 5):
-        raise NotImplementedError('normalisr_b200 accelerates single=0 and single=4; single={} is '
-                                  'outside the hot path (SURVEY.md 8f).'.format(single))
+    if single == 5:
+        raise NotImplementedError('normalisr_b200 accelerates single=0, 1 and 4; single=5 ("under '
+                                  'development" upstream) is outside the hot path (SURVEY.md 8f).')
     if np.ndim(dimreduce) != 0:
         # the reference's scalar comparison at association.py:213 raises for arrays as well
         raise ValueError('dimreduce must be a scalar.')
@@ -270,6 +270,12 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     n = dx.shape[1]
     if (not samexy and dy.shape[1] != n) or dc.shape[1] != n:
         raise ValueError('Unmatching dx/dy/dc dimensions.')
+    if single == 1:
+        from .single1 import association_tests_single1
+        if samexy:
+            raise NotImplementedError('dy=None with single=1')                # association.py:911-912
+        return association_tests_single1(dx, dy, dc, lowmem=lowmem, return_dot=return_dot,
+                                         dimreduce=dimreduce, device=device, **ka)
     if single == 4:
         from .single4 import association_tests_single4
         if samexy:

@@ -11,15 +11,14 @@
 // iterate never drops below k*, and a fixed point c = g(c) is itself an index set that passes.
 // The kernel evaluates the SAME floating-point expression as the reference, p / (c / n0) <= qcut
 // (binnet.py:122-124 computes w = cumsum / n0 and p / w), so the boolean output is bit-identical.
-// Only entries with p <= qcut can ever pass (c / n0 <= 1), so the iteration runs over those
-// candidates, compacted into shared memory while the row streams in (a row with more candidates
-// than fit re-reads itself from L2 instead).
+// One CTA per row: the row is read from HBM once into shared memory (rows up to 28,000 entries;
+// wider rows re-read themselves from L2) and the iteration and the final threshold run from there.
 #include "nsr_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 512;
-constexpr int kCandCap = 6000;     // candidates kept in shared memory (47 KB, static limit 48 KB)
+constexpr int kThreads = 1024;
+constexpr int kSmemRowMax = 28000;     // doubles of a row kept in shared memory (224 KB of the 227 KB)
 
 __device__ __forceinline__ int block_sum(int v, int* s_red) {
 #pragma unroll
@@ -33,57 +32,141 @@ __device__ __forceinline__ int block_sum(int v, int* s_red) {
     return t;
 }
 
+// Largest double t with fl(t / w) <= qcut.  Correctly rounded division is monotone in its
+// numerator, so  fl(p / w) <= qcut  <=>  p <= t : the row passes compare against t instead of
+// dividing every entry.  fl(qcut * w) is within a few ulp of t; step to it exactly.
+__device__ __forceinline__ double bh_threshold(double w, double qcut) {
+    double t = qcut * w;
+    while (t / w > qcut) t = nextafter(t, 0.0);
+    for (;;) {
+        const double u = nextafter(t, 2.0);
+        if (u / w <= qcut) t = u; else break;
+    }
+    return t;
+}
+
+__device__ __forceinline__ uint32_t bn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// entries <= thr among s_row[0, cols): two per 16-byte shared-memory load
+__device__ __forceinline__ int count_le(const double* s_row, int64_t cols, double thr) {
+    int mine = 0;
+    const double2* v = reinterpret_cast<const double2*>(s_row);
+    const int64_t half = cols >> 1;
+#pragma unroll 4
+    for (int64_t j = threadIdx.x; j < half; j += kThreads) {
+        const double2 p = v[j];
+        mine += (p.x <= thr ? 1 : 0) + (p.y <= thr ? 1 : 0);
+    }
+    if ((cols & 1) && threadIdx.x == 0) mine += s_row[cols - 1] <= thr ? 1 : 0;
+    return mine;
+}
+
+// SMEM = true: the row is staged once in shared memory (one bulk asynchronous copy when the row is
+// 16-byte aligned, plain loads otherwise) and every later pass reads it from there; false: rows
+// wider than shared memory re-read themselves from L2.
+template <bool SMEM>
 __global__ void __launch_bounds__(kThreads)
 binnet_rows_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64_t diag0, double qcut,
                    uint8_t* __restrict__ net, int64_t ld_net, unsigned long long* __restrict__ stats) {
-    __shared__ double s_cand[kCandCap];
+    extern __shared__ __align__(16) double s_row[];
     __shared__ int s_red[kThreads / 32];
-    __shared__ int s_count;
+    __shared__ __align__(8) uint64_t s_bar;
     const int64_t row = blockIdx.x;
     const double* p_row = P + row * ld;
     const int64_t diag = row + diag0;                  // column of this row's diagonal entry
-    const int64_t n0 = cols - ((diag >= 0 && diag < cols) ? 1 : 0);
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
+    const bool has_diag = diag >= 0 && diag < cols;
+    const int64_t n0 = cols - (has_diag ? 1 : 0);
+    int bad = 0, mine = 0;
 
-    // pass 1: stream the row, validate, compact the candidates
-    int bad = 0;
-    for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
-        const double p = p_row[j];
-        if (!(p >= 0.0 && p <= 1.0)) bad = 1;          // also catches NaN (binnet.py:152-153)
-        if (j != diag && p <= qcut) {
-            const int slot = atomicAdd(&s_count, 1);
-            if (slot < kCandCap) s_cand[slot] = p;
+    if (SMEM) {
+        const bool bulk = (((uintptr_t)p_row & 15) == 0) && ((cols & 1) == 0);
+        if (bulk) {
+            // one thread posts the whole row (cols * 8 bytes) as a single bulk copy; all wait on the mbarrier
+            const uint32_t bar = bn_smem_u32(&s_bar);
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const uint32_t bytes = (uint32_t)(cols * sizeof(double));
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(bn_smem_u32(s_row)), "l"(p_row), "r"(bytes), "r"(bar) : "memory");
+            }
+            uint32_t ok = 0;
+            const long long t0 = clock64();
+            while (!ok) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+                if (!ok && clock64() - t0 > 4000000000ll) __trap();      // never hang the device
+            }
+        } else {
+#pragma unroll 8
+            for (int64_t j = threadIdx.x; j < cols; j += kThreads) s_row[j] = p_row[j];
+            __syncthreads();
+        }
+        // validate (binnet.py:152-153, the diagonal included), then make the diagonal entry inert
+#pragma unroll 4
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
+            const double p = s_row[j];
+            if (!(p >= 0.0 && p <= 1.0)) bad = 1;      // also catches NaN
+        }
+        __syncthreads();
+        if (has_diag && threadIdx.x == 0) s_row[diag] = 2.0;
+        __syncthreads();
+        mine = count_le(s_row, cols, qcut);            // only p <= qcut can pass at all (c / n0 <= 1)
+    } else {
+#pragma unroll 8
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
+            const double p = p_row[j];
+            if (!(p >= 0.0 && p <= 1.0)) bad = 1;
+            mine += (j != diag && p <= qcut) ? 1 : 0;
         }
     }
     if (bad) atomicAdd(&stats[1], 1ull);
-    __syncthreads();
-    int c = s_count;                                   // g(n0): w = n0 / n0 = 1, p / 1 <= qcut
-    const bool in_smem = c <= kCandCap;
+    int c = block_sum(mine, s_red);                    // g(n0): w = 1
     const double n0d = (double)n0;
-    double w = 1.0;
+    double thr = qcut;
     while (c > 0) {
-        w = (double)c / n0d;
-        int mine = 0;
-        if (in_smem) {
-            for (int k = threadIdx.x; k < s_count; k += kThreads) mine += (s_cand[k] / w <= qcut) ? 1 : 0;
+        thr = bh_threshold((double)c / n0d, qcut);
+        if (SMEM) {
+            mine = count_le(s_row, cols, thr);
         } else {
-            for (int64_t j = threadIdx.x; j < cols; j += kThreads)
-                mine += (j != diag && p_row[j] / w <= qcut) ? 1 : 0;
+            mine = 0;
+#pragma unroll 8
+            for (int64_t j = threadIdx.x; j < cols; j += kThreads) mine += (j != diag && p_row[j] <= thr) ? 1 : 0;
         }
         const int c_new = block_sum(mine, s_red);
         if (c_new == c) break;
         c = c_new;
     }
-    // pass 2: the row again (L2), threshold with the final w
+    // pass 2: threshold with the final rank
     uint8_t* o_row = net + row * ld_net;
-    if (c == 0) {
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads) o_row[j] = 0;
+    if (c == 0) thr = -1.0;
+    if (SMEM) {
+        int64_t done = 0;
+        if (((uintptr_t)o_row & 7) == 0) {             // 8 entries -> one 8-byte store
+            const double2* v = reinterpret_cast<const double2*>(s_row);
+            const int64_t oct = cols >> 3;
+            for (int64_t j = threadIdx.x; j < oct; j += kThreads) {
+                uint64_t bits = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const double2 p = v[4 * j + q];
+                    bits |= (uint64_t)(p.x <= thr ? 1 : 0) << (16 * q);
+                    bits |= (uint64_t)(p.y <= thr ? 1 : 0) << (16 * q + 8);
+                }
+                reinterpret_cast<uint64_t*>(o_row)[j] = bits;
+            }
+            done = oct << 3;
+        }
+        for (int64_t j = done + threadIdx.x; j < cols; j += kThreads) o_row[j] = (s_row[j] <= thr) ? 1 : 0;
     } else {
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads)
-            o_row[j] = (j != diag && p_row[j] / w <= qcut) ? 1 : 0;
-        if (threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)c);
+#pragma unroll 8
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) o_row[j] = (j != diag && p_row[j] <= thr) ? 1 : 0;
     }
+    if (c > 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)c);
 }
 
 }  // namespace
@@ -95,7 +178,16 @@ extern "C" int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64
                 "nsr_binnet: bad shape rows=%lld cols=%lld", (long long)rows, (long long)cols);
     NSR_REQUIRE(qcut > 0.0 && qcut < 1.0, "nsr_binnet: qcut must be in (0, 1)");
     NSR_CHECK(cudaSetDevice(ctx->device));
-    binnet_rows_kernel<<<(unsigned)rows, kThreads, 0, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net, ld_net, stats);
+    if (cols <= kSmemRowMax) {
+        const int smem = (int)(cols * sizeof(double));
+        NSR_CHECK(cudaFuncSetAttribute(binnet_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kSmemRowMax * (int)sizeof(double)));
+        binnet_rows_kernel<true><<<(unsigned)rows, kThreads, smem, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
+                                                                                            ld_net, stats);
+    } else {
+        binnet_rows_kernel<false><<<(unsigned)rows, kThreads, 0, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
+                                                                                          ld_net, stats);
+    }
     NSR_CHECK(cudaGetLastError());
     return 0;
 }

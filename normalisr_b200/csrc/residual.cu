@@ -548,6 +548,64 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     return 0;
 }
 
+namespace {
+// coef[row][c] = sum over cell splits (fixed order), sumsq[row] likewise
+__global__ void coef_sum_kernel(const double* __restrict__ partial, const double* __restrict__ psq, int64_t rows,
+                                int rank, int ksplit, double* __restrict__ coef, double* __restrict__ sumsq) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    for (int c = 0; c < rank; ++c) {
+        double s = 0.0;
+        for (int ks = 0; ks < ksplit; ++ks) s += partial[((int64_t)ks * rows + row) * rank + c];
+        coef[row * rank + c] = s;
+    }
+    if (sumsq) {
+        double sq = 0.0;
+        for (int ks = 0; ks < ksplit; ++ks) sq += psq[(int64_t)ks * rows + row];
+        sumsq[row] = sq;
+    }
+}
+}  // namespace
+
+// Pass A of the projection on its own: coef = X Q^T (rows x rank, row-major) and sumsq = sum_k x^2
+// for ANY (rank x n) matrix Q (no orthonormality assumed).  One streaming read of X on the FP64
+// tensor cores; partial sums over the n-only cell splits are combined in a fixed order.
+extern "C" int nsr_project_coef(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows, int64_t n,
+                                int64_t ldx, const double* Q, int rank, int64_t ldq, double* coef, double* sumsq) {
+    NSR_REQUIRE(ctx != nullptr && X != nullptr, "nsr_project_coef: null argument");
+    NSR_REQUIRE(rows > 0 && rows < (1ll << 31) && n > 0 && ldx >= n, "nsr_project_coef: bad shape rows=%lld n=%lld",
+                (long long)rows, (long long)n);
+    NSR_REQUIRE(rank >= 0 && rank <= NSR_MAX_RANK && (rank == 0 || (Q != nullptr && ldq >= n && coef != nullptr)),
+                "nsr_project_coef: bad Q (rank %d)", rank);
+    NSR_REQUIRE(rank > 0 || sumsq != nullptr, "nsr_project_coef: nothing to compute");
+    cudaStream_t st = (cudaStream_t)stream;
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    const int vec = ((uintptr_t)X % 16 == 0) && (ldx % 2 == 0) && (rank == 0 || (((uintptr_t)Q % 16 == 0) && (ldq % 2 == 0)));
+    const int ksplit = nsr_cell_splits(n);
+    const int64_t groups_w = (rows + kWarps * kRowsW - 1) / (kWarps * kRowsW);
+    const int64_t groups_s = (rows + kWarps - 1) / kWarps;
+    const int rk = rank > 0 ? rank : 1;
+    const size_t n_part = (size_t)ksplit * rows * rk, n_psq = (size_t)ksplit * rows;
+    void* scratch = nullptr;
+    if (nsr_scratch(ctx, (n_part + n_psq) * sizeof(double), &scratch)) return 1;
+    double* partial = (double*)scratch;
+    double* psq = partial + n_part;
+    if (rank > 0) {
+        const dim3 grid((unsigned)groups_w, (unsigned)ksplit);
+        for (int c0 = 0; c0 < rank; c0 += 16) {
+#define NSR_LAUNCH_A(NQ, V) coef_mma_kernel<NQ, V><<<grid, kThreads, 0, st>>>(X, rows, n, ldx, Q, rank, ldq, c0, ksplit, partial, psq)
+            if (rank - c0 <= 8) { if (vec) NSR_LAUNCH_A(1, true); else NSR_LAUNCH_A(1, false); }
+            else { if (vec) NSR_LAUNCH_A(2, true); else NSR_LAUNCH_A(2, false); }
+#undef NSR_LAUNCH_A
+        }
+    } else {
+        sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ksplit), kThreads, 0, st>>>(X, rows, n, ldx, ksplit, psq);
+    }
+    coef_sum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial, psq, rows, rank, ksplit, coef, sumsq);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int nsr_unslice(nsr_ctx* ctx, uintptr_t stream, const int8_t* slices, int64_t rows,
                            int64_t rows_alloc, int64_t n_pad, int n_slices, const double* quantum,
                            double* out) {

@@ -7,7 +7,8 @@ def de(dg, dt, dc, bs=0, **ka):
     """Differential expression of every gene against every grouping:
     ``(P, gamma, alpha|None, varg, vart)`` with the reference's shapes and fill values
     (groupings with a single value are skipped: P = 1, everything else 0; de.py:92-122).
-    ``single`` = 0 (default) or 4 ("other groupings as covariates")."""
+    ``single`` = 0 (default), 1 (low MOI: every grouping tested on the cells that carry only it or
+    nothing) or 4 ("other groupings as covariates")."""
     from .association import association_tests
     on_dev = isinstance(dg, torch.Tensor) and dg.is_cuda
     dg0 = dg

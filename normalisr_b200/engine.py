@@ -64,12 +64,20 @@ def padded_cells(n):
 class Sliced:
     """Residualised rows as int8 digit planes + per-row quantum / variance (device)."""
 
-    def __init__(self, rows, n, n_slices, device):
+    def __init__(self, rows, n, n_slices, device, storage=None):
         self.rows, self.n, self.n_slices = rows, n, n_slices
         self.n_pad = padded_cells(n)
-        self.slices = torch.empty((n_slices, rows, self.n_pad), dtype=torch.int8, device=device)
-        self.quantum = torch.empty(rows, dtype=torch.float64, device=device)
-        self.var = torch.empty(rows, dtype=torch.float64, device=device)
+        if storage is None:
+            self.slices = torch.empty((n_slices, rows, self.n_pad), dtype=torch.int8, device=device)
+            self.quantum = torch.empty(rows, dtype=torch.float64, device=device)
+            self.var = torch.empty(rows, dtype=torch.float64, device=device)
+        else:
+            # carve planes | quantum | var out of one uint8 buffer (peer-mapped exchange buffers)
+            nb = n_slices * rows * self.n_pad
+            assert storage.dtype == torch.uint8 and storage.numel() >= self.storage_bytes(rows, n, n_slices)
+            self.slices = storage[:nb].view(torch.int8).view(n_slices, rows, self.n_pad)
+            self.quantum = storage[nb:nb + 8 * rows].view(torch.float64)
+            self.var = storage[nb + 8 * rows:nb + 16 * rows].view(torch.float64)
         self.coef = None
         # [cell split][plane]: largest per-row sum of squared digits (see nsr_residualize)
         self.energy_max = torch.zeros((_lib.MAX_SPLITS, _lib.MAX_SLICES), dtype=torch.float64, device=device)
@@ -77,6 +85,10 @@ class Sliced:
     @property
     def rows_alloc(self):
         return self.slices.shape[1]
+
+    @staticmethod
+    def storage_bytes(rows, n, n_slices):
+        return n_slices * rows * padded_cells(n) + 16 * rows
 
 
 def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
@@ -147,6 +159,40 @@ def cov_apply(ctx, M, C):
     global LAUNCHES
     LAUNCHES += 1
     return Q
+
+
+def project_coef(ctx, X, Q):
+    """(coef, sumsq): coef = X Q^T (rows, rank) and sumsq = row sums of X^2 (nsr_project_coef).
+    X (rows, n), Q (rank, n) CUDA float64 with unit column stride; Q may be None (sumsq only)."""
+    rows, n = X.shape
+    rank = 0 if Q is None else Q.shape[0]
+    coef = torch.empty((rows, max(rank, 1)), dtype=torch.float64, device=X.device)
+    sumsq = torch.empty(rows, dtype=torch.float64, device=X.device)
+    ldx = X.stride(0) if rows > 1 else n
+    ldq = (Q.stride(0) if rank > 1 else n) if rank else n
+    _lib.check(ctx.lib.nsr_project_coef(ctx.handle, _stream(), X.data_ptr(), rows, n, ldx,
+                                        Q.data_ptr() if rank else None, rank, ldq, coef.data_ptr(), sumsq.data_ptr()),
+               "nsr_project_coef")
+    global LAUNCHES
+    LAUNCHES += ((rank + 15) // 16 if rank else 1) + 1
+    return coef[:, :rank], sumsq
+
+
+def group_stats(ctx, Ys, Cs, goff):
+    """out[g, y, :] = [Cs[:, group g] @ Ys[y, group g], sum Ys[y, group g]^2] (nsr_group_stats).
+    Ys (genes, m), Cs (nc1, m) CUDA float64, goff (n_groups + 1,) int64 CUDA."""
+    genes, m = Ys.shape
+    nc1 = Cs.shape[0]
+    ng = goff.numel() - 1
+    out = torch.empty((ng, genes, nc1 + 1), dtype=torch.float64, device=Ys.device)
+    ldy = Ys.stride(0) if genes > 1 else max(m, 1)
+    ldc = Cs.stride(0) if nc1 > 1 else max(m, 1)
+    _lib.check(ctx.lib.nsr_group_stats(ctx.handle, _stream(), Ys.data_ptr(), genes, ldy,
+                                       Cs.data_ptr() if nc1 else None, nc1, ldc, goff.data_ptr(), ng, out.data_ptr()),
+               "nsr_group_stats")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out
 
 
 def coex_tiles(rows, strip=12):

@@ -17,6 +17,8 @@ The path shards naturally:
     blocks it owns; ``gather_dense`` mirrors them into the full symmetric matrices.
 Because the sums over cells are exact integers, every schedule gives bit-identical results.
 """
+import logging
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -146,10 +148,61 @@ def gather_sliced(local, rows_total, group=None):
     return full
 
 
-def residualize_block(ctx, x_block, Qt_dev, n_slices, blk):
+_SYMM = {}            # (bytes, device, group) -> (symmetric uint8 buffer, handle) or None, decided once
+# Plane exchange: "ce" = copy-engine pulls from peer-mapped memory (no SMs taken from the
+# contraction; N = 2: 67.5 vs 72.9 ms per step), "nccl" = point-to-point send/recv kernels,
+# "auto" = "ce" when peer-mapped (symmetric) memory can be set up on all ranks, else "nccl".
+TRANSPORT = "auto"
+
+
+def _symm_block(nbytes, device, group):
+    """A buffer of ``nbytes`` every rank of ``group`` can map (torch symmetric memory over NVLink)."""
+    key = (nbytes, torch.device(device).index, id(group))
+    if key not in _SYMM:
+        import torch.distributed._symmetric_memory as symm
+        t = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        hdl = symm.rendezvous(t, group if group is not None else dist.group.WORLD)
+        _SYMM[key] = (t, hdl)
+    return _SYMM[key]
+
+
+def start_exchange_ce(local_store, hdl, local, group=None):
+    """Copy-engine variant of ``start_exchange``: every remote block is PULLED from the owner's
+    peer-mapped buffer with an asynchronous device-to-device copy on a side stream, so the exchange
+    uses no SMs while the contraction runs.  Returns [(src, parity, Sliced, [event])]."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    hdl.barrier(channel=1, timeout_ms=60000)            # every rank's planes are written
+    side = torch.cuda.Stream(device=local.slices.device)
+    side.wait_stream(torch.cuda.current_stream())
+    nbytes = local_store.numel()
+    rounds = []
+    for _, src, parity in exchange_plan(world, rank):
+        store = torch.empty(nbytes, dtype=torch.uint8, device=local.slices.device)
+        store.record_stream(side)
+        with torch.cuda.stream(side):
+            store.copy_(hdl.get_buffer(src, (nbytes,), torch.uint8, 0), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        buf = engine.Sliced(local.rows_alloc, local.n, local.n_slices, local.slices.device, storage=store)
+        rounds.append((src, parity, buf, [_EventWork(ev)]))
+    return rounds
+
+
+class _EventWork:
+    """Adapter: ``wait()`` makes the current stream wait for a CUDA event (like a c10d Work)."""
+
+    def __init__(self, ev):
+        self.ev = ev
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+
+def residualize_block(ctx, x_block, Qt_dev, n_slices, blk, storage=None):
     """Residualise this rank's rows into a block padded to ``blk`` rows (padding rows are zero
     planes with quantum 1, var 1)."""
-    out = engine.Sliced(blk, x_block.shape[1], n_slices, ctx.device)
+    out = engine.Sliced(blk, x_block.shape[1], n_slices, ctx.device, storage=storage)
     rows = x_block.shape[0]
     if rows < blk:
         out.slices[:, rows:].zero_()
@@ -171,7 +224,7 @@ def _timed(events, fn):
     events.append((e0, e1))
 
 
-def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None):
+def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None):
     """Pairs schedule on an already residualised block: post the exchange, contract the diagonal
     block, then each block pair as soon as its round has arrived.  Returns (P, dot, var_all).
     ``events`` (a list) receives one CUDA event pair per contraction launch (bench bookkeeping).
@@ -192,7 +245,7 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
         # behind the plane exchange on the communication stream
         var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
         dist.all_gather_into_tensor(var_all, local.var, group=group)
-        rounds = start_exchange(local, group)
+        rounds = start_exchange(local, group) if symm is None else start_exchange_ce(symm[0], symm[1], local, group)
     em_h = em.cpu().numpy()
     k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_h, em_h))
     if out is None:
@@ -251,6 +304,33 @@ def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events=None):
     return P, D, full.var[:n_gene], (r0, r1)
 
 
+def _symm_for(blk, n, n_slices, device, group):
+    """Peer-mapped home of this rank's block when TRANSPORT == "ce" (None otherwise).  The barrier
+    keeps a rank from overwriting its planes while a peer still pulls the previous call's."""
+    if TRANSPORT == "nccl":
+        return None
+    nbytes = engine.Sliced.storage_bytes(blk, n, n_slices)
+    key = (nbytes, torch.device(device).index, id(group))
+    if key not in _SYMM:
+        try:
+            _symm_block(nbytes, device, group)
+            ok = 1
+        except Exception as e:                      # no peer mapping on this system
+            if TRANSPORT == "ce":
+                raise
+            logging.warning('peer-mapped memory unavailable (%r): NCCL transport', e)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)        # every rank takes the same path
+        if int(flag.item()) == 0:
+            _SYMM[key] = None
+    if _SYMM[key] is None:
+        return None
+    store, hdl = _SYMM[key]
+    hdl.barrier(channel=0, timeout_ms=60000)
+    return store, hdl
+
+
 def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduce=0, out=None,
                  schedule="pairs", events=None):
     """Co-expression over all ranks of ``group``.
@@ -273,10 +353,11 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
                          'removed + covariate + 1.')
     dof_a = (n - 1 - crank - dimreduce) / 2
     blk = row_split(n_gene, world)
-    local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk)
+    symm = _symm_for(blk, n, n_slices, ctx.device, group) if (schedule == "pairs" and world > 1) else None
+    local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk, storage=None if symm is None else symm[0])
     if schedule == "allgather":
         return _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events)
-    P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events)
+    P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events, symm=symm)
     return P, D, var, (rank * blk, rank * blk + block_rows(n_gene, world, rank))
 
 
@@ -300,7 +381,8 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
     dof_a = (n - 1 - crank - dimreduce) / 2
     with torch.cuda.device(ctx.device):
         blk = row_split(n_gene, world)
-        local = engine.Sliced(blk, n, n_slices, ctx.device)
+        symm = _symm_for(blk, n, n_slices, ctx.device, group) if (schedule == "pairs" and world > 1) else None
+        local = engine.Sliced(blk, n, n_slices, ctx.device, storage=None if symm is None else symm[0])
         if xh.shape[0] < blk:
             local.slices.zero_(); local.quantum.fill_(1.0); local.var.fill_(1.0)
         if xh.shape[0]:
@@ -308,7 +390,7 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         if schedule == "allgather":
             P, D, var, (r0, r1) = _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out_dev)
         else:
-            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host)
+            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host, symm=symm)
             r0, r1 = rank * blk, rank * blk + block_rows(n_gene, world, rank)
         if out_host is not None:
             if schedule == "allgather":

@@ -188,13 +188,59 @@ def _blocks(n, bs):
     return [(s, min(s + bs, n)) for s in range(0, n, bs)]
 
 
+def tile_single1(dx, dy, dc, sselectx, dimreduce=0, lowmem=True, pvalue_backend="auto"):
+    """association_test_2 (association.py:263-390): like the single=0 tile, but every x is tested
+    on its own subset of cells; covariates are projected out within that subset (own pseudo-inverse
+    and rank per x)."""
+    nx, n = dx.shape
+    ny, nc = dy.shape[0], dc.shape[0]
+    r2 = np.zeros((nx, ny))
+    vx = np.zeros(nx)
+    vy = np.zeros((nx, ny))
+    gamma = np.zeros((nx, ny))
+    alpha = None if lowmem else np.zeros((nx, ny, nc))
+    rank = np.zeros((nx, ny), dtype=int)
+    for xi in range(nx):
+        sel = np.nonzero(sselectx[xi])[0]                       # :337-342
+        ns = len(sel)
+        if len(np.unique(dx[xi, sel])) < 2:
+            continue
+        x1, y1 = dx[xi, sel], dy[:, sel]
+        r = 0
+        if nc > 0:                                              # :343-350
+            c1 = dc[:, sel]
+            ci, r = pinv_rank(c1 @ c1.T)
+        rank[xi] = r
+        if r > 0:                                               # :352-357
+            ccx = (ci @ (c1 @ x1.T)).T
+            ccy = (ci @ (c1 @ y1.T)).T
+            x1 = x1 - ccx @ c1
+            y1 = y1 - ccy @ c1
+        v = (x1 ** 2).mean()                                    # :358-362
+        if v == 0:
+            v = 1
+        vx[xi] = v
+        vy[xi] = (y1 ** 2).mean(axis=1)
+        gamma[xi] = (x1 @ y1.T).ravel() / (ns * v)              # :364
+        if not lowmem and r > 0:                                # :365-367
+            alpha[xi] = ccy - gamma[xi][:, None] * ccx.ravel()
+        r2[xi] = gamma[xi] ** 2 * v / vy[xi]                    # :368
+    assert (r2 >= 0).all() and (r2 <= 1 + 1e-8).all()
+    dof = (sselectx.sum(axis=1) - 1 - rank.T - dimreduce).T     # :372
+    if (dof <= 0).any():
+        raise RuntimeError('Insufficient number of cells: must be greater than degrees of freedom '
+                           'removed + covariate + 1.')
+    pv = beta_cdf(1 - r2, dof / 2, 0.5, backend=pvalue_backend)  # :377
+    return pv, gamma, alpha, vx, vy
+
+
 def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=True, single=0,
                       bs4=500, pvalue_backend="auto", **ka):
     """Driver: tiling, per-tile kernels, assembly, gamma<->dot conversion and (for
     dy=None) symmetrisation.  ``nth`` > 1 maps tiles over a thread pool exactly like
     the reference's ``autopooler(..., dummy=True)`` (parallel.py:49-71)."""
-    if single not in (0, 4):
-        raise ValueError("oracle covers single=0 and single=4 (the BASELINE configs)")
+    if single not in (0, 1, 4):
+        raise ValueError("oracle covers single=0, 1 and 4")
     samexy = dy is None
     if samexy:
         dy = dx
@@ -204,7 +250,7 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     ny = dy.shape[0]
     nc = dc.shape[0]
     dimreduce = ka.pop("dimreduce", 0)
-    capx, capy = (500, 500) if single == 0 else (10, 500000)     # :854-875
+    capx, capy = (500, 500) if single in (0, 1) else (10, 500000)     # :854-875
     bsx = _batch(bsx, dx.dtype.itemsize, nc, ns, capx)
     bsy = bsx if samexy else _batch(bsy, dy.dtype.itemsize, nc, ns, capy)
     tiles = list(itertools.product(_blocks(nx, bsx), _blocks(ny, bsy)))
@@ -241,6 +287,25 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
             if not samexy:
                 varx[x0:x1] = vx
             vary[y0:y1] = vy
+    elif single == 1:
+        if samexy:
+            raise NotImplementedError('dy=None with single=1')          # :911-912
+        assert dx.max() == 1                                            # :914
+        sselectx = dx == dx.sum(axis=0)                                 # :915-916
+        for xi in range(nx):
+            assert len(np.unique(dx[xi, sselectx[xi]])) > 1             # :917-918
+        vary = np.zeros((nx, ny))
+
+        def run1(t):
+            (x0, x1), (y0, y1) = t
+            return t, tile_single1(dx[x0:x1], dy[y0:y1], dc, sselectx[x0:x1], dimreduce, lowmem, pvalue_backend)
+        for ((x0, x1), (y0, y1)), (pv, g, al, vx, vy) in pmap(run1, tiles):
+            P[x0:x1, y0:y1] = pv
+            coef[x0:x1, y0:y1] = g
+            if not lowmem:
+                alpha[x0:x1, y0:y1] = al
+            varx[x0:x1] = vx
+            vary[x0:x1, y0:y1] = vy
     else:
         A = np.concatenate([dx, dc], axis=0)                        # :935
         m = nx + nc

@@ -107,7 +107,7 @@ def test_binnet_large_against_oracle_and_row_chunks(monkeypatch):
         assert np.array_equal(norm.binnet(P, q), want)
     monkeypatch.setattr(bn, "_ROW_CHUNK_BYTES", 8 * 1500 * 100)          # 100 rows per chunk
     assert np.array_equal(norm.binnet(P, 0.2), _oracle_net(P, 0.2))
-    # rows whose candidates overflow the shared-memory buffer (fallback: iterate over the row in L2)
+    # dense rows (most entries significant) and a hub matrix
     rng = np.random.default_rng(8)
     W = rng.random((40, 7000)) ** 6
     W = np.concatenate([W, rng.random((7000 - 40, 7000))])              # square, 40 dense rows on top
@@ -115,6 +115,30 @@ def test_binnet_large_against_oracle_and_row_chunks(monkeypatch):
     for i in (0, 17, 39, 40, 6999):
         row = np.delete(W[i], i)
         assert np.array_equal(np.delete(got[i], i), orc.bh(row) <= 0.5) and not got[i, i]
+
+
+@gpu
+def test_binnet_rows_wider_than_shared_memory():
+    """Rows of more than 28,000 entries take the kernel variant that re-reads the row from L2;
+    also rows of a row block whose diagonal sits at an offset, or outside the block."""
+    from normalisr_b200 import binnet as bn, engine
+    rng = np.random.default_rng(9)
+    ctx = engine.context(0)
+    for cols, diag0 in ((30011, 0), (30011, 29990), (30011, -5), (5000, 4990), (4999, 3), (27999, 100)):
+        Pm = rng.random((24, cols)) ** rng.integers(1, 8, size=(24, 1))
+        out, stats = bn.binnet_rows(ctx, torch.from_numpy(Pm).cuda(), 0.1, diag0)
+        got = out.cpu().numpy().astype(bool)
+        edges = 0
+        for i in range(24):
+            d = i + diag0
+            keep = np.ones(cols, dtype=bool)
+            if 0 <= d < cols:
+                keep[d] = False
+                assert not got[i, d]
+            want = orc.bh(Pm[i, keep]) <= 0.1
+            assert np.array_equal(got[i, keep], want)
+            edges += int(want.sum())
+        assert int(stats[0]) == edges and int(stats[1]) == 0
 
 
 @gpu

@@ -62,7 +62,10 @@ def test_coex_golden_simt_engine():
 
 
 @pytest.mark.parametrize("case,ka", [("de_single0", {}), ("de_single0_alpha", {"lowmem": False}),
-                                     ("de_single4", {"single": 4}), ("de_single4_rankdef", {"single": 4})])
+                                     ("de_single4", {"single": 4}), ("de_single4_rankdef", {"single": 4}),
+                                     ("de_single1", {"single": 1}),
+                                     ("de_single1_alpha", {"single": 1, "lowmem": False, "dimreduce": 1}),
+                                     ("de_single1_rankdef", {"single": 1}), ("de_single1_nocov", {"single": 1})])
 def test_de_golden(case, ka):
     g = load_golden(case)
     P, gamma, alpha, varg, vart = norm.de(g["dg"], g["dt"], g["dc"], **ka)
@@ -109,6 +112,37 @@ def test_de_config_like_against_oracle():
         np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
         scale = np.sqrt(ref[4] / ref[3][:, None])
         assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+
+
+def test_de_single1_low_moi_against_oracle(monkeypatch):
+    """Low-MOI screen (single=1): 40 gRNAs, 12,000 cells, 700 genes; also with genes processed in
+    several chunks and with device tensors."""
+    from normalisr_b200 import single1
+    rng = np.random.default_rng(77)
+    n, g, k = 12000, 700, 40
+    dc = np.concatenate([rng.normal(size=(4, n)), (rng.random((2, n)) < 0.3).astype(float), np.ones((1, n))])
+    dg = np.zeros((k, n))
+    u = rng.random(n)
+    has = u > 0.5
+    dg[rng.integers(0, k, size=n)[has], np.nonzero(has)[0]] = 1
+    two = np.nonzero(u > 0.93)[0]
+    dg[rng.integers(0, k, size=two.size), two] = 1
+    dt = rng.normal(size=(g, n)) + 0.3 * dc[1] + 4.0
+    dt[:k] += np.linspace(0, 2.5, k)[:, None] * dg                    # P from ~1 down to < 1e-100
+    ref = orc.de(dg, dt, dc, single=1, lowmem=False)
+    for chunk in (1 << 29, 8 * k * 9 * 100):
+        monkeypatch.setattr(single1, "_CHUNK_BYTES", chunk)
+        got = norm.de(dg, dt, dc, single=1, lowmem=False)
+        assert_p_close(got[0], ref[0])
+        np.testing.assert_allclose(got[3], ref[3], rtol=1e-9)
+        np.testing.assert_allclose(got[4], ref[4], rtol=1e-9)
+        scale = np.sqrt(ref[4] / ref[3][:, None])
+        assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+        np.testing.assert_allclose(got[2], ref[2], atol=1e-8 * np.abs(ref[2]).max())
+    assert ref[0].min() < 1e-100
+    dev = norm.de(torch.from_numpy(dg).cuda(), torch.from_numpy(dt).cuda(), torch.from_numpy(dc).cuda(), single=1)
+    assert dev[0].is_cuda and dev[2] is None
+    assert_p_close(dev[0].cpu().numpy(), ref[0])
 
 
 def test_de_million_cells_uses_cell_chunks():

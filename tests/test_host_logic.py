@@ -134,7 +134,9 @@ def test_argument_validation_needs_no_gpu():
     with pytest.raises(ValueError):
         association.association_tests(x, None, np.ones((1, 10)), single=7)
     with pytest.raises(NotImplementedError):
-        association.association_tests(x, x, np.ones((1, 10)), single=1)
+        association.association_tests(x, x, np.ones((1, 10)), single=5)
+    with pytest.raises(NotImplementedError):
+        association.association_tests(x, None, np.ones((1, 10)), single=1)
     with pytest.raises(ValueError):
         association.association_tests(x, None, np.ones((1, 10)), dimreduce=np.zeros(3))
 
@@ -157,3 +159,41 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception) as e:
         association.association_tests(g["dt"], None, g["dc"])
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+@pytest.mark.parametrize("case", ["de_single1", "de_single1_alpha", "de_single1_rankdef", "de_single1_nocov"])
+def test_single1_sufficient_statistics_equal_reference(case):
+    """The decomposition single1.py relies on (sums over S_x = sums over U + sums over T_x, closed
+    form with the pseudo-inverse of the subset's covariate Gram matrix), in plain numpy, against the
+    reference's per-x subset regression."""
+    from scipy.special import betainc
+    g = load_golden(case)
+    keep = np.array([len(np.unique(x)) > 1 for x in g["dg"]])
+    dx, dy, dc = g["dg"][keep], g["dt"], g["dc"]
+    dimreduce = int(g["dimreduce"]) if "dimreduce" in g else 0
+    nx, nc = dx.shape[0], dc.shape[0]
+    colsum = dx.sum(0)
+    in_u = colsum == 0
+    owner = np.where(colsum == 1, dx.argmax(0), nx)
+    c_u = dc[:, in_u] @ dc[:, in_u].T
+    cy_u, yy_u = dy[:, in_u] @ dc[:, in_u].T, (dy[:, in_u] ** 2).sum(1)
+    for x in range(nx):
+        t = np.nonzero(owner == x)[0]
+        ns = in_u.sum() + len(t)
+        ct = dc[:, t]
+        cx = ct.sum(1)
+        ci, r = association.inv_rank(c_u + ct @ ct.T) if nc else (np.zeros((0, 0)), 0)
+        ccx = ci @ cx
+        vx = (len(t) - cx @ ccx) / ns
+        cy = cy_u + dy[:, t] @ ct.T
+        ccy = cy @ ci
+        vy = (yy_u + (dy[:, t] ** 2).sum(1) - (ccy * cy).sum(1)) / ns
+        gam = (dy[:, t].sum(1) - ccy @ cx) / (ns * vx)
+        P = betainc((ns - 1 - r - dimreduce) / 2, 0.5, 1 - gam * gam * vx / vy)
+        row = np.nonzero(keep)[0][x]
+        np.testing.assert_allclose(P, g["P"][row], rtol=1e-9)
+        np.testing.assert_allclose(gam, g["gamma"][row], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(vx, g["varg"][row], rtol=1e-11)
+        np.testing.assert_allclose(vy, g["vart"][row], rtol=1e-11)
+        if "alpha" in g:
+            np.testing.assert_allclose(ccy - gam[:, None] * ccx[None, :], g["alpha"][row], atol=1e-11)

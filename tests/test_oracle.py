@@ -39,7 +39,11 @@ def test_coex_threads_match_serial():
 
 @pytest.mark.parametrize("case,ka", [("de_single0", {}), ("de_single0_alpha", {"lowmem": False}),
                                      ("de_single4", {"single": 4}),
-                                     ("de_single4_rankdef", {"single": 4})])
+                                     ("de_single4_rankdef", {"single": 4}),
+                                     ("de_single1", {"single": 1}),
+                                     ("de_single1_alpha", {"single": 1, "lowmem": False, "dimreduce": 1}),
+                                     ("de_single1_rankdef", {"single": 1}),
+                                     ("de_single1_nocov", {"single": 1})])
 def test_de_matches_reference(case, ka):
     g = load_golden(case)
     P, gamma, alpha, varg, vart = orc.de(g["dg"], g["dt"], g["dc"], **ka)

@@ -32,14 +32,15 @@ def main():
     if rank == 0:
         res = association.association_tests(dt, None, dc)
         P1, D1, var1 = res[0], res[1], res[4]
-    for schedule in ("pairs", "allgather"):
+    for schedule, transport in (("pairs", "nccl"), ("pairs", "ce"), ("pairs", "ce"), ("allgather", "nccl")):
+        parallel.TRANSPORT = transport
         P_s, D_s, var, (r0, r1) = parallel.coex_sharded(mine, dc, genes, schedule=schedule)
         P, D = parallel.gather_dense(P_s, D_s, None, genes, schedule=schedule)
         if rank == 0:
             good = bool(torch.equal(P, P1) and torch.equal(D, D1) and torch.equal(var, var1))
             ok = ok and good
-            print("multi-GPU check [%s]: world %d genes %d cells %d: identical to single GPU: %s (max|dP| %.3e)" % (
-                schedule, world, genes, cells, good, float((P - P1).abs().max())), flush=True)
+            print("multi-GPU check [%s/%s]: world %d genes %d cells %d: identical to single GPU: %s (max|dP| %.3e)" % (
+                schedule, transport, world, genes, cells, good, float((P - P1).abs().max())), flush=True)
         # host-buffer API
         Ph, Dh, varh, (a0, a1) = parallel.coex_host(mine.cpu(), dc.cpu().numpy(), genes, schedule=schedule)
         s_ok = bool(torch.equal(torch.from_numpy(Ph).to(dev), P_s) and torch.equal(torch.from_numpy(Dh).to(dev), D_s)
