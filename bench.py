@@ -390,11 +390,16 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
 
     # ---- secondary metric of BASELINE.json: DE tests/s (config 3 shape), N = 1 only
     de = None
+    normvar_info = None
     if world == 1 and not args.no_de:
         try:
             de = bench_de(torch, dev, args)
         except Exception as e:          # the headline line must still be printed
             de = {"error": repr(e)[:300]}
+        try:
+            normvar_info = bench_normvar(torch, dev)
+        except Exception as e:
+            normvar_info = {"error": repr(e)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -413,7 +418,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                                        else "copy engines over peer-mapped memory")),
                    "note": wl_desc},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-        "de": de, "binnet": binnet_info,
+        "de": de, "binnet": binnet_info, "normvar": normvar_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -498,6 +503,41 @@ def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):
     return {"workload": "binnet_%dk" % (n_gene // 1000), "qcut": qcut, "ms": ms, "edges": int(stats[0].item()) // reps,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": 9 * n_gene * n_gene}}
+
+
+def bench_normvar(torch, dev, n_gene=10000, n_cell=50000, reps=3):
+    """normalisr_b200.normvar (the step upstream of coex / de) on device-resident inputs: 16 B of
+    algorithmic traffic per matrix entry (8 read + 8 written); the kernels read dt twice."""
+    from normalisr_b200 import normalisr as norm, synth
+    torch.cuda.empty_cache()
+    p = synth.device_problem(1002, n_gene, n_cell, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(5)
+    w = torch.exp(0.3 * torch.randn(n_cell, generator=g, device=dev, dtype=torch.float64))
+    wt = torch.rand(n_gene, generator=g, device=dev, dtype=torch.float64) * 1.5
+    for _ in range(2):
+        norm.normvar(p["dt"], p["dc"], w, wt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        norm.normvar(p["dt"], p["dc"], w, wt)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs") or 6545.0
+    gbs = 16.0 * n_gene * n_cell / (ms * 1e-3) / 1e9
+    del p
+    torch.cuda.empty_cache()
+    return {"workload": "normvar_%dk_x_%dk" % (n_cell // 1000, n_gene // 1000), "covariates": 9, "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": 16 * n_gene * n_cell,
+                         "note": "the statistics pass is bound by the float64 FMA pipe (67 FMA + exp per entry at 9 covariates)"}}
 
 
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):

@@ -146,6 +146,34 @@ int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, int64_t gen
                     const double* C, int nc1, int64_t ldc, const int64_t* goff, int n_groups,
                     double* out);
 
+/* Variance normalisation, the step upstream of coex / de (norm.normvar / normvar1,
+ * src/normalisr/norm.py:131-289): gene x is scaled per cell by s_k = w_k ** wt_x and its own
+ * weighted covariates dc * s are projected out of it.  Two streaming passes over dt (genes x n):
+ *   nsr_normvar_stats  stats[x] = { upper triangle (row-major, W(W+1)/2) of G = sum_k s^2 dc dc^T,
+ *                      b = sum_k s^2 dc dt (W), S1 = sum_k s dt, S2 = sum_k (s dt)^2 }, with
+ *                      W = nsr_normvar_width(nc) >= nc the padded covariate count (rows beyond nc
+ *                      are zero); replaces the per-gene np.matmul(dc, dc.T) / np.matmul(dc, dt.T)
+ *                      of normvar1 (norm.py:159-163);
+ *   nsr_normvar_apply  out = scale[x] * s * (dt - coef[x]^T dc), coef (genes x nc) = G+ b from the
+ *                      host layer (pseudo-inverse with the rank rule of inv_rank), scale = the
+ *                      keepvar factor (norm.py:251-254) or 1.
+ * logw = log(w) per cell, wt per gene; s = exp(wt * logw), 1 when wt == 0.  1 <= nc <= 12. */
+int nsr_normvar_width(int nc);
+int nsr_normvar_stats(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
+                      int64_t ld, const double* dc, int nc, int64_t ldc, const double* logw,
+                      const double* wt, double* stats);
+int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
+                      int64_t ld, const double* dc, int nc, int64_t ldc, const double* logw,
+                      const double* wt, const double* coef, const double* scale, double* out,
+                      int64_t ldo);
+
+/* Batched inv_rank (association.py:66-80) for `batch` symmetric positive semi-definite n x n
+ * matrices (n <= 16), row-major, contiguous: pinv[m] = pseudo-inverse keeping the eigenvalues
+ * >= tol * largest (and > 0), rank[m] = how many were kept.  One warp per matrix, cyclic Jacobi.
+ * Replaces the per-gene / per-grouping scipy.linalg.svd calls of normvar1 (norm.py:159-160). */
+int nsr_sym_pinv(nsr_ctx* ctx, uintptr_t stream, const double* G, int64_t batch, int n, double tol,
+                 double* pinv, int32_t* rank);
+
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,

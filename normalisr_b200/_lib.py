@@ -44,6 +44,11 @@ _SIGNATURES = {
     "nsr_binnet": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp]),
     "nsr_project_coef": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
     "nsr_group_stats": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_int, c_vp]),
+    "nsr_normvar_width": (c_int, [c_int]),
+    "nsr_normvar_stats": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "nsr_normvar_apply": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_i64]),
+    "nsr_sym_pinv": (c_int, [c_vp, c_up, c_vp, c_i64, c_int, c_dbl, c_vp, c_vp]),
     "nsr_cov_gram": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_vp]),
     "nsr_cov_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64]),
 }

@@ -195,6 +195,19 @@ def group_stats(ctx, Ys, Cs, goff):
     return out
 
 
+def sym_pinv(ctx, G, tol=1e-8):
+    """(pinv, rank) of a stack (batch, n, n) of symmetric PSD matrices, inv_rank's rule (nsr_sym_pinv)."""
+    G = G.contiguous()
+    batch, n, _ = G.shape
+    out = torch.empty_like(G)
+    rank = torch.empty(batch, dtype=torch.int32, device=G.device)
+    _lib.check(ctx.lib.nsr_sym_pinv(ctx.handle, _stream(), G.data_ptr(), batch, n, float(tol), out.data_ptr(),
+                                    rank.data_ptr()), "nsr_sym_pinv")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out, rank
+
+
 def coex_tiles(rows, strip=12):
     """Upper-triangular 128x128 tile list (tile_row <= tile_col), ordered in column strips so
     that the ~148 tiles in flight share few row blocks (L2 reuse of the operand planes)."""

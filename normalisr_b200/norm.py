@@ -1,0 +1,139 @@
+"""``normalisr.norm.normvar`` on the GPU (reference src/normalisr/norm.py:131-289), the step
+directly upstream of ``coex`` / ``de``: mean and variance normalisation of the
+log-CPM matrix.  Gene x is multiplied by ``w ** wt[x]`` per cell and its OWN weighted covariates
+``dc * w ** wt[x]`` are projected out (one pseudo-inverse per gene, ``normvar1``); optionally the
+variance of every gene is restored (``keepvar``), continuous covariates are scaled by ``w``.
+
+The reference loops over genes in Python.  Here the per-gene Gram matrices and right-hand sides
+come from one streaming pass over dt (``nsr_normvar_stats``), the nc x nc pseudo-inverses are
+batched on the device (``nsr_sym_pinv``), and a second pass writes the result (``nsr_normvar_apply``); the residual
+variance needed by ``keepvar`` follows from the same statistics (S2 - b^T G+ b), so there is no
+third pass.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
+"""
+import numpy as np
+import torch
+
+from . import _lib, engine
+
+_ROW_CHUNK_BYTES = 1 << 30
+
+
+def _is_dev(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _dev64(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(dev, torch.float64)
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev, torch.float64)
+
+
+def _normvar_rows(ctx, dt_d, dc_d, logw, wt_d, keepvar):
+    """One block of genes resident on the device -> normalised block."""
+    genes, n = dt_d.shape
+    nc = dc_d.shape[0]
+    W = ctx.lib.nsr_normvar_width(nc)
+    tri = W * (W + 1) // 2
+    stats = torch.empty((genes, tri + W + 2), dtype=torch.float64, device=dt_d.device)
+    ld = dt_d.stride(0) if genes > 1 else n
+    ldc = dc_d.stride(0) if nc > 1 else n
+    _lib.check(ctx.lib.nsr_normvar_stats(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
+                                         ldc, logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()), "nsr_normvar_stats")
+    iu = torch.triu_indices(W, W, device=dt_d.device)
+    G = torch.zeros((genes, W, W), dtype=torch.float64, device=dt_d.device)
+    G[:, iu[0], iu[1]] = stats[:, :tri]
+    G = G + torch.triu(G, 1).transpose(1, 2)
+    G = G[:, :nc, :nc]
+    b = stats[:, tri:tri + nc]
+    s1, s2 = stats[:, tri + W], stats[:, tri + W + 1]
+    ci, rank = engine.sym_pinv(ctx, G)                                      # inv_rank per gene, norm.py:159-160
+    if bool((rank <= 0).any()):
+        raise RuntimeError('Zero-rank covariates found.')                    # norm.py:161-162
+    coef = torch.einsum('gij,gj->gi', ci, b).contiguous()
+    if keepvar:                                                              # norm.py:241-243, 251-254
+        dv = torch.sqrt(s2 / n - (s1 / n) ** 2)
+        dv2 = torch.sqrt((s2 - (b * coef).sum(dim=1)) / n)
+        scale = (dv / dv2) ** wt_d
+    else:
+        scale = torch.ones(genes, dtype=torch.float64, device=dt_d.device)
+    out = torch.empty((genes, n), dtype=torch.float64, device=dt_d.device)
+    _lib.check(ctx.lib.nsr_normvar_apply(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
+                                         ldc, logw.data_ptr(), wt_d.data_ptr(), coef.data_ptr(), scale.contiguous().data_ptr(),
+                                         out.data_ptr(), n), "nsr_normvar_apply")
+    engine.LAUNCHES += 2
+    return out
+
+
+def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, normmean=False, device=None):
+    """Performs mean and variance normalisations; same arguments, checks and return value as the
+    reference (norm.py:169-289): ``[dtn, dcn]`` or ``[dtn, dcn, dextran]``.  ``nth`` / ``bs`` are
+    accepted and ignored."""
+    from .association import inv_rank
+    if any(x.ndim != 2 for x in (dt, dc)):
+        raise ValueError('dt and dc should have 2 dimensions.')
+    if any(x.ndim != 1 for x in (w, wt)):
+        raise ValueError('w and wt should have 1 dimension.')
+    nt, ns = dt.shape
+    if dc.shape[0] == 0:
+        raise ValueError('No covariates.')
+    if dc.shape[1] != ns or w.shape[0] != ns or wt.shape[0] != nt:
+        raise ValueError('Unmatched gene or cell counts.')
+    if dextra is not None and (dextra.ndim != 2 or dextra.shape[0] == 0 or dextra.shape[1] != ns):
+        raise ValueError('Unmatched shape or size for dextra.')
+    if float(w.min()) <= 0:
+        raise ValueError('w must be positive.')
+    if float(wt.min()) < 0:
+        raise ValueError('wt must be non-negative.')
+    if cat not in (0, 1, 2):
+        raise ValueError('Invalid cat value.')
+    nc = dc.shape[0]
+    if nc > 12:
+        raise NotImplementedError('normvar is accelerated for up to 12 covariates.')
+    to_host = not _is_dev(dt)
+    ctx = engine.context(device if device is not None else (dt.device if _is_dev(dt) else None))
+    dev = ctx.device
+    with torch.cuda.device(dev):
+        dc_d = _dev64(dc, dev).contiguous()
+        w_d = _dev64(w, dev).contiguous()
+        wt_d = _dev64(wt, dev).contiguous()
+        logw = torch.log(w_d)
+        # covariates: continuous rows (and, for cat = 1, the intercept) are scaled by w   norm.py:257-269
+        if cat == 2:
+            sel = torch.ones(nc, dtype=torch.bool, device=dev)
+        else:
+            sel = ((dc_d != 0) & (dc_d != 1)).any(dim=1)
+            if cat == 1:
+                sel = sel | (dc_d == 1).all(dim=1)
+        dcn = torch.where(sel[:, None], dc_d * w_d, dc_d)
+        # expression, in row blocks (genes are independent)
+        if to_host:
+            src = dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt))
+            dtn = torch.empty((nt, ns), dtype=torch.float64)
+            step = max(1, _ROW_CHUNK_BYTES // (8 * ns))
+        else:
+            src = dt.to(torch.float64)
+            if src.stride(1) != 1:
+                src = src.contiguous()
+            dtn = torch.empty((nt, ns), dtype=torch.float64, device=dev)
+            step = nt
+        if normmean:                                                         # norm.py:271-273 (normvar1 on dcn)
+            gi, r = inv_rank(engine.cov_gram(ctx, dcn.contiguous()).cpu().numpy())
+            if r <= 0:
+                raise RuntimeError('Zero-rank covariates found.')
+            gi_d = torch.from_numpy(gi).to(dev)
+        for g0 in range(0, nt, step):
+            g1 = min(nt, g0 + step)
+            blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
+            res = _normvar_rows(ctx, blk, dc_d, logw, wt_d[g0:g1].contiguous(), keepvar)
+            if normmean:
+                cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
+                res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
+            dtn[g0:g1] = res if not to_host else res.cpu()
+        if not bool(torch.isfinite(dtn).all()) or not bool(torch.isfinite(dcn).all()):
+            raise AssertionError('non-finite values in the normalised matrices')   # norm.py:277
+        ans = [dtn, dcn]
+        if dextra is not None:
+            ans.append(_dev64(dextra, dev) * w_d)
+        if to_host:
+            ans = [a.cpu().numpy() if a.is_cuda else a.numpy() for a in ans]
+    return ans

@@ -1,11 +1,12 @@
 """Drop-in namespace for the hot path: ``import normalisr_b200.normalisr as norm`` then
 ``norm.coex(dt, dc)`` / ``norm.de(dg, dt, dc)`` exactly as with
 ``import normalisr.normalisr as norm`` (reference src/normalisr/normalisr.py:3-9).
-Only the association-testing entry points and their immediate consumer ``binnet`` are provided
-here; the upstream steps (``lcpm``, ``normcov``, ``normvar`` ...) stay with the reference package
+The association-testing entry points, their immediate consumer ``binnet`` and the step directly
+upstream, ``normvar``, are provided here; the other steps (``lcpm``, ``normcov``, ``compute_var`` ...) stay with the reference package
 and their output feeds these functions unchanged."""
 from .binnet import binnet
 from .coex import coex
 from .de import de
+from .norm import normvar
 
-__all__ = ["coex", "de", "binnet"]
+__all__ = ["coex", "de", "binnet", "normvar"]

@@ -422,3 +422,69 @@ def binnet(net, qcut):
     if ans.sum() == 0:
         raise RuntimeError("Empty binary network.")
     return ans
+
+
+# --------------------------------------------------------------------------------------
+# variance normalisation, the step directly upstream of coex / de
+# (reference src/normalisr/norm.py:131-289)
+# --------------------------------------------------------------------------------------
+def normvar1(dt, dc, w2=None):
+    """norm.py:131-166: remove covariates from every row of dt; with w2 (n_gene, n_cell) each
+    gene uses its own covariates dc * w2[gene]."""
+    if w2 is not None:
+        return np.concatenate([normvar1(dt[[x]], dc * w2[x]) for x in range(dt.shape[0])], axis=0)
+    g = dc @ dc.T                                                   # :159
+    gi, r = pinv_rank(g)
+    if r <= 0:
+        raise RuntimeError('Zero-rank covariates found.')
+    out = dt - (dc.T @ (gi @ (dc @ dt.T))).T                        # :163
+    assert np.isfinite(out).all()
+    return out
+
+
+def normvar(dt, dc, w, wt, dextra=None, cat=1, keepvar=True, normmean=False, **ignored):
+    """norm.py:169-289: dt * w**wt[gene], covariates dc * w**wt[gene] removed per gene, variance
+    restored (keepvar), continuous covariates scaled by w."""
+    if any(x.ndim != 2 for x in (dt, dc)):
+        raise ValueError('dt and dc should have 2 dimensions.')
+    if any(x.ndim != 1 for x in (w, wt)):
+        raise ValueError('w and wt should have 1 dimension.')
+    nt, ns = dt.shape
+    if dc.shape[0] == 0:
+        raise ValueError('No covariates.')
+    if dc.shape[1] != ns or w.shape[0] != ns or wt.shape[0] != nt:
+        raise ValueError('Unmatched gene or cell counts.')
+    if dextra is not None and (dextra.ndim != 2 or dextra.shape[0] == 0 or dextra.shape[1] != ns):
+        raise ValueError('Unmatched shape or size for dextra.')
+    if w.min() <= 0:
+        raise ValueError('w must be positive.')
+    if wt.min() < 0:
+        raise ValueError('wt must be non-negative.')
+    w2 = (np.repeat([w], nt, axis=0).T ** wt).T                     # :238
+    w2[wt == 0] = 1
+    dt = dt * w2
+    if keepvar:                                                     # :241-243
+        dv = dt.mean(axis=1)
+        dv = np.sqrt(((dt.T - dv) ** 2).mean(axis=0))
+    dtn = normvar1(dt, dc, w2)                                      # :245-249
+    if keepvar:                                                     # :251-254
+        dv2 = np.sqrt((dtn ** 2).mean(axis=1))
+        dtn = (dtn.T * ((dv / dv2) ** wt)).T
+    if cat == 2:                                                    # :257-269
+        dcn = dc * w
+    elif cat == 1:
+        dcn = dc.copy()
+        t0 = ((dc != 0) & (dc != 1)).any(axis=1) | ((dc == 1).all(axis=1))
+        dcn[t0] = dc[t0] * w
+    elif cat == 0:
+        dcn = dc.copy()
+        t0 = ((dc != 0) & (dc != 1)).any(axis=1)
+        dcn[t0] = dc[t0] * w
+    else:
+        raise ValueError('Invalid cat value.')
+    if normmean:                                                    # :271-273
+        dtn = normvar1(dtn, dcn)
+    ans = [dtn, dcn]
+    if dextra is not None:
+        ans.append(dextra * w)
+    return ans

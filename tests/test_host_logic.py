@@ -197,3 +197,21 @@ def test_single1_sufficient_statistics_equal_reference(case):
         np.testing.assert_allclose(vy, g["vart"][row], rtol=1e-11)
         if "alpha" in g:
             np.testing.assert_allclose(ccy - gam[:, None] * ccx[None, :], g["alpha"][row], atol=1e-11)
+
+
+def test_single1_batched_pinv_matches_inv_rank():
+    from normalisr_b200 import single1
+    rng = np.random.default_rng(12)
+    mats = []
+    for k in range(20):
+        a = rng.normal(size=(6, 40))
+        if k % 3 == 0:
+            a[2] = a[0] - 2 * a[5]                     # rank 5
+        if k % 7 == 0:
+            a[4] = 0                                   # a zero covariate
+        mats.append(a @ a.T)
+    inv, rank = single1._pinv_rank_batched(np.array(mats))
+    for m, i, r in zip(mats, inv, rank):
+        want, r0 = association.inv_rank(m)
+        assert r == r0
+        np.testing.assert_allclose(i, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())

@@ -1,0 +1,112 @@
+"""normvar (reference src/normalisr/norm.py:131-289).  CPU: the oracle against the
+golden vectors made by the unmodified reference.  GPU: the CUDA path against both."""
+import numpy as np
+import pytest
+import torch
+
+import normalisr_oracle as orc
+from conftest import load_golden
+
+gpu = pytest.mark.gpu
+
+
+def _args(g):
+    ka = {}
+    if "dextra" in g:
+        ka = dict(dextra=g["dextra"], cat=int(g["cat"]), keepvar=False, normmean=True)
+    return (g["dt"], g["dc"], g["w"], g["wt"]), ka
+
+
+@pytest.mark.parametrize("case", ["normvar_chain", "normvar_cat0", "normvar_cat2"])
+def test_oracle_normvar_matches_reference(case):
+    g = load_golden(case)
+    a, ka = _args(g)
+    out = orc.normvar(*a, **ka)
+    np.testing.assert_allclose(out[0], g["dtn"], rtol=1e-9, atol=1e-10)
+    np.testing.assert_array_equal(out[1], g["dcn"])
+    if "dextran" in g:
+        np.testing.assert_array_equal(out[2], g["dextran"])
+    with pytest.raises(ValueError):
+        orc.normvar(g["dt"], g["dc"][:0], g["w"], g["wt"])
+    with pytest.raises(ValueError):
+        orc.normvar(g["dt"], g["dc"], -g["w"], g["wt"])
+
+
+@gpu
+@pytest.mark.parametrize("case", ["normvar_chain", "normvar_cat0", "normvar_cat2"])
+def test_normvar_golden(case):
+    from normalisr_b200 import normalisr as norm
+    g = load_golden(case)
+    a, ka = _args(g)
+    out = norm.normvar(*a, **ka)
+    assert all(isinstance(x, np.ndarray) and x.dtype == np.float64 for x in out)
+    np.testing.assert_allclose(out[0], g["dtn"], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(out[1], g["dcn"], rtol=1e-15)
+    if "dextran" in g:
+        np.testing.assert_allclose(out[2], g["dextran"], rtol=1e-15)
+    dev = norm.normvar(*[torch.from_numpy(x).cuda() for x in a],
+                       **{k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v) for k, v in ka.items()})
+    assert all(x.is_cuda for x in dev)
+    np.testing.assert_allclose(dev[0].cpu().numpy(), g["dtn"], rtol=1e-9, atol=1e-9)
+
+
+@gpu
+def test_normvar_against_oracle_shapes_and_chunks(monkeypatch):
+    from normalisr_b200 import norm as nv
+    rng = np.random.default_rng(41)
+    for genes, n, nc in ((37, 300, 1), (500, 3000, 9), (260, 1001, 12), (64, 128, 5)):
+        dc = np.concatenate([rng.normal(size=(nc - 1, n)), np.ones((1, n))]) if nc > 1 else np.ones((1, n))
+        if nc >= 5:
+            dc[1] = rng.random(n) < 0.3                       # a categorical covariate (cat = 1 leaves it alone)
+            dc[2] = 2 * dc[0] - dc[-1]                         # rank-deficient covariates
+        dt = rng.normal(size=(genes, n)) * rng.uniform(0.2, 3, size=(genes, 1)) - 6.0
+        w = np.exp(rng.normal(size=n) * 0.3)
+        wt = rng.uniform(0, 1.5, size=genes)
+        wt[::7] = 0
+        for ka in ({}, {"keepvar": False, "cat": 0}, {"normmean": True, "cat": 2, "dextra": rng.normal(size=(3, n))}):
+            want = orc.normvar(dt, dc, w, wt, **ka)
+            monkeypatch.setattr(nv, "_ROW_CHUNK_BYTES", 8 * n * 100)            # several row blocks
+            got = nv.normvar(dt, dc, w, wt, **ka)
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max()))
+
+
+@gpu
+def test_normvar_errors():
+    from normalisr_b200 import normalisr as norm
+    dt, dc, w, wt = np.zeros((4, 10)), np.ones((2, 10)), np.ones(10), np.ones(4)
+    for bad in ((dt, dc[:0], w, wt), (dt, dc[:, :9], w, wt), (dt, dc, w[:9], wt), (dt, dc, w, wt[:3]),
+                (dt, dc, -w, wt), (dt, dc, w, -wt), (dt[0], dc, w, wt)):
+        with pytest.raises(ValueError):
+            norm.normvar(*bad)
+    with pytest.raises(ValueError):
+        norm.normvar(dt, dc, w, wt, cat=3)
+    with pytest.raises(RuntimeError):
+        norm.normvar(dt + 1, np.zeros((2, 10)), w, wt)        # zero-rank covariates (norm.py:161)
+    with pytest.raises(NotImplementedError):
+        norm.normvar(np.zeros((4, 40)), np.ones((13, 40)), np.ones(40), wt)
+
+
+@gpu
+def test_sym_pinv_matches_inv_rank():
+    """nsr_sym_pinv (batched Jacobi) against the host inv_rank, rank-deficient cases included."""
+    from normalisr_b200 import association, engine
+    rng = np.random.default_rng(6)
+    ctx = engine.context(0)
+    for n in (1, 2, 5, 9, 12, 16):
+        mats = []
+        for k in range(40):
+            a = rng.normal(size=(n, 3 * n + 2)) * rng.uniform(0.01, 100, size=(n, 1))
+            if n > 2 and k % 3 == 0:
+                a[1] = a[0] - 2 * a[n - 1]
+            if n > 3 and k % 5 == 0:
+                a[2] = 0
+            mats.append(a @ a.T)
+        G = torch.from_numpy(np.array(mats)).cuda()
+        inv, rank = engine.sym_pinv(ctx, G)
+        inv, rank = inv.cpu().numpy(), rank.cpu().numpy()
+        for m, i, r in zip(mats, inv, rank):
+            want, r0 = association.inv_rank(m)
+            assert r == r0
+            np.testing.assert_allclose(i, want, rtol=0, atol=1e-9 * np.abs(want).max())
