@@ -11,14 +11,14 @@
 // iterate never drops below k*, and a fixed point c = g(c) is itself an index set that passes.
 // The kernel evaluates the SAME floating-point expression as the reference, p / (c / n0) <= qcut
 // (binnet.py:122-124 computes w = cumsum / n0 and p / w), so the boolean output is bit-identical.
-// One CTA per row: the row is read from HBM once into shared memory (rows up to 28,000 entries;
-// wider rows re-read themselves from L2) and the iteration and the final threshold run from there.
+// One CTA per row: the row is read from HBM once into shared memory (rows up to 25,000 entries;
+// wider rows re-read themselves from L2).
 #include "nsr_common.cuh"
 
 namespace {
 
 constexpr int kThreads = 1024;
-constexpr int kSmemRowMax = 28000;     // doubles of a row kept in shared memory (224 KB of the 227 KB)
+constexpr int kSmemRowMax = 25000;     // doubles of a row kept in shared memory (200 KB; + 21 KB of tables)
 
 __device__ __forceinline__ int block_sum(int v, int* s_red) {
 #pragma unroll
@@ -61,68 +61,260 @@ __device__ __forceinline__ int count_le(const double* s_row, int64_t cols, doubl
     return mine;
 }
 
-// SMEM = true: the row is staged once in shared memory (one bulk asynchronous copy when the row is
-// 16-byte aligned, plain loads otherwise) and every later pass reads it from there; false: rows
-// wider than shared memory re-read themselves from L2.
-template <bool SMEM>
+// ---------------------------------------------------------------------------------------------
+// Rows that fit in shared memory: the fixed point is bracketed with a histogram, then finished
+// exactly on the handful of entries inside the bracket - 4 passes over the row however slowly the
+// plain iteration would converge (dense networks need dozens of iterations).
+//   * non-negative doubles order like their bit patterns; key(p) = bits(p) >> (52 - m) is a
+//     monotone bin index (relative width 2^-m).  Only thresholds between t(1) and qcut can occur,
+//     so bins cover [key(t(1)), key(qcut)]: entries below are always counted, entries above never;
+//   * cum[b] = #{p : bin(p) < b}.  With b = bin(t(c)):  cum[b] <= g(c) <= cum[b + 1].  Iterating
+//     c <- cum[bin(t(c)) + 1] from the top ends at c_hi >= k*, iterating c <- cum[bin(t(c))] from
+//     c_hi ends at c_lo <= k* (every fixed point of a minorant of g lies below k*);
+//   * for c in [c_lo, c_hi] only entries in bins bin(t(c_lo)) .. bin(t(c_hi)) are undecided; they
+//     are gathered (a few) and the exact iteration c <- base + #{window <= t(c)} runs on them.
+constexpr int kBins = 4096;
+constexpr int kWindow = 512;
+
+struct RowShared {
+    int hist[kBins + 1];
+    double window[kWindow];
+    int red[kThreads / 32];
+    int n_window, c_final, fallback, b_lo, b_hi, base_w, c_hi;
+    double thr;
+    unsigned long long bar;
+};
+
+__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+
 __global__ void __launch_bounds__(kThreads)
-binnet_rows_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64_t diag0, double qcut,
-                   uint8_t* __restrict__ net, int64_t ld_net, unsigned long long* __restrict__ stats) {
+binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64_t diag0, double qcut,
+                        uint8_t* __restrict__ net, int64_t ld_net, unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) double s_row[];
-    __shared__ int s_red[kThreads / 32];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ RowShared sh;
     const int64_t row = blockIdx.x;
     const double* p_row = P + row * ld;
-    const int64_t diag = row + diag0;                  // column of this row's diagonal entry
+    const int64_t diag = row + diag0;
     const bool has_diag = diag >= 0 && diag < cols;
     const int64_t n0 = cols - (has_diag ? 1 : 0);
-    int bad = 0, mine = 0;
+    const double n0d = (double)n0;
+    if (n0 <= 0) {                                       // a 1 x 1 block holding only its diagonal entry
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) net[row * ld_net + j] = 0;
+        return;
+    }
 
-    if (SMEM) {
-        const bool bulk = (((uintptr_t)p_row & 15) == 0) && ((cols & 1) == 0);
-        if (bulk) {
-            // one thread posts the whole row (cols * 8 bytes) as a single bulk copy; all wait on the mbarrier
-            const uint32_t bar = bn_smem_u32(&s_bar);
-            if (threadIdx.x == 0) {
-                asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const uint32_t bytes = (uint32_t)(cols * sizeof(double));
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(bn_smem_u32(s_row)), "l"(p_row), "r"(bytes), "r"(bar) : "memory");
-            }
-            uint32_t ok = 0;
-            const long long t0 = clock64();
-            while (!ok) {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
-                if (!ok && clock64() - t0 > 4000000000ll) __trap();      // never hang the device
-            }
-        } else {
-#pragma unroll 8
-            for (int64_t j = threadIdx.x; j < cols; j += kThreads) s_row[j] = p_row[j];
-            __syncthreads();
-        }
-        // validate (binnet.py:152-153, the diagonal included), then make the diagonal entry inert
-#pragma unroll 4
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
-            const double p = s_row[j];
-            if (!(p >= 0.0 && p <= 1.0)) bad = 1;      // also catches NaN
+    // ---- stage the row
+    const bool bulk = (((uintptr_t)p_row & 15) == 0) && ((cols & 1) == 0);
+    if (bulk) {
+        const uint32_t bar = bn_smem_u32(&sh.bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
-        if (has_diag && threadIdx.x == 0) s_row[diag] = 2.0;
-        __syncthreads();
-        mine = count_le(s_row, cols, qcut);            // only p <= qcut can pass at all (c / n0 <= 1)
+        if (threadIdx.x == 0) {
+            const uint32_t bytes = (uint32_t)(cols * sizeof(double));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(bn_smem_u32(s_row)), "l"(p_row), "r"(bytes), "r"(bar) : "memory");
+        }
+        for (int b = threadIdx.x; b <= kBins; b += kThreads) sh.hist[b] = 0;     // overlaps the copy
+        uint32_t ok = 0;
+        const long long t0 = clock64();
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(0u) : "memory");
+            if (!ok && clock64() - t0 > 4000000000ll) __trap();      // never hang the device
+        }
     } else {
 #pragma unroll 8
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
-            const double p = p_row[j];
-            if (!(p >= 0.0 && p <= 1.0)) bad = 1;
-            mine += (j != diag && p <= qcut) ? 1 : 0;
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) s_row[j] = p_row[j];
+        for (int b = threadIdx.x; b <= kBins; b += kThreads) sh.hist[b] = 0;
+    }
+    if (threadIdx.x == 0) { sh.n_window = 0; sh.fallback = 0; }
+    __syncthreads();
+
+    // ---- bins: keys between t(1) and qcut; m mantissa bits so that they fit
+    // t_dn(c) <= t(c) <= t_up(c): fl(qcut * c / n0) moved a few ulp either way.  The bracketing only
+    // needs bounds (a multiply instead of the divisions and nextafter steps of the exact threshold,
+    // whose latency - not the passes over the row - dominated the first version of this kernel).
+    const double kUp = 1.0 + 0x1p-48, kDn = 1.0 - 0x1p-48;
+    const double t1 = (qcut / n0d) * kDn;
+    int shift = 52 - 8;
+    while ((long long)(dbits(qcut) >> shift) - (long long)(dbits(t1) >> shift) + 1 > kBins - 1) ++shift;
+    const long long lo_key = (long long)(dbits(t1) >> shift);
+    const int n_bins = (int)((long long)(dbits(qcut) >> shift) - lo_key) + 1;
+    const unsigned long long q_bits = dbits(qcut);
+
+    // ---- pass 1: validate (binnet.py:152-153, diagonal included), histogram of the candidates
+    int bad = 0, below = 0;
+#pragma unroll 4
+    for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
+        double p = s_row[j];
+        if (!(p >= 0.0 && p <= 1.0)) bad = 1;            // also catches NaN
+        if (j == diag) p = 2.0;                          // inert: never a candidate
+        if (p == 0.0) p = 0.0;                           // -0.0 -> +0.0 so that bit patterns order like values
+        s_row[j] = p;
+        const unsigned long long u = dbits(p);
+        if (u <= q_bits) {
+            const long long key = (long long)(u >> shift) - lo_key;
+            if (key < 0) ++below;
+            else atomicAdd(&sh.hist[key < n_bins ? (int)key : n_bins - 1], 1);
         }
+    }
+    if (bad) atomicAdd(&stats[1], 1ull);
+    below = block_sum(below, sh.red);                    // (syncs: histogram complete)
+
+    // ---- exclusive prefix over the bins (4 per thread), cum[b] = below + sum_{b' < b} hist[b']
+    {
+        const int b0 = 4 * threadIdx.x;
+        int h[4], tot = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h[i] = (b0 + i < n_bins) ? sh.hist[b0 + i] : 0; tot += h[i]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += v;
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 31) sh.red[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        int warp_off = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) warp_off += sh.red[w];
+        int run = below + warp_off + incl - tot;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (b0 + i <= n_bins) sh.hist[b0 + i] = run;   // entry n_bins = all candidates
+            run += h[i];
+        }
+        __syncthreads();
+    }
+
+    // ---- bracket the fixed point (one thread; a multiply and two table reads per step)
+    if (threadIdx.x == 0) {
+        auto bin_of = [&](double t) {
+            long long k = (long long)(dbits(t) >> shift) - lo_key;
+            return (int)(k < 0 ? 0 : (k >= n_bins ? n_bins - 1 : k));
+        };
+        const double qn = qcut / n0d;
+        int c = sh.hist[n_bins];
+        while (c > 0) {                                   // majorant of g: ends at c_hi >= k*
+            const int c2 = sh.hist[bin_of(fmin((double)c * qn * kUp, qcut)) + 1];
+            if (c2 == c) break;
+            c = c2;
+        }
+        const int c_hi = c;
+        while (c > 0) {                                   // minorant of g: ends at c_lo <= k*
+            const int c2 = sh.hist[bin_of((double)c * qn * kDn)];
+            if (c2 == c) break;
+            c = c2;
+        }
+        sh.c_hi = c_hi;
+        if (c_hi > 0) {
+            sh.b_lo = bin_of((double)(c > 1 ? c : 1) * qn * kDn);
+            sh.b_hi = bin_of(fmin((double)c_hi * qn * kUp, qcut));
+            sh.base_w = sh.hist[sh.b_lo];
+        }
+    }
+    __syncthreads();
+    int c = sh.c_hi;
+    double thr = -1.0;
+    if (c > 0) {
+        // ---- gather the undecided entries
+        const int b_lo = sh.b_lo, b_hi = sh.b_hi;
+#pragma unroll 4
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
+            const unsigned long long u = dbits(s_row[j]);
+            if (u <= q_bits) {
+                long long key = (long long)(u >> shift) - lo_key;
+                if (key >= n_bins) key = n_bins - 1;
+                if (key >= b_lo && key <= b_hi) {
+                    const int slot = atomicAdd(&sh.n_window, 1);
+                    if (slot < kWindow) sh.window[slot] = s_row[j]; else sh.fallback = 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (!sh.fallback) {
+            // ---- exact finish on the window (warp 0): the reference's own test, p / (c / n0) <= qcut
+            if (threadIdx.x < 32) {
+                const int nw = sh.n_window, base_w = sh.base_w;
+                while (c > 0) {
+                    const double w = (double)c / n0d;
+                    int mine = 0;
+                    for (int k = threadIdx.x; k < nw; k += 32) mine += sh.window[k] / w <= qcut ? 1 : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+                    const int c2 = base_w + mine;
+                    if (c2 == c) break;
+                    c = c2;
+                }
+                if (threadIdx.x == 0) { sh.c_final = c; sh.thr = c > 0 ? bh_threshold((double)c / n0d, qcut) : -1.0; }
+            }
+            __syncthreads();
+            c = sh.c_final;
+            thr = sh.thr;
+        } else {
+            // window too large (a row packed with near-ties around the BH line): plain exact iteration
+            // over the whole row from c_hi
+            while (c > 0) {
+                const double w = (double)c / n0d;
+                int mine = 0;
+#pragma unroll 4
+                for (int64_t j = threadIdx.x; j < cols; j += kThreads) mine += s_row[j] / w <= qcut ? 1 : 0;
+                const int c2 = block_sum(mine, sh.red);
+                if (c2 == c) break;
+                c = c2;
+            }
+            thr = c > 0 ? bh_threshold((double)c / n0d, qcut) : -1.0;
+        }
+    }
+    // ---- output
+    uint8_t* o_row = net + row * ld_net;
+    const unsigned long long t_bits = thr >= 0.0 ? dbits(thr) : 0ull;
+    const bool none = !(thr >= 0.0);
+    int64_t done = 0;
+    if (((uintptr_t)o_row & 7) == 0) {                   // 8 entries -> one 8-byte store
+        const ulonglong2* v = reinterpret_cast<const ulonglong2*>(s_row);
+        const int64_t oct = cols >> 3;
+        for (int64_t j = threadIdx.x; j < oct; j += kThreads) {
+            uint64_t out_bits = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const ulonglong2 p = v[4 * j + q];
+                out_bits |= (uint64_t)((!none && p.x <= t_bits) ? 1 : 0) << (16 * q);
+                out_bits |= (uint64_t)((!none && p.y <= t_bits) ? 1 : 0) << (16 * q + 8);
+            }
+            reinterpret_cast<uint64_t*>(o_row)[j] = out_bits;
+        }
+        done = oct << 3;
+    }
+    for (int64_t j = done + threadIdx.x; j < cols; j += kThreads) o_row[j] = (!none && dbits(s_row[j]) <= t_bits) ? 1 : 0;
+    if (c > 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)c);
+}
+
+// Rows wider than shared memory: plain iteration, the row re-read from L2 every step.
+__global__ void __launch_bounds__(kThreads)
+binnet_rows_wide_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64_t diag0, double qcut,
+                        uint8_t* __restrict__ net, int64_t ld_net, unsigned long long* __restrict__ stats) {
+    __shared__ int s_red[kThreads / 32];
+    const int64_t row = blockIdx.x;
+    const double* p_row = P + row * ld;
+    const int64_t diag = row + diag0;
+    const bool has_diag = diag >= 0 && diag < cols;
+    const int64_t n0 = cols - (has_diag ? 1 : 0);
+    if (n0 <= 0) {
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) net[row * ld_net + j] = 0;
+        return;
+    }
+    int bad = 0, mine = 0;
+#pragma unroll 8
+    for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
+        const double p = p_row[j];
+        if (!(p >= 0.0 && p <= 1.0)) bad = 1;
+        mine += (j != diag && p <= qcut) ? 1 : 0;
     }
     if (bad) atomicAdd(&stats[1], 1ull);
     int c = block_sum(mine, s_red);                    // g(n0): w = 1
@@ -130,42 +322,17 @@ binnet_rows_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64
     double thr = qcut;
     while (c > 0) {
         thr = bh_threshold((double)c / n0d, qcut);
-        if (SMEM) {
-            mine = count_le(s_row, cols, thr);
-        } else {
-            mine = 0;
+        mine = 0;
 #pragma unroll 8
-            for (int64_t j = threadIdx.x; j < cols; j += kThreads) mine += (j != diag && p_row[j] <= thr) ? 1 : 0;
-        }
+        for (int64_t j = threadIdx.x; j < cols; j += kThreads) mine += (j != diag && p_row[j] <= thr) ? 1 : 0;
         const int c_new = block_sum(mine, s_red);
         if (c_new == c) break;
         c = c_new;
     }
-    // pass 2: threshold with the final rank
     uint8_t* o_row = net + row * ld_net;
     if (c == 0) thr = -1.0;
-    if (SMEM) {
-        int64_t done = 0;
-        if (((uintptr_t)o_row & 7) == 0) {             // 8 entries -> one 8-byte store
-            const double2* v = reinterpret_cast<const double2*>(s_row);
-            const int64_t oct = cols >> 3;
-            for (int64_t j = threadIdx.x; j < oct; j += kThreads) {
-                uint64_t bits = 0;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double2 p = v[4 * j + q];
-                    bits |= (uint64_t)(p.x <= thr ? 1 : 0) << (16 * q);
-                    bits |= (uint64_t)(p.y <= thr ? 1 : 0) << (16 * q + 8);
-                }
-                reinterpret_cast<uint64_t*>(o_row)[j] = bits;
-            }
-            done = oct << 3;
-        }
-        for (int64_t j = done + threadIdx.x; j < cols; j += kThreads) o_row[j] = (s_row[j] <= thr) ? 1 : 0;
-    } else {
 #pragma unroll 8
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads) o_row[j] = (j != diag && p_row[j] <= thr) ? 1 : 0;
-    }
+    for (int64_t j = threadIdx.x; j < cols; j += kThreads) o_row[j] = (j != diag && p_row[j] <= thr) ? 1 : 0;
     if (c > 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)c);
 }
 
@@ -179,14 +346,14 @@ extern "C" int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64
     NSR_REQUIRE(qcut > 0.0 && qcut < 1.0, "nsr_binnet: qcut must be in (0, 1)");
     NSR_CHECK(cudaSetDevice(ctx->device));
     if (cols <= kSmemRowMax) {
-        const int smem = (int)(cols * sizeof(double));
-        NSR_CHECK(cudaFuncSetAttribute(binnet_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        const int smem = (int)(((cols + 1) & ~(int64_t)1) * sizeof(double));
+        NSR_CHECK(cudaFuncSetAttribute(binnet_rows_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kSmemRowMax * (int)sizeof(double)));
-        binnet_rows_kernel<true><<<(unsigned)rows, kThreads, smem, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
-                                                                                            ld_net, stats);
-    } else {
-        binnet_rows_kernel<false><<<(unsigned)rows, kThreads, 0, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
+        binnet_rows_smem_kernel<<<(unsigned)rows, kThreads, smem, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
                                                                                           ld_net, stats);
+    } else {
+        binnet_rows_wide_kernel<<<(unsigned)rows, kThreads, 0, (cudaStream_t)stream>>>(P, cols, ld, diag0, qcut, net,
+                                                                                       ld_net, stats);
     }
     NSR_CHECK(cudaGetLastError());
     return 0;

@@ -17,7 +17,8 @@ namespace {
 
 constexpr int kNvThreads = 256;
 constexpr int kNvWarps = kNvThreads / 32;
-constexpr int kNvChunk = 256;          // cells staged per step
+constexpr int kNvChunk = 384;          // cells staged per step (12 x 384 doubles + log w < 48 KB static)
+constexpr int kNvAhead = 4;            // cells per lane whose loads are issued before any arithmetic
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -54,21 +55,34 @@ normvar_stats_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
         for (int k = threadIdx.x; k < kNvChunk; k += kNvThreads) s_lw[k] = k < len ? logw[k0 + k] : 0.0;
         __syncthreads();
         if (live) {
-#pragma unroll 2
-            for (int k = lane; k < len; k += 32) {
-                const double s = wtx == 0.0 ? 1.0 : exp(wtx * s_lw[k]);        // norm.py:238-239
-                const double v = row[k0 + k] * s;
-                s1 += v;
-                s2 = fma(v, v, s2);
-                double a[NC];
+            for (int kq = lane; kq < len; kq += 32 * kNvAhead) {
+                // issue the loads of kNvAhead cells first: 8 resident warps per SM cannot hide HBM latency otherwise
+                double x[kNvAhead], lw[kNvAhead];
 #pragma unroll
-                for (int j = 0; j < NC; ++j) a[j] = s_c[j][k] * s;
-                int t = 0;
+                for (int u = 0; u < kNvAhead; ++u) {
+                    const int k = kq + 32 * u;
+                    x[u] = k < len ? row[k0 + k] : 0.0;
+                    lw[u] = s_lw[k < kNvChunk ? k : 0];
+                }
 #pragma unroll
-                for (int i = 0; i < NC; ++i) {
-                    b[i] = fma(a[i], v, b[i]);
+                for (int u = 0; u < kNvAhead; ++u) {
+                    const int k = kq + 32 * u;
+                    if (k < len) {
+                        const double s = wtx == 0.0 ? 1.0 : exp(wtx * lw[u]);  // norm.py:238-239
+                        const double v = x[u] * s;
+                        s1 += v;
+                        s2 = fma(v, v, s2);
+                        double a[NC];
 #pragma unroll
-                    for (int j = i; j < NC; ++j) { g[t] = fma(a[i], a[j], g[t]); ++t; }
+                        for (int j = 0; j < NC; ++j) a[j] = s_c[j][k] * s;
+                        int t = 0;
+#pragma unroll
+                        for (int i = 0; i < NC; ++i) {
+                            b[i] = fma(a[i], v, b[i]);
+#pragma unroll
+                            for (int j = i; j < NC; ++j) { g[t] = fma(a[i], a[j], g[t]); ++t; }
+                        }
+                    }
                 }
             }
         }
@@ -122,13 +136,24 @@ normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
         for (int k = threadIdx.x; k < kNvChunk; k += kNvThreads) s_lw[k] = k < len ? logw[k0 + k] : 0.0;
         __syncthreads();
         if (live) {
-#pragma unroll 4
-            for (int k = lane; k < len; k += 32) {
-                const double s = wtx == 0.0 ? 1.0 : exp(wtx * s_lw[k]);
-                double r = row[k0 + k];
+            for (int kq = lane; kq < len; kq += 32 * kNvAhead) {
+                double x[kNvAhead];
 #pragma unroll
-                for (int j = 0; j < NC; ++j) r = fma(-c[j], s_c[j][k], r);
-                orow[k0 + k] = sc * (s * r);
+                for (int u = 0; u < kNvAhead; ++u) {
+                    const int k = kq + 32 * u;
+                    x[u] = k < len ? row[k0 + k] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kNvAhead; ++u) {
+                    const int k = kq + 32 * u;
+                    if (k < len) {
+                        const double s = wtx == 0.0 ? 1.0 : exp(wtx * s_lw[k]);
+                        double r = x[u];
+#pragma unroll
+                        for (int j = 0; j < NC; ++j) r = fma(-c[j], s_c[j][k], r);
+                        orow[k0 + k] = sc * (s * r);
+                    }
+                }
             }
         }
     }

@@ -119,12 +119,12 @@ def test_binnet_large_against_oracle_and_row_chunks(monkeypatch):
 
 @gpu
 def test_binnet_rows_wider_than_shared_memory():
-    """Rows of more than 28,000 entries take the kernel variant that re-reads the row from L2;
+    """Rows of more than 25,000 entries take the kernel variant that re-reads the row from L2;
     also rows of a row block whose diagonal sits at an offset, or outside the block."""
     from normalisr_b200 import binnet as bn, engine
     rng = np.random.default_rng(9)
     ctx = engine.context(0)
-    for cols, diag0 in ((30011, 0), (30011, 29990), (30011, -5), (5000, 4990), (4999, 3), (27999, 100)):
+    for cols, diag0 in ((30011, 0), (30011, 29990), (30011, -5), (5000, 4990), (4999, 3), (24999, 100), (25000, 7)):
         Pm = rng.random((24, cols)) ** rng.integers(1, 8, size=(24, 1))
         out, stats = bn.binnet_rows(ctx, torch.from_numpy(Pm).cuda(), 0.1, diag0)
         got = out.cpu().numpy().astype(bool)
@@ -139,6 +139,31 @@ def test_binnet_rows_wider_than_shared_memory():
             assert np.array_equal(got[i, keep], want)
             edges += int(want.sum())
         assert int(stats[0]) == edges and int(stats[1]) == 0
+
+
+@gpu
+def test_binnet_slowly_converging_and_tied_rows():
+    """Rows on which the plain fixed-point iteration needs many steps (a staircase just under the BH
+    line), rows packed with ties (window overflow -> fallback path), negative zero, all-equal rows."""
+    from normalisr_b200 import binnet as bn, engine
+    rng = np.random.default_rng(10)
+    ctx = engine.context(0)
+    cols = 6000
+    rows = []
+    k = np.arange(1, cols + 1)
+    rows.append(0.1 * k / cols * (1 - 1e-9 * rng.random(cols)))                  # every rank passes barely
+    rows.append(0.1 * k / cols * (1 + 1e-3 * rng.random(cols)))                  # every rank fails barely
+    rows.append(np.where(rng.random(cols) < 0.5, 0.0123456, rng.random(cols)))   # 3000 ties inside the window
+    rows.append(np.full(cols, 0.04))
+    rows.append(np.where(rng.random(cols) < 0.3, -0.0, rng.random(cols) ** 4))
+    rows.append(np.exp(-rng.exponential(size=cols) * 40))
+    rows.append(np.sort(rng.random(cols)) ** 2 * 0.2)
+    Pm = np.array([rng.permutation(r) for r in rows])
+    for q in (0.1, 0.05, 1e-3):
+        out, stats = bn.binnet_rows(ctx, torch.from_numpy(Pm).cuda(), q, -cols - 10)   # no diagonal inside any row
+        got = out.cpu().numpy().astype(bool)
+        for i in range(len(rows)):
+            assert np.array_equal(got[i], orc.bh(Pm[i]) <= q), (i, q)
 
 
 @gpu
