@@ -22,7 +22,6 @@ extern int nsr_umma_pair;
 extern int nsr_epi_warps;
 extern int nsr_umma_stack;
 extern int nsr_umma_dynamic;
-extern int nsr_epi_overlap;
 extern int nsr_epi_sleep_ns;
 
 static thread_local char g_err[1024] = "";
@@ -99,7 +98,6 @@ extern "C" int nsr_set_option(const char* name, int value) {
         nsr_epi_warps = value;
         return 0;
     }
-    if (!strcmp(name, "epi_overlap")) { nsr_epi_overlap = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_sleep_ns")) { nsr_epi_sleep_ns = value < 0 ? 0 : value; return 0; }
     if (!strcmp(name, "umma_kblock")) {
         NSR_REQUIRE(value == 64 || value == 128, "umma_kblock must be 64 or 128");

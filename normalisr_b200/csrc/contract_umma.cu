@@ -36,7 +36,6 @@ struct UmmaArgs {
     int num_kb;                   // k-blocks of KB cells in this launch
     int kb_begin;                 // first k-block (cell chunking)
     int stack_b;                  // 1: N = 256 MMAs over two stacked B planes (single-CTA kernel)
-    int epi_overlap;              // 1: release TMEM before the P-value math (overlap with next tile)
     int epi_sleep_ns;             // back-off of the epilogue warps while they wait for a tile
     int* tile_counter;            // dynamic tile scheduler (single-CTA kernel): next unclaimed list index,
                                   // zeroed before the launch; nullptr = static round-robin
@@ -622,7 +621,6 @@ int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensor
 int nsr_umma_stack = 1;      // test hook: stacked-B N = 256 MMAs in the single-CTA kernel
 int nsr_epi_warps = 8;       // test hook: epilogue warps of the single-CTA kernel (8 or 16)
 int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sustained), 1 -> cta_group::2 kernel
-int nsr_epi_overlap = 1;     // test hook: release TMEM before (1) or after (0) the P-value math
 int nsr_epi_sleep_ns = 500;  // test hook: epilogue wait back-off
 int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
 int nsr_umma_dynamic = 1;    // 1: tiles claimed from a global counter, 0: static round-robin (single-CTA kernel)
@@ -644,7 +642,6 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.kb_begin = (int)(cell_begin / 128);
         g.stack_b = 0;
         g.tile_counter = nullptr;
-        g.epi_overlap = nsr_epi_overlap;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
@@ -668,7 +665,6 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.tile_counter = ctx->tile_counters + (ctx->launch_seq++ % NSR_TILE_COUNTERS);
         NSR_CHECK(cudaMemsetAsync(g.tile_counter, 0, sizeof(int), st));
     }
-    g.epi_overlap = nsr_epi_overlap;
     g.epi_sleep_ns = nsr_epi_sleep_ns;
     g.ep = ep;
     if (n_slices == 3 && wmax == 4 && kb == 128) return launch<3, 4, 128>(ctx, st, ma, mb, g);
