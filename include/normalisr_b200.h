@@ -149,18 +149,22 @@ int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, int64_t gen
 /* Variance normalisation, the step upstream of coex / de (norm.normvar / normvar1,
  * src/normalisr/norm.py:131-289): gene x is scaled per cell by s_k = w_k ** wt_x and its own
  * weighted covariates dc * s are projected out of it.  Two streaming passes over dt (genes x n):
- *   nsr_normvar_stats  stats[x] = { upper triangle (row-major, W(W+1)/2) of G = sum_k s^2 dc dc^T,
- *                      b = sum_k s^2 dc dt (W), S1 = sum_k s dt, S2 = sum_k (s dt)^2 }, with
- *                      W = nsr_normvar_width(nc) >= nc the padded covariate count (rows beyond nc
- *                      are zero); replaces the per-gene np.matmul(dc, dc.T) / np.matmul(dc, dt.T)
- *                      of normvar1 (norm.py:159-163);
+ *   nsr_normvar_stats  G_x = sum_k s^2 dc dc^T depends on the gene only through s, so with the
+ *                      gene-independent matrix M = [ products c_i c_j (i <= j, row-major), zero rows
+ *                      up to 8 T | dc, zero rows up to 16 ] ((8 T + 16) x n, built by the host
+ *                      layer, T from nsr_normvar_width) the statistics are two skinny GEMMs over
+ *                      cells on the FP64 tensor cores:  stats[x] = { [s^2] M_D^T (8 T columns: the
+ *                      upper triangle of G), [s^2 dt] M_C^T (16 columns: b = sum_k s^2 dc dt),
+ *                      S1 = sum_k s dt, S2 = sum_k (s dt)^2 };  nsr_normvar_width(nc) = 8 T + 18 is
+ *                      the length of one stats row.  Replaces the per-gene np.matmul(dc, dc.T) /
+ *                      np.matmul(dc, dt.T) of normvar1 (norm.py:159-163);
  *   nsr_normvar_apply  out = scale[x] * s * (dt - coef[x]^T dc), coef (genes x nc) = G+ b from the
  *                      host layer (pseudo-inverse with the rank rule of inv_rank), scale = the
  *                      keepvar factor (norm.py:251-254) or 1.
  * logw = log(w) per cell, wt per gene; s = exp(wt * logw), 1 when wt == 0.  1 <= nc <= 12. */
 int nsr_normvar_width(int nc);
 int nsr_normvar_stats(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
-                      int64_t ld, const double* dc, int nc, int64_t ldc, const double* logw,
+                      int64_t ld, const double* M, int nc, int64_t ldm, const double* logw,
                       const double* wt, double* stats);
 int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
                       int64_t ld, const double* dc, int nc, int64_t ldc, const double* logw,

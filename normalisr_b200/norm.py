@@ -5,7 +5,8 @@ log-CPM matrix.  Gene x is multiplied by ``w ** wt[x]`` per cell and its OWN wei
 variance of every gene is restored (``keepvar``), continuous covariates are scaled by ``w``.
 
 The reference loops over genes in Python.  Here the per-gene Gram matrices and right-hand sides
-come from one streaming pass over dt (``nsr_normvar_stats``), the nc x nc pseudo-inverses are
+come from one streaming pass over dt (``nsr_normvar_stats``: two skinny GEMMs over cells on the
+FP64 tensor cores, because G_x = sum_k s^2 (c c^T) depends on the gene only through s), the nc x nc pseudo-inverses are
 batched on the device (``nsr_sym_pinv``), and a second pass writes the result (``nsr_normvar_apply``); the residual
 variance needed by ``keepvar`` follows from the same statistics (S2 - b^T G+ b), so there is no
 third pass.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
@@ -28,24 +29,37 @@ def _dev64(x, dev):
     return torch.from_numpy(np.ascontiguousarray(x)).to(dev, torch.float64)
 
 
-def _normvar_rows(ctx, dt_d, dc_d, logw, wt_d, keepvar):
+def _design(ctx, dc_d):
+    """Gene-independent right-hand matrix of the statistics GEMM: the nc (nc + 1) / 2 products
+    c_i c_j (row-major upper triangle), zero rows up to a multiple of 8 tiles, then the covariates
+    themselves, zero rows up to 16.  Returns (M, tri, first row of the covariate part)."""
+    nc, n = dc_d.shape
+    cols = ctx.lib.nsr_normvar_width(nc)                  # 8 * (D tiles + 2) + 2
+    d_rows = cols - 2 - 16
+    iu = torch.triu_indices(nc, nc, device=dc_d.device)
+    M = torch.zeros((d_rows + 16, n), dtype=torch.float64, device=dc_d.device)
+    M[:iu.shape[1]] = dc_d[iu[0]] * dc_d[iu[1]]
+    M[d_rows:d_rows + nc] = dc_d
+    return M, iu, d_rows
+
+
+def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar):
     """One block of genes resident on the device -> normalised block."""
     genes, n = dt_d.shape
     nc = dc_d.shape[0]
-    W = ctx.lib.nsr_normvar_width(nc)
-    tri = W * (W + 1) // 2
-    stats = torch.empty((genes, tri + W + 2), dtype=torch.float64, device=dt_d.device)
+    M, iu, d_rows = design
+    tri = iu.shape[1]
+    stats = torch.empty((genes, M.shape[0] + 2), dtype=torch.float64, device=dt_d.device)
     ld = dt_d.stride(0) if genes > 1 else n
     ldc = dc_d.stride(0) if nc > 1 else n
-    _lib.check(ctx.lib.nsr_normvar_stats(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
-                                         ldc, logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()), "nsr_normvar_stats")
-    iu = torch.triu_indices(W, W, device=dt_d.device)
-    G = torch.zeros((genes, W, W), dtype=torch.float64, device=dt_d.device)
+    _lib.check(ctx.lib.nsr_normvar_stats(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, M.data_ptr(), nc,
+                                         M.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
+               "nsr_normvar_stats")
+    G = torch.zeros((genes, nc, nc), dtype=torch.float64, device=dt_d.device)
     G[:, iu[0], iu[1]] = stats[:, :tri]
     G = G + torch.triu(G, 1).transpose(1, 2)
-    G = G[:, :nc, :nc]
-    b = stats[:, tri:tri + nc]
-    s1, s2 = stats[:, tri + W], stats[:, tri + W + 1]
+    b = stats[:, d_rows:d_rows + nc]
+    s1, s2 = stats[:, M.shape[0]], stats[:, M.shape[0] + 1]
     ci, rank = engine.sym_pinv(ctx, G)                                      # inv_rank per gene, norm.py:159-160
     if bool((rank <= 0).any()):
         raise RuntimeError('Zero-rank covariates found.')                    # norm.py:161-162
@@ -56,11 +70,15 @@ def _normvar_rows(ctx, dt_d, dc_d, logw, wt_d, keepvar):
         scale = (dv / dv2) ** wt_d
     else:
         scale = torch.ones(genes, dtype=torch.float64, device=dt_d.device)
+    # the reference asserts that its output is finite (norm.py:277); S2 = sum (s dt)^2, coef and scale
+    # finite imply it, without another pass over the matrix
+    if not bool(torch.isfinite(stats).all() & torch.isfinite(coef).all() & torch.isfinite(scale).all()):
+        raise AssertionError('non-finite values in the normalised expression matrix')
     out = torch.empty((genes, n), dtype=torch.float64, device=dt_d.device)
     _lib.check(ctx.lib.nsr_normvar_apply(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
                                          ldc, logw.data_ptr(), wt_d.data_ptr(), coef.data_ptr(), scale.contiguous().data_ptr(),
                                          out.data_ptr(), n), "nsr_normvar_apply")
-    engine.LAUNCHES += 2
+    engine.LAUNCHES += 3
     return out
 
 
@@ -97,6 +115,7 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         w_d = _dev64(w, dev).contiguous()
         wt_d = _dev64(wt, dev).contiguous()
         logw = torch.log(w_d)
+        design = _design(ctx, dc_d)
         # covariates: continuous rows (and, for cat = 1, the intercept) are scaled by w   norm.py:257-269
         if cat == 2:
             sel = torch.ones(nc, dtype=torch.bool, device=dev)
@@ -124,13 +143,13 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         for g0 in range(0, nt, step):
             g1 = min(nt, g0 + step)
             blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
-            res = _normvar_rows(ctx, blk, dc_d, logw, wt_d[g0:g1].contiguous(), keepvar)
+            res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar)
             if normmean:
                 cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
                 res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
             dtn[g0:g1] = res if not to_host else res.cpu()
-        if not bool(torch.isfinite(dtn).all()) or not bool(torch.isfinite(dcn).all()):
-            raise AssertionError('non-finite values in the normalised matrices')   # norm.py:277
+        if not bool(torch.isfinite(dcn).all()):
+            raise AssertionError('non-finite values in the normalised covariates')  # norm.py:277
         ans = [dtn, dcn]
         if dextra is not None:
             ans.append(_dev64(dextra, dev) * w_d)
