@@ -507,7 +507,8 @@ def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):
 
 def bench_normvar(torch, dev, n_gene=10000, n_cell=50000, reps=3):
     """normalisr_b200.normvar (the step upstream of coex / de) on device-resident inputs: 16 B of
-    algorithmic traffic per matrix entry (8 read + 8 written); the kernels read dt twice."""
+    algorithmic traffic per matrix entry (8 read + 8 written); the kernels read dt twice and spend
+    one float64 exp per entry in each pass."""
     from normalisr_b200 import normalisr as norm, synth
     torch.cuda.empty_cache()
     p = synth.device_problem(1002, n_gene, n_cell, dev)
@@ -537,7 +538,7 @@ def bench_normvar(torch, dev, n_gene=10000, n_cell=50000, reps=3):
     return {"workload": "normvar_%dk_x_%dk" % (n_cell // 1000, n_gene // 1000), "covariates": 9, "ms": ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": 16 * n_gene * n_cell,
-                         "note": "the statistics pass is bound by the float64 FMA pipe (67 FMA + exp per entry at 9 covariates)"}}
+                         "note": "two passes over dt; the statistics pass is a skinny float64 tensor-core GEMM with one exp per entry"}}
 
 
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
