@@ -85,7 +85,6 @@ struct RowShared {
     unsigned long long bar;
 };
 
-__device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
 
 __global__ void __launch_bounds__(kThreads)
 binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, int64_t diag0, double qcut,
@@ -131,36 +130,53 @@ binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, 
         for (int64_t j = threadIdx.x; j < cols; j += kThreads) s_row[j] = p_row[j];
         for (int b = threadIdx.x; b <= kBins; b += kThreads) sh.hist[b] = 0;
     }
-    if (threadIdx.x == 0) { sh.n_window = 0; sh.fallback = 0; }
+    int bad = 0;
+    if (threadIdx.x == 0) {
+        sh.n_window = 0;
+        sh.fallback = 0;
+    }
     __syncthreads();
+    if (has_diag && threadIdx.x == 0) {                  // the diagonal entry: validated, then made inert
+        const double d = s_row[diag];
+        if (!(d >= 0.0 && d <= 1.0)) bad = 1;
+        s_row[diag] = 2.0;
+    }
 
-    // ---- bins: keys between t(1) and qcut; m mantissa bits so that they fit
+    // ---- bins: keys between t(1) and qcut; m mantissa bits so that they fit.  The key is taken from
+    // the high word of the double (sign, exponent, 20 mantissa bits): 32-bit integer arithmetic only;
+    // -0.0 has a negative high word and lands below the first bin, like every entry under t(1).
     // t_dn(c) <= t(c) <= t_up(c): fl(qcut * c / n0) moved a few ulp either way.  The bracketing only
     // needs bounds (a multiply instead of the divisions and nextafter steps of the exact threshold,
     // whose latency - not the passes over the row - dominated the first version of this kernel).
     const double kUp = 1.0 + 0x1p-48, kDn = 1.0 - 0x1p-48;
     const double t1 = (qcut / n0d) * kDn;
-    int shift = 52 - 8;
-    while ((long long)(dbits(qcut) >> shift) - (long long)(dbits(t1) >> shift) + 1 > kBins - 1) ++shift;
-    const long long lo_key = (long long)(dbits(t1) >> shift);
-    const int n_bins = (int)((long long)(dbits(qcut) >> shift) - lo_key) + 1;
-    const unsigned long long q_bits = dbits(qcut);
+    int sh32 = 20 - 8;
+    while ((__double2hiint(qcut) >> sh32) - (__double2hiint(t1) >> sh32) + 1 > kBins - 1) ++sh32;
+    const int lo_key = __double2hiint(t1) >> sh32;
+    const int n_bins = (__double2hiint(qcut) >> sh32) - lo_key + 1;
+    __syncthreads();
 
-    // ---- pass 1: validate (binnet.py:152-153, diagonal included), histogram of the candidates
-    int bad = 0, below = 0;
-#pragma unroll 4
-    for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
-        double p = s_row[j];
-        if (!(p >= 0.0 && p <= 1.0)) bad = 1;            // also catches NaN
-        if (j == diag) p = 2.0;                          // inert: never a candidate
-        if (p == 0.0) p = 0.0;                           // -0.0 -> +0.0 so that bit patterns order like values
-        s_row[j] = p;
-        const unsigned long long u = dbits(p);
-        if (u <= q_bits) {
-            const long long key = (long long)(u >> shift) - lo_key;
+    // ---- pass 1: validate (binnet.py:152-153), histogram of the candidates (p <= qcut)
+    int below = 0;
+    const int diag_i = has_diag ? (int)diag : -1;
+    auto visit = [&](double p, int idx) {
+        if (!(p >= 0.0 && p <= 1.0) && idx != diag_i) bad = 1;       // also catches NaN (the patched diagonal holds 2.0)
+        if (p <= qcut) {
+            const int key = (__double2hiint(p) >> sh32) - lo_key;
             if (key < 0) ++below;
-            else atomicAdd(&sh.hist[key < n_bins ? (int)key : n_bins - 1], 1);
+            else atomicAdd(&sh.hist[key < n_bins ? key : n_bins - 1], 1);
         }
+    };
+    {
+        const double2* v = reinterpret_cast<const double2*>(s_row);
+        const int64_t half = cols >> 1;
+#pragma unroll 4
+        for (int64_t j = threadIdx.x; j < half; j += kThreads) {
+            const double2 p = v[j];
+            visit(p.x, 2 * (int)j);
+            visit(p.y, 2 * (int)j + 1);
+        }
+        if ((cols & 1) && threadIdx.x == 0) visit(s_row[cols - 1], (int)cols - 1);
     }
     if (bad) atomicAdd(&stats[1], 1ull);
     below = block_sum(below, sh.red);                    // (syncs: histogram complete)
@@ -195,8 +211,8 @@ binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, 
     // ---- bracket the fixed point (one thread; a multiply and two table reads per step)
     if (threadIdx.x == 0) {
         auto bin_of = [&](double t) {
-            long long k = (long long)(dbits(t) >> shift) - lo_key;
-            return (int)(k < 0 ? 0 : (k >= n_bins ? n_bins - 1 : k));
+            const int k = (__double2hiint(t) >> sh32) - lo_key;
+            return k < 0 ? 0 : (k >= n_bins ? n_bins - 1 : k);
         };
         const double qn = qcut / n0d;
         int c = sh.hist[n_bins];
@@ -224,17 +240,26 @@ binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, 
     if (c > 0) {
         // ---- gather the undecided entries
         const int b_lo = sh.b_lo, b_hi = sh.b_hi;
-#pragma unroll 4
-        for (int64_t j = threadIdx.x; j < cols; j += kThreads) {
-            const unsigned long long u = dbits(s_row[j]);
-            if (u <= q_bits) {
-                long long key = (long long)(u >> shift) - lo_key;
+        auto pick = [&](double p) {
+            if (p <= qcut) {
+                int key = (__double2hiint(p) >> sh32) - lo_key;
                 if (key >= n_bins) key = n_bins - 1;
                 if (key >= b_lo && key <= b_hi) {
                     const int slot = atomicAdd(&sh.n_window, 1);
-                    if (slot < kWindow) sh.window[slot] = s_row[j]; else sh.fallback = 1;
+                    if (slot < kWindow) sh.window[slot] = p; else sh.fallback = 1;
                 }
             }
+        };
+        {
+            const double2* v = reinterpret_cast<const double2*>(s_row);
+            const int64_t half = cols >> 1;
+#pragma unroll 4
+            for (int64_t j = threadIdx.x; j < half; j += kThreads) {
+                const double2 p = v[j];
+                pick(p.x);
+                pick(p.y);
+            }
+            if ((cols & 1) && threadIdx.x == 0) pick(s_row[cols - 1]);
         }
         __syncthreads();
         if (!sh.fallback) {
@@ -271,27 +296,25 @@ binnet_rows_smem_kernel(const double* __restrict__ P, int64_t cols, int64_t ld, 
             thr = c > 0 ? bh_threshold((double)c / n0d, qcut) : -1.0;
         }
     }
-    // ---- output
+    // ---- output (thr = -1 when nothing passes; the patched diagonal holds 2.0)
     uint8_t* o_row = net + row * ld_net;
-    const unsigned long long t_bits = thr >= 0.0 ? dbits(thr) : 0ull;
-    const bool none = !(thr >= 0.0);
     int64_t done = 0;
     if (((uintptr_t)o_row & 7) == 0) {                   // 8 entries -> one 8-byte store
-        const ulonglong2* v = reinterpret_cast<const ulonglong2*>(s_row);
+        const double2* v = reinterpret_cast<const double2*>(s_row);
         const int64_t oct = cols >> 3;
         for (int64_t j = threadIdx.x; j < oct; j += kThreads) {
             uint64_t out_bits = 0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const ulonglong2 p = v[4 * j + q];
-                out_bits |= (uint64_t)((!none && p.x <= t_bits) ? 1 : 0) << (16 * q);
-                out_bits |= (uint64_t)((!none && p.y <= t_bits) ? 1 : 0) << (16 * q + 8);
+                const double2 p = v[4 * j + q];
+                out_bits |= (uint64_t)(p.x <= thr ? 1 : 0) << (16 * q);
+                out_bits |= (uint64_t)(p.y <= thr ? 1 : 0) << (16 * q + 8);
             }
             reinterpret_cast<uint64_t*>(o_row)[j] = out_bits;
         }
         done = oct << 3;
     }
-    for (int64_t j = done + threadIdx.x; j < cols; j += kThreads) o_row[j] = (!none && dbits(s_row[j]) <= t_bits) ? 1 : 0;
+    for (int64_t j = done + threadIdx.x; j < cols; j += kThreads) o_row[j] = s_row[j] <= thr ? 1 : 0;
     if (c > 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)c);
 }
 

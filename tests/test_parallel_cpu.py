@@ -104,6 +104,20 @@ def _worker(rank, world, port, rows_total, q):
             ok = ok and torch.equal(full.slices[:, k * blk:(k + 1) * blk], want)
             ok = ok and bool((full.quantum[k * blk:(k + 1) * blk] == k + 1.0).all())
             ok = ok and bool((full.var[k * blk:(k + 1) * blk] == 10.0 * (k + 1)).all())
+        # assembly of the full symmetric matrices from the rows each rank owns (pairs schedule)
+        for total in (rows_total, 300, 700):
+            gen = torch.Generator().manual_seed(7)
+            F = torch.rand((total, total), generator=gen, dtype=torch.float64)
+            F = torch.triu(F, 1)
+            F = F + F.T
+            b = parallel.row_split(total, world)
+            r0, r1 = rank * b, rank * b + parallel.block_rows(total, world, rank)
+            m = torch.from_numpy(parallel.owned_tile_mask(total, world, rank))
+            m = m.repeat_interleave(128, 0)[:max(r1 - r0, 0)].repeat_interleave(128, 1)[:, :total]
+            mine = torch.where(m, F[r0:r1], torch.zeros_like(F[r0:r1])) if r1 > r0 else torch.zeros((1, total), dtype=torch.float64)
+            Pf, Df = parallel.gather_dense(mine, 2 * mine, None, total)
+            if rank == 0:
+                ok = ok and torch.equal(Pf, F) and torch.equal(Df, 2 * F)
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
