@@ -168,6 +168,26 @@ def test_de_million_cells_uses_cell_chunks():
     assert engine.plan_k_chunk(A, A, 8) > 0
 
 
+def test_host_pipeline_many_chunks_equals_device_path(monkeypatch):
+    """The end-to-end path for host matrices (row chunks staged on a copy stream, tiles contracted
+    as their columns arrive, finished blocks copied back on a third stream, geometric tail chunks)
+    gives the same bits as the device-resident path, with and without caller-provided pinned
+    output buffers."""
+    monkeypatch.setattr(association, "_ROW_CHUNK_BYTES", 1)                # smallest row chunks: 1,536 rows, then a tail
+    p = synth.host_problem(1007, 5003, 1200)
+    dt_d, dc_d = torch.from_numpy(p["dt"]).cuda(), torch.from_numpy(p["dc"]).cuda()
+    Pd, Dd, vd = norm.coex(dt_d, dc_d)
+    Pd, Dd, vd = Pd.cpu().numpy(), Dd.cpu().numpy(), vd.cpu().numpy()
+    Ph, Dh, vh = norm.coex(p["dt"], p["dc"])
+    assert np.array_equal(Ph, Pd) and np.array_equal(Dh, Dd) and np.array_equal(vh, vd)
+    g = p["dt"].shape[0]
+    P_pin = torch.full((g, g), -1.0, dtype=torch.float64).pin_memory()
+    D_pin = torch.full((g, g), -1.0, dtype=torch.float64).pin_memory()
+    Po, Do, vo = norm.coex(p["dt"], p["dc"], out=(P_pin, D_pin))
+    assert np.array_equal(P_pin.numpy(), Pd) and np.array_equal(D_pin.numpy(), Dd) and np.array_equal(vo, vd)
+    assert np.array_equal(Po, Pd) and np.array_equal(Do, Dd)
+
+
 def test_device_tensors_in_device_tensors_out():
     g = load_golden("coex_chain")
     dt = torch.from_numpy(g["dt"]).cuda()
