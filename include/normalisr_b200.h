@@ -145,6 +145,18 @@ int nsr_project_coef(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t ro
 int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, int64_t genes, int64_t ldy,
                     const double* C, int nc1, int64_t ldc, const int64_t* goff, int n_groups,
                     double* out);
+/* Closed form of association_test_2 (association.py:352-377) for `genes` genes x n_groups groupings,
+ * fused with the P-value: cu [genes][nc+1] = nsr_project_coef output for the covariates masked to
+ * U (+ the mask), yy_u[genes] = sum_U y^2, st = nsr_group_stats output; per grouping x: ci = C+
+ * (nc x nc, pseudo-inverse of the covariate Gram matrix of S_x), cx = sum_{T_x} dc, ccx = C+ cx,
+ * ns = |S_x|, vx = var_x, dof = ns - 1 - rank - dimreduce.  Writes P, gamma, vy at
+ * [x * ld_out + col0 + gene] and alpha (optional, [..][nc]); *flag |= 1 if an R^2 leaves [0, 1].
+ * nc <= 16. */
+int nsr_single1_finish(nsr_ctx* ctx, uintptr_t stream, const double* cu, const double* yy_u,
+                       const double* st, int64_t genes, int n_groups, int nc, const double* ci,
+                       const double* cx, const double* ccx, const double* ns, const double* vx,
+                       const double* dof, double* P, double* gamma, double* vy, double* alpha,
+                       int64_t ld_out, int64_t col0, int* flag);
 
 /* Variance normalisation, the step upstream of coex / de (norm.normvar / normvar1,
  * src/normalisr/norm.py:131-289): gene x is scaled per cell by s_k = w_k ** wt_x and its own

@@ -12,6 +12,7 @@
 //     out[g][y][nc1] = sum_{k in g} Y[y][k]^2
 // Y is read once (HBM-streaming, 8 B per gathered entry); sums run in a fixed order.
 #include "nsr_common.cuh"
+#include "pvalue.cuh"
 
 namespace {
 
@@ -98,6 +99,65 @@ group_stats_kernel(const double* __restrict__ Y, int64_t genes, int64_t ldy, con
     }
 }
 
+// Closed form of association_test_2 for one block of genes (association.py:352-377), fused: from
+// the U parts (cu: [genes][nc + 1] = covariate-y products over U and sum_U y; yy_u[genes]) and the
+// T_x parts (st: nsr_group_stats output, [groups][genes][nc + 2]) to gamma, var_y, P (and alpha):
+//   cy = cu + st,  ccy = C+ cy,  Syy = yy - ccy.cy,  Sxy = sum_{T_x} y - ccy.cx,
+//   var_y = Syy / ns, gamma = Sxy / (ns var_x), R2 = gamma^2 var_x / var_y, P = I_{1-R2}(dof/2, 1/2).
+// One CTA per (grouping x, 256 genes); C+ (nc x nc), cx, C+ cx of the grouping sit in shared memory.
+constexpr int kFinNc = 16;             // covariates handled in registers
+
+__global__ void __launch_bounds__(256)
+single1_finish_kernel(const double* __restrict__ cu, const double* __restrict__ yy_u, const double* __restrict__ st,
+                      int64_t genes, int nc, const double* __restrict__ ci, const double* __restrict__ cx,
+                      const double* __restrict__ ccx, const double* __restrict__ ns, const double* __restrict__ vx,
+                      const double* __restrict__ dof, double* __restrict__ P, double* __restrict__ gamma,
+                      double* __restrict__ vy, double* __restrict__ alpha, int64_t ld_out, int64_t col0,
+                      int* __restrict__ flag) {
+    __shared__ double s_ci[kFinNc * kFinNc], s_cx[kFinNc], s_ccx[kFinNc];
+    __shared__ NsrPvalParams s_pv;
+    const int x = blockIdx.y;
+    for (int i = threadIdx.x; i < nc * nc; i += blockDim.x) s_ci[i] = ci[(int64_t)x * nc * nc + i];
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) { s_cx[i] = cx[(int64_t)x * nc + i]; s_ccx[i] = ccx[(int64_t)x * nc + i]; }
+    if (threadIdx.x == 0) s_pv = nsr_pval_params(dof[x] * 0.5);
+    __syncthreads();
+    const int64_t y = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= genes) return;
+    const double* u = cu + y * (nc + 1);
+    const double* t = st + ((int64_t)x * genes + y) * (nc + 2);
+    double cy[kFinNc];
+#pragma unroll
+    for (int j = 0; j < kFinNc; ++j) cy[j] = j < nc ? u[j] + t[j] : 0.0;
+    double quad = 0.0, cross = 0.0, ccy[kFinNc];
+#pragma unroll
+    for (int i = 0; i < kFinNc; ++i) {
+        double a = 0.0;
+        if (i < nc) {
+#pragma unroll
+            for (int j = 0; j < kFinNc; ++j) if (j < nc) a = fma(s_ci[i * nc + j], cy[j], a);   // C+ symmetric
+            quad = fma(a, cy[i], quad);
+            cross = fma(a, s_cx[i], cross);
+        }
+        ccy[i] = a;
+    }
+    const double nsx = ns[x], vxx = vx[x];
+    const double syy = (yy_u[y] + t[nc + 1]) - quad;
+    const double sxy = t[nc] - cross;
+    const double v_y = syy / nsx;
+    const double gam = sxy / (nsx * vxx);                               // association.py:364
+    const double r2 = gam * gam * vxx / v_y;                            // :368
+    if (!(r2 >= 0.0 && r2 <= 1.0 + 1e-8)) atomicOr(flag, 1);           // :371
+    const int64_t o = (int64_t)x * ld_out + col0 + y;
+    P[o] = nsr_pvalue_r2(r2 > 1.0 ? 1.0 : r2, s_pv);
+    gamma[o] = gam;
+    vy[o] = v_y;
+    if (alpha) {                                                        // :365-367
+#pragma unroll
+        for (int j = 0; j < kFinNc; ++j)
+            if (j < nc) alpha[o * nc + j] = ccy[j] - gam * s_ccx[j];
+    }
+}
+
 }  // namespace
 
 extern "C" int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, int64_t genes, int64_t ldy,
@@ -117,6 +177,22 @@ extern "C" int nsr_group_stats(nsr_ctx* ctx, uintptr_t stream, const double* Y, 
     else if (nc1 <= 12) NSR_GS(12);
     else NSR_GS(16);
 #undef NSR_GS
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nsr_single1_finish(nsr_ctx* ctx, uintptr_t stream, const double* cu, const double* yy_u,
+                                  const double* st, int64_t genes, int n_groups, int nc, const double* ci,
+                                  const double* cx, const double* ccx, const double* ns, const double* vx,
+                                  const double* dof, double* P, double* gamma, double* vy, double* alpha,
+                                  int64_t ld_out, int64_t col0, int* flag) {
+    NSR_REQUIRE(ctx && cu && yy_u && st && ns && vx && dof && P && gamma && vy && flag, "nsr_single1_finish: null argument");
+    NSR_REQUIRE(genes >= 1 && n_groups >= 1 && n_groups <= 65535 && nc >= 0 && nc <= kFinNc && (nc == 0 || (ci && cx && ccx)),
+                "nsr_single1_finish: bad shape genes=%lld groups=%d nc=%d (nc <= %d)", (long long)genes, n_groups, nc, kFinNc);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    const dim3 grid((unsigned)((genes + 255) / 256), (unsigned)n_groups);
+    single1_finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cu, yy_u, st, genes, nc, ci, cx, ccx, ns, vx, dof, P, gamma,
+                                                                    vy, alpha, ld_out, col0, flag);
     NSR_CHECK(cudaGetLastError());
     return 0;
 }

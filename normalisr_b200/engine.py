@@ -208,6 +208,21 @@ def sym_pinv(ctx, G, tol=1e-8):
     return out, rank
 
 
+def single1_finish(ctx, cu, yy_u, st, n_groups, nc, ci, cx, ccx, ns, vx, dof, P, gamma, vy, alpha, col0, flag):
+    """Closed form + P-value of de(single=1) for one block of genes (nsr_single1_finish): writes
+    columns [col0, col0 + genes) of P / gamma / vy (n_groups, ny) and alpha (n_groups, ny, nc)."""
+    genes = cu.shape[0]
+    assert cu.is_contiguous() and st.is_contiguous() and yy_u.is_contiguous() and P.is_contiguous()
+    assert cu.shape[1] == nc + 1 and st.shape[1] == genes and st.shape[2] == nc + 2 and st.shape[0] >= n_groups
+    _lib.check(ctx.lib.nsr_single1_finish(
+        ctx.handle, _stream(), cu.data_ptr(), yy_u.data_ptr(), st.data_ptr(), genes, n_groups, nc,
+        ci.data_ptr() if nc else None, cx.data_ptr() if nc else None, ccx.data_ptr() if nc else None,
+        ns.data_ptr(), vx.data_ptr(), dof.data_ptr(), P.data_ptr(), gamma.data_ptr(), vy.data_ptr(),
+        alpha.data_ptr() if alpha is not None else None, P.shape[1], col0, flag.data_ptr()), "nsr_single1_finish")
+    global LAUNCHES
+    LAUNCHES += 1
+
+
 def coex_tiles(rows, strip=12):
     """Upper-triangular 128x128 tile list (tile_row <= tile_col), ordered in column strips so
     that the ~148 tiles in flight share few row blocks (L2 reuse of the operand planes)."""

@@ -100,6 +100,8 @@ def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
         t_ns = torch.from_numpy(ns).to(dev)
         t_vx = torch.from_numpy(vx).to(dev)
         has_rank = torch.from_numpy(rank > 0).to(dev)[:, None, None]
+        t_dof = torch.from_numpy(np.ascontiguousarray(dof, dtype=np.float64)).to(dev)
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
 
         P = torch.empty((nx, ny), dtype=torch.float64, device=dev)
         gamma = torch.empty_like(P)
@@ -121,6 +123,10 @@ def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
             ys = y.index_select(1, t_order)                                      # non-U columns in group order
             st = engine.group_stats(ctx, ys, c_s, t_goff)                        # (nx + 1, gc, nc + 2)
             yy_u = yy_all - st[:, :, nc + 1].sum(dim=0)
+            if nc <= 16:                                                         # fused closed form + P-value
+                engine.single1_finish(ctx, coef_u, yy_u, st, nx, nc, t_ci, t_cx, t_ccx, t_ns, t_vx, t_dof,
+                                      P, gamma, vy, alpha, g0, flag)
+                continue
             cy = coef_u[None, :, :nc] + st[:nx, :, :nc]                          # (nx, gc, nc)
             xy = st[:nx, :, nc]                                                  # sum_{T_x} y
             yy = yy_u[None, :] + st[:nx, :, nc + 1]
@@ -138,6 +144,8 @@ def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
             if alpha is not None:                                                # :365-367
                 al = ccy - gam[:, :, None] * t_ccx[:, None, :]
                 alpha[:, g0:g1] = torch.where(has_rank, al, torch.zeros_like(al))
+        if int(flag.item()):
+            raise AssertionError('R^2 outside [0, 1].')                          # association.py:371
         out2 = gamma * t_vx[:, None] if return_dot else gamma                    # association.py:1058-1061
         res = (P, out2, alpha, t_vx, vy)
         if to_host:

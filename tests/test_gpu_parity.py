@@ -143,6 +143,13 @@ def test_de_single1_low_moi_against_oracle(monkeypatch):
     dev = norm.de(torch.from_numpy(dg).cuda(), torch.from_numpy(dt).cuda(), torch.from_numpy(dc).cuda(), single=1)
     assert dev[0].is_cuda and dev[2] is None
     assert_p_close(dev[0].cpu().numpy(), ref[0])
+    # more than 16 covariates: the closed form runs as batched tensor operations instead of the fused kernel
+    dc20 = np.concatenate([dc, rng.normal(size=(13, n))])
+    ref20 = orc.de(dg[:8], dt[:60], dc20, single=1, lowmem=False)
+    got20 = norm.de(dg[:8], dt[:60], dc20, single=1, lowmem=False)
+    assert_p_close(got20[0], ref20[0])
+    np.testing.assert_allclose(got20[4], ref20[4], rtol=1e-9)
+    np.testing.assert_allclose(got20[2], ref20[2], atol=1e-8 * np.abs(ref20[2]).max())
 
 
 def test_de_million_cells_uses_cell_chunks():
