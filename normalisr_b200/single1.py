@@ -12,9 +12,9 @@ covariates, x and y, and sum_{S_x} = sum_U + sum_{T_x}:
     covariates masked to U, FP64 tensor cores);
   * the columns of dy outside U are gathered once in group order and ``nsr_group_stats`` gives the
     T_x parts for all x in one pass over them;
-  * per x: pseudo-inverse of its nc x nc Gram matrix with the reference's rank rule (host, tiny),
-    then gamma, R^2 and d.o.f. in closed form for all genes at once (batched float64 on the
-    device) and exact P-values from ``nsr_pvalue``.
+  * per x: pseudo-inverse of its nc x nc Gram matrix with the reference's rank rule
+    (``nsr_sym_pinv``, batched Jacobi), then gamma, R^2, d.o.f. and the exact P-value in closed
+    form for all genes at once (``nsr_single1_finish``).
 With C = sum dc dc^T, cx = sum dc x, cy = sum dc y over S_x and C+ the pseudo-inverse:
   Sxx = sum x^2 - cx^T C+ cx,  Syy = sum y^2 - cy^T C+ cy,  Sxy = sum x y - cx^T C+ cy,
   var_x = Sxx / ns, var_y = Syy / ns, gamma = Sxy / (ns var_x), R^2 = gamma^2 var_x / var_y,
@@ -69,39 +69,44 @@ def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
         t_order = non_u[torch.sort(owner[non_u], stable=True).indices]           # non-U cells in group order
         counts = torch.bincount(owner[non_u], minlength=nx + 1)
         t_goff = torch.cat([torch.zeros(1, dtype=torch.int64, device=dev), torch.cumsum(counts, 0)])
-        n_t = counts[:nx].cpu().numpy().astype(np.float64)
-        n_u = float(in_u.sum())
-        assert n_u > 0 and (n_t > 0).all()                       # :917-918: both values of x occur in S_x
-        ns = n_u + n_t
+        n_t = counts[:nx].to(torch.float64)
+        n_u = in_u.sum().to(torch.float64)
+        t_ns = n_u + n_t
 
-        # ---- per-x covariate algebra: Gram matrices on the device, nc x nc pseudo-inverses on the
-        # host with the reference's rank rule                         (association.py:343-357)
+        # ---- per-x covariate algebra, all on the device: Gram matrices of S_x = U + T_x, their
+        # pseudo-inverses with the reference's rank rule (nsr_sym_pinv)   (association.py:343-357)
         u_row = in_u.to(torch.float64)
         ones = torch.ones((1, n), dtype=torch.float64, device=dev)
         q_u = torch.cat([dc_d * u_row, u_row[None]], 0).contiguous()             # covariates masked to U (+ mask)
         c_s = torch.cat([dc_d, ones], 0)[:, t_order].contiguous()                # (nc + 1, m) in group order
         if nc:
-            c_u = engine.cov_gram(ctx, q_u[:nc]).cpu().numpy()
-            gst = engine.group_stats(ctx, c_s[:nc], c_s, t_goff)[:nx].cpu().numpy()   # (nx, nc, nc + 2)
-            gram, cx = c_u[None] + gst[:, :, :nc], gst[:, :, nc]
-            ci, rank = _pinv_rank_batched(gram)
+            gst = engine.group_stats(ctx, c_s[:nc], c_s, t_goff)[:nx]            # (nx, nc, nc + 2)
+            gram = engine.cov_gram(ctx, q_u[:nc])[None] + gst[:, :, :nc]
+            t_cx = gst[:, :, nc].contiguous()
+            if nc <= 16:
+                t_ci, rank = engine.sym_pinv(ctx, gram)
+                rank = rank.to(torch.float64)
+            else:
+                ci_h, rank_h = _pinv_rank_batched(gram.cpu().numpy())
+                t_ci, rank = torch.from_numpy(ci_h).to(dev), torch.from_numpy(rank_h).to(dev)
         else:
-            ci, rank, cx = np.zeros((nx, 0, 0)), np.zeros(nx), np.zeros((nx, 0))
-        ccx = np.einsum('xij,xj->xi', ci, cx)                    # C+ cx
-        vx = (n_t - np.einsum('xi,xi->x', cx, ccx)) / ns
-        vx[vx == 0] = 1                                          # :359-361
-        dof = ns - 1 - rank - dimreduce
-        if (dof <= 0).any():
+            t_ci = torch.zeros((nx, 0, 0), dtype=torch.float64, device=dev)
+            t_cx = torch.zeros((nx, 0), dtype=torch.float64, device=dev)
+            rank = torch.zeros(nx, dtype=torch.float64, device=dev)
+        t_ccx = torch.einsum('xij,xj->xi', t_ci, t_cx).contiguous()              # C+ cx
+        t_vx = (n_t - (t_cx * t_ccx).sum(dim=1)) / t_ns
+        t_vx = torch.where(t_vx == 0, torch.ones_like(t_vx), t_vx)               # :359-361
+        t_dof = (t_ns - 1 - rank - dimreduce).contiguous()
+        # one synchronisation for the design checks                       (association.py:917-918, 373-376)
+        chk = torch.stack([(n_u > 0).to(torch.float64), (n_t > 0).all().to(torch.float64),
+                           (t_dof > 0).all().to(torch.float64)]).cpu().numpy()
+        assert chk[0] and chk[1]                                  # both values of x occur in S_x
+        if not chk[2]:
             raise RuntimeError('Insufficient number of cells: must be greater than degrees of freedom '
                                'removed + covariate + 1.')
-        t_ci = torch.from_numpy(ci).to(dev)
-        t_cx = torch.from_numpy(cx).to(dev)
-        t_ccx = torch.from_numpy(ccx).to(dev)
-        t_ns = torch.from_numpy(ns).to(dev)
-        t_vx = torch.from_numpy(vx).to(dev)
-        has_rank = torch.from_numpy(rank > 0).to(dev)[:, None, None]
-        t_dof = torch.from_numpy(np.ascontiguousarray(dof, dtype=np.float64)).to(dev)
+        has_rank = (rank > 0)[:, None, None]
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        dof = t_dof
 
         P = torch.empty((nx, ny), dtype=torch.float64, device=dev)
         gamma = torch.empty_like(P)
