@@ -372,8 +372,10 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                 "kernel_ms_per_step": [round(x, 2) for x in k_list], "peak_source": peak_src,
                 "executed_int8_tops": 2.0 * n_products * n_my_tiles * 128 * 128 *
                                       engine.padded_cells(n_cell) / (k_ms * 1e-3) / 1e12,
-                "note": "algorithmic flop = 2*cells per unique pair; the kernel executes %d int8 digit-plane products per "
-                        "pair so its ceiling on this scale is 2/%d of the bf16 peak" % (n_products, n_products)}
+                "ceiling_frac": 2.0 / n_products, "frac_of_ceiling": (ach / peak_tf) / (2.0 / n_products),
+                "note": "algorithmic flop = 2*cells per unique pair; the exact-integer kernel executes %d int8 digit-plane "
+                        "products per pair at 2x the bf16 rate, so its ceiling on this scale is 2/%d of the bf16 peak "
+                        "(ceiling_frac); frac_of_ceiling = how much of that the kernel reaches" % (n_products, n_products)}
 
     # ---- CPU baseline on a bounded sample (N = 1 only)
     cpu = None
