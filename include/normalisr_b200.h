@@ -190,6 +190,18 @@ int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t 
 int nsr_sym_pinv(nsr_ctx* ctx, uintptr_t stream, const double* G, int64_t batch, int n, double tol,
                  double* pinv, int32_t* rank);
 
+/* Adaptive digit-product schedule of nsr_contract, opt-in (tcgen05 engine, n_slices = 3,
+ * n_products = 8, k_chunk = 0, any mode but RAW, n >= option "adaptive_min_cells"; default 0 = off,
+ * 8192 or more sensible; pays only when extremely significant pairs are confined to few tiles): every
+ * tile first runs 6 products; a tile holding a pair with r^2 n > 64 is recomputed with all 8 by a
+ * second launch whose tile list and count stay on the device.  Unrefined pairs carry |dr| ~
+ * 1e-6 / sqrt(n) (random sign) from the two dropped weight-5 products, i.e. a relative error of P
+ * of at most 8e-6 (1 sigma); refined tiles are bit-identical to the full schedule.  Decisions are
+ * per 128 x 128 tile of the global pair grid, so results do not depend on tiling or GPU count.
+ * nsr_last_refined: number of tiles the most recent adaptive nsr_contract call of `n_tiles` tiles
+ * recomputed (synchronises `stream`; bookkeeping for benchmarks). */
+int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined);
+
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,
@@ -218,7 +230,7 @@ int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, con
 /* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
  * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
  * kernel, default 128), "umma_dynamic" (1 = tiles claimed from a global counter, default; 0 = static
- * round-robin). Process-wide. */
+ * round-robin), "adaptive_min_cells" (see nsr_last_refined). Process-wide. */
 int nsr_set_option(const char* name, int value);
 
 /* Debug / test helper: reconstruct z' (float64, rows x n_pad) from slices and quantum. */

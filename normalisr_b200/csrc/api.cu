@@ -15,7 +15,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
-                             int64_t cell_begin, int64_t cell_end);
+                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev);
 extern int nsr_use_hadamard;
 extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
@@ -23,6 +23,31 @@ extern int nsr_epi_warps;
 extern int nsr_umma_stack;
 extern int nsr_umma_dynamic;
 extern int nsr_epi_sleep_ns;
+
+// Adaptive digit-product schedule, OPT-IN (tcgen05 engine, 3 planes / 8 products, one pass over the
+// cells): for n >= nsr_adaptive_min_cells every tile first runs the 6-product schedule (weight-5 products
+// (2,3), (3,2) dropped: |dr| ~ 1.0e-6 / sqrt(n) at random sign, harmless unless the pair is extremely
+// significant), tiles holding a pair with r^2 n > kRefineZ2 are redone with all 8.  For an
+// unrefined pair the relative error of P is n |r| dr <= sqrt(kRefineZ2) * 1.0e-6 = 8e-6 (1 sigma).
+// It pays only when extremely significant pairs are confined to few tiles (screens, sparse networks):
+// on the 100k x 20k benchmark matrix 86 % of the tiles hold such a pair and the two phases cost twice
+// the full schedule (profiles/r01am_adaptive_ab.md), hence off unless asked for.
+int nsr_adaptive_min_cells = 0;        // 0 = always the full schedule; >= 8192 sensible when enabled
+static constexpr double kRefineZ2 = 64.0;
+
+namespace {
+// tiles flagged by the first phase -> compact list (order irrelevant: integer sums) + count
+__global__ void refine_compact_kernel(const int* __restrict__ need, const int32_t* __restrict__ tiles, int n_tiles,
+                                      int32_t* __restrict__ out_tiles, int* __restrict__ out_count) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += gridDim.x * blockDim.x) {
+        if (need[t]) {
+            const int slot = atomicAdd(out_count, 1);
+            out_tiles[2 * slot] = tiles[2 * t];
+            out_tiles[2 * slot + 1] = tiles[2 * t + 1];
+        }
+    }
+}
+}  // namespace
 
 static thread_local char g_err[1024] = "";
 
@@ -83,6 +108,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tiles_dev) cudaFree(ctx->tiles_dev);
     if (ctx->tile_counters) cudaFree(ctx->tile_counters);
+    if (ctx->refine_dev) cudaFree(ctx->refine_dev);
     delete ctx;
     return 0;
 }
@@ -92,6 +118,7 @@ extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_dynamic")) { nsr_umma_dynamic = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "adaptive_min_cells")) { nsr_adaptive_min_cells = value < 0 ? 0 : value; return 0; }
     if (!strcmp(name, "umma_stack")) { nsr_umma_stack = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_warps")) {
         NSR_REQUIRE(value == 8 || value == 16, "epi_warps must be 8 or 16");
@@ -192,6 +219,8 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
     ep.inv_n = 1.0 / (double)n;
     ep.acc_in = 0;
     ep.raw_out = 0;
+    ep.refine_r2 = -1.0;
+    ep.need = nullptr;
     for (int g = 0; g < 4; ++g) ep.group_scale[g] = (g < ep.n_groups) ? ldexp(1.0, 8 * (ep.n_groups - 1 - g)) : 0.0;
     ep.scale_all = ldexp(1.0, 8 * (2 * n_slices - wmax));
     ep.pv = nsr_pval_params(mode == NSR_MODE_RAW ? 1.0 : dof_a);
@@ -201,6 +230,37 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
     // but the last leave the float64 running sum in out2; the last one adds it and finishes.
     NSR_REQUIRE(k_chunk >= 0 && k_chunk % NSR_KBLOCK == 0, "nsr_contract: k_chunk must be a multiple of %d", NSR_KBLOCK);
     const int64_t chunk = (k_chunk == 0 || k_chunk >= n_pad) ? n_pad : k_chunk;
+    if (engine == NSR_ENGINE_UMMA && !pair && chunk == n_pad && mode != NSR_MODE_RAW && n_slices == 3 && wmax == 5 &&
+        nsr_adaptive_min_cells > 0 && n >= nsr_adaptive_min_cells) {
+        // ---- adaptive schedule: 6 products everywhere, 8 where a pair is extremely significant
+        const size_t want = 3 * (size_t)n_tiles + 4;
+        if (want > ctx->refine_cap) {
+            if (ctx->refine_dev) NSR_CHECK(cudaFree(ctx->refine_dev));
+            ctx->refine_dev = nullptr;
+            ctx->refine_cap = 0;
+            NSR_CHECK(cudaMalloc(&ctx->refine_dev, want * 2 * sizeof(int32_t)));
+            ctx->refine_cap = want * 2;
+        }
+        int* need = ctx->refine_dev;
+        int32_t* list = ctx->refine_dev + n_tiles;
+        int* count = ctx->refine_dev + 3 * n_tiles;
+        NSR_CHECK(cudaMemsetAsync(need, 0, (size_t)n_tiles * sizeof(int32_t), st));
+        NSR_CHECK(cudaMemsetAsync(count, 0, sizeof(int32_t), st));
+        ContractParams ep1 = ep;
+        ep1.n_groups = 3;                                             // wmax = 4
+        for (int g = 0; g < 4; ++g) ep1.group_scale[g] = (g < 3) ? ldexp(1.0, 8 * (2 - g)) : 0.0;
+        ep1.scale_all = ldexp(1.0, 8 * (2 * n_slices - 4));
+        ep1.refine_r2 = kRefineZ2 / (double)n;
+        ep1.need = need;
+        int rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b, n_pad,
+                                          n_slices, 4, ctx->tiles_dev, n_tiles, ep1, 0, n_pad, nullptr);
+        if (rc) return rc;
+        refine_compact_kernel<<<(unsigned)((n_tiles + 255) / 256 < 64 ? (n_tiles + 255) / 256 : 64), 256, 0, st>>>(
+            need, ctx->tiles_dev, (int)n_tiles, list, count);
+        NSR_CHECK(cudaGetLastError());
+        return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b, n_pad,
+                                        n_slices, 5, list, n_tiles, ep, 0, n_pad, count);
+    }
     for (int64_t c0 = 0; c0 < n_pad; c0 += chunk) {
         const int64_t c1 = c0 + chunk < n_pad ? c0 + chunk : n_pad;
         ep.acc_in = c0 > 0;
@@ -215,10 +275,21 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
             }
         } else {
             rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
-                                          n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep, c0, c1);
+                                          n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep, c0, c1, nullptr);
             if (rc) return rc;
         }
     }
+    return 0;
+}
+
+extern "C" int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined) {
+    NSR_REQUIRE(ctx && refined && n_tiles >= 1, "nsr_last_refined: bad arguments");
+    NSR_REQUIRE(ctx->refine_dev != nullptr && 3 * (size_t)n_tiles + 1 <= ctx->refine_cap, "nsr_last_refined: no adaptive launch of that size yet");
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    int32_t c = 0;
+    NSR_CHECK(cudaMemcpyAsync(&c, ctx->refine_dev + 3 * n_tiles, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    NSR_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    *refined = c;
     return 0;
 }
 

@@ -39,6 +39,8 @@ struct UmmaArgs {
     int epi_sleep_ns;             // back-off of the epilogue warps while they wait for a tile
     int* tile_counter;            // dynamic tile scheduler (single-CTA kernel): next unclaimed list index,
                                   // zeroed before the launch; nullptr = static round-robin
+    const int* n_tiles_dev;       // if set, the tile count is read from device memory (second phase of the
+                                  // adaptive schedule: the list was compacted on the device)
     ContractParams ep;
 };
 
@@ -167,7 +169,8 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
 // the chip is power-bound here, and that variant costs more energy per tile than it saves time.
 template <int GROUPS, int EW>
 __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t tmem_base, int warp, int lane,
-                                              int tr, int tc, bool wanted, uint32_t empty_bar, bool remote) {
+                                              int tr, int tc, bool wanted, uint32_t empty_bar, bool remote,
+                                              int tile_idx = -1) {
     constexpr int kCols = NSR_TILE / (EW / 4);          // columns per epilogue warp
     constexpr int CH = EW > 8 ? 8 : 16;                 // columns per TMEM read (register budget)
     const int quad = warp & 3;
@@ -178,6 +181,7 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     const double vi = (row_ok && ep.va) ? ep.va[i] : 1.0;
     const bool mirror = ep.mode == NSR_MODE_COEX && tr != tc;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    bool refine = false;
     if (wanted) {
 #pragma unroll 1
         for (int c0 = half * kCols; c0 < half * kCols + kCols; c0 += CH) {
@@ -194,7 +198,7 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
                         int32_t a4[4] = {0, 0, 0, 0};
 #pragma unroll
                         for (int grp = 0; grp < GROUPS; ++grp) a4[grp] = (int32_t)v[grp][c];
-                        nsr_finish(ep, i, j, qi, vi, ep.qb[j], ep.vb ? ep.vb[j] : 1.0, nsr_combine(ep, a4), mirror);
+                        refine |= nsr_finish(ep, i, j, qi, vi, ep.qb[j], ep.vb ? ep.vb[j] : 1.0, nsr_combine(ep, a4), mirror);
                     }
                 }
             }
@@ -206,6 +210,8 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
         if (remote) mbar_arrive_cluster_addr(empty_bar);
         else mbar_arrive(empty_bar);
     }
+    // adaptive schedule, first phase: any element beyond the threshold sends the tile to the second phase
+    if (ep.need != nullptr && tile_idx >= 0 && __any_sync(0xffffffffu, refine) && lane == 0) atomicOr(&ep.need[tile_idx], 1);
 }
 
 // int8 x int8 -> int32, M = 128, N = 256 (two stacked B planes)
@@ -284,9 +290,10 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const int n_tiles = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
             for (int it = 0;; ++it) {
                 int t = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
-                if (t >= g.n_tiles) t = -1;
+                if (t >= n_tiles) t = -1;
                 s_tile[it % kTileRing] = t;
                 mbar_arrive(smem_u32(&bar_tile[it % kTileRing]));
                 if (t < 0) break;
@@ -371,7 +378,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
-            epilogue_tile<C::kGroups, EW>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false);
+            epilogue_tile<C::kGroups, EW>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false, t);
             tphase ^= 1;
         }
     }
@@ -591,7 +598,7 @@ int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtens
     const int smem = C::kStages * C::kStageBytes + 1024;
     auto kern = contract_umma_kernel<S, WMAX, KB, EW>;
     NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = g.n_tiles < ctx->sm_count ? g.n_tiles : ctx->sm_count;
+    const int grid = (g.n_tiles_dev == nullptr && g.n_tiles < ctx->sm_count) ? g.n_tiles : ctx->sm_count;
     kern<<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, g);
     NSR_CHECK(cudaGetLastError());
     return 0;
@@ -629,7 +636,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
                              int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
-                             int64_t cell_begin, int64_t cell_end) {
+                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev) {
     if (n_tiles < 0) {
         // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
         CUtensorMap ma, mb;
@@ -642,6 +649,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.kb_begin = (int)(cell_begin / 128);
         g.stack_b = 0;
         g.tile_counter = nullptr;
+        g.n_tiles_dev = nullptr;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
@@ -661,6 +669,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     g.kb_begin = (int)(cell_begin / kb);
     g.stack_b = (nsr_umma_stack != 0 && kb == 128) ? 1 : 0;
     g.tile_counter = nullptr;
+    g.n_tiles_dev = n_tiles_dev;
     if (nsr_umma_dynamic && ctx->tile_counters) {
         g.tile_counter = ctx->tile_counters + (ctx->launch_seq++ % NSR_TILE_COUNTERS);
         NSR_CHECK(cudaMemsetAsync(g.tile_counter, 0, sizeof(int), st));

@@ -14,6 +14,9 @@ struct ContractParams {
     double inv_n;
     int acc_in;                  // add the float64 partial already stored at out2[i][j] (cell chunking)
     int raw_out;                 // store the running sum instead of finishing (not the last chunk)
+    double refine_r2;            // adaptive schedule, first phase: r^2 above this marks the tile for the
+                                 // full-precision second phase (< 0: off)
+    int* need;                   // [n_tiles] flags of the first phase (device), or nullptr
     double group_scale[4];       // 256^(2S - w), relative to the least significant kept group
     double scale_all;            // weight of the least significant kept group
     NsrPvalParams pv;
@@ -28,22 +31,25 @@ __device__ __forceinline__ double nsr_combine(const ContractParams& p, const int
     return s * p.scale_all;
 }
 
-// one output element (i = row in A, j = row in B); `mirror` also writes (j, i) (COEX, i != j tile)
-__device__ __forceinline__ void nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
+// one output element (i = row in A, j = row in B); `mirror` also writes (j, i) (COEX, i != j tile).
+// Returns true when the element asks for the full-precision phase (adaptive schedule).
+__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
                                            double vi, double qj, double vj, double acc,
                                            bool mirror) {
     double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
     if (p.acc_in) sum += p.out2[i * p.ld + j];     // earlier cell chunks
     if (p.mode == NSR_MODE_RAW || p.raw_out) {
         p.out2[i * p.ld + j] = sum;
-        return;
+        return false;
     }
     const double dot = sum * p.inv_n;
     double P, o2;
+    bool refine = false;
     if ((p.mode == NSR_MODE_COEX || p.mode == NSR_MODE_COEX_UPPER) && i == j) {
         P = 0.0; o2 = 0.0;                         // triu(.,1) + transpose leaves a zero diagonal
     } else {
         const double r2 = (dot * dot) / (vi * vj);
+        refine = p.refine_r2 >= 0.0 && !(r2 <= p.refine_r2);
         P = nsr_pvalue_r2(r2, p.pv);
         o2 = (p.mode == NSR_MODE_DE) ? dot / vi : dot;
     }
@@ -53,4 +59,5 @@ __device__ __forceinline__ void nsr_finish(const ContractParams& p, int64_t i, i
         p.P[j * p.ld + i] = P;
         p.out2[j * p.ld + i] = o2;
     }
+    return refine;
 }

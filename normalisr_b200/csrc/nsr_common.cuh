@@ -21,6 +21,9 @@ struct nsr_ctx {
     // launches in flight on different streams never share one
     int* tile_counters = nullptr;
     unsigned launch_seq = 0;
+    // adaptive schedule: per-tile flags | compacted tile list | count
+    int32_t* refine_dev = nullptr;
+    size_t refine_cap = 0;
 };
 
 void nsr_set_error(const char* fmt, ...);

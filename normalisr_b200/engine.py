@@ -324,6 +324,13 @@ def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_U
     LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
 
 
+def last_refined(ctx, n_tiles):
+    """Tiles recomputed with all digit products by the latest adaptive contraction of n_tiles tiles."""
+    out = ctypes.c_int64(0)
+    _lib.check(ctx.lib.nsr_last_refined(ctx.handle, _stream(), int(n_tiles), ctypes.byref(out)), "nsr_last_refined")
+    return int(out.value)
+
+
 def pvalue(ctx, r2, a):
     """P = I_{1-r2}(a, 1/2); r2 (rows, cols) CUDA float64, a scalar or (rows,) per-row."""
     r2 = r2.contiguous()

@@ -337,6 +337,73 @@ def test_cell_chunking_is_exact(eng):
             torch.testing.assert_close(P, outs[0][0], rtol=1e-9, atol=0)
 
 
+def test_adaptive_schedule_refines_significant_tiles_only():
+    """Opt-in adaptive schedule (option "adaptive_min_cells"): tiles run 6 digit products first and
+    only tiles holding a pair with r^2 n > 64 are redone with all 8.  Refined tiles equal the full schedule bit for bit, the others
+    stay within |dr| <= 1e-7 and rel dP <= 1e-4, and the decision is per tile (any tile subset, the
+    rectangular mode and the mirrored tile give the same bits)."""
+    rows, n = 3000, 16384
+    ctx, p, A, rank, prods = _sliced(rows, n)
+    dof = (n - 1 - rank) / 2
+    tiles = engine.coex_tiles(rows)
+
+    def run(adaptive, mode=engine.MODE_COEX, tl=tiles):
+        engine.set_option("adaptive_min_cells", 8192 if adaptive else 0)
+        try:
+            P = torch.zeros((rows, rows), dtype=torch.float64, device="cuda")
+            D = torch.zeros_like(P)
+            engine.contract(ctx, mode, A, A, tl, dof, P, D, prods)
+            torch.cuda.synchronize()
+            return P, D
+        finally:
+            engine.set_option("adaptive_min_cells", 0)
+
+    Pf, Df = run(False)
+    Pa, Da = run(True)
+    refined = engine.last_refined(ctx, len(tiles))
+    assert 0 < refined < len(tiles), (refined, len(tiles))
+    sd = torch.sqrt(A.var[:, None] * A.var[None, :])
+    assert float(((Da - Df).abs() / sd).max()) <= 1e-7
+    big = Pf >= 1e-300
+    assert float(((Pa - Pf).abs()[big] / Pf[big]).max()) <= 1e-4
+    z2 = (Df / sd) ** 2 * n
+    hot = (z2 > 64.5) & ~torch.eye(rows, dtype=torch.bool, device="cuda")        # clearly beyond the threshold
+    assert bool(hot.any()) and torch.equal(Pa[hot], Pf[hot]) and torch.equal(Da[hot], Df[hot])
+    # same decision whatever the launch looks like
+    perm = np.random.default_rng(1).permutation(len(tiles))
+    P2 = torch.zeros_like(Pa)
+    D2 = torch.zeros_like(Pa)
+    engine.set_option("adaptive_min_cells", 8192)
+    try:
+        for chunk in np.array_split(perm, 4):
+            engine.contract(ctx, engine.MODE_COEX, A, A, tiles[chunk], dof, P2, D2, prods)
+        torch.cuda.synchronize()
+    finally:
+        engine.set_option("adaptive_min_cells", 0)
+    assert torch.equal(P2, Pa) and torch.equal(D2, Da)
+    Pr, Gr = run(True, engine.MODE_DE, engine.rect_tiles(rows, rows))
+    # (diagonal tiles hold r = 1 in the rectangular mode and are always refined there: compare the others)
+    tid = torch.arange(rows, device="cuda") // 128
+    off = tid[:, None] != tid[None, :]
+    assert torch.equal(Pr[off], Pa[off])
+    assert torch.equal(Pr[off], Pr.T[off])                                       # tile (i, j) and tile (j, i) agree
+
+
+def test_coex_adaptive_against_oracle():
+    """End to end with the adaptive schedule switched on: 12,000 cells x 700 genes with planted
+    modules (P down to < 1e-300), against the CPU oracle at the BASELINE tolerances."""
+    p = synth.host_problem(1009, 700, 12000)
+    ref = orc.coex(p["dt"], p["dc"])
+    engine.set_option("adaptive_min_cells", 8192)
+    try:
+        got = norm.coex(p["dt"], p["dc"])
+    finally:
+        engine.set_option("adaptive_min_cells", 0)
+    _check_coex(got, ref)
+    iu = np.triu_indices(700, 1)
+    assert (ref[0][iu] < 1e-250).sum() > 10 and (ref[0][iu] > 1e-3).sum() > 1000
+
+
 def test_dynamic_and_static_tile_schedulers_agree():
     """The tcgen05 kernel claims tiles from a global counter by default; the static round-robin
     order gives the same bits (few tiles, many tiles, and a tile count below the SM count)."""
