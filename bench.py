@@ -402,6 +402,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     # ---- secondary metric of BASELINE.json: DE tests/s (config 3 shape), N = 1 only
     de = None
     normvar_info = None
+    lcpm_info = None
     if world == 1 and not args.no_de:
         try:
             de = bench_de(torch, dev, args)
@@ -411,6 +412,10 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             normvar_info = bench_normvar(torch, dev)
         except Exception as e:
             normvar_info = {"error": repr(e)[:300]}
+        try:
+            lcpm_info = bench_lcpm(torch, dev)
+        except Exception as e:
+            lcpm_info = {"error": repr(e)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -429,7 +434,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                                        else "copy engines over peer-mapped memory")),
                    "note": wl_desc},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-        "de": de, "binnet": binnet_info, "normvar": normvar_info,
+        "de": de, "binnet": binnet_info, "normvar": normvar_info, "lcpm": lcpm_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -550,6 +555,40 @@ def bench_normvar(torch, dev, n_gene=10000, n_cell=50000, reps=3):
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": 16 * n_gene * n_cell,
                          "note": "two passes over dt; the statistics pass is a skinny float64 tensor-core GEMM with one exp per entry"}}
+
+
+def bench_lcpm(torch, dev, n_gene=10000, n_cell=50000, reps=3):
+    """normalisr_b200.lcpm on a device-resident int32 count matrix: 12 B of algorithmic traffic per
+    entry (4 read + 8 written); the kernels read the counts twice."""
+    from normalisr_b200 import normalisr as norm
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    lam = torch.rand((n_gene, 1), generator=g, device=dev) ** 3 * 20 + 0.05
+    reads = torch.poisson(lam.expand(n_gene, n_cell), generator=g).to(torch.int32)
+    reads[0] += 1
+    for _ in range(2):
+        norm.lcpm(reads)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        norm.lcpm(reads)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs") or 6545.0
+    gbs = 12.0 * n_gene * n_cell / (ms * 1e-3) / 1e9
+    del reads
+    torch.cuda.empty_cache()
+    return {"workload": "lcpm_%dk_x_%dk" % (n_cell // 1000, n_gene // 1000), "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": 12 * n_gene * n_cell}}
 
 
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):

@@ -202,6 +202,19 @@ int nsr_sym_pinv(nsr_ctx* ctx, uintptr_t stream, const double* G, int64_t batch,
  * recomputed (synchronises `stream`; bookkeeping for benchmarks). */
 int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined);
 
+/* Bayesian logCPM (lcpm.lcpm, src/normalisr/lcpm.py:21-208, default arguments): reads is a
+ * (genes x n) matrix of non-negative counts (int32 or int64, itemsize 4 / 8), lut[c] =
+ * digamma(1 + c) - digamma(total + 2) for c = 0 .. lut_len - 1 (the reference's table, :96-109).
+ *   nsr_lcpm_colstats  colstats = [3][n]: per cell sum_g exp(lut[reads]), total reads, number of
+ *                      genes with a non-zero count (per-cell normaliser :155-157 and the
+ *                      covariates :193-199 from one pass over the counts);
+ *   nsr_lcpm_apply     out[g][k] = lut[reads[g][k]] - shift[k]  (shift may be NULL). */
+int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
+                      int64_t n, int64_t ld, const double* lut, int64_t lut_len, double* colstats);
+int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
+                   int64_t n, int64_t ld, const double* lut, int64_t lut_len, const double* shift,
+                   double* out, int64_t ldo);
+
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,

@@ -1,0 +1,102 @@
+// Bayesian logCPM (reference src/normalisr/lcpm.py:21-208, default arguments):
+//   lcpm[g][k] = digamma(1 + reads[g][k]) - digamma(total + 2) - log(sum_g exp(.)) + log(1e6)
+// The digamma values come from a look-up table over the count values (the reference builds the
+// same table, lcpm.py:96-109); the per-cell normalisation is a column reduction of exp(LUT[reads])
+// (lcpm.py:155-157).  Two HBM-streaming passes over the count matrix: column statistics (sum of
+// exp, total reads, non-zero genes: the covariates of lcpm.py:193-199 come from the same pass),
+// then the gather + shift.  Rows = genes, columns = cells: a thread owns a cell column, so every
+// access is coalesced; gene ranges are split over blockIdx.y and combined in a fixed order.
+#include "nsr_common.cuh"
+
+namespace {
+
+constexpr int kLcThreads = 256;
+constexpr int kLcGeneSplit = 64;       // genes per CTA in the column pass
+
+template <typename T>
+__global__ void __launch_bounds__(kLcThreads)
+lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld,
+                     const double* __restrict__ lut, int64_t lut_len, double* __restrict__ partial) {
+    const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
+    if (k >= n) return;
+    const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
+    double se = 0.0, tot = 0.0, nz = 0.0;
+#pragma unroll 8
+    for (int64_t g = g0; g < g1; ++g) {
+        const long long c = (long long)reads[g * ld + k];
+        const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
+        se += exp(lut[ci]);
+        tot += (double)c;
+        nz += c != 0 ? 1.0 : 0.0;
+    }
+    double* o = partial + ((int64_t)blockIdx.y * 3) * n + k;
+    o[0] = se;
+    o[n] = tot;
+    o[2 * n] = nz;
+}
+
+__global__ void lcpm_colreduce_kernel(const double* __restrict__ partial, int64_t n, int n_split, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over 3 * n
+    if (i >= 3 * n) return;
+    double s = 0.0;
+    for (int p = 0; p < n_split; ++p) s += partial[(int64_t)p * 3 * n + i];
+    out[i] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kLcThreads)
+lcpm_apply_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld, const double* __restrict__ lut,
+                  int64_t lut_len, const double* __restrict__ shift, double* __restrict__ out, int64_t ldo) {
+    const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
+    if (k >= n) return;
+    const double sh = shift ? shift[k] : 0.0;
+    const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
+#pragma unroll 8
+    for (int64_t g = g0; g < g1; ++g) {
+        const long long c = (long long)reads[g * ld + k];
+        const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
+        out[g * ldo + k] = lut[ci] - sh;
+    }
+}
+
+}  // namespace
+
+extern "C" int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
+                                 int64_t n, int64_t ld, const double* lut, int64_t lut_len, double* colstats) {
+    NSR_REQUIRE(ctx && reads && lut && colstats, "nsr_lcpm_colstats: null argument");
+    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && lut_len >= 1,
+                "nsr_lcpm_colstats: bad arguments (itemsize %d)", itemsize);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_split = (int)((genes + kLcGeneSplit - 1) / kLcGeneSplit);
+    NSR_REQUIRE(n_split <= 65535, "nsr_lcpm_colstats: too many genes for one call");
+    void* scratch = nullptr;
+    if (nsr_scratch(ctx, (size_t)n_split * 3 * n * sizeof(double), &scratch)) return 1;
+    const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
+    if (itemsize == 4)
+        lcpm_colstats_kernel<int32_t><<<grid, kLcThreads, 0, st>>>((const int32_t*)reads, genes, n, ld, lut, lut_len, (double*)scratch);
+    else
+        lcpm_colstats_kernel<int64_t><<<grid, kLcThreads, 0, st>>>((const int64_t*)reads, genes, n, ld, lut, lut_len, (double*)scratch);
+    lcpm_colreduce_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, st>>>((const double*)scratch, n, n_split, colstats);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes, int64_t n,
+                              int64_t ld, const double* lut, int64_t lut_len, const double* shift, double* out,
+                              int64_t ldo) {
+    NSR_REQUIRE(ctx && reads && lut && out, "nsr_lcpm_apply: null argument");
+    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && ldo >= n && lut_len >= 1,
+                "nsr_lcpm_apply: bad arguments (itemsize %d)", itemsize);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_split = (int)((genes + kLcGeneSplit - 1) / kLcGeneSplit);
+    NSR_REQUIRE(n_split <= 65535, "nsr_lcpm_apply: too many genes for one call");
+    const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
+    if (itemsize == 4)
+        lcpm_apply_kernel<int32_t><<<grid, kLcThreads, 0, st>>>((const int32_t*)reads, genes, n, ld, lut, lut_len, shift, out, ldo);
+    else
+        lcpm_apply_kernel<int64_t><<<grid, kLcThreads, 0, st>>>((const int64_t*)reads, genes, n, ld, lut, lut_len, shift, out, ldo);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -7,6 +7,7 @@ and their output feeds these functions unchanged."""
 from .binnet import binnet
 from .coex import coex
 from .de import de
+from .lcpm import lcpm
 from .norm import normvar
 
-__all__ = ["coex", "de", "binnet", "normvar"]
+__all__ = ["coex", "de", "binnet", "normvar", "lcpm"]

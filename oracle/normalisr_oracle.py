@@ -491,3 +491,37 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, keepvar=True, normmean=False, **i
     if dextra is not None:
         ans.append(dextra * w)
     return ans
+
+
+# --------------------------------------------------------------------------------------
+# Bayesian logCPM (reference src/normalisr/lcpm.py:21-208, supported
+# configuration: varscale = 0)
+# --------------------------------------------------------------------------------------
+def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, **ignored):
+    """(lcpm, mean|None, var|None, cov|None): digamma(1 + reads) - digamma(total + 2), per-cell
+    log-sum-exp normalisation to log counts per million, cellular covariates."""
+    from scipy.special import digamma
+    d = np.asarray(reads)
+    if d.ndim != 2:
+        raise ValueError('reads must have 2 dimensions.')
+    if (d < 0).any():
+        raise ValueError('Negative value in d detected.')
+    if not np.issubdtype(d.dtype, np.integer):
+        d = d.astype(int)
+    nt, nc = d.shape
+    t0 = d.sum() + 2 if ntot is None else ntot + 2                   # :90
+    assert t0 > 2                                                    # :91
+    table = digamma(1.0 + np.arange(int(d.max()) + 1)) - float(digamma(t0))   # :96-109
+    dtn = table[d]                                                   # :150
+    if normalize:                                                    # :155-157
+        dtn = dtn - (np.log(np.exp(dtn).sum(axis=0)) - np.log(1e6))
+    dcov = None
+    if not nocov:                                                    # :193-199
+        t1 = d.sum(axis=0)
+        if (t1 == 0).any():
+            raise ValueError('Found cell with no read at all. Please remove.')
+        t1 = np.log(t1)
+        dcov = np.array([t1, nt - (d != 0).sum(axis=0), t1 ** 2])
+    if lowmem:
+        return dtn, None, None, dcov
+    return dtn, dtn.copy(), np.zeros(dtn.shape), dcov

@@ -1,0 +1,36 @@
+#!/usr/bin/env python3
+"""Golden fixtures for lcpm (reference src/normalisr/lcpm.py:21-208), made by the
+UNMODIFIED reference.
+
+    python tests/golden/make_golden_lcpm.py     # writes tests/golden/lcpm_*.npz
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+
+REF = os.environ.get("NSR_REFERENCE_SRC", "/root/reference/src")
+sys.path.insert(0, REF)
+warnings.simplefilter("ignore")
+import normalisr.normalisr as norm  # noqa: E402  (the reference)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from make_golden import nb_counts  # noqa: E402
+
+
+def main():
+    rng = np.random.default_rng(2024)
+    reads = nb_counts(rng, 260, 300, 10)
+    reads[3, 5] = 70000                              # one large count: long look-up table
+    dt, dmean, dvar, dcov = norm.lcpm(reads, nth=1)
+    dt2, dmean2, dvar2, _ = norm.lcpm(reads, nth=1, lowmem=False, nocov=True)
+    dt3, _, _, dcov3 = norm.lcpm(reads, nth=1, normalize=False, ntot=10**9)
+    np.savez_compressed(os.path.join(HERE, "lcpm_counts.npz"), reads=reads, lcpm=dt, cov=dcov, mean=dmean2, var=dvar2,
+                        lcpm_raw=dt3, cov_raw=dcov3)
+    print("lcpm_counts", reads.shape, reads.dtype, dt.shape)
+
+
+if __name__ == "__main__":
+    main()

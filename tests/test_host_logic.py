@@ -215,3 +215,14 @@ def test_single1_batched_pinv_matches_inv_rank():
         want, r0 = association.inv_rank(m)
         assert r == r0
         np.testing.assert_allclose(i, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
+
+
+def test_every_module_imports_without_a_gpu():
+    """The package (and the reference-shaped namespace) must import on a CPU-only box: the driver's
+    build check does exactly that."""
+    import importlib
+    for name in ("normalisr", "association", "coex", "de", "single1", "single4", "binnet", "norm", "lcpm",
+                 "parallel", "engine", "synth", "_build", "_lib"):
+        importlib.import_module("normalisr_b200." + name)
+    import normalisr_b200.normalisr as norm
+    assert set(norm.__all__) == {"coex", "de", "binnet", "normvar", "lcpm"}

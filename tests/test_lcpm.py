@@ -1,0 +1,74 @@
+"""lcpm (reference src/normalisr/lcpm.py:21-208).  CPU: the oracle against the golden
+vectors made by the unmodified reference.  GPU: the CUDA path against both."""
+import numpy as np
+import pytest
+import torch
+
+import normalisr_oracle as orc
+from conftest import load_golden
+
+gpu = pytest.mark.gpu
+
+
+def test_oracle_lcpm_matches_reference():
+    g = load_golden("lcpm_counts")
+    a = orc.lcpm(g["reads"])
+    np.testing.assert_allclose(a[0], g["lcpm"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(a[3], g["cov"], rtol=1e-14)
+    assert a[1] is None and a[2] is None
+    b = orc.lcpm(g["reads"], lowmem=False, nocov=True)
+    np.testing.assert_allclose(b[1], g["mean"], rtol=1e-13, atol=1e-13)
+    assert (b[2] == 0).all() and b[3] is None
+    c = orc.lcpm(g["reads"], normalize=False, ntot=10 ** 9)
+    np.testing.assert_allclose(c[0], g["lcpm_raw"], rtol=1e-13, atol=1e-13)
+    empty_cell = np.array([[1, 0, 2], [3, 0, 1]])
+    with pytest.raises(ValueError):
+        orc.lcpm(empty_cell)                                     # a cell without reads (lcpm.py:195-196)
+    with pytest.raises(AssertionError):
+        orc.lcpm(np.zeros((3, 4), dtype=int))                    # no reads at all (lcpm.py:91)
+
+
+@gpu
+def test_lcpm_golden(monkeypatch):
+    from normalisr_b200 import lcpm as lc, normalisr as norm
+    g = load_golden("lcpm_counts")
+    for chunk in (1 << 30, 8 * 300 * 50):                           # one block / several row blocks
+        monkeypatch.setattr(lc, "_ROW_CHUNK_BYTES", chunk)
+        out = norm.lcpm(g["reads"])
+        assert isinstance(out[0], np.ndarray) and out[1] is None and out[2] is None
+        np.testing.assert_allclose(out[0], g["lcpm"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(out[3], g["cov"], rtol=1e-13)
+    out = norm.lcpm(g["reads"].astype(np.int32), lowmem=False, nocov=True)
+    np.testing.assert_allclose(out[1], g["mean"], rtol=1e-12, atol=1e-12)
+    assert (out[2] == 0).all() and out[3] is None
+    out = norm.lcpm(g["reads"], normalize=False, ntot=10 ** 9)
+    np.testing.assert_allclose(out[0], g["lcpm_raw"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(out[3], g["cov_raw"], rtol=1e-13)
+    dev = norm.lcpm(torch.from_numpy(g["reads"].astype(np.int64)).cuda())
+    assert dev[0].is_cuda and dev[3].is_cuda
+    np.testing.assert_allclose(dev[0].cpu().numpy(), g["lcpm"], rtol=1e-12, atol=1e-12)
+
+
+@gpu
+def test_lcpm_larger_against_oracle_and_errors():
+    from normalisr_b200 import normalisr as norm
+    rng = np.random.default_rng(12)
+    reads = rng.negative_binomial(2, 2.0 / (2.0 + rng.gamma(0.5, 4.0, size=(1500, 1)) * rng.lognormal(0, 0.4, size=(1, 2000))))
+    reads[:, 7] += 1                                               # no empty cell
+    want = orc.lcpm(reads)
+    got = norm.lcpm(reads)
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got[3], want[3], rtol=1e-13)
+    np.testing.assert_allclose(np.exp(got[0]).sum(axis=0), 1e6, rtol=1e-10)        # counts per million
+    with pytest.raises(ValueError):
+        norm.lcpm(np.array([[1, 0, 2], [3, 0, 1]]))
+    with pytest.raises(AssertionError):
+        norm.lcpm(np.zeros((3, 4), dtype=int))
+    with pytest.raises(ValueError):
+        norm.lcpm(-np.ones((3, 4), dtype=int))
+    with pytest.raises(ValueError):
+        norm.lcpm(np.ones(4, dtype=int))
+    with pytest.raises(ValueError):
+        norm.lcpm(np.ones((3, 4), dtype=int), varscale=-1)
+    with pytest.raises(NotImplementedError):
+        norm.lcpm(np.ones((3, 4), dtype=int), varscale=1)

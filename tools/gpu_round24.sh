@@ -1,0 +1,2 @@
+#!/bin/bash
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -14
