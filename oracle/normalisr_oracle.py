@@ -2,8 +2,8 @@
 
 This file is a numpy restatement of the reference algorithm
 (lingfeiwang/normalisr v1.0.0, ``src/normalisr/association.py``, ``coex.py``,
-``de.py``; and, for the rows of SURVEY 8(f) that were built, ``binnet.py`` and
-``norm.py:normvar``).  It exists so that the CUDA path can be checked on a box where
+``de.py``; and, for the rows of SURVEY 8(f) that were built, ``binnet.py``,
+``norm.py:normvar`` and ``lcpm.py:lcpm``).  It exists so that the CUDA path can be checked on a box where
 ``/root/reference`` is absent.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
 product package ``normalisr_b200`` never does.
@@ -11,9 +11,9 @@ product package ``normalisr_b200`` never does.
 Parity status: PINNED.  The reference ships no tests or golden vectors
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference
 itself, run in the authoring container by ``tests/golden/make_golden*.py`` (coex / de
-single 0 and 4, de single=1, binnet / bh, normvar) and committed as
-``tests/golden/*.npz`` (``tests/test_oracle.py``, ``test_binnet.py`` and
-``test_normvar.py`` check every one).
+single 0 and 4, de single=1, binnet / bh, normvar, lcpm) and committed as
+``tests/golden/*.npz`` (``tests/test_oracle.py``, ``test_binnet.py``,
+``test_normvar.py`` and ``test_lcpm.py`` check every one).
 
 Third-party arithmetic the reference calls and that is not under /root/reference:
 ``numpy.matmul`` (BLAS dgemm), ``scipy.linalg.svd`` (LAPACK gesdd) and
