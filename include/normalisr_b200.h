@@ -215,6 +215,13 @@ int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsi
                    int64_t n, int64_t ld, const double* lut, int64_t lut_len, const double* shift,
                    double* out, int64_t ldo);
 
+/* compute_var (norm.compute_var, src/normalisr/norm.py:56-128), column pass: with res = X - coef Qt
+ * (the covariate-projection residual, not materialised; coef from nsr_project_coef),
+ *   out[k] = sum_g ((res[g][k] - mean[g]) * inv_std[g])^2      (norm.py:103).   rank <= 16. */
+int nsr_colvar(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t genes, int64_t n, int64_t ld,
+               const double* Qt, int rank, int64_t ldq, const double* coef, int64_t ldcoef,
+               const double* mean, const double* inv_std, double* out);
+
 /* P[i] = I_{1 - r2[i]}(a[i / row_len], 1/2)  -- scipy.stats.beta.cdf(1-r2, a, 0.5),
  * association.py:249, 563.  `a` holds one value per row of row_len entries. */
 int nsr_pvalue(nsr_ctx* ctx, uintptr_t stream, const double* r2, const double* a,

@@ -100,3 +100,75 @@ extern "C" int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads,
     NSR_CHECK(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// compute_var (norm.py:56-128), column pass: with res = X - coef Qt (the covariate-projection
+// residual, never materialised), per cell k
+//     out[k] = sum_g ((res[g][k] - mean[g]) * inv_std[g])^2          (norm.py:103)
+// A thread owns a cell column and keeps Qt[:, k] in registers; the coefficients, means and inverse
+// standard deviations of the CTA's gene range sit in shared memory.  Gene ranges are split over
+// blockIdx.y and combined in a fixed order.
+namespace {
+
+constexpr int kCvRank = 16;            // covariate rank handled in registers
+
+__global__ void __launch_bounds__(kLcThreads)
+colvar_kernel(const double* __restrict__ X, int64_t genes, int64_t n, int64_t ld, const double* __restrict__ Qt,
+              int rank, int64_t ldq, const double* __restrict__ coef, int64_t ldcoef,
+              const double* __restrict__ mean, const double* __restrict__ inv_std, double* __restrict__ partial) {
+    __shared__ double s_coef[kLcGeneSplit][kCvRank];
+    __shared__ double s_mean[kLcGeneSplit], s_istd[kLcGeneSplit];
+    const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
+    for (int idx = threadIdx.x; idx < kLcGeneSplit * kCvRank; idx += kLcThreads) {
+        const int g = idx / kCvRank, j = idx % kCvRank;
+        s_coef[g][j] = (g0 + g < g1 && j < rank) ? coef[(g0 + g) * ldcoef + j] : 0.0;
+    }
+    for (int g = threadIdx.x; g < kLcGeneSplit; g += kLcThreads) {
+        s_mean[g] = g0 + g < g1 ? mean[g0 + g] : 0.0;
+        s_istd[g] = g0 + g < g1 ? inv_std[g0 + g] : 0.0;
+    }
+    __syncthreads();
+    const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
+    if (k >= n) return;
+    double q[kCvRank];
+#pragma unroll
+    for (int j = 0; j < kCvRank; ++j) q[j] = j < rank ? Qt[(int64_t)j * ldq + k] : 0.0;
+    double acc = 0.0;
+    for (int64_t g = g0; g < g1; ++g) {
+        double r = X[g * ld + k];
+#pragma unroll
+        for (int j = 0; j < kCvRank; ++j) r = fma(-s_coef[g - g0][j], q[j], r);
+        const double z = (r - s_mean[g - g0]) * s_istd[g - g0];
+        acc = fma(z, z, acc);
+    }
+    partial[(int64_t)blockIdx.y * n + k] = acc;
+}
+
+__global__ void colvar_reduce_kernel(const double* __restrict__ partial, int64_t n, int n_split, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    for (int p = 0; p < n_split; ++p) s += partial[(int64_t)p * n + k];
+    out[k] = s;
+}
+
+}  // namespace
+
+extern "C" int nsr_colvar(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t genes, int64_t n, int64_t ld,
+                          const double* Qt, int rank, int64_t ldq, const double* coef, int64_t ldcoef,
+                          const double* mean, const double* inv_std, double* out) {
+    NSR_REQUIRE(ctx && X && mean && inv_std && out, "nsr_colvar: null argument");
+    NSR_REQUIRE(genes >= 1 && n >= 1 && ld >= n && rank >= 0 && rank <= kCvRank && (rank == 0 || (Qt && coef && ldq >= n && ldcoef >= rank)),
+                "nsr_colvar: bad arguments (rank %d, at most %d)", rank, kCvRank);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_split = (int)((genes + kLcGeneSplit - 1) / kLcGeneSplit);
+    NSR_REQUIRE(n_split <= 65535, "nsr_colvar: too many genes for one call");
+    void* scratch = nullptr;
+    if (nsr_scratch(ctx, (size_t)n_split * n * sizeof(double), &scratch)) return 1;
+    const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
+    colvar_kernel<<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch);
+    colvar_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)scratch, n, n_split, out);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}

@@ -156,3 +156,69 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         if to_host:
             ans = [a.cpu().numpy() if a.is_cuda else a.numpy() for a in ans]
     return ans
+
+
+def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
+    """Computes the variance normalisation multiplier of every cell (reference norm.py:56-128): a
+    log-linear fit of each cell's residual variance on the covariates.  Same arguments, checks and
+    return value (``(n_cell,)`` array, minimum 1).  Only ``stepmax=1`` (the reference's default, no
+    EM-like iterations) is accelerated.
+
+    The residual matrix is never materialised: one pass over dt gives every gene's projection
+    coefficients, residual mean and variance (``nsr_project_coef`` on the orthonormal covariate
+    basis plus a row of ones), a second one the per-cell sums of squared standardised residuals
+    (``nsr_colvar``); the fit of the log variances on the covariates is a rank-sized problem."""
+    from .association import covariate_basis_device
+    if eps <= 0 or stepmax <= 0:
+        raise ValueError('eps and stepmax must be positive.')
+    if dt.ndim != 2 or dc.ndim != 2:
+        raise ValueError('dt and dc must both have 2 dimensions.')
+    if dt.shape[1] != dc.shape[1]:
+        raise ValueError('dt and dc must have the same cell count.')
+    if stepmax != 1:
+        raise NotImplementedError('compute_var is accelerated for stepmax=1 (no EM-like iterations).')
+    to_host = not _is_dev(dt)
+    ctx = engine.context(device if device is not None else (dt.device if _is_dev(dt) else None))
+    dev = ctx.device
+    nt, ns = dt.shape
+    with torch.cuda.device(dev):
+        dc_d = _dev64(dc, dev).contiguous()
+        Qt, rank, _ = covariate_basis_device(ctx, dc_d)           # least squares without intercept = projection
+        if rank > 16:
+            raise NotImplementedError('compute_var is accelerated for covariate rank <= 16.')
+        ones = torch.ones((1, ns), dtype=torch.float64, device=dev)
+        q1 = torch.cat([Qt, ones], 0).contiguous() if rank else ones
+        qsum = Qt.sum(dim=1) if rank else None
+        src = dt if not to_host else (dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt)))
+        step = nt if not to_host else max(1, _ROW_CHUNK_BYTES // (8 * ns))
+        col = torch.zeros(ns, dtype=torch.float64, device=dev)
+        for g0 in range(0, nt, step):
+            g1 = min(nt, g0 + step)
+            blk = src[g0:g1].to(dev, torch.float64, non_blocking=True)
+            if blk.stride(1) != 1:
+                blk = blk.contiguous()
+            cf, sxx = engine.project_coef(ctx, blk, q1)                       # (gc, rank + 1), (gc,)
+            coef = cf[:, :rank]
+            mean = (cf[:, rank] - (coef @ qsum if rank else 0.0)) / ns        # norm.py:101
+            var = (sxx - (coef * coef).sum(dim=1)) / ns - mean * mean         # :102 (Qt is orthonormal)
+            istd = (1.0 / torch.sqrt(var)).contiguous()
+            part = torch.empty(ns, dtype=torch.float64, device=dev)
+            _lib.check(ctx.lib.nsr_colvar(ctx.handle, engine._stream(), blk.data_ptr(), g1 - g0, ns,
+                                          blk.stride(0) if g1 - g0 > 1 else ns, Qt.data_ptr() if rank else None, rank,
+                                          Qt.stride(0) if rank > 1 else ns, cf.data_ptr(), cf.stride(0),
+                                          mean.contiguous().data_ptr(), istd.data_ptr(), part.data_ptr()), "nsr_colvar")
+            engine.LAUNCHES += 2
+            col += part
+        y = torch.log(torch.sqrt(col / nt))                                   # :103
+        # log-linear fit with intercept (:104-105): mean + projection on the centred covariates
+        xc = dc_d - dc_d.mean(dim=1, keepdim=True)
+        Qc, rc, _ = covariate_basis_device(ctx, xc)
+        ym = y.mean()
+        pred = ym + (Qc.T @ (Qc @ (y - ym)) if rc else 0.0)
+        new = torch.exp(pred)                                                 # :107 (scale was 1)
+        new = new / new.min()
+        w = 1.0 / new                                                         # :122-123
+        w = w / w.min()
+        if not bool(torch.isfinite(w).all() & (w > 0).all()):
+            raise AssertionError('non-finite variance normalisation multipliers')
+        return w.cpu().numpy() if to_host else w

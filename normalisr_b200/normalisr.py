@@ -8,6 +8,6 @@ from .binnet import binnet
 from .coex import coex
 from .de import de
 from .lcpm import lcpm
-from .norm import normvar
+from .norm import compute_var, normvar
 
-__all__ = ["coex", "de", "binnet", "normvar", "lcpm"]
+__all__ = ["coex", "de", "binnet", "normvar", "lcpm", "compute_var"]

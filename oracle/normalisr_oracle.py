@@ -3,7 +3,7 @@
 This file is a numpy restatement of the reference algorithm
 (lingfeiwang/normalisr v1.0.0, ``src/normalisr/association.py``, ``coex.py``,
 ``de.py``; and, for the rows of SURVEY 8(f) that were built, ``binnet.py``,
-``norm.py:normvar`` and ``lcpm.py:lcpm``).  It exists so that the CUDA path can be checked on a box where
+``norm.py:normvar`` / ``compute_var`` and ``lcpm.py:lcpm``).  It exists so that the CUDA path can be checked on a box where
 ``/root/reference`` is absent.  Only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
 product package ``normalisr_b200`` never does.
@@ -11,7 +11,7 @@ product package ``normalisr_b200`` never does.
 Parity status: PINNED.  The reference ships no tests or golden vectors
 (SURVEY.md section 4), so the oracle is pinned against outputs of the reference
 itself, run in the authoring container by ``tests/golden/make_golden*.py`` (coex / de
-single 0 and 4, de single=1, binnet / bh, normvar, lcpm) and committed as
+single 0 and 4, de single=1, binnet / bh, normvar, compute_var, lcpm) and committed as
 ``tests/golden/*.npz`` (``tests/test_oracle.py``, ``test_binnet.py``,
 ``test_normvar.py`` and ``test_lcpm.py`` check every one).
 
@@ -525,3 +525,37 @@ def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, **ignored):
     if lowmem:
         return dtn, None, None, dcov
     return dtn, dtn.copy(), np.zeros(dtn.shape), dcov
+
+
+def compute_var(dt, dc, stepmax=1, eps=1e-6):
+    """norm.py:56-128: per-cell variance normalisation multiplier from a log-linear fit of each
+    cell's residual variance on the covariates (EM-like iterations for stepmax > 1).  The
+    reference fits with sklearn LinearRegression, i.e. least squares (minimum norm), without and
+    with intercept."""
+    if eps <= 0 or stepmax <= 0:
+        raise ValueError('eps and stepmax must be positive.')
+    if dt.ndim != 2 or dc.ndim != 2:
+        raise ValueError('dt and dc must both have 2 dimensions.')
+    if dt.shape[1] != dc.shape[1]:
+        raise ValueError('dt and dc must have the same cell count.')
+    ns = dc.shape[1]
+    scale = np.ones(ns)
+    best, bestv, n = None, 1e300, 0
+    while n < stepmax and bestv > eps:
+        td1, tdx = dt / scale, dc / scale                                     # :96-97
+        beta = np.linalg.lstsq(tdx.T, td1.T, rcond=None)[0]                   # :98 (no intercept)
+        td1 = td1 - (tdx.T @ beta).T                                          # :99
+        m = td1.mean(axis=1)                                                  # :101
+        sd = np.sqrt(((td1.T - m) ** 2).mean(axis=0))                         # :102
+        y = np.log(np.sqrt((((td1.T - m) / sd) ** 2).mean(axis=1)))           # :103
+        xc = dc.T - dc.T.mean(axis=0)                                         # :104-105 (with intercept)
+        b2 = np.linalg.lstsq(xc, y - y.mean(), rcond=None)[0]
+        new = np.exp(y.mean() + xc @ b2) * scale                              # :107
+        new /= new.min()
+        t1 = np.abs((new - scale) / scale).max()
+        scale = new
+        n += 1
+        if t1 < bestv:
+            bestv, best = t1, scale
+    w = 1 / best
+    return w / w.min()

@@ -225,4 +225,4 @@ def test_every_module_imports_without_a_gpu():
                  "parallel", "engine", "synth", "_build", "_lib"):
         importlib.import_module("normalisr_b200." + name)
     import normalisr_b200.normalisr as norm
-    assert set(norm.__all__) == {"coex", "de", "binnet", "normvar", "lcpm"}
+    assert set(norm.__all__) == {"coex", "de", "binnet", "normvar", "lcpm", "compute_var"}

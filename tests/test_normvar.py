@@ -72,6 +72,41 @@ def test_normvar_against_oracle_shapes_and_chunks(monkeypatch):
                 np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max()))
 
 
+def test_oracle_compute_var_matches_reference():
+    g = load_golden("compute_var")
+    np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc"]), g["w"], rtol=1e-12)
+    np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc2"]), g["w2"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        orc.compute_var(g["dt"], g["dc"][:, :-1])
+
+
+@gpu
+def test_compute_var_golden_and_oracle(monkeypatch):
+    from normalisr_b200 import norm as nv, normalisr as norm
+    g = load_golden("compute_var")
+    for dc, w in ((g["dc"], g["w"]), (g["dc2"], g["w2"])):
+        got = norm.compute_var(g["dt"], dc)
+        assert isinstance(got, np.ndarray) and got.shape == w.shape and got.min() == 1.0
+        np.testing.assert_allclose(got, w, rtol=1e-10)
+    dev = norm.compute_var(torch.from_numpy(g["dt"]).cuda(), torch.from_numpy(g["dc"]).cuda())
+    assert dev.is_cuda
+    np.testing.assert_allclose(dev.cpu().numpy(), g["w"], rtol=1e-10)
+    rng = np.random.default_rng(14)
+    n, genes = 3000, 900
+    dc = np.concatenate([rng.normal(size=(4, n)), (rng.random((2, n)) < 0.3).astype(float), np.ones((1, n))])
+    dt = rng.normal(size=(genes, n)) * np.exp(0.3 * dc[0]) * rng.uniform(0.5, 2, size=(genes, 1)) + 0.5 * dc[1] - 7.0
+    want = orc.compute_var(dt, dc)
+    monkeypatch.setattr(nv, "_ROW_CHUNK_BYTES", 8 * n * 200)                  # several row blocks
+    np.testing.assert_allclose(norm.compute_var(dt, dc), want, rtol=1e-10)
+    assert want.max() / want.min() > 1.5                                       # the cell-level trend is there
+    with pytest.raises(ValueError):
+        norm.compute_var(dt, dc[:, :-1])
+    with pytest.raises(ValueError):
+        norm.compute_var(dt, dc, eps=0)
+    with pytest.raises(NotImplementedError):
+        norm.compute_var(dt, dc, stepmax=3)
+
+
 @gpu
 def test_normvar_errors():
     from normalisr_b200 import normalisr as norm
