@@ -403,6 +403,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
     de = None
     normvar_info = None
     lcpm_info = None
+    cvar_info = None
     if world == 1 and not args.no_de:
         try:
             de = bench_de(torch, dev, args)
@@ -416,6 +417,10 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             lcpm_info = bench_lcpm(torch, dev)
         except Exception as e:
             lcpm_info = {"error": repr(e)[:300]}
+        try:
+            cvar_info = bench_compute_var(torch, dev)
+        except Exception as e:
+            cvar_info = {"error": repr(e)[:300]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -434,7 +439,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                                        else "copy engines over peer-mapped memory")),
                    "note": wl_desc},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-        "de": de, "binnet": binnet_info, "normvar": normvar_info, "lcpm": lcpm_info,
+        "de": de, "binnet": binnet_info, "normvar": normvar_info, "lcpm": lcpm_info, "compute_var": cvar_info,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -589,6 +594,36 @@ def bench_lcpm(torch, dev, n_gene=10000, n_cell=50000, reps=3):
     return {"workload": "lcpm_%dk_x_%dk" % (n_cell // 1000, n_gene // 1000), "ms": ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": 12 * n_gene * n_cell}}
+
+
+def bench_compute_var(torch, dev, n_gene=10000, n_cell=50000, reps=3):
+    """normalisr_b200.compute_var on device-resident inputs: 8 B of algorithmic traffic per entry
+    (dt read once); the kernels read dt twice (coefficients / moments, then the column pass)."""
+    from normalisr_b200 import normalisr as norm, synth
+    torch.cuda.empty_cache()
+    p = synth.device_problem(1002, n_gene, n_cell, dev)
+    for _ in range(2):
+        norm.compute_var(p["dt"], p["dc"])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        norm.compute_var(p["dt"], p["dc"])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs") or 6545.0
+    gbs = 8.0 * n_gene * n_cell / (ms * 1e-3) / 1e9
+    del p
+    torch.cuda.empty_cache()
+    return {"workload": "compute_var_%dk_x_%dk" % (n_cell // 1000, n_gene // 1000), "covariates": 9, "ms": ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "algorithmic_bytes": 8 * n_gene * n_cell}}
 
 
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
