@@ -43,7 +43,19 @@ WORKLOADS = {
 METRIC = "coex gene-pairs/s (r+P)"
 UNIT = "pairs/s"
 SEED = 1004
-CPU_SAMPLE_GENES = 3000
+
+
+def cpu_sample_genes(cores, n_gene):
+    """Genes of the CPU sample: a whole number nb of the reference's 500-gene blocks, chosen so that
+    its nb (nb + 1) / 2 tiles fill the thread pool's waves as evenly as possible (15 tiles on 16
+    cores, 28 on 32): extrapolating by tile count then does not charge the CPU for idle threads."""
+    best, best_eff = 4, 0.0
+    for nb in range(4, 12):
+        tiles = nb * (nb + 1) // 2
+        eff = tiles / float(-(-tiles // cores) * cores)
+        if eff > best_eff + 1e-9:
+            best, best_eff = nb, eff
+    return min(best * 500, n_gene)
 
 
 # --------------------------------------------------------------------------------------
@@ -112,7 +124,7 @@ def reference_tiles(n_gene, bs=500):
 
 def cpu_sample_problem(n_gene, n_cell):
     from normalisr_b200 import synth
-    g = min(CPU_SAMPLE_GENES, n_gene)
+    g = cpu_sample_genes(os.cpu_count() or 1, n_gene)
     p = synth.host_problem(SEED, g, n_cell, n_module=2, module_size=20)
     return p["dt"], p["dc"]
 
@@ -159,9 +171,13 @@ def run_reference(args, n_gene, n_cell, wl_name, wl_desc):
     ts = [cpu_time_once(dt, dc, setting) for _ in range(args.steps)]
     total = sum(ts)
     value = cpu_extrapolate(total / args.steps, sg, n_gene)
-    sample = ("%d of %d genes x all %d cells = %d of the reference's %d 500x500 tiles per step, extrapolated by tile "
-              "count; thread setting %s (%s)" % (sg, n_gene, n_cell, reference_tiles(sg), reference_tiles(n_gene), setting,
-                                                 "BLAS=1 thread, nth=cores" if setting == "A" else "nth=1, BLAS=all cores"))
+    sample = ("%d of %d genes x all %d cells = %d of the reference's %d 500x500 tiles per step (a tile count that fills "
+              "the %d-thread pool's waves to %.0f %%), extrapolated by tile count; thread setting %s (%s); s per tile: "
+              "A (BLAS=1 thread, nth=cores) %.3f, B (nth=1, BLAS=all cores) %.3f" % (
+                  sg, n_gene, n_cell, reference_tiles(sg), reference_tiles(n_gene), os.cpu_count(),
+                  100.0 * reference_tiles(sg) / (-(-reference_tiles(sg) // os.cpu_count()) * os.cpu_count()), setting,
+                  "BLAS=1 thread, nth=cores" if setting == "A" else "nth=1, BLAS=all cores",
+                  best["A"] / reference_tiles(sg), best["B"] / reference_tiles(sg)))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -232,6 +248,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         P = torch.zeros((max(my_rows, 1), n_gene), dtype=torch.float64, device=dev)
         D = torch.zeros_like(P)
     contract_ms = []
+    project_ms = []
     k_plan = {}
 
     def step_device(record=False):
@@ -245,7 +262,13 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             return
         Qt_dev, crank, _ = association.covariate_basis_device(ctx, dc_dev)
         dof_a = (n_cell - 1 - crank) / 2
+        if record:
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
         engine.residualize(ctx, dt_dev, Qt_dev, n_slices, out=local_sl, row_offset=0)
+        if record:
+            p1.record()
+            project_ms.append((p0, p1))
         full = local_sl
         full.rows = n_gene
         if record:
@@ -386,6 +409,21 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                         "products per pair at 2x the bf16 rate, so its ceiling on this scale is 2/%.2f of the bf16 peak (ceiling_frac); "
                         "frac_of_ceiling = how much of that the kernel reaches" % (eff_products, eff_products)}
 
+    # ---- roofline of the projection (HBM-bound): algorithmic bytes per SURVEY 8(d) = 16 B per matrix element
+    roof_proj = None
+    if project_ms:
+        pm = float(np.mean([a.elapsed_time(b) for a, b in project_ms]))
+        hbm = peaks.get("hbm_gbs") or 6650.0
+        elems = float(g1 - g0) * n_cell
+        roof_proj = {"bound": "hbm", "achieved": 16.0 * elems / (pm * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                     "frac": 16.0 * elems / (pm * 1e-3) / 1e9 / hbm, "kernel": "coef_mma_kernel + residual_mma_kernel",
+                     "kernel_ms": pm, "algorithmic_bytes": 16.0 * elems,
+                     "executed_bytes": (16.0 + n_slices) * elems,
+                     "executed_frac": (16.0 + n_slices) * elems / (pm * 1e-3) / 1e9 / hbm,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
+                     "note": "algorithmic = 8 B read + 8 B residual written per element (SURVEY 8d); executed = X read "
+                             "twice (coefficients, then residual + Hadamard + digits) + %d int8 digit planes written" % n_slices}
+
     # ---- CPU baseline on a bounded sample (N = 1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -394,10 +432,13 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         s_best = min(tb, key=tb.get)
         cpu = {"value": cpu_extrapolate(tb[s_best], dt_s.shape[0], n_gene), "unit": UNIT, "cores": os.cpu_count(),
                "kind": "port",
-               "sample": "%d of %d genes x all %d cells (%d of the reference's %d 500x500 tiles), one pass per thread setting, "
-                         "faster one (%s) extrapolated by tile count; A=%.2fs B=%.2fs" % (
-                             dt_s.shape[0], n_gene, n_cell, reference_tiles(dt_s.shape[0]), reference_tiles(n_gene), s_best,
-                             tb["A"], tb["B"])}
+               "sample": "%d of %d genes x all %d cells (%d of the reference's %d 500x500 tiles: fills the %d-thread pool's "
+                         "waves to %.0f %%), one pass per thread setting, faster one (%s) extrapolated by tile count; "
+                         "s per tile: A (BLAS=1 thread, nth=cores) %.3f, B (nth=1, BLAS=all cores) %.3f" % (
+                             dt_s.shape[0], n_gene, n_cell, reference_tiles(dt_s.shape[0]), reference_tiles(n_gene),
+                             os.cpu_count(), 100.0 * reference_tiles(dt_s.shape[0]) /
+                             (-(-reference_tiles(dt_s.shape[0]) // os.cpu_count()) * os.cpu_count()), s_best,
+                             tb["A"] / reference_tiles(dt_s.shape[0]), tb["B"] / reference_tiles(dt_s.shape[0]))}
 
     # ---- secondary metric of BASELINE.json: DE tests/s (config 3 shape), N = 1 only
     de = None
@@ -438,7 +479,7 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                                        world, world // 2, "nccl" if (parallel.TRANSPORT == "nccl" or None in parallel._SYMM.values())
                                        else "copy engines over peer-mapped memory")),
                    "note": wl_desc},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_projection": roof_proj, "cpu_baseline": cpu,
         "de": de, "binnet": binnet_info, "normvar": normvar_info, "lcpm": lcpm_info, "compute_var": cvar_info,
     }
     print(json.dumps(line), flush=True)
@@ -495,6 +536,36 @@ def run_de_sweep(args, n_gene, n_cell, wl_name, wl_desc, n_group=1000, genes_per
             "gpu_launches": engine.LAUNCHES - launches0, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_int8_peak(torch, dev, seconds=3.0):
+    """Dense int8 tensor-core throughput of this box (cuBLASLt through torch._int_mm, 8192^3): best of
+    10 (burst) and back to back for ``seconds`` (sustained, under the power cap) - the denominator of
+    the contraction's EXECUTED int8 utilisation.  Library call, measurement only."""
+    n = 8192
+    a = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+    b = torch.randint(-128, 127, (n, n), dtype=torch.int8, device=dev)
+    for _ in range(3):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    ops = 2.0 * n ** 3
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(20, int(seconds / (ops / (best * 1e12))))
+    e0.record()
+    for _ in range(reps):
+        torch._int_mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    sus = reps * ops / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return {"int8_tops_burst": best, "int8_tops_sustained": sus, "how": "torch._int_mm 8192^3, best of 10 / %d back to back" % reps}
 
 
 def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):

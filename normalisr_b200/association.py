@@ -76,7 +76,10 @@ def covariate_basis(dc, tol=1e-8):
     nc, n = dc.shape
     if nc == 0 or not (dc != 0).any():          # association.py:899-903
         return None, 0, np.zeros((0, nc))
-    w0, rank = _basis_weights(dc @ dc.T, tol)
+    gram = dc @ dc.T
+    if not np.isfinite(gram).all():
+        raise AssertionError('Non-finite values (NaN / Inf) in the covariates.')
+    w0, rank = _basis_weights(gram, tol)
     q0 = w0 @ dc
     Linv, W = _reorthonormalise(q0 @ q0.T, w0)
     return np.ascontiguousarray(Linv @ q0), rank, W
@@ -99,6 +102,8 @@ def covariate_basis_device(ctx, dc, tol=1e-8):
         dc_d = dc_d.contiguous()
     with torch.cuda.device(ctx.device):
         gram = engine.cov_gram(ctx, dc_d).cpu().numpy()
+        if not np.isfinite(gram).all():
+            raise AssertionError('Non-finite values (NaN / Inf) in the covariates.')
         if not gram.any():                       # all-zero covariates, association.py:899-903
             return None, 0, np.zeros((0, nc))
         w0, rank = _basis_weights(gram, tol)

@@ -17,6 +17,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev);
 extern int nsr_use_hadamard;
+extern int nsr_prefetch;
 extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
 extern int nsr_epi_warps;
@@ -116,6 +117,7 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
 // test hooks: "hadamard" (0/1), "umma_kblock" (64/128)
 extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "hadamard")) { nsr_use_hadamard = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "prefetch")) { nsr_prefetch = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_dynamic")) { nsr_umma_dynamic = value ? 1 : 0; return 0; }
     if (!strcmp(name, "adaptive_min_cells")) { nsr_adaptive_min_cells = value < 0 ? 0 : value; return 0; }

@@ -112,6 +112,7 @@ NSR_HD double nsr_pvalue_r2(double r2_in, const NsrPvalParams& p) {
     // (association.py:249); R2 below 1.1e-16 therefore gives exactly P = 1.  Keep
     // that rounding so tiny correlations agree with it to the last digit.
     const double x = 1.0 - r2_in;
+    if (x != x) return x;                          // NaN in, NaN out (the reference asserts on it)
     if (!(x < 1.0)) return 1.0;
     if (!(x > 0.0)) return 0.0;
     const double r2 = 1.0 - x;                     // exact (Sterbenz) for x >= 1/2

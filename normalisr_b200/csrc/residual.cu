@@ -32,6 +32,8 @@
 // fixed permutation is as good as the natural order, and every lane stores 32 contiguous bytes.
 #include "nsr_common.cuh"
 
+extern int nsr_prefetch;
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -232,7 +234,7 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
                     int nblk, int ksplit, uint64_t cell_offset,
                     const double* __restrict__ inv_quantum, double* __restrict__ part_sumsq,
                     double* __restrict__ part_amax, int8_t* __restrict__ slices, int64_t rows_alloc,
-                    int64_t n_pad, unsigned long long* __restrict__ energy_max) {
+                    int64_t n_pad, unsigned long long* __restrict__ energy_max, int prefetch) {
     // covariate block of the current 128 cells, shared by the CTA's 8 warps (they walk the same
     // cells): [buffer][covariate][cell], pitch 132 so that a B-fragment read (4 covariates x 8 cells
     // per half-warp) touches 16 distinct banks
@@ -281,6 +283,14 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
             mb = ((t & 1) ? m[3] : m[1]) >> (t >> 1);
         }
         double v[32];
+        // ---- pull the NEXT block's 8 KB of X into L2 while this one is processed: the loads below then
+        // wait for an L2 hit instead of DRAM (each warp spends thousands of issue slots per block, so one
+        // block of lead is plenty); a quad covers its row's 8 lines, two per lane
+        if (prefetch && blk + 1 < b_end && blk + 1 < nblk_full) {
+            const double* nx = xr - 2 * t + k0 + 128 + 32 * t;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
+        }
         // ---- all X loads of the block first (independent, 8 KB per warp in flight)
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
@@ -395,7 +405,7 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
                                       int ksplit, int64_t n, double vmax,
                                       double* __restrict__ var, double* __restrict__ quantum,
                                       double* __restrict__ inv_quantum, int32_t* __restrict__ fix_list,
-                                      int32_t* __restrict__ fix_count) {
+                                      int32_t* __restrict__ fix_count, unsigned long long* __restrict__ energy_max) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     double s = 0.0, m = 0.0;
@@ -403,6 +413,11 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
         s += part_sumsq[(int64_t)ks * rows + i];
         m = fmax(m, part_amax[(int64_t)ks * rows + i]);
     }
+    // A NaN / Inf anywhere in the row (or in the covariate basis) makes the sum of squares non-finite.
+    // The reference asserts finite results (association.py:252-255); here the row poisons entry (0, 0) of
+    // the energy report with a NaN - as an integer its bit pattern beats every finite energy under
+    // atomicMax - and the host, which reads the report before every contraction, raises.
+    if (!isfinite(s) && energy_max != nullptr) atomicMax(energy_max, 0x7ff8000000000000ull);
     double v = s / (double)n;
     if (v == 0.0) v = 1.0;                       // association.py:231,233
     var[i] = v;
@@ -434,6 +449,7 @@ __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, 
 }  // namespace
 
 int nsr_use_hadamard = 1;   // test hook (nsr_set_option)
+int nsr_prefetch = 1;       // test hook: L2 prefetch of the next block in pass B
 
 extern "C" int64_t nsr_padded_cells(int64_t n) { return (n + NSR_KBLOCK - 1) / NSR_KBLOCK * NSR_KBLOCK; }
 
@@ -515,7 +531,7 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
 #define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
     residual_mma_kernel<S_, H_, V_, N_><<<gridb, kThreads, 0, st>>>(                                         \
         X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
-        rows_alloc, n_pad, (unsigned long long*)energy_max)
+        rows_alloc, n_pad, (unsigned long long*)energy_max, nsr_prefetch)
 #define NSR_LAUNCH_B_N(S_, H_, V_, LIST, COUNT, PS, PA)                                                      \
     do {                                                                                                     \
         switch (nch) {                                                                                       \
@@ -538,7 +554,8 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     } while (0)
     NSR_LAUNCH_B_ALL(nullptr, nullptr, p_sumsq, p_amax);
     stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
-                                                                        quantum, invq, fix_list, fix_count);
+                                                                        quantum, invq, fix_list, fix_count,
+                                                                        (unsigned long long*)energy_max);
     // sparse fix-up: warps beyond the (device-side) count exit at once
     NSR_LAUNCH_B_ALL(fix_list, fix_count, nullptr, nullptr);
 #undef NSR_LAUNCH_B_ALL

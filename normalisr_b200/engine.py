@@ -271,6 +271,9 @@ def plan_k_chunk(A, B, n_products, energies=None):
         ea, eb = A.energy_max.cpu().numpy(), (A if B is A else B).energy_max.cpu().numpy()   # one small sync
     else:
         ea, eb = energies
+    if not (np.isfinite(ea).all() and np.isfinite(eb).all()):
+        # nsr_residualize poisons the report when a row's sum of squares is not finite
+        raise AssertionError('Non-finite values (NaN / Inf) in the input matrix or the covariates.')
     ks = _lib.load().nsr_cell_splits(A.n)
     nblk = A.n_pad // _lib.KBLOCK
     groups = products_of(A.n_slices, n_products)

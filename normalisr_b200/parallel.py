@@ -248,6 +248,19 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
         rounds = start_exchange(local, group) if symm is None else start_exchange_ce(symm[0], symm[1], local, group)
     em_h = em.cpu().numpy()
     k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_h, em_h))
+    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out, events, out_host)
+    return P, D, var_all[:n_gene]
+
+
+def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out=None, events=None,
+                  out_host=None):
+    """Contract everything ``rank`` owns under the pairs schedule: the upper triangle of its diagonal
+    block, then the block pairs of ``rounds`` = [(src, parity, Sliced of block src, works)] (``works``
+    are waited for on the current stream before the block is touched; [] when it is already there, as
+    in the one-GPU emulation of the schedule in tests/test_gpu_parity.py).  Returns (P, dot): rows of
+    block ``rank`` x all n_gene columns, owned tiles filled in."""
+    blk = local.rows_alloc
+    rows_a = block_rows(n_gene, world, rank)
     if out is None:
         P = torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=local.slices.device)
         D = torch.zeros_like(P)
@@ -281,7 +294,7 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
             send_home(c0, c0 + rows_b)
     if copy_stream is not None:
         torch.cuda.current_stream().wait_stream(copy_stream)
-    return P, D, var_all[:n_gene]
+    return P, D
 
 
 def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events=None):
@@ -422,48 +435,64 @@ def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products, k_chu
     engine.LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
 
 
+def block_spans(n_gene, world, schedule="pairs"):
+    """Global row range [r0, r1) every rank's output rows cover (same ``schedule`` as coex_sharded)."""
+    t = (n_gene + TILE - 1) // TILE
+    if schedule == "allgather":
+        return [(a * TILE, min(b * TILE, n_gene)) for a, b in strip_bounds(t, world)]
+    blk = row_split(n_gene, world)
+    return [(k * blk, k * blk + block_rows(n_gene, world, k)) for k in range(world)]
+
+
+def assemble_dense(row_blocks, n_gene, world, schedule="pairs"):
+    """Full symmetric (n_gene, n_gene) matrix from the per-rank outputs of ``coex_sharded`` /
+    ``_coex_pairs``: ``row_blocks[k]`` holds rank k's rows (tiles it owns filled in, zeros elsewhere).
+    Entry (i, j) was computed by the owner of tile (i, j) or, mirrored, of tile (j, i); this is the
+    one assembly rule, shared by ``gather_dense`` (multi-process), ``coex_all_devices`` (one process)
+    and the one-GPU emulation of the schedule in the tests."""
+    spans = block_spans(n_gene, world, schedule)
+    dev = row_blocks[0].device
+    full = torch.zeros((n_gene, n_gene), dtype=torch.float64, device=dev)
+    for (r0, r1), blk_t in zip(spans, row_blocks):
+        if r1 > r0:
+            full[r0:r1] = blk_t[:r1 - r0].to(dev)
+    if schedule == "allgather":
+        up = torch.triu(full, 1)
+        return up + up.T
+    res = torch.empty_like(full)
+    for k, (r0, r1) in enumerate(spans):
+        if r1 <= r0:
+            continue
+        m = torch.from_numpy(owned_tile_mask(n_gene, world, k)).to(dev)
+        m = m.repeat_interleave(TILE, 0)[:r1 - r0].repeat_interleave(TILE, 1)[:, :n_gene]
+        res[r0:r1] = torch.where(m, full[r0:r1], full[:, r0:r1].T)
+    return res
+
+
 def gather_dense(P_rows, D_rows, bounds, n_gene, group=None, dst=0, schedule="pairs"):
     """Assemble the full symmetric (n_gene, n_gene) P and dot on rank ``dst`` (None elsewhere)
     from the per-rank outputs of ``coex_sharded`` (same ``schedule``)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = P_rows.device
-    t = (n_gene + TILE - 1) // TILE
-    if schedule == "allgather":
-        spans = [(a * TILE, min(b * TILE, n_gene)) for a, b in strip_bounds(t, world)]
-    else:
-        blk = row_split(n_gene, world)
-        spans = [(k * blk, k * blk + block_rows(n_gene, world, k)) for k in range(world)]
+    spans = block_spans(n_gene, world, schedule)
     outs = []
     for src_t in (P_rows, D_rows):
-        full = torch.zeros((n_gene, n_gene), dtype=torch.float64, device=dev) if rank == dst else None
+        blocks = []
         for k, (r0, r1) in enumerate(spans):
             if r1 <= r0:
-                continue
-            if k == dst:
-                if rank == dst:
-                    full[r0:r1] = src_t[:r1 - r0]
+                blocks.append(torch.empty((0, n_gene), dtype=torch.float64, device=dev))
+            elif k == dst:
+                blocks.append(src_t[:r1 - r0] if rank == dst else None)
             elif rank == dst:
                 buf = torch.empty((r1 - r0, n_gene), dtype=torch.float64, device=dev)
                 dist.recv(buf, src=k, group=group)
-                full[r0:r1] = buf
-            elif rank == k:
-                dist.send(src_t[:r1 - r0].contiguous(), dst=dst, group=group)
-        if rank == dst:
-            if schedule == "allgather":
-                up = torch.triu(full, 1)
-                full = up + up.T
+                blocks.append(buf)
             else:
-                # entry (i, j) was computed by the owner of tile (i, j) or, mirrored, of tile (j, i)
-                res = torch.empty_like(full)
-                for k, (r0, r1) in enumerate(spans):
-                    if r1 <= r0:
-                        continue
-                    m = torch.from_numpy(owned_tile_mask(n_gene, world, k)).to(dev)
-                    m = m.repeat_interleave(TILE, 0)[:r1 - r0].repeat_interleave(TILE, 1)[:, :n_gene]
-                    res[r0:r1] = torch.where(m, full[r0:r1], full[:, r0:r1].T)
-                full = res
-        outs.append(full)
+                if rank == k:
+                    dist.send(src_t[:r1 - r0].contiguous(), dst=dst, group=group)
+                blocks.append(None)
+        outs.append(assemble_dense(blocks, n_gene, world, schedule) if rank == dst else None)
     return outs[0], outs[1]
 
 

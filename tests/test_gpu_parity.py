@@ -488,3 +488,126 @@ def test_pvalue_kernel_known_answers():
     ctx = engine.context(0)
     got = engine.pvalue(ctx, torch.from_numpy(g["r2"]).cuda(), g["a"][:, 0]).cpu().numpy()
     assert_p_close(got, g["P"], rtol=1e-9)
+
+
+# ---- the regime the exact-integer design exists for: 100k cells, P down to 1e-300 ----------
+def _planted_loadings(rng, n_gene, lo, hi, n_null):
+    """Loadings a_g on one shared factor: r_ij = a_i a_j / sqrt((1+a_i^2)(1+a_j^2))."""
+    a = rng.uniform(lo, hi, size=n_gene)
+    a[:n_null] = 0.0
+    return a
+
+
+def test_coex_100k_cells_tail():
+    """100,000 cells x 300 genes, 9 covariates, planted |r| from ~0.02 to ~0.13: P spans 1 .. < 1e-300.
+    At this cell count the P = 1e-300 edge needs |dr| <~ 8e-9 (d ln P / dr ~ n r): the reason the
+    contraction is exact-integer.  Against the float64 oracle at the BASELINE tolerances."""
+    rng = np.random.default_rng(4100)
+    n, g = 100_000, 300
+    b = rng.integers(0, 6, size=n)
+    dc = np.array([(b == i).astype(float) for i in range(1, 6)] + [rng.normal(size=n) for _ in range(3)] + [np.ones(n)])
+    a = _planted_loadings(rng, g, 0.14, 0.38, 60)
+    f = rng.normal(size=n)
+    dt = rng.normal(size=(g, n))
+    dt += a[:, None] * f[None, :]
+    dt += 0.3 * dc[5][None, :] + rng.uniform(2, 6, size=(g, 1))            # covariate effect + gene level
+    ref = orc.coex(dt, dc)
+    got = norm.coex(dt, dc)
+    _check_coex(got, ref)
+    iu = np.triu_indices(g, 1)
+    Pu = ref[0][iu]
+    assert ((Pu >= 1e-300) & (Pu <= 1e-200)).sum() >= 50, ((Pu >= 1e-300) & (Pu <= 1e-200)).sum()
+    assert (Pu < 1e-300).sum() >= 50 and (Pu > 1e-3).sum() >= 1000
+    r = np.abs(pearson_from(ref[1], ref[2], ref[2])[iu])
+    assert r.max() > 0.12 and (r < 0.02).sum() > 1000
+    # device tensors in: same bits as the host path
+    P_d, D_d, v_d = norm.coex(torch.from_numpy(dt).cuda(), torch.from_numpy(dc).cuda())
+    assert np.array_equal(P_d.cpu().numpy(), got[0]) and np.array_equal(D_d.cpu().numpy(), got[1])
+
+
+def test_de_million_cells_tail():
+    """1,000,000 cells, binary groupings: P down to 1e-300 needs |r| ~ 0.037 (SURVEY 8c tail point
+    r = 0.037 -> 7.19e-300).  de(single=0) against the oracle; cell-chunked int32 accumulation."""
+    rng = np.random.default_rng(4101)
+    n, g, k = 1_000_000, 40, 8
+    dc = np.concatenate([rng.normal(size=(2, n)), np.ones((1, n))])
+    dg = (rng.random((k, n)) < 0.01).astype(np.float64)
+    dt = rng.normal(size=(g, n)) + 2.0
+    eff = np.linspace(0.02, 0.46, g)                       # r = eff * sqrt(p (1 - p)) / sd: up to ~0.045
+    for j in range(g):
+        dt[j] += eff[j] * dg[j % k]
+    ref = orc.de(dg, dt, dc)
+    got = norm.de(dg, dt, dc)
+    assert_p_close(got[0], ref[0])
+    np.testing.assert_allclose(got[3], ref[3], rtol=1e-7)
+    np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
+    scale = np.sqrt(ref[4] / ref[3][:, None])
+    assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+    assert ((ref[0] >= 1e-300) & (ref[0] <= 1e-150)).sum() >= 5 and (ref[0] < 1e-300).sum() >= 1
+
+
+def test_de_single4_config3_shape():
+    """BASELINE configs[2] shape with fewer genes: 50,000 cells x 400 genes x 300 gRNAs (Bernoulli 0.02),
+    de(single=4): every gRNA tested with the other 299 as covariates (association_test_4,
+    association.py:421-576).  The 300 x 300 Gram matrix of the residualised gRNAs is factorised on
+    the device (nsr_de4_solve); against the oracle's per-gRNA pseudo-inverses."""
+    p = synth.host_problem(1003, 400, 50000, n_group=300, group_p=0.02)
+    ref = orc.de(p["dg"], p["dt"], p["dc"], single=4)
+    got = norm.de(p["dg"], p["dt"], p["dc"], single=4)
+    assert_p_close(got[0], ref[0])
+    np.testing.assert_allclose(got[3], ref[3], rtol=1e-7)
+    np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
+    scale = np.sqrt(ref[4] / ref[3][:, None])
+    assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+    assert ref[0].min() < 1e-20
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_pairs_schedule_emulated(world):
+    """The multi-GPU block-pair schedule, emulated on ONE device: every rank's plan (diagonal block in
+    NSR_MODE_COEX_UPPER, block pairs in NSR_MODE_COEX_RECT incl. the split pair at distance world/2)
+    is run in turn through the product's own ``parallel.contract_plan`` and assembled with the
+    product's own ``parallel.assemble_dense``; the result must equal the single-GPU NSR_MODE_COEX
+    matrices bit for bit (ragged last block: 1,900 genes)."""
+    from normalisr_b200 import parallel
+    n_gene, n = 1900, 3000
+    ctx = engine.context(0)
+    p = synth.device_problem(1011, n_gene, n, "cuda")
+    Qt, crank, _ = association.covariate_basis_device(ctx, p["dc"])
+    S, prods = engine.PRESETS["default"]
+    dof = (n - 1 - crank) / 2
+    full = engine.residualize(ctx, p["dt"], Qt, S)
+    P1 = torch.zeros((n_gene, n_gene), dtype=torch.float64, device="cuda")
+    D1 = torch.zeros_like(P1)
+    engine.contract(ctx, engine.MODE_COEX, full, full, engine.coex_tiles(n_gene), dof, P1, D1, prods)
+    blk = parallel.row_split(n_gene, world)
+    blocks = [parallel.residualize_block(ctx, p["dt"][r * blk:(r + 1) * blk], Qt, S, blk) for r in range(world)]
+    Ps, Ds = [], []
+    for r in range(world):
+        rounds = [(src, parity, blocks[src], []) for _, src, parity in parallel.exchange_plan(world, r)]
+        P, D = parallel.contract_plan(ctx, blocks[r], rounds, r, world, n_gene, dof, prods, 0)
+        Ps.append(P)
+        Ds.append(D)
+    torch.cuda.synchronize()
+    assert torch.equal(parallel.assemble_dense(Ps, n_gene, world), P1)
+    assert torch.equal(parallel.assemble_dense(Ds, n_gene, world), D1)
+    assert torch.equal(torch.cat([b.var[:parallel.block_rows(n_gene, world, r)] for r, b in enumerate(blocks)]), full.var)
+
+
+def test_nonfinite_input_raises():
+    """The reference asserts finite outputs (association.py:252-255, 1077): a NaN / Inf in dt must not
+    come back as 'not significant'."""
+    rng = np.random.default_rng(3)
+    dt = rng.normal(size=(40, 500))
+    dc = np.ones((1, 500))
+    for bad in (np.nan, np.inf):
+        x = dt.copy()
+        x[7, 123] = bad
+        with pytest.raises(AssertionError):
+            norm.coex(x, dc)
+        with pytest.raises(AssertionError):
+            norm.de((rng.random((3, 500)) < 0.3).astype(float), x, dc)
+    c = np.ones((2, 500))
+    c[1, 5] = np.nan
+    with pytest.raises(AssertionError):
+        norm.coex(dt, c)
