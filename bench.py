@@ -36,9 +36,6 @@ WORKLOADS = {
                                        "size the metric is quoted on; fits one B200)"),
     "coex_10k_x_5k": (5000, 10000, "GSE123139-shaped: 10k cells x 5k genes norm.coex (BASELINE configs[1])"),
     "coex_2k_x_1k": (1000, 2000, "2,000 cells x 1,000 genes (BASELINE configs[0])"),
-    # extra (not the headline): gene-block sharded DE sweep, 2,500 genes per GPU (20k genes on 8 GPUs)
-    "de_1m_x_20k_x_1000": (20000, 1000000, "atlas-scale DE sweep: 1M cells x 20k genes x 1,000 perturbations, gene blocks "
-                                           "sharded over the GPUs (BASELINE configs[4]); 2,500 genes per GPU"),
 }
 METRIC = "coex gene-pairs/s (r+P)"
 UNIT = "pairs/s"
@@ -409,6 +406,16 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                         "products per pair at 2x the bf16 rate, so its ceiling on this scale is 2/%.2f of the bf16 peak (ceiling_frac); "
                         "frac_of_ceiling = how much of that the kernel reaches" % (eff_products, eff_products)}
 
+    # ---- the box's dense int8 rate (cuBLASLt), the denominator of the EXECUTED tensor-pipe utilisation
+    if roof is not None and single and not args.no_cpu:
+        try:
+            i8 = measure_int8_peak(torch, dev)
+            roof["int8_peak"] = i8
+            roof["executed_frac_of_int8_sustained"] = roof["executed_int8_tops"] / i8["int8_tops_sustained"]
+            roof["executed_frac_of_int8_burst"] = roof["executed_int8_tops"] / i8["int8_tops_burst"]
+        except Exception as e:
+            roof["int8_peak"] = {"error": repr(e)[:200]}
+
     # ---- roofline of the projection (HBM-bound): algorithmic bytes per SURVEY 8(d) = 16 B per matrix element
     roof_proj = None
     if project_ms:
@@ -487,11 +494,175 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         dist.destroy_process_group()
 
 
-def run_de_sweep(args, n_gene, n_cell, wl_name, wl_desc, n_group=1000, genes_per_gpu=2500):
-    """DE tests/s, genes sharded over ranks, no exchange step (weak scaling: 2,500 genes per GPU)."""
+DE_WORKLOADS = {
+    # name: (genes per GPU, cells, groupings, group_p, single, description)
+    "de_50k_x_10k_x_300": (10000, 50000, 300, 0.02, 4,
+                           "GSE120861-shaped CRISPRi screen DE: 50k cells x 10k genes x 300 gRNAs, norm.de(single=4): every gRNA "
+                           "tested with the other 299 as covariates (BASELINE configs[2]); N > 1: 10k genes per GPU"),
+    "de_1m_x_20k_x_1000": (2500, 1000000, 1000, 0.002, 0,
+                           "atlas-scale DE sweep: 1M cells x 20k genes x 1,000 perturbations, gene blocks sharded over the GPUs "
+                           "(BASELINE configs[4]); 2,500 genes per GPU"),
+}
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def _de_cpu_sample(wl_name, seed):
+    """Bounded CPU sample of a DE workload (host numpy, SURVEY 8d): returns (callable, scale, text);
+    time(callable) * scale estimates the reference's time for ONE GPU's share of the workload."""
+    import normalisr_oracle as orc
+    from normalisr_b200 import synth
+    genes, cells, groups, gp, single, _ = DE_WORKLOADS[wl_name]
+    if single == 4:
+        # the reference runs single=4 in y batches (association.py:866-875): one batch of genes x all cells x all gRNAs
+        nc = 9
+        bsy = orc._batch(0, 8, nc, cells, 500000)
+        sg = min(genes, bsy)
+        p = synth.host_problem(seed, sg, cells, n_group=groups, group_p=gp, n_module=0)
+        n_batches = -(-genes // bsy)
+        text = ("%d of %d genes (one of the reference's %d y-batches, association.py:866-875) x all %d cells x all %d gRNAs, "
+                "oracle port de(single=4), time x %d" % (sg, genes, n_batches, cells, groups, n_batches))
+        return (lambda: orc.de(p["dg"], p["dt"], p["dc"], single=4)), float(genes) / sg, text
+    # single=0: the reference maps 500 x 500 tiles over (groupings, genes) at all cells; sample one tile at 1/16 of the cells
+    sc = cells // 16
+    p = synth.host_problem(seed, 500, sc, n_group=min(500, groups), group_p=max(gp, 0.002), n_module=0)
+    tiles = (-(-groups // 500)) * (-(-genes // 500))
+    text = ("one 500 x 500 tile of the reference's %d (groupings x genes) tiles at %d of %d cells, oracle port de(single=0), "
+            "time x 16 x %d (SURVEY 8d: linear in cells and tiles)" % (tiles, sc, cells, tiles))
+    return (lambda: orc.de(p["dg"], p["dt"], p["dc"])), 16.0 * tiles, text
+
+
+def run_de_reference(args, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    genes, cells, groups, gp, single, desc = DE_WORKLOADS[wl_name]
+    fn, scale, text = _de_cpu_sample(wl_name, SEED + 1)
+    try:
+        from threadpoolctl import threadpool_limits  # noqa: F401
+    except ImportError:
+        pass
+    for _ in range(max(1, args.warmup)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    sec = (time.perf_counter() - t0) / args.steps
+    value = groups * genes / (sec * scale)                      # a rate: the same for every N under weak scaling
+    line = {
+        "impl": "reference", "metric": "DE tests/s (single=%d)" % single, "value": value, "unit": "tests/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "genes": genes * args.gpus, "cells": cells, "groupings": groups, "genes_per_gpu": genes,
+                   "note": desc},
+        "cpu_baseline": {"value": value, "unit": "tests/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": text + "; nth=1, BLAS = all cores (the faster setting for this path in the survey)"},
+        "e2e": {"value": value, "unit": "tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def de_phase_times(torch, ctx, p, single, n_slices, n_products, reps=3):
+    """Device times of the phases of one de() call on device-resident inputs (CUDA events around the same
+    engine calls the public API makes): covariate basis, projection of the groupings, projection of the
+    genes, contraction(s), solve (single=4)."""
+    from normalisr_b200 import association, engine
+    out = {}
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn()
+        e1.record()
+        out.setdefault(name, []).append((e0, e1))
+        return r
+
+    n = p["dt"].shape[1]
+    for _ in range(reps):
+        Qt, rank_c, _ = timed("basis", lambda: association.covariate_basis_device(ctx, p["dc"]))
+        Rx, xd = timed("project_groupings", lambda: association._residualize_groupings(ctx, p["dg"], Qt, n_slices, single == 4))
+        Ry = timed("project_genes", lambda: engine.residualize(ctx, p["dt"], Qt, n_slices))
+        nx, ny = Rx.rows, Ry.rows
+        if single == 0:
+            P = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+            G = torch.empty_like(P)
+            timed("contract", lambda: engine.contract(ctx, engine.MODE_DE, Rx, Ry, engine.rect_tiles(nx, ny),
+                                                     (n - 1 - rank_c) / 2, P, G, n_products))
+        else:
+            Gxy = torch.empty((nx, ny), dtype=torch.float64, device=ctx.device)
+            Gxx = torch.empty((nx, nx), dtype=torch.float64, device=ctx.device)
+
+            def grams():
+                engine.contract(ctx, engine.MODE_RAW, Rx, Ry, engine.rect_tiles(nx, ny), 1.0, None, Gxy, n_products)
+                if Rx.n_slices == 1:
+                    engine.contract(ctx, engine.MODE_RAW, Rx, Rx, engine.rect_tiles(nx, nx), 1.0, None, Gxx, 1)
+                    engine.gram_correct(ctx, Gxx, Rx.coef)
+                    return Gxx
+                return engine.gram_f64(ctx, xd, Rx.coef)
+            g = timed("contract", grams)
+            timed("solve", lambda: engine.de4_solve(ctx, g, Gxy, Ry.var * n, n, rank_c, 0, 1e-8, False))
+    torch.cuda.synchronize()
+    return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in out.items()}, Rx.n_slices
+
+
+def de_roofline(phases, planes_x, genes, cells, groups, single, n_slices, n_products):
+    """Per-phase rooflines of one de() call from the phase times: projection of the genes (HBM,
+    algorithmic 16 B per element), contraction (tensor, 2 n flop per test + the groupings'
+    Gram matrix for single=4), solve."""
+    peaks = _peaks()
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    tf = peaks.get("bf16_tflops_sustained") or 1400.0
+    src = "of measured" if peaks else "of fallback"
+    proj_ms = phases["project_genes"]
+    alg_proj = 16.0 * genes * cells
+    con_ms = phases["contract"]
+    flop = 2.0 * cells * groups * genes + (2.0 * cells * groups * (groups + 1) / 2 if single == 4 else 0.0)
+    prods = n_slices if planes_x == 1 else n_products
+    roof_phases = {
+        "project_genes": {"bound": "hbm", "ms": proj_ms, "achieved": alg_proj / (proj_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": alg_proj / (proj_ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": alg_proj,
+                          "executed_bytes": (16.0 + n_slices) * genes * cells},
+        "project_groupings": {"bound": "hbm", "ms": phases["project_groupings"],
+                              "achieved": 16.0 * groups * cells / (phases["project_groupings"] * 1e-3) / 1e9, "peak": hbm,
+                              "unit": "GB/s", "frac": 16.0 * groups * cells / (phases["project_groupings"] * 1e-3) / 1e9 / hbm,
+                              "digit_planes": planes_x},
+        "contract": {"bound": "tensor", "ms": con_ms, "achieved": flop / (con_ms * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                     "frac": flop / (con_ms * 1e-3) / 1e12 / tf, "algorithmic_flop": flop,
+                     "digit_products_executed": prods, "ceiling_frac": 2.0 / prods},
+    }
+    if "solve" in phases:
+        roof_phases["solve"] = {"bound": "latency", "ms": phases["solve"],
+                                "note": "blocked Cholesky of the %d x %d Gram matrix + w = K Gxy + closed form + P-values" % (groups, groups)}
+    dom = max(("project_genes", "contract"), key=lambda k: roof_phases[k]["ms"])
+    return dict(roof_phases[dom], kernel=("coef_mma_kernel + residual_mma_kernel" if dom == "project_genes" else "contract_umma_kernel"),
+                kernel_ms=roof_phases[dom]["ms"], traffic=None, peak_source="MEASURED_PEAKS.json (%s)" % src, phases=roof_phases,
+                phase_ms={k: round(v, 3) for k, v in phases.items()})
+
+
+def de_cpu_baseline(wl_name):
+    genes, cells, groups, gp, single, _ = DE_WORKLOADS[wl_name]
+    fn, scale, text = _de_cpu_sample(wl_name, SEED + 1)
+    t0 = time.perf_counter()
+    fn()
+    sec = time.perf_counter() - t0
+    return {"value": groups * genes / (sec * scale), "unit": "tests/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": text + "; nth=1, BLAS = all cores; one timed pass (%.1f s)" % sec}
+
+
+def run_de(args, wl_name):
+    """DE tests/s through the public API norm.de, genes sharded over ranks with no exchange step
+    (weak scaling: a fixed gene block per GPU)."""
     import torch
     import torch.distributed as dist
-    from normalisr_b200 import engine, parallel, synth
+    from normalisr_b200 import engine, synth
+    from normalisr_b200 import normalisr as norm
+    genes, cells, groups, gp, single, desc = DE_WORKLOADS[wl_name]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -499,41 +670,87 @@ def run_de_sweep(args, n_gene, n_cell, wl_name, wl_desc, n_group=1000, genes_per
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    p = synth.device_problem(SEED + 1, genes_per_gpu, n_cell, dev, n_group=n_group, group_p=0.002,
-                             gene_seed=SEED * 77 + rank, n_module=0)
-    total_genes = genes_per_gpu * world
+    ctx = engine.context(local)
+    precision = args.precision
+    n_slices, n_products = engine.PRESETS[precision]
+    p = synth.device_problem(SEED + 1, genes, cells, dev, n_group=groups, group_p=gp, gene_seed=SEED * 77 + rank, n_module=0)
+    total_genes = genes * world
+    tests = float(groups) * total_genes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def step():
-        return parallel.de_sharded(p["dg"], p["dt"], p["dc"], total_genes)
+        return norm.de(p["dg"], p["dt"], p["dc"], single=single, precision=precision)
 
     for _ in range(args.warmup):
         step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     launches0 = engine.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    if rank == 0:
-        ms_step = ms / args.steps
-        print(json.dumps({
-            "metric": "DE tests/s (single=0)", "value": n_group * total_genes / (ms_step * 1e-3), "unit": "tests/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl_name, "genes": total_genes, "cells": n_cell, "groupings": n_group,
-                       "genes_per_gpu": genes_per_gpu, "note": wl_desc},
-            "gpu_launches": engine.LAUNCHES - launches0, "e2e": None, "roofline": None, "cpu_baseline": None}), flush=True)
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    launches = engine.LAUNCHES - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    phases, planes_x = de_phase_times(torch, ctx, p, single, n_slices, n_products)
+
+    # ---- end to end: pinned host dg / dt / dc in, host P / gamma / variances out
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hosts = {k: torch.empty(p[k].shape, dtype=torch.float64, pin_memory=True).copy_(p[k]) for k in ("dg", "dt", "dc")}
+            torch.cuda.synchronize()
+            del p
+            torch.cuda.empty_cache()
+            steps_e = max(1, min(args.steps, args.e2e_steps))
+            for _ in range(min(args.warmup, 2)):
+                res = norm.de(hosts["dg"], hosts["dt"], hosts["dc"], single=single, precision=precision)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps_e):
+                res = norm.de(hosts["dg"], hosts["dt"], hosts["dc"], single=single, precision=precision)
+            barrier()
+            sec = max_over_ranks(time.perf_counter() - t0) / steps_e
+            h2d = sum(v.numel() * 8 for v in hosts.values()) * world
+            d2h = sum(r.nbytes for r in res if r is not None) * world
+            e2e = {"value": tests / sec, "unit": "tests/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "steps": steps_e, "ms_per_step": 1e3 * sec, "api": "normalisr_b200.normalisr.de(dg_host, dt_host, dc_host, single=%d)" % single}
+        except Exception as e:
+            e2e = {"error": repr(e)[:300]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    roof = de_roofline(phases, planes_x, genes, cells, groups, single, n_slices, n_products)
+    cpu = de_cpu_baseline(wl_name) if (world == 1 and not args.no_cpu) else None
+    line = {
+        "metric": "DE tests/s (single=%d)" % single, "value": tests / (ms_step * 1e-3), "unit": "tests/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "genes": total_genes, "cells": cells, "groupings": groups, "genes_per_gpu": genes,
+                   "single": single, "precision": precision, "grouping_planes": planes_x,
+                   "arithmetic": "f64 projection, solve and epilogue; int8 x int8 -> int32 exact tensor-core sums",
+                   "l2": "inputs (%.1f GB per rank) are larger than L2, no explicit flush" % (genes * cells * 8 / 1e9),
+                   "parallelism": "1 GPU" if world == 1 else "%d GPUs: gene blocks, no exchange" % world, "note": desc},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -698,18 +915,23 @@ def bench_compute_var(torch, dev, n_gene=10000, n_cell=50000, reps=3):
 
 
 def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
-    """DE tests/s on the GSE120861-shaped config (50k cells x 10k genes x 300 gRNAs), inputs resident
-    in HBM, through the public API: single=0 and single=4 ("untested gRNAs as covariates")."""
-    from normalisr_b200 import normalisr as norm, synth
+    """DE tests/s on the GSE120861-shaped config (BASELINE configs[2]: 50k cells x 10k genes x 300 gRNAs)
+    through the public API: single=4 ("untested gRNAs as covariates", the configuration BASELINE names)
+    with its per-phase roofline, a CPU baseline on a bounded sample and an end-to-end number from
+    pinned host buffers; single=0 and single=1 device-resident times beside it."""
+    from normalisr_b200 import engine, normalisr as norm, synth
     torch.cuda.empty_cache()
+    ctx = engine.context(dev.index)
+    n_slices, n_products = engine.PRESETS["default"]
     p = synth.device_problem(1003, n_gene, n_cell, dev, n_group=n_group, group_p=0.02)
-    out = {"workload": "de_50k_x_10k_x_300", "genes": n_gene, "cells": n_cell, "groupings": n_group, "unit": "tests/s"}
+    out = {"workload": "de_50k_x_10k_x_300", "genes": n_gene, "cells": n_cell, "groupings": n_group, "unit": "tests/s",
+           "metric": "DE tests/s"}
     for single in (0, 4):
-        for _ in range(2):
+        for _ in range(3):
             norm.de(p["dg"], p["dt"], p["dc"], single=single)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 3
+        reps = 5
         e0.record()
         for _ in range(reps):
             norm.de(p["dg"], p["dt"], p["dc"], single=single)
@@ -717,6 +939,10 @@ def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         out["single%d" % single] = {"value": n_group * n_gene / (ms * 1e-3), "ms": ms}
+    phases, planes_x = de_phase_times(torch, ctx, p, 4, n_slices, n_products)
+    out["value"] = out["single4"]["value"]
+    out["ms_per_step"] = out["single4"]["ms"]
+    out["roofline"] = de_roofline(phases, planes_x, n_gene, n_cell, n_group, 4, n_slices, n_products)
     # low-MOI design for single=1: 45 % of the cells carry no gRNA, the others one (a few two)
     g = torch.Generator(device=dev)
     g.manual_seed(1004)
@@ -738,8 +964,32 @@ def bench_de(torch, dev, args, n_gene=10000, n_cell=50000, n_group=300):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
     out["single1"] = {"value": n_group * n_gene / (ms * 1e-3), "ms": ms, "design": "low MOI: 45% of cells without gRNA"}
-    del p, dg1
+    del dg1
+    # end to end (single=4): pinned host dg / dt / dc in, host outputs back
+    if not args.no_e2e:
+        try:
+            hosts = {k: torch.empty(p[k].shape, dtype=torch.float64, pin_memory=True).copy_(p[k]) for k in ("dg", "dt", "dc")}
+            torch.cuda.synchronize()
+            for _ in range(2):
+                res = norm.de(hosts["dg"], hosts["dt"], hosts["dc"], single=4)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                res = norm.de(hosts["dg"], hosts["dt"], hosts["dc"], single=4)
+            sec = (time.perf_counter() - t0) / 3
+            out["e2e"] = {"value": n_group * n_gene / sec, "unit": "tests/s", "ms_per_step": 1e3 * sec,
+                          "h2d_bytes_per_step": int(sum(v.numel() * 8 for v in hosts.values())),
+                          "d2h_bytes_per_step": int(sum(r.nbytes for r in res if r is not None)),
+                          "api": "normalisr_b200.normalisr.de(dg_host, dt_host, dc_host, single=4)"}
+            del hosts
+        except Exception as e:
+            out["e2e"] = {"error": repr(e)[:300]}
+    del p
     torch.cuda.empty_cache()
+    if not args.no_cpu:
+        try:
+            out["cpu_baseline"] = de_cpu_baseline("de_50k_x_10k_x_300")
+        except Exception as e:
+            out["cpu_baseline"] = {"error": repr(e)[:300]}
     return out
 
 
@@ -749,7 +999,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="coex_100k_x_20k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="coex_100k_x_20k", choices=sorted(WORKLOADS) + sorted(DE_WORKLOADS))
     ap.add_argument("--precision", default="default", choices=["fast", "default", "precise"])
     ap.add_argument("--e2e-steps", type=int, default=1000000, help="cap on the e2e steps (default: same as --steps)")
     ap.add_argument("--schedule", default="pairs", choices=["pairs", "allgather"],
@@ -762,13 +1012,14 @@ def main():
     ap.add_argument("--umma-pair", type=int, default=None, help="test hook: 1 = cta_group::2 kernel, 0 = single-CTA")
     ap.add_argument("--opt", action="append", default=[], help="test hook: name=value for nsr_set_option")
     args = ap.parse_args()
-    n_gene, n_cell, desc = WORKLOADS[args.workload]
-    if args.workload.startswith("de_"):
+    if args.workload in DE_WORKLOADS:
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the DE sweep is an extra workload without a CPU arm"}))
+            run_de_reference(args, args.workload)
         else:
-            run_de_sweep(args, n_gene, n_cell, args.workload, desc)
-    elif args.impl == "reference":
+            run_de(args, args.workload)
+        return
+    n_gene, n_cell, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
         run_reference(args, n_gene, n_cell, args.workload, desc)
     else:
         run_ours(args, n_gene, n_cell, args.workload, desc)

@@ -32,6 +32,7 @@ typedef struct nsr_ctx nsr_ctx;
 #define NSR_MAX_SLICES 4
 #define NSR_MAX_RANK 64          /* covariate rank handled by the projection kernels */
 #define NSR_MAX_SPLITS 64        /* cell splits of the projection kernels (depends on n only) */
+#define NSR_MAX_SEGMENTS 10      /* column segments of one nsr_contract_segments launch */
 
 /* contraction modes */
 #define NSR_MODE_COEX 0   /* A == B, symmetric: both triangles written, diagonal = 0,
@@ -84,6 +85,9 @@ int nsr_cell_splits(int64_t n);
  *                    (split k = 128-cell blocks [nblk k / ks, nblk (k+1) / ks), nblk = n_pad/128,
  *                    ks = nsr_cell_splits(n)).  With it the caller bounds the contraction's
  *                    int32 partial sums (Cauchy-Schwarz) and picks nsr_contract's k_chunk.
+ *                    A row whose sum of squares is not finite (NaN / Inf in X or Qt) sets entry
+ *                    (0, 0) to NaN: the caller, who reads the report before contracting, must fail
+ *                    like the reference's finite-ness asserts (association.py:252-255).
  * rows_alloc >= rows is the plane pitch in rows; bytes beyond `rows` are not touched.
  */
 int nsr_residualize(nsr_ctx* ctx, uintptr_t stream,
@@ -91,6 +95,23 @@ int nsr_residualize(nsr_ctx* ctx, uintptr_t stream,
                     const double* Qt, int rank, int64_t ldq,
                     int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
                     double* quantum, double* var, double* coef, double* energy_max);
+
+/* nsr_residualize for rows of SMALL INTEGERS (binary gRNA / condition indicators, the dg of de.de,
+ * de.py:4-132): one int8 plane holding the Hadamard mix of the RAW row - sums of +-1 over the row's
+ * non-zero cells of a 128-cell block, i.e. small integers, stored exactly (quantum = 1/sqrt(128)).
+ * Because every y operand is residualised, sum_k res_x res_y = sum_k x res_y: the raw row can stand in
+ * for its residual in every cross product (association.py:234 numerator; prod1 tiles of A dy^T,
+ * :963-966), and with an exact x the contraction needs n_slices_b digit products instead of 8
+ * (nsr_contract_ab, n_slices_a = 1).  var and coef are those of the RESIDUAL, as in nsr_residualize.
+ * status (device int, accumulated with OR): 1 = some mixed value is not an integer of magnitude <= 127
+ * (rows are not small integers: use nsr_residualize), 2 = some row is explained by the covariates to
+ * more than 3/4 of its raw second moment (the partner's quantisation error would be amplified more than
+ * 2x: use nsr_residualize).  The plane is unusable unless *status == 0. */
+int nsr_residualize_exact(nsr_ctx* ctx, uintptr_t stream,
+                          const double* X, int64_t rows, int64_t n, int64_t ldx,
+                          const double* Qt, int rank, int64_t ldq,
+                          int8_t* plane, int64_t rows_alloc, int64_t n_pad,
+                          double* quantum, double* var, double* coef, double* energy_max, int* status);
 
 /* All-pairs contraction over cells + P-value epilogue for a list of output tiles.
  *
@@ -112,6 +133,62 @@ int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
                  int64_t n, int64_t n_pad, int n_slices, int n_products,
                  const int32_t* host_tiles, int64_t n_tiles, double dof_a,
                  double* P, double* out2, int64_t ld, int64_t k_chunk);
+
+/* nsr_contract with different plane counts for the two operands: A with n_slices_a planes, B with
+ * n_slices_b.  Besides the symmetric presets of nsr_contract it takes n_slices_a = 1 (an operand from
+ * nsr_residualize_exact: one plane of exact small integers) against n_slices_b = 3 / 4 / 1 with
+ * n_products = n_slices_b - every digit product is kept, so the sums are exact in the A operand.
+ * Replaces the same reference lines as nsr_contract (association.py:234-249; prod1 :393-418 in RAW mode). */
+int nsr_contract_ab(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
+                    const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a, int n_slices_a,
+                    const double* quantum_a, const double* var_a,
+                    const int8_t* b_slices, int64_t rows_b, int64_t rows_alloc_b, int n_slices_b,
+                    const double* quantum_b, const double* var_b,
+                    int64_t n, int64_t n_pad, int n_products,
+                    const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                    double* P, double* out2, int64_t ld, int64_t k_chunk);
+
+/* Multi-GPU co-expression: everything one GPU owns under the block-pair schedule in ONE persistent
+ * launch.  A = the local gene block (output rows).  Segment s = one block of output columns with its
+ * own B operand: the local block itself (diagonal = 1: tiles with tile_row <= tile_col, zero diagonal,
+ * like NSR_MODE_COEX_UPPER) or a block pulled from a peer (diagonal = 0, like NSR_MODE_COEX_RECT);
+ * B row j of segment s lands in output column col0 + j.  Replaces the thread pool over tiles
+ * (parallel.autopooler, parallel.py:12-74, used at association.py:997) for the multi-device case.
+ *   ready / ready_value  optional device flag (uint32): the kernel does not read the segment's planes
+ *                        or scales before  (int32)(*ready - ready_value) >= 0.  The caller sets it
+ *                        with nsr_stream_signal on the stream that copies the block in, so tiles of
+ *                        blocks that have arrived are contracted while later blocks are in flight;
+ *   done                 optional device counter (uint32): += 8 per finished tile of the segment (one
+ *                        per epilogue warp, after its stores are visible system-wide); a copy stream
+ *                        can nsr_stream_wait_geq on it and send the segment's columns home while the
+ *                        launch continues with the next segment.
+ * host_tiles: n_tiles triples (segment, tile_row, tile_col), processed in list order (claimed from a
+ * global counter), so list segments in the order their blocks arrive.  tcgen05 engine only; the
+ * waiting launch occupies every SM, so the flags must be set by work that needs none (copy engines). */
+typedef struct nsr_segment {
+    const int8_t* b_slices;
+    int64_t rows_b;
+    int64_t rows_alloc_b;
+    const double* quantum_b;
+    const double* var_b;
+    int64_t col0;
+    int32_t diagonal;
+    uint32_t ready_value;
+    const uint32_t* ready;
+    uint32_t* done;
+} nsr_segment;
+int nsr_contract_segments(nsr_ctx* ctx, uintptr_t stream,
+                          const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
+                          const double* quantum_a, const double* var_a,
+                          int64_t n, int64_t n_pad, int n_slices, int n_products,
+                          const nsr_segment* segments, int n_segments,
+                          const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                          double* P, double* out2, int64_t ld, int64_t k_chunk);
+/* Stream-ordered flag operations on a device uint32 (cuStreamWriteValue32 / cuStreamWaitValue32, no
+ * kernel): *flag = value once the stream reaches this point / the stream waits until
+ * (int32)(*flag - value) >= 0. */
+int nsr_stream_signal(nsr_ctx* ctx, uintptr_t stream, uint32_t* flag, uint32_t value);
+int nsr_stream_wait_geq(nsr_ctx* ctx, uintptr_t stream, uint32_t* flag, uint32_t value);
 
 /* Covariate basis: the two products with the (nc x n) covariate matrix C that turn `dc` into the
  * orthonormal basis Qt of nsr_residualize.  Replaces np.matmul(dc, dc.T) feeding inv_rank at
@@ -183,6 +260,33 @@ int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t 
                       const double* wt, const double* coef, const double* scale, double* out,
                       int64_t ldo);
 
+/* de(single=4), association_test_4 (association.py:421-576) without a per-grouping pseudo-inverse.
+ *   nsr_gram_f64   G = X X^T - Cx Cx^T in float64: the Gram matrix of the covariate-residualised rows of
+ *                  X (rows x n) given Cx = X Qt^T (rows x rank, nsr_residualize's coef output).  Replaces
+ *                  the prod1 tiles of A A^T (association.py:393-418, 945-957) for the groupings block.
+ *   nsr_de4_solve  from Gxx (nx x nx, row-major, contiguous; DESTROYED: holds its Cholesky factor on
+ *                  return), Gxy = Rx Ry^T (nx x ny, from nsr_contract in NSR_MODE_RAW) and yy[y] = sum_k
+ *                  res_y^2: K = Gxx^-1 by blocked Cholesky, w = K Gxy (written to w: the full-regression
+ *                  coefficients, needed for alpha), and per (x, y) the leave-one-out quantities the
+ *                  reference gets from one pseudo-inverse per x (:521-544): dxx = 1/(n K_xx) (0 -> 1,
+ *                  :545-547), dxy = w/(n K_xx), dyy = (yy - sum_x Gxy w + w^2/K_xx)/n, gamma = dxy/dxx,
+ *                  R2 = dxy^2/(dxx dyy), P = I_{1-R2}((n - 1 - (nx - 1 + rank_c) - dimreduce)/2, 1/2) (:563).
+ *                  Outputs P, out2 (gamma, or gamma * dxx when return_dot), vary = dyy (nx x ny, ld_out)
+ *                  and varx = dxx (nx).  status (device int, OR-ed): 1 = a Cholesky pivot fell below
+ *                  tol * max diag (rank-deficient groupings: outputs are not usable, the host layer takes
+ *                  the reference's per-grouping branch), 2 = an R2 left [0, 1 + 1e-8] or a result is not
+ *                  finite (the reference's asserts, :557, :565-568). */
+int nsr_gram_f64(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows, int64_t n, int64_t ldx,
+                 const double* coef, int rank, double* G, int64_t ldg);
+/* G = (G + G^T)/2 - Cx Cx^T in place: the same correction for a Gram matrix of RAW rows that was formed
+ * exactly on the tensor cores (nsr_contract_ab, NSR_MODE_RAW, on nsr_residualize_exact planes). */
+int nsr_gram_correct(nsr_ctx* ctx, uintptr_t stream, double* G, int64_t rows, int64_t ldg, const double* coef,
+                     int rank);
+int nsr_de4_solve(nsr_ctx* ctx, uintptr_t stream, double* Gxx, int nx, const double* Gxy, int64_t ny,
+                  int64_t ld_xy, const double* yy, int64_t n_cells, int rank_c, int dimreduce, double tol,
+                  int return_dot, double* P, double* out2, double* vary, int64_t ld_out, double* varx,
+                  double* w, int64_t ld_w, int* status);
+
 /* Batched inv_rank (association.py:66-80) for `batch` symmetric positive semi-definite n x n
  * matrices (n <= 16), row-major, contiguous: pinv[m] = pseudo-inverse keeping the eigenvalues
  * >= tol * largest (and > 0), rank[m] = how many were kept.  One warp per matrix, cyclic Jacobi.
@@ -250,7 +354,8 @@ int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, con
 /* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
  * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
  * kernel, default 128), "umma_dynamic" (1 = tiles claimed from a global counter, default; 0 = static
- * round-robin), "adaptive_min_cells" (see nsr_last_refined). Process-wide. */
+ * round-robin), "adaptive_min_cells" (see nsr_last_refined), "prefetch" (1 = L2 prefetch of the next
+ * cell block in the residual pass; measured neutral, default 0). Process-wide. */
 int nsr_set_option(const char* name, int value);
 
 /* Debug / test helper: reconstruct z' (float64, rows x n_pad) from slices and quantum. */

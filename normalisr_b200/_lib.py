@@ -38,6 +38,20 @@ _SIGNATURES = {
                              c_vp, c_i64, c_i64, c_vp, c_vp,
                              c_vp, c_i64, c_i64, c_vp, c_vp,
                              c_i64, c_i64, c_int, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64, c_i64]),
+    "nsr_contract_ab": (c_int, [c_vp, c_up, c_int, c_int,
+                                c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
+                                c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
+                                c_i64, c_i64, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64, c_i64]),
+    "nsr_contract_segments": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, c_int,
+                                      c_vp, c_int, c_vp, c_i64, c_dbl, c_vp, c_vp, c_i64, c_i64]),
+    "nsr_stream_signal": (c_int, [c_vp, c_up, c_vp, ctypes.c_uint32]),
+    "nsr_stream_wait_geq": (c_int, [c_vp, c_up, c_vp, ctypes.c_uint32]),
+    "nsr_residualize_exact": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp,
+                                      c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nsr_gram_f64": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_vp, c_i64]),
+    "nsr_gram_correct": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_vp, c_int]),
+    "nsr_de4_solve": (c_int, [c_vp, c_up, c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int,
+                              c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
@@ -58,6 +72,16 @@ _SIGNATURES = {
     "nsr_cov_gram": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_vp]),
     "nsr_cov_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64]),
 }
+
+
+MAX_SEGMENTS = 10
+
+
+class Segment(ctypes.Structure):
+    """struct nsr_segment (include/normalisr_b200.h)."""
+    _fields_ = [("b_slices", c_vp), ("rows_b", c_i64), ("rows_alloc_b", c_i64), ("quantum_b", c_vp), ("var_b", c_vp),
+                ("col0", c_i64), ("diagonal", ctypes.c_int32), ("ready_value", ctypes.c_uint32), ("ready", c_vp),
+                ("done", c_vp)]
 
 
 class NsrError(RuntimeError):

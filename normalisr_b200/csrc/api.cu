@@ -5,15 +5,17 @@
 #include <unordered_map>
 #include <vector>
 
+#include <cuda.h>
+
 #include "epilogue.cuh"
 
-int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, const int8_t* b,
-                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, int n_slices_a, const int8_t* b,
+                             int64_t rows_alloc_b, int n_slices_b, int64_t n_pad, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end);
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
-                             int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
-                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+                             int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
+                             int64_t n_pad, int n_slices_b, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev);
 extern int nsr_use_hadamard;
@@ -108,6 +110,8 @@ extern "C" int nsr_ctx_destroy(nsr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->tiles_dev) cudaFree(ctx->tiles_dev);
+    if (ctx->tiles_pinned) cudaFreeHost(ctx->tiles_pinned);
+    if (ctx->tiles_event) cudaEventDestroy(ctx->tiles_event);
     if (ctx->tile_counters) cudaFree(ctx->tile_counters);
     if (ctx->refine_dev) cudaFree(ctx->refine_dev);
     delete ctx;
@@ -137,55 +141,73 @@ extern "C" int nsr_set_option(const char* name, int value) {
     return 2;
 }
 
-extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
-                            const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
-                            const double* quantum_a, const double* var_a, const int8_t* b_slices,
-                            int64_t rows_b, int64_t rows_alloc_b, const double* quantum_b,
-                            const double* var_b, int64_t n, int64_t n_pad, int n_slices,
-                            int n_products, const int32_t* host_tiles, int64_t n_tiles, double dof_a,
-                            double* P, double* out2, int64_t ld, int64_t k_chunk) {
+// Shared implementation of nsr_contract / nsr_contract_ab / nsr_contract_segments.
+// tile_stride = 2: host_tiles holds (tile_row, tile_col), one segment; 3: (segment, tile_row, tile_col).
+static int contract_impl(nsr_ctx* ctx, uintptr_t stream, int engine, int mode, const int8_t* a_slices, int64_t rows_a,
+                         int64_t rows_alloc_a, int n_slices_a, const double* quantum_a, const double* var_a,
+                         const NsrSegOperand* segs, int n_segs, int n_slices_b, int64_t n, int64_t n_pad, int n_products,
+                         const int32_t* host_tiles, int tile_stride, int64_t n_tiles, double dof_a, double* P,
+                         double* out2, int64_t ld, int64_t k_chunk) {
     NSR_REQUIRE(ctx != nullptr, "nsr_contract: null context");
-    NSR_REQUIRE(mode == NSR_MODE_COEX || mode == NSR_MODE_DE || mode == NSR_MODE_RAW ||
-                    mode == NSR_MODE_COEX_UPPER || mode == NSR_MODE_COEX_RECT,
-                "nsr_contract: unknown mode %d", mode);
     NSR_REQUIRE(engine == NSR_ENGINE_UMMA || engine == NSR_ENGINE_SIMT, "nsr_contract: unknown engine %d", engine);
-    NSR_REQUIRE(rows_a > 0 && rows_b > 0 && n > 0 && n_pad == nsr_padded_cells(n),
-                "nsr_contract: bad shape rows_a=%lld rows_b=%lld n=%lld n_pad=%lld", (long long)rows_a,
-                (long long)rows_b, (long long)n, (long long)n_pad);
-    const bool sym = mode == NSR_MODE_COEX || mode == NSR_MODE_COEX_UPPER;
-    NSR_REQUIRE(ld >= rows_b && (!sym || rows_a == rows_b),
-                "nsr_contract: bad leading dimension %lld", (long long)ld);
-    const int wmax = nsr_wmax(n_slices, n_products);
-    NSR_REQUIRE(wmax > 0, "nsr_contract: unsupported (n_slices=%d, n_products=%d)", n_slices, n_products);
-    NSR_REQUIRE(mode == NSR_MODE_RAW || (P != nullptr && var_a != nullptr && var_b != nullptr && dof_a > 0.0),
-                "nsr_contract: P / var / dof missing");
-    NSR_REQUIRE(out2 != nullptr && quantum_a && quantum_b && a_slices && b_slices, "nsr_contract: null buffer");
-    NSR_REQUIRE(((uintptr_t)a_slices & 15) == 0 && ((uintptr_t)b_slices & 15) == 0,
-                "nsr_contract: slice planes must be 16-byte aligned");
+    NSR_REQUIRE(n_segs >= 1 && n_segs <= NSR_MAX_SEGMENTS && segs != nullptr, "nsr_contract: %d segments (1..%d)", n_segs,
+                NSR_MAX_SEGMENTS);
+    NSR_REQUIRE(n_segs == 1 || engine == NSR_ENGINE_UMMA, "nsr_contract: segments need the tcgen05 engine");
+    NSR_REQUIRE(rows_a > 0 && n > 0 && n_pad == nsr_padded_cells(n), "nsr_contract: bad shape rows_a=%lld n=%lld n_pad=%lld",
+                (long long)rows_a, (long long)n, (long long)n_pad);
+    const int wmax = nsr_wmax_ab(n_slices_a, n_slices_b, n_products);
+    NSR_REQUIRE(wmax > 0, "nsr_contract: unsupported (n_slices_a=%d, n_slices_b=%d, n_products=%d)", n_slices_a, n_slices_b,
+                n_products);
+    NSR_REQUIRE(out2 != nullptr && quantum_a && a_slices, "nsr_contract: null buffer");
+    NSR_REQUIRE(((uintptr_t)a_slices & 15) == 0, "nsr_contract: slice planes must be 16-byte aligned");
+    bool need_p = false;
+    for (int s = 0; s < n_segs; ++s) {
+        const SegInfo& si = segs[s].info;
+        NSR_REQUIRE(si.mode == NSR_MODE_COEX || si.mode == NSR_MODE_DE || si.mode == NSR_MODE_RAW ||
+                        si.mode == NSR_MODE_COEX_UPPER || si.mode == NSR_MODE_COEX_RECT,
+                    "nsr_contract: unknown mode %d", si.mode);
+        const bool sym = si.mode == NSR_MODE_COEX || si.mode == NSR_MODE_COEX_UPPER;
+        NSR_REQUIRE(si.rows_b > 0 && si.col0 >= 0 && ld >= si.col0 + si.rows_b && (!sym || rows_a == si.rows_b),
+                    "nsr_contract: bad segment %d (rows_b=%lld col0=%lld ld=%lld)", s, (long long)si.rows_b,
+                    (long long)si.col0, (long long)ld);
+        NSR_REQUIRE(si.mode != NSR_MODE_COEX || n_segs == 1, "nsr_contract: NSR_MODE_COEX (mirrored) takes one segment");
+        NSR_REQUIRE(segs[s].slices && si.qb && ((uintptr_t)segs[s].slices & 15) == 0, "nsr_contract: segment %d: bad planes", s);
+        NSR_REQUIRE(si.mode == NSR_MODE_RAW || si.vb != nullptr, "nsr_contract: segment %d: var missing", s);
+        need_p = need_p || si.mode != NSR_MODE_RAW;
+    }
+    NSR_REQUIRE(!need_p || (P != nullptr && var_a != nullptr && dof_a > 0.0), "nsr_contract: P / var / dof missing");
     if (n_tiles == 0) return 0;
     NSR_REQUIRE(host_tiles != nullptr && n_tiles > 0 && n_tiles < (1ll << 30), "nsr_contract: bad tile list");
-    const int64_t tr_max = (rows_a + NSR_TILE - 1) / NSR_TILE, tc_max = (rows_b + NSR_TILE - 1) / NSR_TILE;
+    const int64_t tr_max = (rows_a + NSR_TILE - 1) / NSR_TILE;
+    std::vector<int32_t> packed((size_t)n_tiles * 2);
     for (int64_t t = 0; t < n_tiles; ++t) {
-        const int32_t tr = host_tiles[2 * t], tc = host_tiles[2 * t + 1];
-        NSR_REQUIRE(tr >= 0 && tr < tr_max && tc >= 0 && tc < tc_max, "nsr_contract: tile %lld = (%d,%d) out of range",
-                    (long long)t, tr, tc);
-        NSR_REQUIRE(!sym || tr <= tc, "nsr_contract: COEX tiles must have row <= col");
+        const int32_t sg = tile_stride == 3 ? host_tiles[3 * t] : 0;
+        const int32_t tr = host_tiles[tile_stride * t + tile_stride - 2], tc = host_tiles[tile_stride * t + tile_stride - 1];
+        NSR_REQUIRE(sg >= 0 && sg < n_segs, "nsr_contract: tile %lld: segment %d out of range", (long long)t, sg);
+        const int64_t tc_max = (segs[sg].info.rows_b + NSR_TILE - 1) / NSR_TILE;
+        NSR_REQUIRE(tr >= 0 && tr < tr_max && tc >= 0 && tc < tc_max && tc < (1 << 24),
+                    "nsr_contract: tile %lld = (%d,%d) out of range", (long long)t, tr, tc);
+        const int m = segs[sg].info.mode;
+        NSR_REQUIRE(!(m == NSR_MODE_COEX || m == NSR_MODE_COEX_UPPER) || tr <= tc, "nsr_contract: COEX tiles must have row <= col");
+        packed[2 * t] = tr;
+        packed[2 * t + 1] = tc | (sg << 24);
     }
     cudaStream_t st = (cudaStream_t)stream;
     NSR_CHECK(cudaSetDevice(ctx->device));
     // the cta_group::2 kernel works on 256 x 128 pair tiles: fold (tr, tc) into (tr/2, tc, half mask),
     // keeping first-appearance order (the caller's order carries the L2-locality plan)
-    const bool pair = engine == NSR_ENGINE_UMMA && nsr_umma_pair != 0;
+    const bool pair = engine == NSR_ENGINE_UMMA && nsr_umma_pair != 0 && n_segs == 1 && n_slices_a == n_slices_b &&
+                      n_slices_a >= 3;
     std::vector<int32_t> folded;
     int64_t n_upload = n_tiles * 2;
-    const int32_t* upload = host_tiles;
+    const int32_t* upload = packed.data();
     int64_t n_entries = n_tiles;
     if (pair) {
         std::unordered_map<uint64_t, int64_t> seen;
         seen.reserve((size_t)n_tiles * 2);
         folded.reserve((size_t)n_tiles * 3);
         for (int64_t t = 0; t < n_tiles; ++t) {
-            const int32_t tr = host_tiles[2 * t], tc = host_tiles[2 * t + 1];
+            const int32_t tr = packed[2 * t], tc = packed[2 * t + 1];
             const uint64_t key = ((uint64_t)(uint32_t)(tr >> 1) << 32) | (uint32_t)tc;
             auto it = seen.find(key);
             if (it == seen.end()) {
@@ -201,22 +223,32 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
         n_upload = n_entries * 3;
         upload = folded.data();
     }
+    // The tile list travels through a pinned staging buffer owned by the context (a pageable source
+    // would make cudaMemcpyAsync block the host until the stream drains, and would tie the lifetime of
+    // the vectors above to that staging behaviour); an event guards its reuse by the next call.
     if ((size_t)n_upload > ctx->tiles_cap) {
+        NSR_CHECK(cudaStreamSynchronize(st));
         if (ctx->tiles_dev) NSR_CHECK(cudaFree(ctx->tiles_dev));
+        if (ctx->tiles_pinned) NSR_CHECK(cudaFreeHost(ctx->tiles_pinned));
         ctx->tiles_dev = nullptr;
+        ctx->tiles_pinned = nullptr;
         ctx->tiles_cap = 0;
         NSR_CHECK(cudaMalloc(&ctx->tiles_dev, (size_t)n_upload * sizeof(int32_t) * 2));
+        NSR_CHECK(cudaMallocHost(&ctx->tiles_pinned, (size_t)n_upload * sizeof(int32_t) * 2));
         ctx->tiles_cap = (size_t)n_upload * 2;
     }
-    // pageable-host copy: staged synchronously with respect to the host, ordered on `st`
-    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, upload, (size_t)n_upload * sizeof(int32_t),
+    if (ctx->tiles_event == nullptr) NSR_CHECK(cudaEventCreateWithFlags(&ctx->tiles_event, cudaEventDisableTiming));
+    else NSR_CHECK(cudaEventSynchronize(ctx->tiles_event));       // previous upload has left the staging buffer
+    memcpy(ctx->tiles_pinned, upload, (size_t)n_upload * sizeof(int32_t));
+    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, ctx->tiles_pinned, (size_t)n_upload * sizeof(int32_t),
                               cudaMemcpyHostToDevice, st));
+    NSR_CHECK(cudaEventRecord(ctx->tiles_event, st));
 
     ContractParams ep;
     ep.mode = mode;
-    ep.n_groups = wmax - 1;
-    ep.rows_a = rows_a; ep.rows_b = rows_b; ep.ld = ld;
-    ep.qa = quantum_a; ep.va = var_a; ep.qb = quantum_b; ep.vb = var_b;
+    ep.n_groups = wmax - 1 < n_slices_a + n_slices_b - 1 ? wmax - 1 : n_slices_a + n_slices_b - 1;
+    ep.rows_a = rows_a; ep.rows_b = segs[0].info.rows_b; ep.ld = ld;
+    ep.qa = quantum_a; ep.va = var_a; ep.qb = segs[0].info.qb; ep.vb = segs[0].info.vb;
     ep.P = P; ep.out2 = out2;
     ep.inv_n = 1.0 / (double)n;
     ep.acc_in = 0;
@@ -224,16 +256,16 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
     ep.refine_r2 = -1.0;
     ep.need = nullptr;
     for (int g = 0; g < 4; ++g) ep.group_scale[g] = (g < ep.n_groups) ? ldexp(1.0, 8 * (ep.n_groups - 1 - g)) : 0.0;
-    ep.scale_all = ldexp(1.0, 8 * (2 * n_slices - wmax));
-    ep.pv = nsr_pval_params(mode == NSR_MODE_RAW ? 1.0 : dof_a);
+    ep.scale_all = ldexp(1.0, 8 * (n_slices_a + n_slices_b - 1 - ep.n_groups));
+    ep.pv = nsr_pval_params(need_p ? dof_a : 1.0);
 
     // Cell chunking: int32 accumulators are exact only while no partial sum can overflow; the caller
     // bounds that (Cauchy-Schwarz on the digit-plane energies) and passes the chunk length.  Chunks
     // but the last leave the float64 running sum in out2; the last one adds it and finishes.
     NSR_REQUIRE(k_chunk >= 0 && k_chunk % NSR_KBLOCK == 0, "nsr_contract: k_chunk must be a multiple of %d", NSR_KBLOCK);
     const int64_t chunk = (k_chunk == 0 || k_chunk >= n_pad) ? n_pad : k_chunk;
-    if (engine == NSR_ENGINE_UMMA && !pair && chunk == n_pad && mode != NSR_MODE_RAW && n_slices == 3 && wmax == 5 &&
-        nsr_adaptive_min_cells > 0 && n >= nsr_adaptive_min_cells) {
+    if (engine == NSR_ENGINE_UMMA && !pair && n_segs == 1 && chunk == n_pad && mode != NSR_MODE_RAW && n_slices_a == 3 &&
+        n_slices_b == 3 && wmax == 5 && nsr_adaptive_min_cells > 0 && n >= nsr_adaptive_min_cells) {
         // ---- adaptive schedule: 6 products everywhere, 8 where a pair is extremely significant
         const size_t want = 3 * (size_t)n_tiles + 4;
         if (want > ctx->refine_cap) {
@@ -251,17 +283,17 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
         ContractParams ep1 = ep;
         ep1.n_groups = 3;                                             // wmax = 4
         for (int g = 0; g < 4; ++g) ep1.group_scale[g] = (g < 3) ? ldexp(1.0, 8 * (2 - g)) : 0.0;
-        ep1.scale_all = ldexp(1.0, 8 * (2 * n_slices - 4));
+        ep1.scale_all = ldexp(1.0, 8 * (2 * 3 - 4));
         ep1.refine_r2 = kRefineZ2 / (double)n;
         ep1.need = need;
-        int rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b, n_pad,
-                                          n_slices, 4, ctx->tiles_dev, n_tiles, ep1, 0, n_pad, nullptr);
+        int rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, 3, segs, 1, n_pad, 3, 4, ctx->tiles_dev,
+                                          n_tiles, ep1, 0, n_pad, nullptr);
         if (rc) return rc;
         refine_compact_kernel<<<(unsigned)((n_tiles + 255) / 256 < 64 ? (n_tiles + 255) / 256 : 64), 256, 0, st>>>(
             need, ctx->tiles_dev, (int)n_tiles, list, count);
         NSR_CHECK(cudaGetLastError());
-        return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b, n_pad,
-                                        n_slices, 5, list, n_tiles, ep, 0, n_pad, count);
+        return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, 3, segs, 1, n_pad, 3, 5, list, n_tiles, ep,
+                                        0, n_pad, count);
     }
     for (int64_t c0 = 0; c0 < n_pad; c0 += chunk) {
         const int64_t c1 = c0 + chunk < n_pad ? c0 + chunk : n_pad;
@@ -269,19 +301,89 @@ extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode
         ep.raw_out = c1 < n_pad;
         int rc;
         if (engine == NSR_ENGINE_SIMT) {
-            rc = nsr_launch_contract_simt(st, a_slices, rows_alloc_a, b_slices, rows_alloc_b, n_pad, n_slices, wmax,
-                                          ctx->tiles_dev, n_tiles, ep, c0, c1);
+            rc = nsr_launch_contract_simt(st, a_slices, rows_alloc_a, n_slices_a, segs[0].slices, segs[0].rows_alloc,
+                                          n_slices_b, n_pad, wmax, ctx->tiles_dev, n_tiles, ep, c0, c1);
             if (rc) {
                 nsr_set_error("nsr_contract: SIMT launch failed: %s", cudaGetErrorString(cudaGetLastError()));
                 return 1;
             }
         } else {
-            rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, b_slices, rows_b, rows_alloc_b,
-                                          n_pad, n_slices, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep, c0, c1, nullptr);
+            rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, n_slices_a, segs, n_segs, n_pad,
+                                          n_slices_b, wmax, ctx->tiles_dev, pair ? -n_entries : n_tiles, ep, c0, c1, nullptr);
             if (rc) return rc;
         }
     }
     return 0;
+}
+
+extern "C" int nsr_contract_ab(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
+                               const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a, int n_slices_a,
+                               const double* quantum_a, const double* var_a, const int8_t* b_slices,
+                               int64_t rows_b, int64_t rows_alloc_b, int n_slices_b, const double* quantum_b,
+                               const double* var_b, int64_t n, int64_t n_pad, int n_products,
+                               const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                               double* P, double* out2, int64_t ld, int64_t k_chunk) {
+    NsrSegOperand sg;
+    sg.slices = b_slices;
+    sg.rows_alloc = rows_alloc_b;
+    sg.info.qb = quantum_b; sg.info.vb = var_b; sg.info.rows_b = rows_b; sg.info.col0 = 0; sg.info.mode = mode;
+    sg.info.ready = nullptr; sg.info.ready_value = 0; sg.info.done = nullptr;
+    return contract_impl(ctx, stream, engine, mode, a_slices, rows_a, rows_alloc_a, n_slices_a, quantum_a, var_a, &sg, 1,
+                         n_slices_b, n, n_pad, n_products, host_tiles, 2, n_tiles, dof_a, P, out2, ld, k_chunk);
+}
+
+extern "C" int nsr_contract(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
+                            const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
+                            const double* quantum_a, const double* var_a, const int8_t* b_slices,
+                            int64_t rows_b, int64_t rows_alloc_b, const double* quantum_b,
+                            const double* var_b, int64_t n, int64_t n_pad, int n_slices,
+                            int n_products, const int32_t* host_tiles, int64_t n_tiles, double dof_a,
+                            double* P, double* out2, int64_t ld, int64_t k_chunk) {
+    return nsr_contract_ab(ctx, stream, engine, mode, a_slices, rows_a, rows_alloc_a, n_slices, quantum_a, var_a, b_slices,
+                           rows_b, rows_alloc_b, n_slices, quantum_b, var_b, n, n_pad, n_products, host_tiles, n_tiles, dof_a,
+                           P, out2, ld, k_chunk);
+}
+
+extern "C" int nsr_contract_segments(nsr_ctx* ctx, uintptr_t stream, const int8_t* a_slices, int64_t rows_a,
+                                     int64_t rows_alloc_a, const double* quantum_a, const double* var_a,
+                                     int64_t n, int64_t n_pad, int n_slices, int n_products,
+                                     const nsr_segment* segments, int n_segments, const int32_t* host_tiles,
+                                     int64_t n_tiles, double dof_a, double* P, double* out2, int64_t ld,
+                                     int64_t k_chunk) {
+    NSR_REQUIRE(segments != nullptr && n_segments >= 1 && n_segments <= NSR_MAX_SEGMENTS, "nsr_contract_segments: %d segments (1..%d)",
+                n_segments, NSR_MAX_SEGMENTS);
+    NsrSegOperand sg[NSR_MAX_SEGMENTS];
+    for (int s = 0; s < n_segments; ++s) {
+        const nsr_segment& in = segments[s];
+        sg[s].slices = in.b_slices;
+        sg[s].rows_alloc = in.rows_alloc_b;
+        sg[s].info.qb = in.quantum_b; sg[s].info.vb = in.var_b; sg[s].info.rows_b = in.rows_b; sg[s].info.col0 = in.col0;
+        sg[s].info.mode = in.diagonal ? NSR_MODE_COEX_UPPER : NSR_MODE_COEX_RECT;
+        sg[s].info.ready = in.ready; sg[s].info.ready_value = in.ready_value; sg[s].info.done = in.done;
+    }
+    return contract_impl(ctx, stream, NSR_ENGINE_UMMA, NSR_MODE_COEX_RECT, a_slices, rows_a, rows_alloc_a, n_slices, quantum_a,
+                         var_a, sg, n_segments, n_slices, n, n_pad, n_products, host_tiles, 3, n_tiles, dof_a, P, out2, ld,
+                         k_chunk);
+}
+
+// Stream-ordered 32-bit flag operations (cuStreamWriteValue32 / cuStreamWaitValue32): no kernel, no SM.
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static int stream_value_op(nsr_ctx* ctx, const char* sym, uintptr_t stream, uint32_t* flag, uint32_t value, unsigned flags) {
+    NSR_REQUIRE(ctx != nullptr && flag != nullptr, "%s: null argument", sym);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaDriverEntryPointQueryResult qres;
+    void* fn = nullptr;
+    cudaError_t e = cudaGetDriverEntryPoint(sym, &fn, cudaEnableDefault, &qres);
+    NSR_REQUIRE(e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr, "%s unavailable", sym);
+    CUresult r = ((StreamValueFn)fn)((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value, flags);
+    NSR_REQUIRE(r == CUDA_SUCCESS, "%s failed with CUresult %d", sym, (int)r);
+    return 0;
+}
+extern "C" int nsr_stream_signal(nsr_ctx* ctx, uintptr_t stream, uint32_t* flag, uint32_t value) {
+    return stream_value_op(ctx, "cuStreamWriteValue32", stream, flag, value, 0 /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+}
+extern "C" int nsr_stream_wait_geq(nsr_ctx* ctx, uintptr_t stream, uint32_t* flag, uint32_t value) {
+    return stream_value_op(ctx, "cuStreamWaitValue32", stream, flag, value, 0 /* CU_STREAM_WAIT_VALUE_GEQ */);
 }
 
 extern "C" int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined) {

@@ -12,7 +12,7 @@ constexpr int kPitchW = kKc / 4 + 1;   // smem row pitch in 32-bit words (+1: ba
 struct SimtArgs {
     const int8_t* a; const int8_t* b;
     int64_t rows_alloc_a, rows_alloc_b, n_pad, cell_begin, cell_end;
-    int n_slices, wmax;
+    int sa, sb, wmax;
     const int32_t* tiles;
     ContractParams ep;
 };
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
     const int64_t col0 = (int64_t)tile_c * NSR_TILE + (blockIdx.y & 1) * kSub;
     if (row0 >= g.ep.rows_a || col0 >= g.ep.rows_b) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int S = g.n_slices;
+    const int SA = g.sa, SB = g.sb;
 
     int32_t acc[4][4][4];
 #pragma unroll
@@ -37,11 +37,11 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
 
     const int lrow = threadIdx.x >> 2, lchunk = threadIdx.x & 3;    // 64 rows x 4 x 16 B
     for (int64_t k0 = g.cell_begin; k0 < g.cell_end; k0 += kKc) {
-        for (int s = 0; s < S; ++s) {
+        for (int s = 0; s < (SA > SB ? SA : SB); ++s) {
             uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
-            if (row0 + lrow < g.ep.rows_a)
+            if (s < SA && row0 + lrow < g.ep.rows_a)
                 va = *reinterpret_cast<const uint4*>(g.a + ((int64_t)s * g.rows_alloc_a + row0 + lrow) * g.n_pad + k0 + 16 * lchunk);
-            if (col0 + lrow < g.ep.rows_b)
+            if (s < SB && col0 + lrow < g.ep.rows_b)
                 vb = *reinterpret_cast<const uint4*>(g.b + ((int64_t)s * g.rows_alloc_b + col0 + lrow) * g.n_pad + k0 + 16 * lchunk);
             uint32_t* da = &sa[s][lrow][4 * lchunk];
             uint32_t* db = &sb[s][lrow][4 * lchunk];
@@ -54,11 +54,11 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
             int32_t av[NSR_MAX_SLICES][4], bv[NSR_MAX_SLICES][4];
 #pragma unroll
             for (int s = 0; s < NSR_MAX_SLICES; ++s)
-                if (s < S) {
+                {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        av[s][r] = (int32_t)sa[s][4 * ty + r][kw];
-                        bv[s][r] = (int32_t)sb[s][4 * tx + r][kw];
+                        av[s][r] = s < SA ? (int32_t)sa[s][4 * ty + r][kw] : 0;
+                        bv[s][r] = s < SB ? (int32_t)sb[s][4 * tx + r][kw] : 0;
                     }
                 }
 #pragma unroll
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
 #pragma unroll
                 for (int db = 0; db < NSR_MAX_SLICES; ++db) {
                     const int w = da + db;               // (a-1)+(b-1) = weight group
-                    if (da < S && db < S && w + 2 <= g.wmax) {
+                    if (da < SA && db < SB && w < 4 && w + 2 <= g.wmax) {
 #pragma unroll
                         for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(256) contract_simt_kernel(const SimtArgs g) {
 
 }  // namespace
 
-int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, const int8_t* b,
-                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+int nsr_launch_contract_simt(cudaStream_t st, const int8_t* a, int64_t rows_alloc_a, int n_slices_a, const int8_t* b,
+                             int64_t rows_alloc_b, int n_slices_b, int64_t n_pad, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end) {
     SimtArgs g;
     g.cell_begin = cell_begin; g.cell_end = cell_end;
     g.a = a; g.b = b; g.rows_alloc_a = rows_alloc_a; g.rows_alloc_b = rows_alloc_b; g.n_pad = n_pad;
-    g.n_slices = n_slices; g.wmax = wmax; g.tiles = tiles_dev; g.ep = ep;
+    g.sa = n_slices_a; g.sb = n_slices_b; g.wmax = wmax; g.tiles = tiles_dev; g.ep = ep;
     contract_simt_kernel<<<dim3((unsigned)n_tiles, 4), 256, 0, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }

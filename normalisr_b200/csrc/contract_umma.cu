@@ -30,8 +30,16 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps
 constexpr uint32_t kTmemCols = 512;
 constexpr int kSmemBudget = 200 * 1024;       // operand ring; barriers live in static smem
 
+constexpr int kMaxSegs = NSR_MAX_SEGMENTS;
+
+// tensor maps of the segments' B operands (a __grid_constant__ kernel parameter: TMA descriptors must
+// live in param / const / global space)
+struct SegMaps {
+    CUtensorMap b[kMaxSegs];
+};
+
 struct UmmaArgs {
-    const int32_t* tiles;
+    const int32_t* tiles;         // pairs (tile_row, tile_col | segment << 24)
     int n_tiles;
     int num_kb;                   // k-blocks of KB cells in this launch
     int kb_begin;                 // first k-block (cell chunking)
@@ -41,6 +49,8 @@ struct UmmaArgs {
                                   // zeroed before the launch; nullptr = static round-robin
     const int* n_tiles_dev;       // if set, the tile count is read from device memory (second phase of the
                                   // adaptive schedule: the list was compacted on the device)
+    int n_segs;
+    SegInfo seg[kMaxSegs];
     ContractParams ep;
 };
 
@@ -94,6 +104,23 @@ __device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity,
             __trap();
         }
     }
+}
+// A segment's B operand arrives from another GPU (copy-engine pull into local memory) while this
+// launch is already running: the producer waits for the stream-ordered flag write that follows the
+// copy before its first TMA read of that segment.  Bounded like every wait in this file.
+__device__ __forceinline__ void wait_ready(const uint32_t* flag, uint32_t want) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int32_t)(v - want) >= 0) break;
+        __nanosleep(200);
+        if (clock64() - t0 > 20000000000ll) {      // ~10 s
+            printf("nsr umma: segment flag timeout block %d (have %u, want %u)\n", blockIdx.x, v, want);
+            __trap();
+        }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");   // later async-proxy (TMA) reads see the copied planes
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint32_t bar, uint32_t dst,
                                             int c0, int c1, int c2) {
@@ -168,8 +195,8 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
 // MMAs overlap the P-value arithmetic) is 13 % faster in a short burst but 25 % SLOWER sustained:
 // the chip is power-bound here, and that variant costs more energy per tile than it saves time.
 template <int GROUPS, int EW>
-__device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t tmem_base, int warp, int lane,
-                                              int tr, int tc, bool wanted, uint32_t empty_bar, bool remote,
+__device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const SegInfo& sg, uint32_t tmem_base, int warp,
+                                              int lane, int tr, int tc, bool wanted, uint32_t empty_bar, bool remote,
                                               int tile_idx = -1) {
     constexpr int kCols = NSR_TILE / (EW / 4);          // columns per epilogue warp
     constexpr int CH = EW > 8 ? 8 : 16;                 // columns per TMEM read (register budget)
@@ -179,7 +206,7 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     const bool row_ok = wanted && i < ep.rows_a;
     const double qi = row_ok ? ep.qa[i] : 0.0;
     const double vi = (row_ok && ep.va) ? ep.va[i] : 1.0;
-    const bool mirror = ep.mode == NSR_MODE_COEX && tr != tc;
+    const bool mirror = sg.mode == NSR_MODE_COEX && tr != tc;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     bool refine = false;
     if (wanted) {
@@ -190,15 +217,19 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
             for (int grp = 0; grp < GROUPS; ++grp) tc_ldN<CH>(lane_base + grp * NSR_TILE + c0, v[grp]);
             tc_ld_wait();
             const int64_t j0 = (int64_t)tc * NSR_TILE + c0;
-            if (row_ok && j0 < ep.rows_b) {
+            if (row_ok && j0 < sg.rows_b) {
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
                     const int64_t j = j0 + c;
-                    if (j < ep.rows_b) {
+                    if (j < sg.rows_b) {
                         int32_t a4[4] = {0, 0, 0, 0};
 #pragma unroll
                         for (int grp = 0; grp < GROUPS; ++grp) a4[grp] = (int32_t)v[grp][c];
-                        refine |= nsr_finish(ep, i, j, qi, vi, ep.qb[j], ep.vb ? ep.vb[j] : 1.0, nsr_combine(ep, a4), mirror);
+                        // (the per-row scales of a remote segment are written by a copy engine during this
+                        // launch, but before the segment's flag: no SM has them in L1 earlier, and L1 does not
+                        // survive a launch boundary - plain cached loads are safe)
+                        refine |= nsr_finish(ep, sg.mode, sg.col0, i, j, qi, vi, sg.qb[j], sg.vb ? sg.vb[j] : 1.0,
+                                             nsr_combine(ep, a4), mirror);
                     }
                 }
             }
@@ -209,6 +240,10 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, uint32_t
     if (lane == 0) {
         if (remote) mbar_arrive_cluster_addr(empty_bar);
         else mbar_arrive(empty_bar);
+        if (sg.done != nullptr) {            // this warp's part of the tile is in memory: count it (D2H streams wait on it)
+            __threadfence_system();
+            atomicAdd(sg.done, 1u);
+        }
     }
     // adaptive schedule, first phase: any element beyond the threshold sends the tile to the second phase
     if (ep.need != nullptr && tile_idx >= 0 && __any_sync(0xffffffffu, refine) && lane == 0) atomicOr(&ep.need[tile_idx], 1);
@@ -219,38 +254,56 @@ constexpr uint32_t kInstrDescN256 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u 
 
 // MMA schedule with stacked B planes: entries (a, b, wide, first): A plane a times B plane b
 // (wide: planes b and b+1 as one N = 256 operand); `first` = the entry initialises its group(s).
-template <int S, int WMAX> struct Sched;
-template <> struct Sched<3, 5> {      // products (0,0)(0,1) | (0,2) | (1,0)(1,1) | (1,2) | (2,0)(2,1)
+template <int SA, int SB, int WMAX> struct Sched;
+template <> struct Sched<3, 3, 5> {      // products (0,0)(0,1) | (0,2) | (1,0)(1,1) | (1,2) | (2,0)(2,1)
     static constexpr int kCount = 5;
     int a[5] = {0, 0, 1, 1, 2}, b[5] = {0, 2, 0, 2, 0};
     bool wide[5] = {true, false, true, false, true}, first[5] = {true, true, false, true, false};
 };
-template <> struct Sched<3, 4> {      // (0,0)(0,1) | (0,2) | (1,0)(1,1) | (2,0)
+template <> struct Sched<3, 3, 4> {      // (0,0)(0,1) | (0,2) | (1,0)(1,1) | (2,0)
     static constexpr int kCount = 4;
     int a[4] = {0, 0, 1, 2}, b[4] = {0, 2, 0, 0};
     bool wide[4] = {true, false, true, false}, first[4] = {true, true, false, false};
 };
-template <> struct Sched<4, 5> {      // (0,0)(0,1) | (0,2)(0,3) | (1,0)(1,1) | (1,2) | (2,0)(2,1) | (3,0)
+template <> struct Sched<4, 4, 5> {      // (0,0)(0,1) | (0,2)(0,3) | (1,0)(1,1) | (1,2) | (2,0)(2,1) | (3,0)
     static constexpr int kCount = 6;
     int a[6] = {0, 0, 1, 1, 2, 3}, b[6] = {0, 2, 0, 2, 0, 0};
     bool wide[6] = {true, true, true, false, true, false}, first[6] = {true, true, false, false, false, false};
 };
+// single-plane A operand (exact small integers: binary groupings after the Hadamard mix, see
+// nsr_residualize_exact): every product of the B planes with the one A plane
+template <> struct Sched<1, 3, 4> {      // (0,0)(0,1) | (0,2)
+    static constexpr int kCount = 2;
+    int a[2] = {0, 0}, b[2] = {0, 2};
+    bool wide[2] = {true, false}, first[2] = {true, true};
+};
+template <> struct Sched<1, 4, 5> {      // (0,0)(0,1) | (0,2)(0,3)
+    static constexpr int kCount = 2;
+    int a[2] = {0, 0}, b[2] = {0, 2};
+    bool wide[2] = {true, true}, first[2] = {true, true};
+};
+template <> struct Sched<1, 1, 2> {      // (0,0)
+    static constexpr int kCount = 1;
+    int a[1] = {0}, b[1] = {0};
+    bool wide[1] = {false}, first[1] = {true};
+};
 
-template <int S, int WMAX, int KB>
+template <int SA, int SB, int WMAX, int KB>
 struct Cfg {
     static constexpr int kSliceBytes = NSR_TILE * KB;
-    static constexpr int kStageBytes = 2 * S * kSliceBytes;
-    static constexpr int kStages = kSmemBudget / kStageBytes;
-    static constexpr int kGroups = WMAX - 1;
+    static constexpr int kStageBytes = (SA + SB) * kSliceBytes;
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kGroups = (WMAX - 1) < (SA + SB - 1) ? (WMAX - 1) : (SA + SB - 1);
     static_assert(kStages >= 1, "stage does not fit");
     static_assert(kGroups * NSR_TILE <= (int)kTmemCols, "TMEM overflow");
 };
 
-template <int S, int WMAX, int KB, int EW>
+template <int SA, int SB, int WMAX, int KB, int EW>
 __global__ void __launch_bounds__(64 + 32 * EW, 1)
 contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
-                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ UmmaArgs g) {
-    using C = Cfg<S, WMAX, KB>;
+                     const __grid_constant__ SegMaps maps, const __grid_constant__ UmmaArgs g) {
+    using C = Cfg<SA, SB, WMAX, KB>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bar_full[8], bar_empty[8], bar_tmem_full, bar_tmem_empty, bar_tile[kTileRing];
     __shared__ uint32_t tmem_base_slot;
@@ -290,6 +343,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t seg_seen = 0;                        // segments whose ready flag this CTA has observed
             const int n_tiles = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
             for (int it = 0;; ++it) {
                 int t = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
@@ -297,17 +351,25 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 s_tile[it % kTileRing] = t;
                 mbar_arrive(smem_u32(&bar_tile[it % kTileRing]));
                 if (t < 0) break;
-                const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = g.tiles[2 * t + 1] * NSR_TILE;
+                const int tcs = g.tiles[2 * t + 1];
+                const int sidx = tcs >> 24;
+                const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = (tcs & 0xFFFFFF) * NSR_TILE;
+                if (g.seg[sidx].ready != nullptr && !((seg_seen >> sidx) & 1u)) {
+                    wait_ready(g.seg[sidx].ready, g.seg[sidx].ready_value);
+                    seg_seen |= 1u << sidx;
+                }
+                const CUtensorMap* mb = &maps.b[sidx];
                 for (int kb = 0; kb < g.num_kb; ++kb) {
                     mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     mbar_expect_tx(full, C::kStageBytes);
                     const uint32_t base = ring_u32 + stage * C::kStageBytes;
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
+                    for (int s = 0; s < SA; ++s)
                         tma_load_3d(&map_a, full, base + s * C::kSliceBytes, (g.kb_begin + kb) * KB, row_a, s);
-                        tma_load_3d(&map_b, full, base + (S + s) * C::kSliceBytes, (g.kb_begin + kb) * KB, row_b, s);
-                    }
+#pragma unroll
+                    for (int s = 0; s < SB; ++s)
+                        tma_load_3d(mb, full, base + (SA + s) * C::kSliceBytes, (g.kb_begin + kb) * KB, row_b, s);
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -335,25 +397,25 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                             // columns) while reading the A tile once: 52 KB instead of 64 KB of
                             // operands per k-step, and 5 instructions instead of 8 (S=3, 8 products).
 #pragma unroll
-                            for (int e = 0; e < Sched<S, WMAX>::kCount; ++e) {
-                                constexpr Sched<S, WMAX> sc{};
+                            for (int e = 0; e < Sched<SA, SB, WMAX>::kCount; ++e) {
+                                constexpr Sched<SA, SB, WMAX> sc{};
                                 const int a = sc.a[e], b = sc.b[e];
                                 const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                const uint64_t db = make_smem_desc<KB>(base + (SA + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
                                 const uint32_t acc = (kb > 0 || ks > 0 || !sc.first[e]) ? 1u : 0u;
                                 tc_mma_i8(tmem_base + (a + b) * NSR_TILE, da, db, sc.wide[e] ? kInstrDescN256 : kInstrDesc, acc);
                             }
                         } else {
 #pragma unroll
-                            for (int a = 0; a < S; ++a) {
+                            for (int a = 0; a < SA; ++a) {
 #pragma unroll
-                                for (int b = 0; b < S; ++b) {
+                                for (int b = 0; b < SB; ++b) {
                                     if (a + b + 2 <= WMAX) {
                                         const int grp = a + b;
                                         // first product of its group in this (a asc, b asc) order
-                                        const bool first = (a == (grp > S - 1 ? grp - (S - 1) : 0));
+                                        const bool first = (a == (grp > SB - 1 ? grp - (SB - 1) : 0));
                                         const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                        const uint64_t db = make_smem_desc<KB>(base + (S + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
+                                        const uint64_t db = make_smem_desc<KB>(base + (SA + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
                                         const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
                                         tc_mma_i8(tmem_base + grp * NSR_TILE, da, db, kInstrDesc, acc);
                                     }
@@ -375,10 +437,11 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait_backoff(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1, g.epi_sleep_ns);
             const int t = s_tile[it % kTileRing];
             if (t < 0) break;
-            const int tr = g.tiles[2 * t], tc = g.tiles[2 * t + 1];
+            const int tr = g.tiles[2 * t], tcs = g.tiles[2 * t + 1];
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
-            epilogue_tile<C::kGroups, EW>(g.ep, tmem_base, warp, lane, tr, tc, true, smem_u32(&bar_tmem_empty), false, t);
+            epilogue_tile<C::kGroups, EW>(g.ep, g.seg[tcs >> 24], tmem_base, warp, lane, tr, tcs & 0xFFFFFF, true,
+                                          smem_u32(&bar_tmem_empty), false, t);
             tphase ^= 1;
         }
     }
@@ -557,7 +620,7 @@ contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
             const bool wanted = (g.tiles[3 * t + 2] >> rank) & 1;
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
-            epilogue_tile<C::kGroups, kEpiWarps>(g.ep, tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
+            epilogue_tile<C::kGroups, kEpiWarps>(g.ep, g.seg[0], tmem_base, warp, lane, tr, tc, wanted, empty_leader, true);
             tphase ^= 1;
         }
     }
@@ -592,11 +655,11 @@ int make_map(nsr_ctx* ctx, CUtensorMap* map, const int8_t* base, int64_t rows, i
     return 0;
 }
 
-template <int S, int WMAX, int KB, int EW>
-int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
-    using C = Cfg<S, WMAX, KB>;
+template <int SA, int SB, int WMAX, int KB, int EW>
+int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const SegMaps& mb, const UmmaArgs& g) {
+    using C = Cfg<SA, SB, WMAX, KB>;
     const int smem = C::kStages * C::kStageBytes + 1024;
-    auto kern = contract_umma_kernel<S, WMAX, KB, EW>;
+    auto kern = contract_umma_kernel<SA, SB, WMAX, KB, EW>;
     NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = (g.n_tiles_dev == nullptr && g.n_tiles < ctx->sm_count) ? g.n_tiles : ctx->sm_count;
     kern<<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, g);
@@ -604,10 +667,10 @@ int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtens
     return 0;
 }
 
-template <int S, int WMAX, int KB>
-int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
-    if (nsr_epi_warps == 16) return launch_ew<S, WMAX, KB, 16>(ctx, st, ma, mb, g);
-    return launch_ew<S, WMAX, KB, 8>(ctx, st, ma, mb, g);
+template <int SA, int SB, int WMAX, int KB>
+int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const SegMaps& mb, const UmmaArgs& g) {
+    if (nsr_epi_warps == 16) return launch_ew<SA, SB, WMAX, KB, 16>(ctx, st, ma, mb, g);
+    return launch_ew<SA, SB, WMAX, KB, 8>(ctx, st, ma, mb, g);
 }
 
 template <int S, int WMAX>
@@ -633,15 +696,20 @@ int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B 
 int nsr_umma_dynamic = 1;    // 1: tiles claimed from a global counter, 0: static round-robin (single-CTA kernel)
 
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
-                             int64_t rows_alloc_a, const int8_t* b, int64_t rows_b,
-                             int64_t rows_alloc_b, int64_t n_pad, int n_slices, int wmax,
+                             int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
+                             int64_t n_pad, int n_slices_b, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev) {
     if (n_tiles < 0) {
         // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
+        if (n_segs != 1 || n_slices_a != n_slices_b) {
+            nsr_set_error("nsr_contract: the cta_group::2 engine takes one segment and equal plane counts");
+            return 2;
+        }
+        const int n_slices = n_slices_a;
         CUtensorMap ma, mb;
         if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices, 128, NSR_TILE)) return 1;
-        if (make_map(ctx, &mb, b, rows_b, rows_alloc_b, n_pad, n_slices, 128, NSR_TILE / 2)) return 1;
+        if (make_map(ctx, &mb, segs[0].slices, segs[0].info.rows_b, segs[0].rows_alloc, n_pad, n_slices, 128, NSR_TILE / 2)) return 1;
         UmmaArgs g;
         g.tiles = tiles_dev;
         g.n_tiles = (int)(-n_tiles);
@@ -651,6 +719,8 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.tile_counter = nullptr;
         g.n_tiles_dev = nullptr;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
+        g.n_segs = 1;
+        g.seg[0] = segs[0].info;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
         if (n_slices == 3 && wmax == 5) return launch2<3, 5>(ctx, st, ma, mb, g);
@@ -658,11 +728,22 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         nsr_set_error("nsr_contract: unsupported (n_slices=%d, wmax=%d) for the tcgen05 pair engine", n_slices, wmax);
         return 2;
     }
-    const int kb = (n_slices == 4) ? 64 : nsr_umma_kblock;
-    CUtensorMap ma, mb;
-    if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices, kb)) return 1;
-    if (make_map(ctx, &mb, b, rows_b, rows_alloc_b, n_pad, n_slices, kb)) return 1;
+    if (n_segs < 1 || n_segs > kMaxSegs) {
+        nsr_set_error("nsr_contract: %d segments (1..%d)", n_segs, kMaxSegs);
+        return 2;
+    }
+    // two stages of (SA + SB) planes x 128 rows x KB cells must fit the operand ring
+    const int kb = (n_slices_a + n_slices_b > 6) ? 64 : nsr_umma_kblock;
+    CUtensorMap ma;
+    SegMaps mb;
+    if (make_map(ctx, &ma, a, rows_a, rows_alloc_a, n_pad, n_slices_a, kb)) return 1;
     UmmaArgs g;
+    for (int s = 0; s < n_segs; ++s) {
+        if (make_map(ctx, &mb.b[s], segs[s].slices, segs[s].info.rows_b, segs[s].rows_alloc, n_pad, n_slices_b, kb)) return 1;
+        g.seg[s] = segs[s].info;
+    }
+    for (int s = n_segs; s < kMaxSegs; ++s) { mb.b[s] = mb.b[0]; g.seg[s] = segs[0].info; }
+    g.n_segs = n_segs;
     g.tiles = tiles_dev;
     g.n_tiles = (int)n_tiles;
     g.num_kb = (int)((cell_end - cell_begin) / kb);
@@ -676,11 +757,16 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     }
     g.epi_sleep_ns = nsr_epi_sleep_ns;
     g.ep = ep;
-    if (n_slices == 3 && wmax == 4 && kb == 128) return launch<3, 4, 128>(ctx, st, ma, mb, g);
-    if (n_slices == 3 && wmax == 5 && kb == 128) return launch<3, 5, 128>(ctx, st, ma, mb, g);
-    if (n_slices == 3 && wmax == 4 && kb == 64) return launch<3, 4, 64>(ctx, st, ma, mb, g);
-    if (n_slices == 3 && wmax == 5 && kb == 64) return launch<3, 5, 64>(ctx, st, ma, mb, g);
-    if (n_slices == 4 && wmax == 5) return launch<4, 5, 64>(ctx, st, ma, mb, g);
-    nsr_set_error("nsr_contract: unsupported (n_slices=%d, wmax=%d) for the tcgen05 engine", n_slices, wmax);
+    const int sa = n_slices_a, sb = n_slices_b;
+    if (sa == 3 && sb == 3 && wmax == 4 && kb == 128) return launch<3, 3, 4, 128>(ctx, st, ma, mb, g);
+    if (sa == 3 && sb == 3 && wmax == 5 && kb == 128) return launch<3, 3, 5, 128>(ctx, st, ma, mb, g);
+    if (sa == 3 && sb == 3 && wmax == 4 && kb == 64) return launch<3, 3, 4, 64>(ctx, st, ma, mb, g);
+    if (sa == 3 && sb == 3 && wmax == 5 && kb == 64) return launch<3, 3, 5, 64>(ctx, st, ma, mb, g);
+    if (sa == 4 && sb == 4 && wmax == 5) return launch<4, 4, 5, 64>(ctx, st, ma, mb, g);
+    if (sa == 1 && sb == 3 && wmax == 4 && kb == 128) return launch<1, 3, 4, 128>(ctx, st, ma, mb, g);
+    if (sa == 1 && sb == 4 && wmax == 5 && kb == 128) return launch<1, 4, 5, 128>(ctx, st, ma, mb, g);
+    if (sa == 1 && sb == 1 && wmax == 2 && kb == 128) return launch<1, 1, 2, 128>(ctx, st, ma, mb, g);
+    nsr_set_error("nsr_contract: unsupported (n_slices_a=%d, n_slices_b=%d, wmax=%d, kblock=%d) for the tcgen05 engine",
+                  sa, sb, wmax, kb);
     return 2;
 }

@@ -31,33 +31,58 @@ __device__ __forceinline__ double nsr_combine(const ContractParams& p, const int
     return s * p.scale_all;
 }
 
+// One column segment of a contraction launch: its B operand's per-row scales and where its columns
+// land in the output.  A plain nsr_contract call is a single segment built from ContractParams; the
+// multi-GPU path (nsr_contract_segments) contracts the local gene block against itself and against
+// every remote block it owns in ONE persistent launch, one segment per block.
+struct SegInfo {
+    const double* qb; const double* vb;      // quantum / variance of the segment's B rows
+    int64_t rows_b;                          // valid B rows
+    int64_t col0;                            // output column of B row 0
+    int mode;                                // NSR_MODE_* of this segment's tiles
+    const uint32_t* ready;                   // device flag: B may be read once *ready - ready_value >= 0 (or nullptr)
+    uint32_t ready_value;
+    uint32_t* done;                          // incremented once per epilogue warp and finished tile (or nullptr)
+};
+
+// host-side description of a segment's operand (what the tensor map is built from) + its SegInfo
+struct NsrSegOperand {
+    const int8_t* slices;
+    int64_t rows_alloc;
+    SegInfo info;
+};
+
 // one output element (i = row in A, j = row in B); `mirror` also writes (j, i) (COEX, i != j tile).
 // Returns true when the element asks for the full-precision phase (adaptive schedule).
-__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
-                                           double vi, double qj, double vj, double acc,
-                                           bool mirror) {
+__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
+                                           double qi, double vi, double qj, double vj, double acc, bool mirror) {
     double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
-    if (p.acc_in) sum += p.out2[i * p.ld + j];     // earlier cell chunks
-    if (p.mode == NSR_MODE_RAW || p.raw_out) {
-        p.out2[i * p.ld + j] = sum;
+    const int64_t at = i * p.ld + col0 + j;
+    if (p.acc_in) sum += p.out2[at];               // earlier cell chunks
+    if (mode == NSR_MODE_RAW || p.raw_out) {
+        p.out2[at] = sum;
         return false;
     }
     const double dot = sum * p.inv_n;
     double P, o2;
     bool refine = false;
-    if ((p.mode == NSR_MODE_COEX || p.mode == NSR_MODE_COEX_UPPER) && i == j) {
+    if ((mode == NSR_MODE_COEX || mode == NSR_MODE_COEX_UPPER) && i == j) {
         P = 0.0; o2 = 0.0;                         // triu(.,1) + transpose leaves a zero diagonal
     } else {
         const double r2 = (dot * dot) / (vi * vj);
         refine = p.refine_r2 >= 0.0 && !(r2 <= p.refine_r2);
         P = nsr_pvalue_r2(r2, p.pv);
-        o2 = (p.mode == NSR_MODE_DE) ? dot / vi : dot;
+        o2 = (mode == NSR_MODE_DE) ? dot / vi : dot;
     }
-    p.P[i * p.ld + j] = P;
-    p.out2[i * p.ld + j] = o2;
+    p.P[at] = P;
+    p.out2[at] = o2;
     if (mirror) {
         p.P[j * p.ld + i] = P;
         p.out2[j * p.ld + i] = o2;
     }
     return refine;
+}
+__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
+                                           double vi, double qj, double vj, double acc, bool mirror) {
+    return nsr_finish(p, p.mode, 0, i, j, qi, vi, qj, vj, acc, mirror);
 }

@@ -15,6 +15,8 @@ struct nsr_ctx {
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     int32_t* tiles_dev = nullptr;
+    int32_t* tiles_pinned = nullptr;   // pinned staging of the tile list (same capacity), guarded by tiles_event
+    cudaEvent_t tiles_event = nullptr;
     size_t tiles_cap = 0;
     void* encode_tiled = nullptr;      // cuTensorMapEncodeTiled, resolved at create
     // dynamic tile scheduler of the tcgen05 kernel: one counter per launch, used round-robin so
@@ -79,5 +81,12 @@ NSR_HDI int nsr_wmax(int n_slices, int n_products) {
     if (n_slices == 3 && n_products == 8) return 5;
     if (n_slices == 4 && n_products == 10) return 5;
     if (n_slices == 2 && n_products == 3) return 3;
+    return -1;
+}
+// A operand with ONE exact plane (nsr_residualize_exact) against sb planes of B: every product is kept
+//   (1, 1): 1 product, wmax 2     (1, 3): 3 products, wmax 4     (1, 4): 4 products, wmax 5
+NSR_HDI int nsr_wmax_ab(int sa, int sb, int n_products) {
+    if (sa == sb) return nsr_wmax(sa, n_products) > 0 ? nsr_wmax(sa, n_products) : ((sa == 1 && n_products == 1) ? 2 : -1);
+    if (sa == 1 && n_products == sb && (sb == 3 || sb == 4)) return sb + 1;
     return -1;
 }

@@ -174,7 +174,8 @@ sumsq_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
 // coef[row][c] = sum_ks partial; inv_quantum estimate from rms_est = sqrt((sum x^2 - |coef|^2)/n)
 __global__ void coef_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ psq,
                                      int64_t rows, int rank, int ksplit, int64_t n, double vmax,
-                                     double* __restrict__ coef, double* __restrict__ invq_est) {
+                                     double* __restrict__ coef, double* __restrict__ invq_est,
+                                     int* __restrict__ exact_status) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows) return;
     double c2 = 0.0;
@@ -187,6 +188,9 @@ __global__ void coef_finalize_kernel(const double* __restrict__ partial, const d
     double sq = 0.0;
     for (int ks = 0; ks < ksplit; ++ks) sq += psq[(int64_t)ks * rows + row];
     const double ms = (sq - c2) / (double)n;
+    // exact single-plane path: the raw row stands in for its residual in the cross products, which
+    // amplifies the partner's quantisation error by sqrt(sum x^2 / sum res^2): refuse beyond 2x
+    if (exact_status != nullptr && !(sq <= 4.0 * (sq - c2))) atomicOr(exact_status, 2);
     const double est = (ms > 0.0 && isfinite(ms)) ? kKappa * sqrt(ms) : 0.0;
     invq_est[row] = est > 0.0 ? vmax / est : 0.0;          // 0 -> digits 0, row goes to the fix-up pass
 }
@@ -226,7 +230,11 @@ __device__ __forceinline__ void store_digits(const double (&v)[32], double invq,
 // row_list == nullptr: logical row == row.  Otherwise the kernel handles rows row_list[0..*row_count).
 // NCH = covariate chunks of 4 handled from shared memory (rank <= 16 -> ceil(rank/4); larger ranks
 // use NCH = 4 plus the global-memory groups).
-template <int S, bool HAD, bool VEC, int NCH>
+// RAW (S = 1, nsr_residualize_exact): the plane holds the Hadamard mix of the RAW row, which for rows
+// of small integers (binary groupings) is itself a small integer - stored exactly, quantum 1/sqrt(128);
+// the residual is still formed for the exact variance.  *exact_status |= 1 if a value is not an integer
+// of magnitude <= 127.
+template <int S, bool HAD, bool VEC, int NCH, bool RAW>
 __global__ void __launch_bounds__(kThreads, 2)
 residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64_t ldx,
                     const double* __restrict__ Qt, int rank, int64_t ldq, const double* __restrict__ coef,
@@ -234,7 +242,8 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
                     int nblk, int ksplit, uint64_t cell_offset,
                     const double* __restrict__ inv_quantum, double* __restrict__ part_sumsq,
                     double* __restrict__ part_amax, int8_t* __restrict__ slices, int64_t rows_alloc,
-                    int64_t n_pad, unsigned long long* __restrict__ energy_max, int prefetch) {
+                    int64_t n_pad, unsigned long long* __restrict__ energy_max, int prefetch,
+                    int* __restrict__ exact_status) {
     // covariate block of the current 128 cells, shared by the CTA's 8 warps (they walk the same
     // cells): [buffer][covariate][cell], pitch 132 so that a B-fragment read (4 covariates x 8 cells
     // per half-warp) touches 16 distinct banks
@@ -252,7 +261,8 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
     const int b_end = (int)((int64_t)nblk * (blockIdx.y + 1) / ksplit);
     const int nblk_full = (int)(n / 128);
     const int ngroup = (rank + 15) / 16;                 // covariates in groups of 16 = 4 MMA k-chunks
-    const double my_invq = (my_row >= 0 && inv_quantum) ? inv_quantum[my_row] * (HAD ? kHadScale : 1.0) : 0.0;
+    const double my_invq = RAW ? 1.0 : ((my_row >= 0 && inv_quantum) ? inv_quantum[my_row] * (HAD ? kHadScale : 1.0) : 0.0);
+    bool inexact = false;
 
     // A fragments (-coef[row g][4 ch + t]) of the first covariate group stay in registers
     double ca[4];
@@ -340,6 +350,7 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
             }
             sumsq = fma(c0v, c0v, sumsq);
             sumsq = fma(c1v, c1v, sumsq);
+            if (RAW) { c0v = v[2 * u]; c1v = v[2 * u + 1]; }      // the plane carries the raw row
             if (HAD) {
                 c0v = __hiloint2double(__double2hiint(c0v) ^ (int)(((ma >> (2 * u)) & 1u) << 31), __double2loint(c0v));
                 c1v = __hiloint2double(__double2hiint(c1v) ^ (int)(((mb >> (2 * u)) & 1u) << 31), __double2loint(c1v));
@@ -367,9 +378,14 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) amax_hi = max(amax_hi, __double2hiint(v[i]) & 0x7fffffff);
+        if (RAW) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) inexact |= !(fabs(v[i]) <= 127.0) || v[i] != rint(v[i]);
+        }
         if (slices != nullptr && my_row >= 0)
             store_digits<S>(v, my_invq, slices + my_row * n_pad + k0 + 32 * t, rows_alloc * n_pad, energy);
     }
+    if (RAW && inexact && my_row >= 0 && exact_status != nullptr) atomicOr(exact_status, 1);
     if (energy_max != nullptr && slices != nullptr) {
         // per-plane digit energy of each row over this CTA's cells -> maximum over rows, kept per
         // cell split: the host bounds every int32 partial sum of the contraction with Cauchy-Schwarz
@@ -405,7 +421,8 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
                                       int ksplit, int64_t n, double vmax,
                                       double* __restrict__ var, double* __restrict__ quantum,
                                       double* __restrict__ inv_quantum, int32_t* __restrict__ fix_list,
-                                      int32_t* __restrict__ fix_count, unsigned long long* __restrict__ energy_max) {
+                                      int32_t* __restrict__ fix_count, unsigned long long* __restrict__ energy_max,
+                                      double raw_quantum) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     double s = 0.0, m = 0.0;
@@ -421,6 +438,7 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part_sumsq,
     double v = s / (double)n;
     if (v == 0.0) v = 1.0;                       // association.py:231,233
     var[i] = v;
+    if (raw_quantum > 0.0) { quantum[i] = raw_quantum; return; }      // exact single-plane rows: fixed scale, no fix-up
     const double iq = inv_quantum[i];
     if (m > 0.0 && isfinite(m) && (iq == 0.0 || !(m * iq <= vmax))) {     // iq == 0: no usable estimate
         const double q = m / vmax;
@@ -449,7 +467,7 @@ __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, 
 }  // namespace
 
 int nsr_use_hadamard = 1;   // test hook (nsr_set_option)
-int nsr_prefetch = 1;       // test hook: L2 prefetch of the next block in pass B
+int nsr_prefetch = 0;       // test hook: L2 prefetch of the next block in pass B (measured neutral: off)
 
 extern "C" int64_t nsr_padded_cells(int64_t n) { return (n + NSR_KBLOCK - 1) / NSR_KBLOCK * NSR_KBLOCK; }
 
@@ -462,10 +480,11 @@ extern "C" int nsr_cell_splits(int64_t n) {
     return (int)ks;
 }
 
-extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows,
-                               int64_t n, int64_t ldx, const double* Qt, int rank, int64_t ldq,
-                               int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
-                               double* quantum, double* var, double* coef, double* energy_max) {
+// n_slices = 1 with exact_status != nullptr: the exact single-plane mode of nsr_residualize_exact
+static int residualize_impl(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows,
+                            int64_t n, int64_t ldx, const double* Qt, int rank, int64_t ldq,
+                            int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
+                            double* quantum, double* var, double* coef, double* energy_max, int* exact_status) {
     NSR_REQUIRE(ctx != nullptr, "nsr_residualize: null context");
     NSR_REQUIRE(rows > 0 && rows < (1ll << 31) && n > 0 && ldx >= n,
                 "nsr_residualize: bad shape rows=%lld n=%lld ldx=%lld", (long long)rows, (long long)n,
@@ -473,7 +492,8 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     NSR_REQUIRE(rank >= 0 && rank <= NSR_MAX_RANK, "nsr_residualize: rank %d outside [0,%d]", rank,
                 NSR_MAX_RANK);
     NSR_REQUIRE(rank == 0 || (Qt != nullptr && ldq >= n), "nsr_residualize: bad covariate basis");
-    NSR_REQUIRE(n_slices == 3 || n_slices == 4, "nsr_residualize: n_slices %d (3 or 4)", n_slices);
+    const bool exact = exact_status != nullptr;
+    NSR_REQUIRE(exact ? n_slices == 1 : (n_slices == 3 || n_slices == 4), "nsr_residualize: n_slices %d (3 or 4)", n_slices);
     NSR_REQUIRE(n_pad == nsr_padded_cells(n) && rows_alloc >= rows,
                 "nsr_residualize: n_pad/rows_alloc inconsistent");
     NSR_REQUIRE(((uintptr_t)slices & 15) == 0, "nsr_residualize: slices must be 16-byte aligned");
@@ -524,14 +544,14 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
         sumsq_kernel<<<dim3((unsigned)groups_s, (unsigned)ks_a), kThreads, 0, st>>>(X, rows, n, ldx, ks_a, psq);
     }
     coef_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial, psq, rows, rank, ks_a, n, vmax,
-                                                                       coef_buf, invq);
+                                                                       coef_buf, invq, exact_status);
     const dim3 gridb((unsigned)groups_w, (unsigned)ks_b);
     const bool had = nsr_use_hadamard != 0;
     const int nch = rank >= 16 ? 4 : (rank + 3) / 4;
 #define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
-    residual_mma_kernel<S_, H_, V_, N_><<<gridb, kThreads, 0, st>>>(                                         \
+    residual_mma_kernel<S_, H_, V_, N_, (S_ == 1)><<<gridb, kThreads, 0, st>>>(                              \
         X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
-        rows_alloc, n_pad, (unsigned long long*)energy_max, nsr_prefetch)
+        rows_alloc, n_pad, (unsigned long long*)energy_max, nsr_prefetch, exact_status)
 #define NSR_LAUNCH_B_N(S_, H_, V_, LIST, COUNT, PS, PA)                                                      \
     do {                                                                                                     \
         switch (nch) {                                                                                       \
@@ -544,7 +564,10 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     } while (0)
 #define NSR_LAUNCH_B_ALL(LIST, COUNT, PS, PA)                                                                \
     do {                                                                                                     \
-        if (n_slices == 3) {                                                                                 \
+        if (n_slices == 1) {                                                                                 \
+            if (had) { if (vec) NSR_LAUNCH_B_N(1, true, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(1, true, false, LIST, COUNT, PS, PA); }     \
+            else { if (vec) NSR_LAUNCH_B_N(1, false, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(1, false, false, LIST, COUNT, PS, PA); }        \
+        } else if (n_slices == 3) {                                                                          \
             if (had) { if (vec) NSR_LAUNCH_B_N(3, true, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(3, true, false, LIST, COUNT, PS, PA); }     \
             else { if (vec) NSR_LAUNCH_B_N(3, false, true, LIST, COUNT, PS, PA); else NSR_LAUNCH_B_N(3, false, false, LIST, COUNT, PS, PA); }        \
         } else {                                                                                             \
@@ -555,14 +578,32 @@ extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, 
     NSR_LAUNCH_B_ALL(nullptr, nullptr, p_sumsq, p_amax);
     stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
                                                                         quantum, invq, fix_list, fix_count,
-                                                                        (unsigned long long*)energy_max);
+                                                                        (unsigned long long*)energy_max,
+                                                                        exact ? (had ? kHadScale : 1.0) : 0.0);
     // sparse fix-up: warps beyond the (device-side) count exit at once
-    NSR_LAUNCH_B_ALL(fix_list, fix_count, nullptr, nullptr);
+    if (!exact) NSR_LAUNCH_B_ALL(fix_list, fix_count, nullptr, nullptr);
 #undef NSR_LAUNCH_B_ALL
 #undef NSR_LAUNCH_B_N
 #undef NSR_LAUNCH_B
     NSR_CHECK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int nsr_residualize(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows,
+                               int64_t n, int64_t ldx, const double* Qt, int rank, int64_t ldq,
+                               int n_slices, int8_t* slices, int64_t rows_alloc, int64_t n_pad,
+                               double* quantum, double* var, double* coef, double* energy_max) {
+    return residualize_impl(ctx, stream, X, rows, n, ldx, Qt, rank, ldq, n_slices, slices, rows_alloc, n_pad, quantum, var,
+                            coef, energy_max, nullptr);
+}
+
+extern "C" int nsr_residualize_exact(nsr_ctx* ctx, uintptr_t stream, const double* X, int64_t rows,
+                                     int64_t n, int64_t ldx, const double* Qt, int rank, int64_t ldq,
+                                     int8_t* plane, int64_t rows_alloc, int64_t n_pad, double* quantum,
+                                     double* var, double* coef, double* energy_max, int* status) {
+    NSR_REQUIRE(status != nullptr, "nsr_residualize_exact: null status");
+    return residualize_impl(ctx, stream, X, rows, n, ldx, Qt, rank, ldq, 1, plane, rows_alloc, n_pad, quantum, var, coef,
+                            energy_max, status);
 }
 
 namespace {

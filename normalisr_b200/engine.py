@@ -64,7 +64,7 @@ def padded_cells(n):
 class Sliced:
     """Residualised rows as int8 digit planes + per-row quantum / variance (device)."""
 
-    def __init__(self, rows, n, n_slices, device, storage=None):
+    def __init__(self, rows, n, n_slices, device, storage=None, fresh=True):
         self.rows, self.n, self.n_slices = rows, n, n_slices
         self.n_pad = padded_cells(n)
         if storage is None:
@@ -79,8 +79,16 @@ class Sliced:
             self.quantum = storage[nb:nb + 8 * rows].view(torch.float64)
             self.var = storage[nb + 8 * rows:nb + 16 * rows].view(torch.float64)
         self.coef = None
-        # [cell split][plane]: largest per-row sum of squared digits (see nsr_residualize)
-        self.energy_max = torch.zeros((_lib.MAX_SPLITS, _lib.MAX_SLICES), dtype=torch.float64, device=device)
+        # [cell split][plane]: largest per-row sum of squared digits (see nsr_residualize); it travels with
+        # the block in the multi-GPU exchange, so every rank can bound its int32 sums without a collective
+        ne = _lib.MAX_SPLITS * _lib.MAX_SLICES
+        if storage is None:
+            self.energy_max = torch.zeros((_lib.MAX_SPLITS, _lib.MAX_SLICES), dtype=torch.float64, device=device)
+        else:
+            nb = n_slices * rows * self.n_pad + 16 * rows
+            self.energy_max = storage[nb:nb + 8 * ne].view(torch.float64).view(_lib.MAX_SPLITS, _lib.MAX_SLICES)
+            if fresh:                # a block about to be written here (not a view of one that is being copied in)
+                self.energy_max.zero_()
 
     @property
     def rows_alloc(self):
@@ -88,7 +96,7 @@ class Sliced:
 
     @staticmethod
     def storage_bytes(rows, n, n_slices):
-        return n_slices * rows * padded_cells(n) + 16 * rows
+        return n_slices * rows * padded_cells(n) + 16 * rows + 8 * _lib.MAX_SPLITS * _lib.MAX_SLICES
 
 
 def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
@@ -125,6 +133,30 @@ def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
     # stats finalize, sparse fix-up pass
     LAUNCHES += ((rank + 7) // 8 if rank else 1) + 4
     return out
+
+
+def residualize_exact(ctx, X, Qt, keep_coef=False):
+    """Rows of small integers (binary groupings) as ONE exact int8 plane (nsr_residualize_exact).
+    Returns (Sliced with n_slices = 1, status): status is a device int32 tensor, non-zero when the rows
+    do not qualify (not small integers / mostly explained by the covariates) and the plane must not be
+    used."""
+    assert X.is_cuda and X.dtype == torch.float64 and X.dim() == 2 and X.stride(1) == 1
+    rows, n = X.shape
+    rank = 0 if Qt is None else Qt.shape[0]
+    out = Sliced(rows, n, 1, X.device)
+    if keep_coef and rank:
+        out.coef = torch.zeros((rows, rank), dtype=torch.float64, device=X.device)
+    status = torch.zeros(1, dtype=torch.int32, device=X.device)
+    ldx = X.stride(0) if rows > 1 else n
+    ldq = Qt.stride(0) if rank > 1 else n
+    st = ctx.lib.nsr_residualize_exact(
+        ctx.handle, _stream(), X.data_ptr(), rows, n, ldx, Qt.data_ptr() if rank else None, rank, ldq,
+        out.slices.data_ptr(), out.rows_alloc, out.n_pad, out.quantum.data_ptr(), out.var.data_ptr(),
+        out.coef.data_ptr() if out.coef is not None else None, out.energy_max.data_ptr(), status.data_ptr())
+    _lib.check(st, "nsr_residualize_exact")
+    global LAUNCHES
+    LAUNCHES += ((rank + 15) // 16 if rank else 1) + 3
+    return out, status
 
 
 def unslice(ctx, s):
@@ -249,12 +281,18 @@ def rect_tiles(rows_a, rows_b, strip=12):
 _INT32_LIMIT = float(2 ** 31 - 1)
 
 
-def products_of(n_slices, n_products):
-    """Kept digit pairs (a, b), 0-based, grouped by weight a + b."""
-    wmax = {(3, 6): 4, (3, 8): 5, (4, 10): 5}[(n_slices, n_products)]
+def products_of(n_slices, n_products, n_slices_b=None):
+    """Kept digit pairs (a, b), 0-based, grouped by weight a + b.  ``n_slices_b`` differs from
+    ``n_slices`` when the A operand is a single exact plane (every product kept)."""
+    sb = n_slices if n_slices_b is None else n_slices_b
+    if sb != n_slices or n_slices == 1:
+        assert n_slices == 1 and n_products == sb
+        wmax = sb + 1
+    else:
+        wmax = {(3, 6): 4, (3, 8): 5, (4, 10): 5}[(n_slices, n_products)]
     groups = {}
     for a in range(n_slices):
-        for b in range(n_slices):
+        for b in range(sb):
             if a + b + 2 <= wmax:
                 groups.setdefault(a + b, []).append((a, b))
     return groups
@@ -276,7 +314,7 @@ def plan_k_chunk(A, B, n_products, energies=None):
         raise AssertionError('Non-finite values (NaN / Inf) in the input matrix or the covariates.')
     ks = _lib.load().nsr_cell_splits(A.n)
     nblk = A.n_pad // _lib.KBLOCK
-    groups = products_of(A.n_slices, n_products)
+    groups = products_of(A.n_slices, n_products, B.n_slices)
 
     ca = np.concatenate([np.zeros((1, ea.shape[1])), np.cumsum(ea[:ks], axis=0)])
     cb = np.concatenate([np.zeros((1, eb.shape[1])), np.cumsum(eb[:ks], axis=0)])
@@ -307,24 +345,124 @@ def plan_k_chunk(A, B, n_products, energies=None):
 
 
 def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_UMMA, k_chunk=None):
-    """Run the contraction + epilogue for ``tiles`` ((k,2) int32 numpy array of tile coords)."""
-    assert A.n == B.n and A.n_slices == B.n_slices
+    """Run the contraction + epilogue for ``tiles`` ((k,2) int32 numpy array of tile coords).
+    A may be a single exact plane (``residualize_exact``): then every product with B's planes is kept
+    and ``n_products`` is ignored."""
+    assert A.n == B.n
+    if A.n_slices != B.n_slices or A.n_slices == 1:
+        assert A.n_slices == 1
+        n_products = B.n_slices
     if k_chunk is None:
         k_chunk = plan_k_chunk(A, B, n_products)
     tiles = np.ascontiguousarray(tiles, dtype=np.int32)
     ld = out2.stride(0) if out2.shape[0] > 1 else out2.shape[1]
     assert out2.stride(1) == 1 and (P is None or P.shape == out2.shape and P.stride(1) == 1)
     assert P is None or out2.shape[0] == 1 or P.stride(0) == ld
-    st = ctx.lib.nsr_contract(
+    st = ctx.lib.nsr_contract_ab(
         ctx.handle, _stream(), engine, mode,
-        A.slices.data_ptr(), A.rows, A.rows_alloc, A.quantum.data_ptr(), A.var.data_ptr(),
-        B.slices.data_ptr(), B.rows, B.rows_alloc, B.quantum.data_ptr(), B.var.data_ptr(),
-        A.n, A.n_pad, A.n_slices, n_products,
+        A.slices.data_ptr(), A.rows, A.rows_alloc, A.n_slices, A.quantum.data_ptr(), A.var.data_ptr(),
+        B.slices.data_ptr(), B.rows, B.rows_alloc, B.n_slices, B.quantum.data_ptr(), B.var.data_ptr(),
+        A.n, A.n_pad, n_products,
         tiles.ctypes.data, tiles.shape[0], float(dof_a),
         P.data_ptr() if P is not None else None, out2.data_ptr(), ld, int(k_chunk))
     _lib.check(st, "nsr_contract")
     global LAUNCHES
     LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
+
+
+def contract_segments(ctx, A, segments, tiles, dof_a, P, out2, n_products, k_chunk=0):
+    """Everything one GPU owns under the block-pair schedule in ONE persistent launch
+    (nsr_contract_segments).  ``segments``: list of dicts with keys B (Sliced), rows_b, col0, diagonal,
+    and optionally ready = (uint32 flag tensor element pointer, value), done = pointer; ``tiles``:
+    (k, 3) int32 array of (segment, tile_row, tile_col)."""
+    assert 1 <= len(segments) <= _lib.MAX_SEGMENTS
+    arr = (_lib.Segment * len(segments))()
+    for i, sg in enumerate(segments):
+        B = sg["B"]
+        assert B.n == A.n and B.n_slices == A.n_slices
+        arr[i].b_slices = B.slices.data_ptr()
+        arr[i].rows_b = int(sg["rows_b"])
+        arr[i].rows_alloc_b = B.rows_alloc
+        arr[i].quantum_b = B.quantum.data_ptr()
+        arr[i].var_b = B.var.data_ptr()
+        arr[i].col0 = int(sg["col0"])
+        arr[i].diagonal = 1 if sg.get("diagonal") else 0
+        ready = sg.get("ready")
+        arr[i].ready = ready[0] if ready else None
+        arr[i].ready_value = int(ready[1]) & 0xFFFFFFFF if ready else 0
+        arr[i].done = sg.get("done")
+    tiles = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3)
+    ld = out2.stride(0) if out2.shape[0] > 1 else out2.shape[1]
+    assert out2.stride(1) == 1 and P.shape == out2.shape and P.stride(1) == 1 and (out2.shape[0] == 1 or P.stride(0) == ld)
+    st = ctx.lib.nsr_contract_segments(
+        ctx.handle, _stream(), A.slices.data_ptr(), A.rows, A.rows_alloc, A.quantum.data_ptr(), A.var.data_ptr(),
+        A.n, A.n_pad, A.n_slices, n_products, arr, len(segments), tiles.ctypes.data, tiles.shape[0], float(dof_a),
+        P.data_ptr(), out2.data_ptr(), ld, int(k_chunk))
+    _lib.check(st, "nsr_contract_segments")
+    global LAUNCHES
+    LAUNCHES += 1 if not k_chunk else -(-A.n_pad // k_chunk)
+
+
+def stream_signal(ctx, flag_ptr, value, stream=None):
+    """*flag = value once ``stream`` (default: current) reaches this point (no kernel)."""
+    st = stream.cuda_stream if stream is not None else _stream()
+    _lib.check(ctx.lib.nsr_stream_signal(ctx.handle, st, flag_ptr, int(value) & 0xFFFFFFFF), "nsr_stream_signal")
+
+
+def stream_wait_geq(ctx, flag_ptr, value, stream=None):
+    """``stream`` waits until (int32)(*flag - value) >= 0 (no kernel)."""
+    st = stream.cuda_stream if stream is not None else _stream()
+    _lib.check(ctx.lib.nsr_stream_wait_geq(ctx.handle, st, flag_ptr, int(value) & 0xFFFFFFFF), "nsr_stream_wait_geq")
+
+
+def gram_f64(ctx, X, coef):
+    """G = X X^T - coef coef^T in float64 (nsr_gram_f64): Gram matrix of the residualised rows."""
+    rows, n = X.shape
+    rank = 0 if coef is None else coef.shape[1]
+    G = torch.empty((rows, rows), dtype=torch.float64, device=X.device)
+    cf = coef.contiguous() if rank else None
+    ldx = X.stride(0) if rows > 1 else n
+    _lib.check(ctx.lib.nsr_gram_f64(ctx.handle, _stream(), X.data_ptr(), rows, n, ldx, cf.data_ptr() if rank else None,
+                                    rank, G.data_ptr(), rows), "nsr_gram_f64")
+    global LAUNCHES
+    LAUNCHES += 3 if rank else 2
+    return G
+
+
+def gram_correct(ctx, G, coef):
+    """G = (G + G^T)/2 - coef coef^T in place (nsr_gram_correct)."""
+    rows = G.shape[0]
+    rank = 0 if coef is None else coef.shape[1]
+    if rank == 0:
+        return G
+    cf = coef.contiguous()
+    _lib.check(ctx.lib.nsr_gram_correct(ctx.handle, _stream(), G.data_ptr(), rows, G.stride(0), cf.data_ptr(), rank),
+               "nsr_gram_correct")
+    global LAUNCHES
+    LAUNCHES += 2
+    return G
+
+
+def de4_solve(ctx, Gxx, Gxy, yy, n_cells, rank_c, dimreduce, tol, return_dot):
+    """Leave-one-out regression of association_test_4 on the device (nsr_de4_solve).  Gxx is destroyed.
+    Returns (P, out2, vary, varx, w, status) - status is a device int32 tensor (see the header)."""
+    nx, ny = Gxy.shape
+    assert Gxx.is_contiguous() and Gxx.shape == (nx, nx) and Gxy.stride(1) == 1 and yy.is_contiguous()
+    dev = Gxy.device
+    P = torch.empty((nx, ny), dtype=torch.float64, device=dev)
+    out2 = torch.empty_like(P)
+    vary = torch.empty_like(P)
+    w = torch.empty_like(P)
+    varx = torch.empty(nx, dtype=torch.float64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ld_xy = Gxy.stride(0) if nx > 1 else ny
+    _lib.check(ctx.lib.nsr_de4_solve(ctx.handle, _stream(), Gxx.data_ptr(), nx, Gxy.data_ptr(), ny, ld_xy, yy.data_ptr(),
+                                     int(n_cells), int(rank_c), int(dimreduce), float(tol), 1 if return_dot else 0,
+                                     P.data_ptr(), out2.data_ptr(), vary.data_ptr(), ny, varx.data_ptr(), w.data_ptr(), ny,
+                                     status.data_ptr()), "nsr_de4_solve")
+    global LAUNCHES
+    LAUNCHES += 3 * ((nx + 31) // 32) + 8
+    return P, out2, vary, varx, w, status
 
 
 def last_refined(ctx, n_tiles):

@@ -8,7 +8,7 @@ The path shards naturally:
   * the int8 digit planes (+ per-row quantum and variance) are exchanged ONCE.  Default schedule
     ("pairs"): the unordered block pairs {i, j} are dealt out on a circulant - rank r computes its
     diagonal block and the pairs (r, r+d mod W) for d = 1 .. W/2 (for even W the pairs at distance
-    W/2 are split between their two owners on a checkerboard of tiles).  Every rank therefore
+    W/2 are split in two halves between their two owners).  Every rank therefore
     needs only W/2 remote blocks instead of W-1, receives them in W/2 point-to-point rounds in
     which all ranks send and receive at once, and contracts block pair d while round d+1 is in
     flight.  The older schedule ("allgather": one all-gather, then a strip of tile rows per rank)
@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine
-from ._lib import MODE_COEX_RECT, MODE_COEX_UPPER, MODE_DE, TILE
+from ._lib import MAX_SEGMENTS, MODE_COEX_RECT, MODE_COEX_UPPER, MODE_DE, TILE
 from .association import covariate_basis_device
 
 
@@ -44,8 +44,8 @@ def block_rows(rows, world, k):
 def exchange_plan(world, rank):
     """Rounds of the block exchange for ``rank``: [(send_to, recv_from, parity)], round d-1 brings
     block (rank + d) mod world.  parity is None for a pair this rank computes in full, or 0 / 1 when
-    the pair is shared with its other owner (even world, distance world/2): this rank takes the
-    tiles with (tile_row + tile_col) % 2 == parity."""
+    the pair is shared with its other owner (even world, distance world/2): this rank takes the tiles
+    ``pair_tiles`` selects for that parity (one half of the block pair, cut along block lo)."""
     plan = []
     for d in range(1, world // 2 + 1):
         src = (rank + d) % world
@@ -57,11 +57,22 @@ def exchange_plan(world, rank):
 
 
 def pair_tiles(rows_a, rows_b, parity=None):
-    """Tiles of the (rows_a x rows_b) block pair this rank computes."""
+    """Tiles of the (rows_a x rows_b) block pair this rank computes.  A shared pair {lo, hi} (parity set)
+    is cut along the tile rows of block lo: the lower-numbered owner (parity 0, its A = block lo) takes
+    the first half of them, the other owner (parity 1, its B = block lo) the rest - two rectangles, so
+    each owner's share is one rectangular block of the output (a 2-D copy home, no tile masks)."""
     tl = engine.rect_tiles(rows_a, rows_b)
     if parity is not None and len(tl):
-        tl = tl[(tl[:, 0] + tl[:, 1]) % 2 == parity]
+        if parity == 0:
+            tl = tl[tl[:, 0] < shared_cut(rows_a)]
+        else:
+            tl = tl[tl[:, 1] >= shared_cut(rows_b)]
     return np.ascontiguousarray(tl, dtype=np.int32).reshape(-1, 2)
+
+
+def shared_cut(rows_lo):
+    """Tile row of block lo at which a shared block pair is cut between its two owners."""
+    return ((rows_lo + TILE - 1) // TILE + 1) // 2
 
 
 def owned_tile_mask(n_gene, world, rank):
@@ -166,27 +177,70 @@ def _symm_block(nbytes, device, group):
     return _SYMM[key]
 
 
-def start_exchange_ce(local_store, hdl, local, group=None):
+def start_exchange_ce(local_store, hdl, local, group=None, ctx=None):
     """Copy-engine variant of ``start_exchange``: every remote block is PULLED from the owner's
     peer-mapped buffer with an asynchronous device-to-device copy on a side stream, so the exchange
-    uses no SMs while the contraction runs.  Returns [(src, parity, Sliced, [event])]."""
+    uses no SMs while the contraction runs.  Each copy is followed by a stream-ordered flag write
+    (``nsr_stream_signal``): the persistent contraction launch, already running, starts on a block's
+    tiles when its flag appears.  Returns [(src, parity, Sliced, _FlagWork)]."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     hdl.barrier(channel=1, timeout_ms=60000)            # every rank's planes are written
-    side = torch.cuda.Stream(device=local.slices.device)
+    side = _side_stream(local.slices.device)
     side.wait_stream(torch.cuda.current_stream())
     nbytes = local_store.numel()
     rounds = []
-    for _, src, parity in exchange_plan(world, rank):
+    sync = _sync_words(ctx) if ctx is not None else None
+    for d, (_, src, parity) in enumerate(exchange_plan(world, rank)):
         store = torch.empty(nbytes, dtype=torch.uint8, device=local.slices.device)
         store.record_stream(side)
         with torch.cuda.stream(side):
             store.copy_(hdl.get_buffer(src, (nbytes,), torch.uint8, 0), non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(side)
-        buf = engine.Sliced(local.rows_alloc, local.n, local.n_slices, local.slices.device, storage=store)
-        rounds.append((src, parity, buf, [_EventWork(ev)]))
+            work = _EventWork(ev)
+            if sync is not None:
+                work = _FlagWork(ev, sync.ready_ptr(d + 1), sync.epoch)
+                engine.stream_signal(ctx, work.flag_ptr, work.value, stream=side)
+        buf = engine.Sliced(local.rows_alloc, local.n, local.n_slices, local.slices.device, storage=store, fresh=False)
+        rounds.append((src, parity, buf, [work]))
     return rounds
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
+class _SyncWords:
+    """Per-device uint32 words shared with the persistent contraction launch: ready flags (one per
+    segment, set to the step's epoch by the copy stream) and done counters (monotonic)."""
+
+    def __init__(self, device):
+        self.words = torch.zeros(64, dtype=torch.int32, device=device)
+        self.epoch = 0
+        self.done_expected = [0] * 16
+
+    def ready_ptr(self, seg):
+        return self.words.data_ptr() + 4 * seg
+
+    def done_ptr(self, seg):
+        return self.words.data_ptr() + 4 * (32 + seg)
+
+
+_SYNC = {}
+
+
+def _sync_words(ctx):
+    key = ctx.device.index
+    if key not in _SYNC:
+        _SYNC[key] = _SyncWords(ctx.device)
+    return _SYNC[key]
 
 
 class _EventWork:
@@ -197,6 +251,15 @@ class _EventWork:
 
     def wait(self):
         torch.cuda.current_stream().wait_event(self.ev)
+
+
+class _FlagWork(_EventWork):
+    """A block whose arrival is also announced by a device flag (see ``start_exchange_ce``): the
+    single-launch contraction waits for the flag inside the kernel instead of on the stream."""
+
+    def __init__(self, ev, flag_ptr, value):
+        super().__init__(ev)
+        self.flag_ptr, self.value = flag_ptr, value
 
 
 def residualize_block(ctx, x_block, Qt_dev, n_slices, blk, storage=None):
@@ -225,40 +288,57 @@ def _timed(events, fn):
 
 
 def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None):
-    """Pairs schedule on an already residualised block: post the exchange, contract the diagonal
-    block, then each block pair as soon as its round has arrived.  Returns (P, dot, var_all).
+    """Pairs schedule on an already residualised block: post the exchange and contract everything this
+    rank owns - with the copy-engine transport in ONE persistent launch that starts on the diagonal
+    block and picks up each block pair when its planes have arrived.  Returns (P, dot, var_all).
     ``events`` (a list) receives one CUDA event pair per contraction launch (bench bookkeeping).
     ``out_host`` = (P, dot) pinned CPU tensors: every finished column block is copied back on a
     side stream while the next block pair is contracted (column blocks this rank does not own are
-    not written)."""
+    not written).
+
+    The int32 partial sums are bounded from the digit energies AFTER the launch is queued (the
+    energies of the remote blocks travel with them): the contraction runs optimistically in one pass
+    over the cells and is redone in cell chunks if the bound fails (not observed below ~260k cells)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     blk = local.rows_alloc
-    rows_a = block_rows(n_gene, world, rank)
-    em = local.energy_max
     var_all = local.var
     rounds = []
     if world > 1:
-        em = em.clone()
-        dist.all_reduce(em, op=dist.ReduceOp.MAX, group=group)       # int32 bound over every rank's rows
-        # small collectives first: the compute stream waits for them, and they must not queue
-        # behind the plane exchange on the communication stream
+        if symm is not None:
+            _sync_words(ctx).epoch += 1
+            rounds = start_exchange_ce(symm[0], symm[1], local, group, ctx=ctx)
+        else:
+            rounds = start_exchange(local, group)
+    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, events, out_host)
+    if world > 1:
         var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
         dist.all_gather_into_tensor(var_all, local.var, group=group)
-        rounds = start_exchange(local, group) if symm is None else start_exchange_ce(symm[0], symm[1], local, group)
-    em_h = em.cpu().numpy()
-    k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_h, em_h))
-    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out, events, out_host)
+    # verification of the optimistic single pass: bound over this rank's rows x every block it used
+    for r in rounds:
+        wait_block(r[3])
+    em_a = local.energy_max.cpu().numpy()
+    em_b = em_a
+    for r in rounds:
+        em_b = np.maximum(em_b, r[2].energy_max.cpu().numpy())
+    k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_a, em_b))
+    if k_chunk:
+        P, D = contract_plan(ctx, local, [(r[0], r[1], r[2], []) for r in rounds], rank, world, n_gene, dof_a,
+                             n_products, k_chunk, (P, D), None, out_host)
     return P, D, var_all[:n_gene]
 
 
 def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out=None, events=None,
-                  out_host=None):
+                  out_host=None, single_launch=True):
     """Contract everything ``rank`` owns under the pairs schedule: the upper triangle of its diagonal
-    block, then the block pairs of ``rounds`` = [(src, parity, Sliced of block src, works)] (``works``
-    are waited for on the current stream before the block is touched; [] when it is already there, as
-    in the one-GPU emulation of the schedule in tests/test_gpu_parity.py).  Returns (P, dot): rows of
-    block ``rank`` x all n_gene columns, owned tiles filled in."""
+    block, then the block pairs of ``rounds`` = [(src, parity, Sliced of block src, works)].
+    ``works``: [] when the block is already there (the one-GPU emulation of the schedule in
+    tests/test_gpu_parity.py), a ``_FlagWork`` when a copy engine is bringing it and will set a device
+    flag (the kernel waits for it), anything else with ``wait()`` (NCCL) is waited for on the stream.
+    One persistent launch over all segments (``nsr_contract_segments``) unless a block arrives over
+    NCCL - its kernels need SMs, which a waiting persistent launch would not release - or
+    ``single_launch`` is off; then one launch per block.  Returns (P, dot): rows of block ``rank`` x
+    all n_gene columns, owned tiles filled in."""
     blk = local.rows_alloc
     rows_a = block_rows(n_gene, world, rank)
     if out is None:
@@ -267,25 +347,59 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
     else:
         P, D = out
     local.rows = max(rows_a, 1)
-    copy_stream = torch.cuda.Stream(device=local.slices.device) if out_host is not None else None
+    if not rows_a:
+        return P, D
+    copy_stream = _side_stream2(local.slices.device) if out_host is not None else None
+    flagged = all(len(w) == 0 or isinstance(w[0], _FlagWork) for _, _, _, w in rounds)
+    if single_launch and flagged and len(rounds) + 1 <= MAX_SEGMENTS:
+        sync = _sync_words(ctx)
+        segs = [dict(B=local, rows_b=rows_a, col0=rank * blk, diagonal=True)]
+        tl = engine.coex_tiles(rows_a)
+        tiles = [np.concatenate([np.zeros((len(tl), 1), np.int32), tl], axis=1)]
+        for k, (src, parity, buf, works) in enumerate(rounds, 1):
+            rows_b = block_rows(n_gene, world, src)
+            if not rows_b:
+                continue
+            buf.rows = rows_b
+            sg = dict(B=buf, rows_b=rows_b, col0=src * blk, diagonal=False)
+            if works:
+                sg["ready"] = (works[0].flag_ptr, works[0].value)
+            tl = pair_tiles(rows_a, rows_b, parity)
+            tiles.append(np.concatenate([np.full((len(tl), 1), len(segs), np.int32), tl], axis=1))
+            segs.append(sg)
+        track = out_host is not None and not k_chunk
+        if track:
+            for i, sg in enumerate(segs):
+                sg["done"] = sync.done_ptr(i)
+        _timed(events, lambda: engine.contract_segments(ctx, local, segs, np.concatenate(tiles), dof_a, P, D,
+                                                        n_products, k_chunk=k_chunk))
+        if out_host is not None:
+            if not track:
+                copy_stream.wait_stream(torch.cuda.current_stream())
+            for i, sg in enumerate(segs):
+                if track:
+                    # the epilogue counts every finished tile of the segment once per epilogue warp
+                    sync.done_expected[i] += EPILOGUE_WARPS * len(tiles[i])
+                    engine.stream_wait_geq(ctx, sync.done_ptr(i), sync.done_expected[i], stream=copy_stream)
+                _send_home(ctx, P, D, out_host, rows_a, sg["col0"], sg["col0"] + sg["rows_b"], copy_stream)
+            torch.cuda.current_stream().wait_stream(copy_stream)
+        return P, D
 
     def send_home(c0, c1):
         if out_host is None:
             return
         copy_stream.wait_stream(torch.cuda.current_stream())
-        for src_t, dst_t in ((P, out_host[0]), (D, out_host[1])):
-            engine.copy_block_to_host(ctx, dst_t, src_t, 0, rows_a, c0, c1, stream=copy_stream)
+        _send_home(ctx, P, D, out_host, rows_a, c0, c1, copy_stream)
 
-    if rows_a:
-        c0 = rank * blk
-        _timed(events, lambda: engine.contract(
-            ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
-            P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk))
-        send_home(c0, c0 + rows_a)
+    c0 = rank * blk
+    _timed(events, lambda: engine.contract(
+        ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
+        P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk))
+    send_home(c0, c0 + rows_a)
     for src, parity, buf, works in rounds:
         wait_block(works)
         rows_b = block_rows(n_gene, world, src)
-        if rows_a and rows_b:
+        if rows_b:
             buf.rows = rows_b
             c0 = src * blk
             _timed(events, lambda: engine.contract(
@@ -295,6 +409,22 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
     if copy_stream is not None:
         torch.cuda.current_stream().wait_stream(copy_stream)
     return P, D
+
+
+EPILOGUE_WARPS = 8        # epilogue warps of the tcgen05 kernel (each counts a finished tile once)
+_SIDE2 = {}
+
+
+def _side_stream2(device):
+    key = torch.device(device).index
+    if key not in _SIDE2:
+        _SIDE2[key] = torch.cuda.Stream(device=device)
+    return _SIDE2[key]
+
+
+def _send_home(ctx, P, D, out_host, rows_a, c0, c1, stream):
+    for src_t, dst_t in ((P, out_host[0]), (D, out_host[1])):
+        engine.copy_block_to_host(ctx, dst_t, src_t, 0, rows_a, c0, c1, stream=stream)
 
 
 def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events=None):

@@ -6,14 +6,27 @@ The reference forms the Gram matrices of A = [dx; dc] (``prod1`` tiles) and then
 x, pseudo-inverts the (m-1)x(m-1) Gram matrix of everything but x.  Algebraically that is the
 multiple regression of y on all rows of A, so here:
 
-  1. dx and dy are residualised against dc by the projection kernel (exact in float64);
-  2. the two Gram blocks  Gxx = Rx Rx^T,  Gxy = Rx Ry^T  come from the tensor-core
-     contraction in NSR_MODE_RAW (exact integer sums);
-  3. one float64 factorisation of Gxx gives every leave-one-out quantity in closed form
-     (Schur complements), and the P-values come from nsr_pvalue.
+  1. dx and dy are residualised against dc by the projection kernels (float64);
+  2. Gxy = Rx Ry^T comes from the tensor-core contraction in NSR_MODE_RAW (exact integer sums;
+     3 digit products when the groupings are small integers and travel as one exact plane);
+     Gxx = Rx Rx^T is formed in float64 from the raw groupings like the reference's own prod1 tiles
+     (exact integer sums on the tensor cores for small-integer groupings, ``nsr_gram_f64`` otherwise)
+     minus the covariate part Cx Cx^T;
+  3. ``nsr_de4_solve``: one blocked Cholesky factorisation of Gxx on the device gives every
+     leave-one-out quantity in closed form (Schur complements), fused with the P-value.
 
-When Gxx is numerically rank deficient the closed form does not apply and step 3 falls back
-to the reference's per-x pseudo-inverse, on the same Gram matrices.
+When a Cholesky pivot falls below tol * max diag (numerically rank-deficient groupings) the closed
+form does not apply and step 3 falls back to the reference's per-x pseudo-inverse, on the same Gram
+matrices (``_loo_pinv``, host; the reference itself fails its range assert on exactly collinear
+groupings, association.py:557).
+
+Deliberate deviations from the reference (documented, both in unusual inputs only):
+  * the rank rule is applied to the covariate-residualised groupings' Gram matrix, not to the joint
+    Gram matrix of [other groupings; covariates] (association.py:527-528): covariates that are not
+    scaled to O(1) (normcov scales them) can make the reference drop grouping directions that are kept
+    here;
+  * a gene that the covariates explain exactly has var 0 -> 1 in the projection (association.py:231) and
+    gets P = 1 here, where the reference's single=4 branch divides by dyy = 0 and fails its assert.
 """
 import logging
 
@@ -25,8 +38,8 @@ from ._lib import MODE_RAW, MAX_RANK
 
 
 def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduce=0,
-                              precision='default', device=None, engine_id=None, **ka):
-    from .association import covariate_basis_device, inv_rank, _residualize_any, _as_host_f64, _is_dev, _out
+                              precision='default', device=None, engine_id=None, exact_groupings=True, **ka):
+    from .association import covariate_basis_device, _residualize_any, _residualize_groupings, _is_dev, _out
     eng = ka.pop('engine', engine.ENGINE_UMMA) if engine_id is None else engine_id
     tol = ka.pop('tol', 1e-8)
     if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
@@ -50,28 +63,42 @@ def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
     Qt_dev, rank_c, W = covariate_basis_device(ctx, dc, tol=tol)
     if rank_c > MAX_RANK:
         raise NotImplementedError('covariate rank {} > {}'.format(rank_c, MAX_RANK))
+    if n - 1 - (nx - 1 + rank_c) - dimreduce <= 0:
+        raise RuntimeError('Insufficient number of cells: must be greater than degrees of '
+                           'freedom removed + covariate + 1.')
     with torch.cuda.device(ctx.device):
         dev = ctx.device
-        Rx = _residualize_any(ctx, dx, Qt_dev, n_slices, not lowmem)
+        Rx, xd = _residualize_groupings(ctx, dx, Qt_dev, n_slices, True, exact=exact_groupings)
         Ry = _residualize_any(ctx, dy, Qt_dev, n_slices, not lowmem)
-        Gxx = torch.empty((nx, nx), dtype=torch.float64, device=dev)
         Gxy = torch.empty((nx, ny), dtype=torch.float64, device=dev)
-        engine.contract(ctx, MODE_RAW, Rx, Rx, engine.rect_tiles(nx, nx), 1.0, None, Gxx, n_products, eng)
         engine.contract(ctx, MODE_RAW, Rx, Ry, engine.rect_tiles(nx, ny), 1.0, None, Gxy, n_products, eng)
-        Gxx = 0.5 * (Gxx + Gxx.T)
+        if Rx.n_slices == 1:
+            # small-integer groupings: raw Gram matrix as exact integer sums (1 digit product), then - Cx Cx^T
+            Gxx = torch.empty((nx, nx), dtype=torch.float64, device=dev)
+            engine.contract(ctx, MODE_RAW, Rx, Rx, engine.rect_tiles(nx, nx), 1.0, None, Gxx, 1, eng)
+            engine.gram_correct(ctx, Gxx, Rx.coef)
+        else:
+            Gxx = engine.gram_f64(ctx, xd, Rx.coef)
         yy = _row_sumsq(Ry)
-
-        dxx, dxy, dyy, rank, w = loo_stats(Gxx, Gxy, yy, n, rank_c, tol)
-        dxx = torch.where(dxx == 0, torch.ones_like(dxx), dxx)               # :545-547
-        gamma = dxy / dxx[:, None]
-        r2 = dxy * dxy / (dxx[:, None] * dyy)
-        if not bool(((r2 >= 0) & (r2 <= 1 + 1e-8)).all()):                   # :557
-            raise AssertionError('R^2 outside [0, 1]: collinear groupings?')
-        dof = n - 1 - rank - dimreduce
-        if bool((dof <= 0).any()):
-            raise RuntimeError('Insufficient number of cells: must be greater than degrees of '
-                               'freedom removed + covariate + 1.')
-        P = engine.pvalue(ctx, r2, dof / 2)
+        Gkeep = Gxx.clone()
+        P, out2, dyy, dxx, w, status = engine.de4_solve(ctx, Gxx, Gxy, yy, n, rank_c, dimreduce, tol, return_dot)
+        st = int(status.item())
+        if st & 1:
+            # numerically rank-deficient groupings: the reference's per-x pseudo-inverse (host)
+            dxx, dxy, dyy, rank, w = _loo_pinv(Gkeep, Gxy, yy, n, rank_c, tol)
+            dxx = torch.where(dxx == 0, torch.ones_like(dxx), dxx)               # :545-547
+            gamma = dxy / dxx[:, None]
+            r2 = dxy * dxy / (dxx[:, None] * dyy)
+            if not bool(((r2 >= 0) & (r2 <= 1 + 1e-8)).all()):                   # :557
+                raise AssertionError('R^2 outside [0, 1]: collinear groupings?')
+            dof = n - 1 - rank - dimreduce
+            if bool((dof <= 0).any()):
+                raise RuntimeError('Insufficient number of cells: must be greater than degrees of '
+                                   'freedom removed + covariate + 1.')
+            P = engine.pvalue(ctx, r2, dof / 2)
+            out2 = gamma * dxx[:, None] if return_dot else gamma
+        elif st & 2:
+            raise AssertionError('R^2 outside [0, 1] or non-finite result: collinear groupings?')       # :557, :565-568
         alpha = None
         if not lowmem:
             if rank_c:
@@ -80,7 +107,6 @@ def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
             else:
                 al = torch.zeros((ny, nc), dtype=torch.float64, device=dev)
             alpha = al[None, :, :].expand(nx, ny, nc).contiguous()
-        out2 = gamma * dxx[:, None] if return_dot else gamma
         res = (P, out2, alpha, dxx, dyy)
         if to_host:
             torch.cuda.current_stream().synchronize()
@@ -116,9 +142,11 @@ def _row_sumsq(R):
     return R.var * R.n
 
 
-def _loo_pinv(Gxx, Gxy, yy, n, rank_c, tol, inv_rank):
+def _loo_pinv(Gxx, Gxy, yy, n, rank_c, tol, inv_rank=None):
     """Rank-deficient groupings: the reference's per-x pseudo-inverse (association.py:521-544)
     on the residualised Gram matrices, in float64 on the host."""
+    if inv_rank is None:
+        from .association import inv_rank
     G = Gxx.cpu().numpy()
     Gy = Gxy.cpu().numpy()
     y2 = yy.cpu().numpy()

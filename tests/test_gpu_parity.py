@@ -611,3 +611,175 @@ def test_nonfinite_input_raises():
     c[1, 5] = np.nan
     with pytest.raises(AssertionError):
         norm.coex(dt, c)
+
+
+# ---- exact single-plane groupings, device solve of single=4, segmented launch -------------------
+def test_exact_groupings_plane():
+    """nsr_residualize_exact: binary rows become one int8 plane holding the Hadamard mix of the RAW row
+    exactly; var / coef are those of the residual; rows that do not qualify raise the status bits."""
+    rng = np.random.default_rng(41)
+    n, k = 5000, 37
+    dc = np.concatenate([rng.normal(size=(3, n)), np.ones((1, n))])
+    dg = (rng.random((k, n)) < 0.03).astype(np.float64)
+    dg[3] = (rng.random(n) < 0.5) * 2.0                       # small integers, dense
+    Qt, rank, _ = association.covariate_basis(dc)
+    ctx = engine.context(0)
+    Qd = torch.from_numpy(Qt).cuda()
+    A, status = engine.residualize_exact(ctx, torch.from_numpy(dg).cuda(), Qd, keep_coef=True)
+    assert int(status.item()) == 0 and A.n_slices == 1
+    got = engine.unslice(ctx, A).cpu().numpy()
+    np.testing.assert_allclose(got, tl.hadamard128(dg), rtol=0, atol=1e-12)          # exact up to the 1/sqrt(128) scale
+    z = tl.residual(dg, Qt)
+    np.testing.assert_allclose(A.var.cpu().numpy(), (z ** 2).mean(1), rtol=1e-12)
+    np.testing.assert_allclose(A.coef.cpu().numpy(), dg @ Qt.T, rtol=1e-10, atol=1e-12)
+    # cross products with residualised genes: exact x -> agrees with float64 to the genes' quantisation error
+    dt = rng.normal(size=(200, n)) + 0.4 * dc[0] + 3
+    B = engine.residualize(ctx, torch.from_numpy(dt).cuda(), Qd, 3)
+    outs = []
+    for eng in (engine.ENGINE_UMMA, engine.ENGINE_SIMT):
+        G = torch.zeros((k, 200), dtype=torch.float64, device="cuda")
+        engine.contract(ctx, engine.MODE_RAW, A, B, engine.rect_tiles(k, 200), 1.0, None, G, 3, eng)
+        outs.append(G)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])                      # tcgen05 and dp4a engines: same integer sums
+    want = z @ tl.residual(dt, Qt).T
+    scale = np.sqrt(np.outer((dg ** 2).sum(1), (tl.residual(dt, Qt) ** 2).sum(1)))
+    assert (np.abs(outs[0].cpu().numpy() - want) / scale).max() < 2e-8
+    # Gram matrix of the raw rows: exact integers
+    Gxx = torch.zeros((k, k), dtype=torch.float64, device="cuda")
+    engine.contract(ctx, engine.MODE_RAW, A, A, engine.rect_tiles(k, k), 1.0, None, Gxx, 1)
+    np.testing.assert_allclose(Gxx.cpu().numpy(), dg @ dg.T, rtol=1e-14, atol=0)      # exact integer sums x (1/sqrt(128))^2
+    engine.gram_correct(ctx, Gxx, A.coef)
+    np.testing.assert_allclose(Gxx.cpu().numpy(), z @ z.T, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(engine.gram_f64(ctx, torch.from_numpy(dg).cuda(), A.coef).cpu().numpy(), z @ z.T,
+                               rtol=1e-9, atol=1e-9)
+    # rows that do not qualify
+    _, st = engine.residualize_exact(ctx, torch.from_numpy(dg + 0.25).cuda(), Qd)
+    assert int(st.item()) & 1
+    _, st = engine.residualize_exact(ctx, torch.from_numpy(np.round(40 * rng.normal(size=(4, n)))).cuda(), Qd)
+    assert int(st.item()) & 1                                                          # mixed values beyond +-127
+    batch = np.round(dc[:1] > 0.3).astype(np.float64) + 0.0
+    dcb = np.concatenate([dc, batch])                                                  # a grouping that IS a covariate
+    Qb = torch.from_numpy(association.covariate_basis(dcb)[0]).cuda()
+    _, st = engine.residualize_exact(ctx, torch.from_numpy(batch).cuda(), Qb)
+    assert int(st.item()) & 2
+
+
+@pytest.mark.parametrize("single", [0, 4])
+def test_de_general_and_exact_grouping_paths_agree(single):
+    """de with the groupings as one exact plane (default for binary dg) and through the general
+    3-plane route: both within tolerance of the oracle; continuous groupings take the general route."""
+    p = synth.host_problem(1013, 300, 4000, n_group=20, group_p=0.05)
+    ref = orc.de(p["dg"], p["dt"], p["dc"], single=single)
+    for exact in (True, False):
+        got = norm.de(p["dg"], p["dt"], p["dc"], single=single, exact_groupings=exact)
+        assert_p_close(got[0], ref[0])
+        np.testing.assert_allclose(got[3], ref[3], rtol=1e-7)
+        np.testing.assert_allclose(got[4], ref[4], rtol=1e-7)
+        scale = np.sqrt(ref[4] / ref[3][:, None])
+        assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+    rng = np.random.default_rng(5)
+    dgc = rng.normal(size=(7, 4000)) + 0.2 * p["dc"][5]                # continuous "groupings"
+    ref = orc.de(dgc, p["dt"], p["dc"], single=single)
+    got = norm.de(dgc, p["dt"], p["dc"], single=single)
+    assert_p_close(got[0], ref[0])
+    scale = np.sqrt(ref[4] / ref[3][:, None])
+    assert (np.abs(got[1] - ref[1]) <= R_ATOL * scale + 1e-12).all()
+
+
+def test_de4_solve_matches_float64_closed_form():
+    """nsr_de4_solve (blocked Cholesky + closed form + P-value on the device) against the float64 torch
+    restatement of the same closed form, sizes that cross panel borders; a singular Gram matrix raises bit 1."""
+    from normalisr_b200 import single4
+    rng = np.random.default_rng(9)
+    ctx = engine.context(0)
+    for nx, ny, n in ((1, 5, 400), (31, 70, 900), (97, 300, 5000), (300, 1000, 20000)):
+        rx = (rng.random((nx, n)) < 0.1) - 0.1 + 0.01 * rng.normal(size=(nx, n))
+        ry = rng.normal(size=(ny, n)) + 0.3 * rx[rng.integers(0, nx, size=ny)]
+        Gxx, Gxy, yy = rx @ rx.T, rx @ ry.T, (ry ** 2).sum(1)
+        dxx, dxy, dyy, rank, w = single4.loo_stats(torch.from_numpy(Gxx), torch.from_numpy(Gxy), torch.from_numpy(yy), n, 2)
+        P, gam, vy, vx, wd, st = engine.de4_solve(ctx, torch.from_numpy(Gxx).cuda(), torch.from_numpy(Gxy).cuda(),
+                                                  torch.from_numpy(yy).cuda(), n, 2, 0, 1e-8, False)
+        assert int(st.item()) == 0
+        np.testing.assert_allclose(vx.cpu().numpy(), dxx.numpy(), rtol=1e-9)
+        np.testing.assert_allclose(vy.cpu().numpy(), dyy.numpy(), rtol=1e-9)
+        np.testing.assert_allclose(gam.cpu().numpy(), (dxy / dxx[:, None]).numpy(), rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose(wd.cpu().numpy(), w.numpy(), rtol=1e-7, atol=1e-12)
+        r2 = (dxy * dxy / (dxx[:, None] * dyy)).numpy()
+        assert_p_close(P.cpu().numpy(), orc.beta_cdf(1 - r2, (n - 1 - (nx - 1 + 2)) / 2), rtol=1e-6)
+    rx[5] = rx[0] + rx[1]
+    G = rx @ rx.T
+    st = engine.de4_solve(ctx, torch.from_numpy(G).cuda(), torch.from_numpy(rx @ ry.T).cuda(), torch.from_numpy(yy).cuda(),
+                          n, 2, 0, 1e-8, False)[5]
+    assert int(st.item()) & 1
+
+
+def test_de_single4_rank_deficient_groupings_fall_back():
+    """A grouping that duplicates nothing but is the sum of two others: Cholesky breaks down, the host
+    branch (the reference's per-x pseudo-inverse) takes over; the reference itself fails its range
+    assert here, so only sanity is checked."""
+    p = synth.host_problem(1014, 50, 3000, n_group=6, group_p=0.2)
+    dg = p["dg"].copy()
+    dg[5] = np.minimum(dg[0] + dg[1], 1.0) * 0 + dg[0] + dg[1]
+    try:
+        got = norm.de(dg, p["dt"], p["dc"], single=4)
+        assert np.isfinite(got[0]).all() and ((got[0] >= 0) & (got[0] <= 1)).all()
+    except AssertionError:
+        pass            # like the reference (association.py:557)
+
+
+def test_segments_flags_and_done_counters():
+    """nsr_contract_segments with its device-side synchronisation, on one GPU: the remote blocks are
+    copied in on a side stream that sets the ready flags afterwards (the launch is already queued),
+    and a copy stream waits on the done counters before sending each column block home.  Result:
+    bit-identical to the single-launch NSR_MODE_COEX matrices."""
+    from normalisr_b200 import parallel
+    world, n_gene, n = 4, 2300, 2500
+    ctx = engine.context(0)
+    p = synth.device_problem(1015, n_gene, n, "cuda")
+    Qt, crank, _ = association.covariate_basis_device(ctx, p["dc"])
+    S, prods = engine.PRESETS["default"]
+    dof = (n - 1 - crank) / 2
+    full = engine.residualize(ctx, p["dt"], Qt, S)
+    P1 = torch.zeros((n_gene, n_gene), dtype=torch.float64, device="cuda")
+    D1 = torch.zeros_like(P1)
+    engine.contract(ctx, engine.MODE_COEX, full, full, engine.coex_tiles(n_gene), dof, P1, D1, prods)
+    blk = parallel.row_split(n_gene, world)
+    nbytes = engine.Sliced.storage_bytes(blk, n, S)
+    homes = []
+    for r in range(world):
+        store = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        homes.append((store, parallel.residualize_block(ctx, p["dt"][r * blk:(r + 1) * blk], Qt, S, blk, storage=store)))
+    torch.cuda.synchronize()
+    sync = parallel._sync_words(ctx)
+    side = torch.cuda.Stream()
+    Ps, Ds = [], []
+    for rep in range(2):                    # twice: epochs and monotonic counters
+        Ps, Ds = [], []
+        for r in range(world):
+            sync.epoch += 1
+            rows_a = parallel.block_rows(n_gene, world, r)
+            rounds, stores = [], []
+            for d, (_, src, parity) in enumerate(parallel.exchange_plan(world, r)):
+                store = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+                stores.append((store, src))
+                work = parallel._FlagWork(None, sync.ready_ptr(d + 1), sync.epoch)
+                rounds.append((src, parity, engine.Sliced(blk, n, S, "cuda", storage=store, fresh=False), [work]))
+            Ph = torch.full((max(rows_a, 1), n_gene), -1.0, dtype=torch.float64).pin_memory()
+            Dh = torch.full((max(rows_a, 1), n_gene), -1.0, dtype=torch.float64).pin_memory()
+            # the launch is queued first: it contracts the diagonal block and then waits inside the kernel ...
+            P, D = parallel.contract_plan(ctx, homes[r][1], rounds, r, world, n_gene, dof, prods, 0, out_host=(Ph, Dh))
+            # ... for the "remote" blocks, which only now start to arrive on the side stream
+            with torch.cuda.stream(side):
+                for d, (store, src) in enumerate(stores):
+                    store.copy_(homes[src][0], non_blocking=True)
+                    engine.stream_signal(ctx, sync.ready_ptr(d + 1), sync.epoch, stream=side)
+            torch.cuda.synchronize()
+            Ps.append(P)
+            Ds.append(D)
+            m = torch.from_numpy(parallel.owned_tile_mask(n_gene, world, r)).repeat_interleave(128, 0)[:rows_a]
+            m = m.repeat_interleave(128, 1)[:, :n_gene]
+            assert torch.equal(torch.where(m, Ph[:rows_a], torch.zeros(())), torch.where(m, P[:rows_a].cpu(), torch.zeros(())))
+            assert torch.equal(torch.where(m, Dh[:rows_a], torch.zeros(())), torch.where(m, D[:rows_a].cpu(), torch.zeros(())))
+    assert torch.equal(parallel.assemble_dense(Ps, n_gene, world), P1)
+    assert torch.equal(parallel.assemble_dense(Ds, n_gene, world), D1)
