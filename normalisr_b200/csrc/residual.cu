@@ -464,6 +464,7 @@ __global__ void unslice_kernel(const int8_t* __restrict__ slices, int64_t rows, 
     out[r * n_pad + (k - p) + m] = (double)v * quantum[r];     // natural (transformed-index) order
 }
 
+
 }  // namespace
 
 int nsr_use_hadamard = 1;   // test hook (nsr_set_option)
@@ -514,13 +515,20 @@ static int residualize_impl(nsr_ctx* ctx, uintptr_t stream, const double* X, int
     const int ks_a = ksplit, ks_b = ksplit;
     const int rk = rank > 0 ? rank : 1;
 
+    const bool had = nsr_use_hadamard != 0;
+    const int nch = rank >= 16 ? 4 : (rank + 3) / 4;
+
+    const int ks_stat = ks_b;
+
     // scratch (doubles): coef partials | sum-x^2 partials | sumsq partials | amax partials | inv_quantum
     //                    | coef (if the caller passed none) ; then int32: fix_count(+pad) | fix_list
-    const size_t n_part = (size_t)ks_a * rows * rk, n_psq = (size_t)ks_a * rows;
-    const size_t n_stat = (size_t)ks_b * rows, n_coef = (size_t)rows * rk;
+    const size_t n_part = (size_t)ks_a * rows * rk;
+    const size_t n_psq = (size_t)ks_a * rows;
+    const size_t n_stat = (size_t)ks_stat * rows, n_coef = (size_t)rows * rk;
     const size_t n_dbl = n_part + n_psq + 2 * n_stat + rows + n_coef;
+    const size_t n_i32 = (size_t)(rows + 4);
     void* scratch = nullptr;
-    if (nsr_scratch(ctx, n_dbl * sizeof(double) + (size_t)(rows + 4) * sizeof(int32_t), &scratch)) return 1;
+    if (nsr_scratch(ctx, n_dbl * sizeof(double) + n_i32 * sizeof(int32_t), &scratch)) return 1;
     double* partial = (double*)scratch;
     double* psq = partial + n_part;
     double* p_sumsq = psq + n_psq;
@@ -546,8 +554,6 @@ static int residualize_impl(nsr_ctx* ctx, uintptr_t stream, const double* X, int
     coef_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(partial, psq, rows, rank, ks_a, n, vmax,
                                                                        coef_buf, invq, exact_status);
     const dim3 gridb((unsigned)groups_w, (unsigned)ks_b);
-    const bool had = nsr_use_hadamard != 0;
-    const int nch = rank >= 16 ? 4 : (rank + 3) / 4;
 #define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
     residual_mma_kernel<S_, H_, V_, N_, (S_ == 1)><<<gridb, kThreads, 0, st>>>(                              \
         X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
@@ -576,7 +582,7 @@ static int residualize_impl(nsr_ctx* ctx, uintptr_t stream, const double* X, int
         }                                                                                                    \
     } while (0)
     NSR_LAUNCH_B_ALL(nullptr, nullptr, p_sumsq, p_amax);
-    stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_b, n, vmax, var,
+    stats_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(p_sumsq, p_amax, rows, ks_stat, n, vmax, var,
                                                                         quantum, invq, fix_list, fix_count,
                                                                         (unsigned long long*)energy_max,
                                                                         exact ? (had ? kHadScale : 1.0) : 0.0);

@@ -783,3 +783,4 @@ def test_segments_flags_and_done_counters():
             assert torch.equal(torch.where(m, Dh[:rows_a], torch.zeros(())), torch.where(m, D[:rows_a].cpu(), torch.zeros(())))
     assert torch.equal(parallel.assemble_dense(Ps, n_gene, world), P1)
     assert torch.equal(parallel.assemble_dense(Ds, n_gene, world), D1)
+
