@@ -306,17 +306,30 @@ int nsr_sym_pinv(nsr_ctx* ctx, uintptr_t stream, const double* G, int64_t batch,
  * recomputed (synchronises `stream`; bookkeeping for benchmarks). */
 int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined);
 
-/* Bayesian logCPM (lcpm.lcpm, src/normalisr/lcpm.py:21-208, default arguments): reads is a
- * (genes x n) matrix of non-negative counts (int32 or int64, itemsize 4 / 8), lut[c] =
- * digamma(1 + c) - digamma(total + 2) for c = 0 .. lut_len - 1 (the reference's table, :96-109).
- *   nsr_lcpm_colstats  colstats = [3][n]: per cell sum_g exp(lut[reads]), total reads, number of
- *                      genes with a non-zero count (per-cell normaliser :155-157 and the
- *                      covariates :193-199 from one pass over the counts);
- *   nsr_lcpm_apply     out[g][k] = lut[reads[g][k]] - shift[k]  (shift may be NULL). */
+/* Bayesian logCPM (lcpm.lcpm, src/normalisr/lcpm.py:21-208): reads is a (genes x n) matrix of
+ * non-negative counts (int32 or int64, itemsize 4 / 8), lut[c] = digamma(1 + c) - digamma(total + 2) for
+ * c = 0 .. lut_len - 1 (the reference's table, :96-109) and lut_exp[c] = exp(lut[c]).
+ *   nsr_lcpm_scan      out3 (device, 3 x int64) = min, max and total of the counts in one pass (the
+ *                      negativity check :88-89, the table length :98 and the total :95);
+ *   nsr_lcpm_colstats  colstats = [3][n]: per cell sum_g exp(value), total reads, number of genes with a
+ *                      non-zero count (per-cell normaliser :155-157 and the covariates :193-199 from one
+ *                      pass over the counts; without resampling the exponentials are a table gather);
+ *   nsr_lcpm_apply     out[g][k] = value[g][k] - shift[k]  (shift may be NULL).
+ * value = lut[reads] or, with posterior resampling (varscale != 0, :134-150), lut[reads] + lut_sd[reads] z
+ * with lut_sd[c] = sqrt(varscale (trigamma(1 + c) - trigamma(total + 2))) and z a standard normal
+ * deviate per entry: read from `noise` (genes x n, ld_noise; e.g. numpy's own stream for a bit-exact
+ * drop-in of the reference) or, noise == NULL, generated by Philox4x32-10 keyed by `seed` with the entry's
+ * global index (row0 + g) * n + k as counter (the same in both passes and for any row chunking).
+ * lut_sd == NULL: no resampling. */
+int nsr_lcpm_scan(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes, int64_t n,
+                  int64_t ld, long long* out3);
 int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
-                      int64_t n, int64_t ld, const double* lut, int64_t lut_len, double* colstats);
+                      int64_t n, int64_t ld, const double* lut, const double* lut_exp, int64_t lut_len,
+                      const double* lut_sd, const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0,
+                      double* colstats);
 int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
-                   int64_t n, int64_t ld, const double* lut, int64_t lut_len, const double* shift,
+                   int64_t n, int64_t ld, const double* lut, int64_t lut_len, const double* lut_sd,
+                   const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0, const double* shift,
                    double* out, int64_t ldo);
 
 /* compute_var (norm.compute_var, src/normalisr/norm.py:56-128), column pass: with res = X - coef Qt
@@ -350,6 +363,25 @@ int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64_t rows, in
  * host, 1 = host to device.  Pitches and width in bytes. */
 int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
                int64_t src_pitch, int64_t width_bytes, int64_t height, int kind);
+
+/* Text I/O of the command-line layer around the hot path (run.py:10-35), host side: files are mapped and
+ * parsed by a pool of threads straight into the caller's buffers (page-locked memory in the Python layer,
+ * so a matrix reaches the device with one asynchronous copy).  threads <= 0: all cores.
+ *   nsr_tsv_shape / nsr_tsv_read   numpy.loadtxt(f, delimiter) (file_read_tsv, run.py:20-27): data lines
+ *                                  (blank lines and '#' comments skipped) x delimiter-separated fields ->
+ *                                  out[r * ld + c], float64;
+ *   nsr_tsv_write                  numpy.savetxt(f, d, delimiter, fmt='%.<precision>G') (file_write_tsv,
+ *                                  run.py:30-35; the reference's fmt_float is '%.8G', run.py:6): same bytes;
+ *   nsr_mtx_shape / nsr_mtx_read   scipy.io.mmread of a 'matrix coordinate' file (file_read_coo,
+ *                                  run.py:10-17): the stored entries as 0-based triplets (pattern files
+ *                                  give 1.0); *symmetric = 0 general / 1 symmetric / 2 skew-symmetric (the
+ *                                  caller mirrors the entries, as scipy does). */
+int nsr_tsv_shape(const char* path, char delimiter, int64_t* rows, int64_t* cols);
+int nsr_tsv_read(const char* path, char delimiter, double* out, int64_t rows, int64_t cols, int64_t ld, int threads);
+int nsr_tsv_write(const char* path, char delimiter, const double* data, int64_t rows, int64_t cols, int64_t ld,
+                  int precision, int threads);
+int nsr_mtx_shape(const char* path, int64_t* rows, int64_t* cols, int64_t* nnz, int* is_integer);
+int nsr_mtx_read(const char* path, int64_t nnz, int32_t* row, int32_t* col, double* val, int* symmetric, int threads);
 
 /* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
  * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA

@@ -52,6 +52,12 @@ _SIGNATURES = {
     "nsr_gram_correct": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_vp, c_int]),
     "nsr_de4_solve": (c_int, [c_vp, c_up, c_vp, c_int, c_vp, c_i64, c_i64, c_vp, c_i64, c_int, c_int, c_dbl, c_int,
                               c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "nsr_tsv_shape": (c_int, [ctypes.c_char_p, ctypes.c_char, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "nsr_tsv_read": (c_int, [ctypes.c_char_p, ctypes.c_char, c_vp, c_i64, c_i64, c_i64, c_int]),
+    "nsr_tsv_write": (c_int, [ctypes.c_char_p, ctypes.c_char, c_vp, c_i64, c_i64, c_i64, c_int, c_int]),
+    "nsr_mtx_shape": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                              ctypes.POINTER(c_int)]),
+    "nsr_mtx_read": (c_int, [ctypes.c_char_p, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_int]),
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
@@ -66,8 +72,11 @@ _SIGNATURES = {
     "nsr_single1_finish": (c_int, [c_vp, c_up, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_last_refined": (c_int, [c_vp, c_up, c_i64, c_vp]),
-    "nsr_lcpm_colstats": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
-    "nsr_lcpm_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64]),
+    "nsr_lcpm_scan": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp]),
+    "nsr_lcpm_colstats": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64,
+                                  ctypes.c_uint64, c_i64, c_vp]),
+    "nsr_lcpm_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64,
+                               ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64]),
     "nsr_colvar": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nsr_cov_gram": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_vp]),
     "nsr_cov_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_int, c_vp, c_i64, c_i64, c_vp, c_i64]),

@@ -6,6 +6,8 @@
 // exp, total reads, non-zero genes: the covariates of lcpm.py:193-199 come from the same pass),
 // then the gather + shift.  Rows = genes, columns = cells: a thread owns a cell column, so every
 // access is coalesced; gene ranges are split over blockIdx.y and combined in a fixed order.
+#include <limits.h>
+
 #include "nsr_common.cuh"
 
 namespace {
@@ -13,10 +15,69 @@ namespace {
 constexpr int kLcThreads = 256;
 constexpr int kLcGeneSplit = 64;       // genes per CTA in the column pass
 
+// ---- counter-based normal deviates (posterior resampling, lcpm.py:134-150 with varscale != 0) ----
+// Philox4x32-10 (Salmon et al. 2011) keyed by the seed, counter = the entry's global index: the same
+// entry gets the same deviate in both passes and for any chunking of the matrix.  Box-Muller on the
+// first two 32-bit outputs.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+}
+__device__ __forceinline__ double philox_normal(uint64_t index, uint64_t seed) {
+    uint32_t c[4] = {(uint32_t)index, (uint32_t)(index >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    const double u1 = ((double)c[0] + 0.5) * 2.3283064365386963e-10;       // (0, 1)
+    const double u2 = ((double)c[1] + 0.5) * 2.3283064365386963e-10;
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+
+struct LcNoise {
+    const double* lut_sd;      // sqrt(varscale * (trigamma(1 + c) - trigamma(total + 2))) per count value, or nullptr
+    const double* noise;       // standard normal deviates, one per entry (ld_noise), or nullptr -> Philox
+    int64_t ld_noise;
+    uint64_t seed;
+    int64_t row0, n_total;     // global gene index of row 0 and global row length (Philox counters)
+};
+
+// min / max / total of the counts in one pass (the checks and the table size of lcpm.py:88-99)
 template <typename T>
 __global__ void __launch_bounds__(kLcThreads)
+lcpm_scan_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld, long long* __restrict__ out) {
+    long long mn = LLONG_MAX, mx = LLONG_MIN, tot = 0;
+    const int64_t count = genes * n;
+    for (int64_t i = (int64_t)blockIdx.x * kLcThreads + threadIdx.x; i < count; i += (int64_t)gridDim.x * kLcThreads) {
+        const long long c = (long long)reads[(i / n) * ld + (i % n)];
+        mn = c < mn ? c : mn;
+        mx = c > mx ? c : mx;
+        tot += c;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const long long a = __shfl_xor_sync(0xffffffffu, mn, m), b = __shfl_xor_sync(0xffffffffu, mx, m);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+        tot += __shfl_xor_sync(0xffffffffu, tot, m);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, mn);
+        atomicMax(out + 1, mx);
+        atomicAdd((unsigned long long*)(out + 2), (unsigned long long)tot);
+    }
+}
+
+template <typename T, bool NOISY>
+__global__ void __launch_bounds__(kLcThreads)
 lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld,
-                     const double* __restrict__ lut, int64_t lut_len, double* __restrict__ partial) {
+                     const double* __restrict__ lut, const double* __restrict__ lut_exp, int64_t lut_len, LcNoise nz_,
+                     double* __restrict__ partial) {
     const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
     if (k >= n) return;
     const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
@@ -25,7 +86,13 @@ lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int6
     for (int64_t g = g0; g < g1; ++g) {
         const long long c = (long long)reads[g * ld + k];
         const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
-        se += exp(lut[ci]);
+        if (NOISY) {
+            const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
+                                       : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
+            se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
+        } else {
+            se += lut_exp[ci];                       // exp(lut[c]) tabulated: the pass is a pure gather
+        }
         tot += (double)c;
         nz += c != 0 ? 1.0 : 0.0;
     }
@@ -43,10 +110,10 @@ __global__ void lcpm_colreduce_kernel(const double* __restrict__ partial, int64_
     out[i] = s;
 }
 
-template <typename T>
+template <typename T, bool NOISY>
 __global__ void __launch_bounds__(kLcThreads)
 lcpm_apply_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld, const double* __restrict__ lut,
-                  int64_t lut_len, const double* __restrict__ shift, double* __restrict__ out, int64_t ldo) {
+                  int64_t lut_len, LcNoise nz_, const double* __restrict__ shift, double* __restrict__ out, int64_t ldo) {
     const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
     if (k >= n) return;
     const double sh = shift ? shift[k] : 0.0;
@@ -55,16 +122,40 @@ lcpm_apply_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t
     for (int64_t g = g0; g < g1; ++g) {
         const long long c = (long long)reads[g * ld + k];
         const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
-        out[g * ldo + k] = lut[ci] - sh;
+        double v = lut[ci];
+        if (NOISY) {
+            const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
+                                       : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
+            v = fma(nz_.lut_sd[ci], z, v);
+        }
+        out[g * ldo + k] = v - sh;
     }
 }
 
 }  // namespace
 
+extern "C" int nsr_lcpm_scan(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes, int64_t n,
+                             int64_t ld, long long* out3) {
+    NSR_REQUIRE(ctx && reads && out3, "nsr_lcpm_scan: null argument");
+    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n, "nsr_lcpm_scan: bad arguments");
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long init[3] = {LLONG_MAX, LLONG_MIN, 0};
+    NSR_CHECK(cudaMemcpyAsync(out3, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    const unsigned grid = (unsigned)(ctx->sm_count * 8);
+    if (itemsize == 4) lcpm_scan_kernel<int32_t><<<grid, kLcThreads, 0, st>>>((const int32_t*)reads, genes, n, ld, out3);
+    else lcpm_scan_kernel<int64_t><<<grid, kLcThreads, 0, st>>>((const int64_t*)reads, genes, n, ld, out3);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
-                                 int64_t n, int64_t ld, const double* lut, int64_t lut_len, double* colstats) {
-    NSR_REQUIRE(ctx && reads && lut && colstats, "nsr_lcpm_colstats: null argument");
-    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && lut_len >= 1,
+                                 int64_t n, int64_t ld, const double* lut, const double* lut_exp, int64_t lut_len,
+                                 const double* lut_sd, const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0,
+                                 double* colstats) {
+    NSR_REQUIRE(ctx && reads && lut && colstats && (lut_sd || lut_exp), "nsr_lcpm_colstats: null argument");
+    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && lut_len >= 1 &&
+                    (!noise || ld_noise >= n),
                 "nsr_lcpm_colstats: bad arguments (itemsize %d)", itemsize);
     NSR_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -73,30 +164,34 @@ extern "C" int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* rea
     void* scratch = nullptr;
     if (nsr_scratch(ctx, (size_t)n_split * 3 * n * sizeof(double), &scratch)) return 1;
     const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
-    if (itemsize == 4)
-        lcpm_colstats_kernel<int32_t><<<grid, kLcThreads, 0, st>>>((const int32_t*)reads, genes, n, ld, lut, lut_len, (double*)scratch);
-    else
-        lcpm_colstats_kernel<int64_t><<<grid, kLcThreads, 0, st>>>((const int64_t*)reads, genes, n, ld, lut, lut_len, (double*)scratch);
+    const LcNoise nz{lut_sd, noise, ld_noise, seed, row0, n};
+#define NSR_LC(T_, N_) lcpm_colstats_kernel<T_, N_><<<grid, kLcThreads, 0, st>>>((const T_*)reads, genes, n, ld, lut, lut_exp, lut_len, nz, (double*)scratch)
+    if (itemsize == 4) { if (lut_sd) NSR_LC(int32_t, true); else NSR_LC(int32_t, false); }
+    else { if (lut_sd) NSR_LC(int64_t, true); else NSR_LC(int64_t, false); }
+#undef NSR_LC
     lcpm_colreduce_kernel<<<(unsigned)((3 * n + 255) / 256), 256, 0, st>>>((const double*)scratch, n, n_split, colstats);
     NSR_CHECK(cudaGetLastError());
     return 0;
 }
 
 extern "C" int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes, int64_t n,
-                              int64_t ld, const double* lut, int64_t lut_len, const double* shift, double* out,
+                              int64_t ld, const double* lut, int64_t lut_len, const double* lut_sd, const double* noise,
+                              int64_t ld_noise, uint64_t seed, int64_t row0, const double* shift, double* out,
                               int64_t ldo) {
     NSR_REQUIRE(ctx && reads && lut && out, "nsr_lcpm_apply: null argument");
-    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && ldo >= n && lut_len >= 1,
+    NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && ldo >= n && lut_len >= 1 &&
+                    (!noise || ld_noise >= n),
                 "nsr_lcpm_apply: bad arguments (itemsize %d)", itemsize);
     NSR_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int n_split = (int)((genes + kLcGeneSplit - 1) / kLcGeneSplit);
     NSR_REQUIRE(n_split <= 65535, "nsr_lcpm_apply: too many genes for one call");
     const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
-    if (itemsize == 4)
-        lcpm_apply_kernel<int32_t><<<grid, kLcThreads, 0, st>>>((const int32_t*)reads, genes, n, ld, lut, lut_len, shift, out, ldo);
-    else
-        lcpm_apply_kernel<int64_t><<<grid, kLcThreads, 0, st>>>((const int64_t*)reads, genes, n, ld, lut, lut_len, shift, out, ldo);
+    const LcNoise nz{lut_sd, noise, ld_noise, seed, row0, n};
+#define NSR_LA(T_, N_) lcpm_apply_kernel<T_, N_><<<grid, kLcThreads, 0, st>>>((const T_*)reads, genes, n, ld, lut, lut_len, nz, shift, out, ldo)
+    if (itemsize == 4) { if (lut_sd) NSR_LA(int32_t, true); else NSR_LA(int32_t, false); }
+    else { if (lut_sd) NSR_LA(int64_t, true); else NSR_LA(int64_t, false); }
+#undef NSR_LA
     NSR_CHECK(cudaGetLastError());
     return 0;
 }

@@ -42,12 +42,16 @@ constexpr int kRowsW = 8;                  // rows per warp (one MMA row tile)
 constexpr double kHadScale = 0.088388347648318440550;   // 1/sqrt(128)
 constexpr double kKappa = 6.0;
 constexpr int kQPitch = 132;
+constexpr int kXPitch = 136;                // row pitch (doubles) of a warp's staged X tile
+constexpr int kResidualSmem = (2 * 16 * kQPitch + kWarps * kRowsW * kXPitch) * (int)sizeof(double);   // 103,424 B: 2 CTAs / SM
 
-__device__ __forceinline__ bool cell_flip(uint64_t k) {
-    uint32_t h = (uint32_t)k ^ (uint32_t)(k >> 32) * 0x9e3779b9u;
-    h ^= h >> 16; h *= 0x7feb352du; h ^= h >> 15; h *= 0x846ca68bu; h ^= h >> 16;
-    return h & 1u;
-}
+// Sign pattern D of the mix z' = z D H: cell m of every 128-cell block (m = 8u + 2t + e in the accumulator
+// layout, t = lane % 4) is negated when bit 2u + e of kSignMask is set.  The pattern is the same for every
+// block and lane, so inside the kernel it is a compile-time property of the register index: the negations
+// fold into the operand modifiers of the first butterfly stage and cost nothing.  (Any fixed diagonal of
+// +-1 keeps all inner products; it only has to break alignments between the data and the Walsh functions.)
+constexpr uint32_t kSignMask = 0x9e3779b9u;
+__host__ __device__ constexpr bool reg_flip(int i) { return (kSignMask >> i) & 1u; }
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
@@ -59,6 +63,13 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <bool VEC>
 __device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
     if (VEC) {
@@ -196,25 +207,32 @@ __global__ void coef_finalize_kernel(const double* __restrict__ partial, const d
 }
 
 // ---- pass B ------------------------------------------------------------------------------
+// Quantise 32 values and write their balanced base-256 digits.  q = round(v * invq) comes from one fused
+// multiply-add with the "magic" constant 1.5 * 2^52: the sum's low mantissa word IS the integer (round
+// to nearest even, the same rounding as cvt.rni), and adding 128 per digit in the same constant makes
+// every byte of the word a digit + 128 with no borrows between bytes (sum_k d_k 256^k + sum_k 128 256^k),
+// so the digits are byte transposes and one XOR 0x80 per word instead of shifts and sign extensions.
+// A value beyond the representable range wraps (the old cvt saturated): such rows are flagged from the
+// exact maximum and rewritten by the fix-up pass either way.
 template <int S>
 __device__ __forceinline__ void store_digits(const double (&v)[32], double invq, int8_t* __restrict__ dst,
                                              int64_t plane_stride, uint32_t (&energy)[S]) {
+    constexpr uint32_t kBias = S == 1 ? 0x80u : (S == 2 ? 0x8080u : (S == 3 ? 0x808080u : 0x80808080u));
+    const double magic = 6755399441055744.0 + (double)kBias;
     uint32_t w[S][8];
 #pragma unroll
     for (int i4 = 0; i4 < 8; ++i4) {
-        // no clamp: a row that overflows here is flagged (exact max|z'| vs quantum) and rewritten by
-        // the fix-up pass; the conversion saturates, it cannot trap
-        int32_t q[4];
+        uint32_t q[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) q[j] = __double2int_rn(v[4 * i4 + j] * invq);
+        for (int j = 0; j < 4; ++j) q[j] = (uint32_t)__double2loint(fma(v[4 * i4 + j], invq, magic));
+        // byte k of q[0..3] -> one word: two interleaves, then one pick per plane
+        const uint32_t lo01 = __byte_perm(q[0], q[1], 0x5140), lo23 = __byte_perm(q[2], q[3], 0x5140);   // bytes 0, 1
+        const uint32_t hi01 = __byte_perm(q[0], q[1], 0x7362), hi23 = __byte_perm(q[2], q[3], 0x7362);   // bytes 2, 3
 #pragma unroll
-        for (int s = S - 1; s >= 0; --s) {
-            // low bytes of q[0..3] -> one word; balanced digit: (q - sext8(q)) >> 8 == (q + 128) >> 8
-            w[s][i4] = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-            if (s > 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = (q[j] + 128) >> 8;
-            }
+        for (int s = 0; s < S; ++s) {
+            const int k = S - 1 - s;                        // plane 0 is the most significant digit
+            const uint32_t a = k < 2 ? lo01 : hi01, b = k < 2 ? lo23 : hi23;
+            w[s][i4] = __byte_perm(a, b, (k & 1) ? 0x7632 : 0x5410) ^ 0x80808080u;
         }
     }
 #pragma unroll
@@ -246,9 +264,18 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
                     int* __restrict__ exact_status) {
     // covariate block of the current 128 cells, shared by the CTA's 8 warps (they walk the same
     // cells): [buffer][covariate][cell], pitch 132 so that a B-fragment read (4 covariates x 8 cells
-    // per half-warp) touches 16 distinct banks
-    __shared__ double s_q[2][16][kQPitch];
+    // per half-warp) touches 16 distinct banks.  With 16-byte aligned operands (VEC) the kernel is
+    // software-pipelined with cp.async: while a warp works on block b, its 8 x 128 tile of X for block
+    // b + 1 (one private 8.5 KB tile per warp, row pitch 136 doubles: conflict-free 128-bit reads) and the
+    // CTA's Qt block for b + 1 are already on their way into shared memory.  Without that the 8 warps of
+    // a CTA, kept in lockstep by the staging barrier, all wait for DRAM at the same time and then all
+    // compute at the same time (ncu r01n: 43 % of DRAM peak, issue slots 32 % busy, and neither fewer
+    // instructions nor an L2 prefetch changed the time).
+    extern __shared__ __align__(16) double s_dyn[];
+    double (*s_q)[16][kQPitch] = reinterpret_cast<double (*)[16][kQPitch]>(s_dyn);
+    constexpr bool ASYNC = VEC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* tile = s_dyn + 2 * 16 * kQPitch + warp * (kRowsW * kXPitch);
     const int g = lane >> 2, t = lane & 3;
     const int64_t n_logical = row_list ? (int64_t)*row_count : rows;
     if ((int64_t)blockIdx.x * kWarps * kRowsW >= n_logical) return;        // whole CTA idle
@@ -278,53 +305,73 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
     int amax_hi = 0;                                     // max over the high words of |z'| (monotone)
     const double sgn1 = (t & 1) ? -1.0 : 1.0, sgn2 = (t & 2) ? -1.0 : 1.0;
 
+    // asynchronous staging of block `b`: this warp's X tile (16 x 16-byte chunks per lane, 512 contiguous
+    // bytes per warp instruction) and the CTA's share of the Qt block
+    const double* xrow = X + (my_row >= 0 ? my_row : 0) * ldx;           // row g of this warp's tile
+    auto stage_async = [&](int b) {
+        const int64_t kk0 = (int64_t)b * 128;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int r = j >> 1, c16 = ((j & 1) << 5) + lane;            // tile row, 16-byte chunk within the row
+            const double* base = (const double*)__shfl_sync(0xffffffffu, (unsigned long long)xrow, 4 * r);
+            const bool ok = __shfl_sync(0xffffffffu, my_row >= 0 ? 1 : 0, 4 * r) != 0;
+            if (ok) cp_async16(tile + r * kXPitch + 2 * c16, base + kk0 + 2 * c16);
+        }
+        const int nchunk = min(rank, 16) * 64;
+        for (int i = threadIdx.x; i < nchunk; i += kThreads) {
+            const int c = i >> 6, c16 = i & 63;
+            cp_async16(&s_q[b & 1][c][2 * c16], Qt + (int64_t)c * ldq + kk0 + 2 * c16);
+        }
+        cp_async_commit();
+    };
+    if (ASYNC) {
+        // rows of s_q beyond the rank are read as zeros and never written again
+        for (int i = threadIdx.x; i < 2 * 16 * kQPitch; i += kThreads) s_dyn[i] = 0.0;
+        __syncthreads();
+        if (b_begin < b_end && b_begin < nblk_full) stage_async(b_begin);
+    }
+
     for (int blk = b_begin; blk < b_end; ++blk) {
         const int64_t k0 = (int64_t)blk * 128;
         const bool full = blk < nblk_full;
-        // sign pattern of the block: lane l evaluates cells 4l .. 4l+3, ballots share them
-        uint32_t ma = 0, mb = 0;
-        if (HAD) {
-            uint32_t m[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-                m[e] = __ballot_sync(0xffffffffu, cell_flip(cell_offset + (uint64_t)(k0 + 4 * lane + e)));
-            // my cells 8u + 2t + e' = 4 (2u + t/2) + (2 (t%2) + e')  ->  mask 2(t%2)+e', bit 2u + t/2
-            ma = ((t & 1) ? m[2] : m[0]) >> (t >> 1);
-            mb = ((t & 1) ? m[3] : m[1]) >> (t >> 1);
-        }
         double v[32];
-        // ---- pull the NEXT block's 8 KB of X into L2 while this one is processed: the loads below then
-        // wait for an L2 hit instead of DRAM (each warp spends thousands of issue slots per block, so one
-        // block of lead is plenty); a quad covers its row's 8 lines, two per lane
-        if (prefetch && blk + 1 < b_end && blk + 1 < nblk_full) {
-            const double* nx = xr - 2 * t + k0 + 128 + 32 * t;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 16));
-        }
-        // ---- all X loads of the block first (independent, 8 KB per warp in flight)
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int64_t k = k0 + 8 * u + 2 * t;
-            if (full) {
-                if (VEC) {
-                    const double2 c2 = __ldg(reinterpret_cast<const double2*>(xr + k0 + 8 * u));
-                    v[2 * u] = c2.x; v[2 * u + 1] = c2.y;
-                } else {
-                    v[2 * u] = __ldg(xr + k0 + 8 * u);
-                    v[2 * u + 1] = __ldg(xr + k0 + 8 * u + 1);
-                }
-            } else {
-                v[2 * u] = (k < n) ? __ldg(xr + k0 + 8 * u) : 0.0;
-                v[2 * u + 1] = (k + 1 < n) ? __ldg(xr + k0 + 8 * u + 1) : 0.0;
-            }
-        }
-        // ---- stage the first 16 covariates of this block in shared memory (coalesced rows)
         const int buf = blk & 1;
-        for (int i = threadIdx.x; i < 4 * NCH * 128; i += kThreads) {
-            const int c = i >> 7, cell = i & 127;
-            s_q[buf][c][cell] = (c < rank && (full || k0 + cell < n)) ? __ldg(Qt + (int64_t)c * ldq + k0 + cell) : 0.0;
+        if (ASYNC && full) {
+            cp_async_wait_all();
+            __syncthreads();              // every warp's Qt chunks of this block have landed (and block - 1 is done with)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const double2 c2 = *reinterpret_cast<const double2*>(tile + g * kXPitch + 8 * u + 2 * t);
+                v[2 * u] = c2.x; v[2 * u + 1] = c2.y;
+            }
+            __syncwarp();                 // the tile is in registers: refill it for the next block
+            if (blk + 1 < b_end && blk + 1 < nblk_full) stage_async(blk + 1);
+        } else {
+            // ---- all X loads of the block first (independent, 8 KB per warp in flight)
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+                const int64_t k = k0 + 8 * u + 2 * t;
+                if (full) {
+                    if (VEC) {
+                        const double2 c2 = __ldg(reinterpret_cast<const double2*>(xr + k0 + 8 * u));
+                        v[2 * u] = c2.x; v[2 * u + 1] = c2.y;
+                    } else {
+                        v[2 * u] = __ldg(xr + k0 + 8 * u);
+                        v[2 * u + 1] = __ldg(xr + k0 + 8 * u + 1);
+                    }
+                } else {
+                    v[2 * u] = (k < n) ? __ldg(xr + k0 + 8 * u) : 0.0;
+                    v[2 * u + 1] = (k + 1 < n) ? __ldg(xr + k0 + 8 * u + 1) : 0.0;
+                }
+            }
+            // ---- stage the first 16 covariates of this block in shared memory (coalesced rows)
+            if (ASYNC) __syncthreads();   // (ragged last block after pipelined ones: the buffer may still be read)
+            for (int i = threadIdx.x; i < 4 * NCH * 128; i += kThreads) {
+                const int c = i >> 7, cell = i & 127;
+                s_q[buf][c][cell] = (c < rank && (full || k0 + cell < n)) ? __ldg(Qt + (int64_t)c * ldq + k0 + cell) : 0.0;
+            }
+            __syncthreads();          // one barrier per block is enough with two buffers
         }
-        __syncthreads();          // one barrier per block is enough with two buffers
         // ---- residual tiles: C = X (8 rows x 8 cells), A = -coef, B = Qt
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
@@ -351,17 +398,20 @@ residual_mma_kernel(const double* __restrict__ X, int64_t rows, int64_t n, int64
             sumsq = fma(c0v, c0v, sumsq);
             sumsq = fma(c1v, c1v, sumsq);
             if (RAW) { c0v = v[2 * u]; c1v = v[2 * u + 1]; }      // the plane carries the raw row
-            if (HAD) {
-                c0v = __hiloint2double(__double2hiint(c0v) ^ (int)(((ma >> (2 * u)) & 1u) << 31), __double2loint(c0v));
-                c1v = __hiloint2double(__double2hiint(c1v) ^ (int)(((mb >> (2 * u)) & 1u) << 31), __double2loint(c1v));
-            }
             v[2 * u] = c0v;
             v[2 * u + 1] = c1v;
         }
         // ---- Walsh-Hadamard over the 128 cells: local index bits 0..4 in registers, t by shuffle
         if (HAD) {
+            // first stage with the sign pattern folded in (compile-time negations of the operands)
 #pragma unroll
-            for (int h = 1; h < 32; h <<= 1)
+            for (int i = 0; i < 32; i += 2) {
+                const double a = reg_flip(i) ? -v[i] : v[i], b = reg_flip(i + 1) ? -v[i + 1] : v[i + 1];
+                v[i] = a + b;
+                v[i + 1] = a - b;
+            }
+#pragma unroll
+            for (int h = 2; h < 32; h <<= 1)
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if ((i & h) == 0) {
@@ -555,7 +605,9 @@ static int residualize_impl(nsr_ctx* ctx, uintptr_t stream, const double* X, int
                                                                        coef_buf, invq, exact_status);
     const dim3 gridb((unsigned)groups_w, (unsigned)ks_b);
 #define NSR_LAUNCH_B(S_, H_, V_, N_, LIST, COUNT, PS, PA)                                                    \
-    residual_mma_kernel<S_, H_, V_, N_, (S_ == 1)><<<gridb, kThreads, 0, st>>>(                              \
+    NSR_CHECK(cudaFuncSetAttribute((const void*)residual_mma_kernel<S_, H_, V_, N_, (S_ == 1)>,              \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kResidualSmem));            \
+    residual_mma_kernel<S_, H_, V_, N_, (S_ == 1)><<<gridb, kThreads, kResidualSmem, st>>>(                  \
         X, rows, n, ldx, Qt, rank, ldq, coef_buf, LIST, COUNT, nblk, ks_b, (uint64_t)0, invq, PS, PA, slices, \
         rows_alloc, n_pad, (unsigned long long*)energy_max, nsr_prefetch, exact_status)
 #define NSR_LAUNCH_B_N(S_, H_, V_, LIST, COUNT, PS, PA)                                                      \

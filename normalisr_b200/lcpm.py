@@ -1,13 +1,21 @@
 """``normalisr.lcpm.lcpm`` on the GPU (reference src/normalisr/lcpm.py:21-208):
 Bayesian logCPM of a read-count matrix, the posterior mean digamma(1 + reads) - digamma(total + 2)
 normalised per cell to log counts per million, plus the three cellular covariates (log total
-reads, number of zero-count genes, its square).
+reads, number of zero-count genes, its square), and optionally the reference's posterior
+resampling (``varscale != 0``).
 
-Two streaming passes over the counts (``nsr_lcpm_colstats``, ``nsr_lcpm_apply``); the digamma
-look-up table over the count values (the reference builds the same table) comes from
-``torch.special.digamma`` on the device.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors
-out.  Only the supported configuration of the reference is accelerated (``varscale=0``: no
-posterior resampling)."""
+Streaming passes over the counts: ``nsr_lcpm_scan`` (min / max / total in one read: the negativity
+check, the table length and the total), ``nsr_lcpm_colstats`` (per-cell sums; a pure table gather
+without resampling) and ``nsr_lcpm_apply`` (gather + shift).  The digamma / trigamma look-up tables
+over the count values (the reference builds the same tables) come from ``torch.special`` on the
+device.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
+
+Resampling draws one standard normal deviate per entry.  For numpy input they come from numpy's
+global generator exactly as in the reference (``numpy.random.seed(seed)`` when a seed is given, then
+one ``numpy.random.randn(n_gene, n_cell)``), so the result is the reference's, deviate for deviate;
+for CUDA input they are generated on the device by Philox4x32-10 keyed by ``seed`` (a fresh random
+key when ``seed`` is None) with the entry's index as counter - same distribution, another stream;
+``noise=`` (a matrix of deviates) overrides both."""
 import logging
 
 import numpy as np
@@ -22,31 +30,30 @@ def _is_dev(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 
 
-def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=True, nocov=False, device=None):
+def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=True, nocov=False, device=None,
+         noise=None):
     """Computes Bayesian log CPM from raw read counts: ``(lcpm, mean|None, var|None, cov|None)``
-    with the reference's shapes (lcpm.py:29-66).  ``nth`` / ``seed`` are accepted and ignored."""
+    with the reference's shapes (lcpm.py:29-66).  ``nth`` is accepted and ignored."""
     if reads.ndim != 2:
         raise ValueError('reads must have 2 dimensions.')
     if varscale < 0:
         raise ValueError('varscale must be non-negative.')
-    if varscale != 0:
-        raise NotImplementedError('normalisr_b200 accelerates lcpm without posterior resampling (varscale=0).')
-    if not normalize or ntot is not None:
+    if not normalize or ntot is not None or varscale != 0:
         logging.warning("Modifying keyword arguments other than nth or seed is neither recommended nor supported "
                         "for function 'lcpm'. Do so at your own risk.")
     to_host = not _is_dev(reads)
     ctx = engine.context(device if device is not None else (reads.device if not to_host else None))
     dev = ctx.device
     if to_host:
+        if seed is not None:
+            np.random.seed(seed)                            # lcpm.py:86-87
         if hasattr(reads, 'toarray'):                       # scipy sparse
             reads = reads.toarray()
         r = np.ascontiguousarray(reads)
         if not np.issubdtype(r.dtype, np.integer):
             r = r.astype(np.int64)                          # lcpm.py:129, 147
-        if r.size and r.min() < 0:
-            raise ValueError('Negative value in d detected.')
         if r.dtype not in (np.int32, np.int64):
-            r = r.astype(np.int64 if r.dtype.itemsize > 4 or (r.size and int(r.max()) > 2**31 - 1) else np.int32)
+            r = r.astype(np.int64 if r.dtype.itemsize > 4 or r.dtype.kind == 'u' and r.dtype.itemsize == 4 else np.int32)
         src = torch.from_numpy(r)
     else:
         src = reads
@@ -54,37 +61,85 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
             src = src.to(torch.int64)
         if src.stride(1) != 1:
             src = src.contiguous()
-        if bool((src < 0).any()):
-            raise ValueError('Negative value in d detected.')
     nt, nc = src.shape
     itemsize = src.element_size()
+    resample = varscale != 0
     with torch.cuda.device(dev):
         step = max(1, _ROW_CHUNK_BYTES // max(1, itemsize * nc)) if to_host else nt
         blocks = [(g0, min(nt, g0 + step)) for g0 in range(0, nt, step)]
-        max_count = int(src.max()) if src.numel() else 0
-        # pass 0 (only when the total is not given): total reads.  Needed before the table exists.
-        if ntot is None:
-            total = int(src.sum(dtype=torch.int64)) if not to_host else int(r.sum(dtype=np.int64))
-        else:
-            total = int(ntot)
+        single = len(blocks) == 1
+        held = {}
+
+        def block(i):
+            g0, g1 = blocks[i]
+            if i in held:
+                return held[i]
+            blk = src[g0:g1].to(dev, non_blocking=True) if to_host else src[g0:g1]
+            if single:
+                held[i] = blk
+            return blk
+
+        # pass 0: min / max / total in one read
+        scan = torch.empty(3, dtype=torch.int64, device=dev)
+        acc = None
+        for i, (g0, g1) in enumerate(blocks):
+            blk = block(i)
+            _lib.check(ctx.lib.nsr_lcpm_scan(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
+                                             blk.stride(0) if g1 - g0 > 1 else nc, scan.data_ptr()), "nsr_lcpm_scan")
+            engine.LAUNCHES += 1
+            cur = scan.cpu().numpy().copy() if nt and nc else np.array([0, 0, 0])
+            acc = cur if acc is None else np.array([min(acc[0], cur[0]), max(acc[1], cur[1]), acc[2] + cur[2]])
+        if acc is None:
+            acc = np.array([0, 0, 0])
+        if acc[0] < 0:
+            raise ValueError('Negative value in d detected.')                # lcpm.py:88-89
+        max_count = int(acc[1])
+        total = int(acc[2]) if ntot is None else int(ntot)
         t0 = total + 2
         assert t0 > 2
-        lut = (torch.special.digamma(torch.arange(1, max_count + 2, dtype=torch.float64, device=dev))
-               - torch.special.digamma(torch.tensor(float(t0), dtype=torch.float64, device=dev)))
-        lut = lut.contiguous()
+        counts1 = torch.arange(1, max_count + 2, dtype=torch.float64, device=dev)
+        t0_t = torch.tensor(float(t0), dtype=torch.float64, device=dev)
+        lut = (torch.special.digamma(counts1) - torch.special.digamma(t0_t)).contiguous()       # :96-103
+        lut_exp = torch.exp(lut)
+        lut_var = lut_sd = None
+        noise_d = None
+        key = 0
+        if resample:
+            lut_var = (torch.special.polygamma(1, counts1) - torch.special.polygamma(1, t0_t)).contiguous()   # :104-109
+            lut_sd = torch.sqrt(lut_var * float(varscale)).contiguous()                                      # :148-150
+            if noise is None and to_host:
+                noise = np.random.randn(nt, nc)             # the reference's own stream (:150)
+            if noise is not None:
+                noise_d = noise if isinstance(noise, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(noise, dtype=np.float64))
+                if tuple(noise_d.shape) != (nt, nc):
+                    raise ValueError('noise must have the shape of reads.')
+            else:
+                key = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+
+        def noise_args(g0, g1):
+            if not resample:
+                return None, None, 0, 0
+            if noise_d is None:
+                return lut_sd.data_ptr(), None, 0, key
+            nb = noise_d[g0:g1].to(dev, torch.float64, non_blocking=True)
+            if nb.stride(1) != 1:
+                nb = nb.contiguous()
+            keep.append(nb)
+            return lut_sd.data_ptr(), nb.data_ptr(), nb.stride(0) if g1 - g0 > 1 else nc, 0
+
+        keep = []
         # pass 1: per-cell statistics
         col = torch.zeros((3, nc), dtype=torch.float64, device=dev)
-        held = []
-        for g0, g1 in blocks:
-            blk = src[g0:g1].to(dev, non_blocking=True) if to_host else src[g0:g1]
+        for i, (g0, g1) in enumerate(blocks):
+            blk = block(i)
             part = torch.empty((3, nc), dtype=torch.float64, device=dev)
+            sd_p, nz_p, ldn, sd_key = noise_args(g0, g1)
             _lib.check(ctx.lib.nsr_lcpm_colstats(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
-                                                 blk.stride(0) if g1 - g0 > 1 else nc, lut.data_ptr(), lut.numel(),
-                                                 part.data_ptr()), "nsr_lcpm_colstats")
+                                                 blk.stride(0) if g1 - g0 > 1 else nc, lut.data_ptr(), lut_exp.data_ptr(),
+                                                 lut.numel(), sd_p, nz_p, ldn, sd_key, g0, part.data_ptr()),
+                       "nsr_lcpm_colstats")
             engine.LAUNCHES += 2
             col += part
-            if len(blocks) == 1:
-                held.append(blk)
         shift = None
         if normalize:                                        # lcpm.py:155-157
             shift = (torch.log(col[0]) - float(np.log(1e6))).contiguous()
@@ -94,24 +149,41 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                 raise ValueError('Found cell with no read at all. Please remove.')
             t1 = torch.log(col[1])
             dcov = torch.stack([t1, nt - col[2], t1 ** 2])
-        # pass 2: gather + per-cell shift
-        out = torch.empty((nt, nc), dtype=torch.float64, device=dev) if not to_host else torch.empty((nt, nc), dtype=torch.float64)
-        for g0, g1 in blocks:
-            blk = held[0] if held else (src[g0:g1].to(dev, non_blocking=True) if to_host else src[g0:g1])
-            res = out[g0:g1] if not to_host else torch.empty((g1 - g0, nc), dtype=torch.float64, device=dev)
-            _lib.check(ctx.lib.nsr_lcpm_apply(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
-                                              blk.stride(0) if g1 - g0 > 1 else nc, lut.data_ptr(), lut.numel(),
+        # pass 2: gather (+ resampling) + per-cell shift
+        host_out = to_host
+        out = torch.empty((nt, nc), dtype=torch.float64, device=dev) if not host_out else torch.empty((nt, nc), dtype=torch.float64)
+        dmean = dvar = None
+        if not lowmem:                                       # lcpm.py:160-190
+            dmean = torch.empty_like(out)
+            dvar = torch.zeros_like(out)
+        for i, (g0, g1) in enumerate(blocks):
+            blk = block(i)
+            res = out[g0:g1] if not host_out else torch.empty((g1 - g0, nc), dtype=torch.float64, device=dev)
+            sd_p, nz_p, ldn, sd_key = noise_args(g0, g1)
+            ld_b = blk.stride(0) if g1 - g0 > 1 else nc
+            _lib.check(ctx.lib.nsr_lcpm_apply(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc, ld_b,
+                                              lut.data_ptr(), lut.numel(), sd_p, nz_p, ldn, sd_key, g0,
                                               shift.data_ptr() if shift is not None else None, res.data_ptr(), nc),
                        "nsr_lcpm_apply")
             engine.LAUNCHES += 1
-            if to_host:
+            if host_out:
                 out[g0:g1] = res.cpu()
+            if not lowmem:
+                if resample:
+                    m = torch.empty((g1 - g0, nc), dtype=torch.float64, device=dev)
+                    _lib.check(ctx.lib.nsr_lcpm_apply(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
+                                                      ld_b, lut.data_ptr(), lut.numel(), None, None, 0, 0, g0,
+                                                      shift.data_ptr() if shift is not None else None, m.data_ptr(), nc),
+                               "nsr_lcpm_apply")
+                    engine.LAUNCHES += 1
+                    v = lut_var[blk.long().clamp_(0, lut_var.numel() - 1)] * float(varscale)
+                else:
+                    m, v = res, None
+                dmean[g0:g1] = m.cpu() if host_out else m
+                if v is not None:
+                    dvar[g0:g1] = v.cpu() if host_out else v
         if not bool(torch.isfinite(shift).all() if shift is not None else True):
             raise AssertionError('non-finite logCPM')        # lcpm.py:201
-        dmean = dvar = None
-        if not lowmem:                                       # lcpm.py:178-190 with varscale = 0
-            dmean = out.clone()
-            dvar = torch.zeros_like(out)
         if to_host:
             torch.cuda.current_stream().synchronize()
             return (out.numpy(), None if dmean is None else dmean.numpy(), None if dvar is None else dvar.numpy(),

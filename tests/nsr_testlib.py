@@ -2,17 +2,15 @@
 import numpy as np
 
 
+SIGN_MASK = 0x9e3779b9
+
+
 def cell_flip(k):
-    """residual.cu cell_flip(): pseudo-random sign per global cell index (k < 2^32 here)."""
-    h = np.asarray(k, dtype=np.uint64) & np.uint64(0xFFFFFFFF)
-    h = h.astype(np.uint32)
-    with np.errstate(over="ignore"):
-        h ^= h >> np.uint32(16)
-        h *= np.uint32(0x7feb352d)
-        h ^= h >> np.uint32(15)
-        h *= np.uint32(0x846ca68b)
-        h ^= h >> np.uint32(16)
-    return (h & np.uint32(1)).astype(bool)
+    """residual.cu reg_flip(): cell m = k % 128 of every block is negated when bit 2 (m // 8) + m % 2 of
+    kSignMask is set (the same pattern for every block)."""
+    m = np.asarray(k, dtype=np.int64) % 128
+    i = 2 * (m >> 3) + (m & 1)
+    return ((SIGN_MASK >> i) & 1).astype(bool)
 
 
 def hadamard128(z):

@@ -70,5 +70,36 @@ def test_lcpm_larger_against_oracle_and_errors():
         norm.lcpm(np.ones(4, dtype=int))
     with pytest.raises(ValueError):
         norm.lcpm(np.ones((3, 4), dtype=int), varscale=-1)
-    with pytest.raises(NotImplementedError):
-        norm.lcpm(np.ones((3, 4), dtype=int), varscale=1)
+
+
+@gpu
+def test_lcpm_posterior_resampling():
+    """varscale != 0 (lcpm.py:104-109, 134-150, 178-190): numpy input reproduces the reference deviate for
+    deviate (it draws from numpy's own stream, like the reference); CUDA input draws from Philox on the
+    device: deterministic per seed, the right mean and variance per entry."""
+    from normalisr_b200 import lcpm as lc, normalisr as norm
+    g = load_golden("lcpm_resample")
+    out = norm.lcpm(g["reads"], varscale=float(g["varscale"]), seed=int(g["seed"]))
+    np.testing.assert_allclose(out[0], g["lcpm"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out[3], g["cov"], rtol=1e-13)
+    out = norm.lcpm(g["reads"], varscale=float(g["varscale"]), seed=int(g["seed"]), lowmem=False)
+    np.testing.assert_allclose(out[0], g["lcpm_full"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out[1], g["mean_full"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(out[2], g["var_full"], rtol=1e-11, atol=1e-14)
+    # the oracle with the same deviates
+    np.random.seed(int(g["seed"]))
+    z = np.random.randn(*g["reads"].shape)
+    want = orc.lcpm(g["reads"], varscale=float(g["varscale"]), noise=z)
+    np.testing.assert_allclose(want[0], g["lcpm"], rtol=1e-12, atol=1e-12)
+    # device path: Philox stream
+    rd = torch.from_numpy(g["reads"].astype(np.int64)).cuda()
+    a = norm.lcpm(rd, varscale=0.7, seed=5, normalize=False, ntot=10 ** 9, lowmem=False)
+    b = norm.lcpm(rd, varscale=0.7, seed=5, normalize=False, ntot=10 ** 9)
+    c = norm.lcpm(rd, varscale=0.7, seed=6, normalize=False, ntot=10 ** 9)
+    assert torch.equal(a[0], b[0]) and not torch.equal(a[0], c[0])
+    zz = ((a[0] - a[1]) / torch.sqrt(a[2])).cpu().numpy().ravel()          # the deviates that were drawn
+    assert abs(zz.mean()) < 5 / np.sqrt(zz.size) and abs(zz.var() - 1) < 10 / np.sqrt(zz.size)
+    assert abs((zz ** 3).mean()) < 20 / np.sqrt(zz.size) and abs((zz ** 4).mean() - 3) < 60 / np.sqrt(zz.size)
+    # the per-cell normaliser sees the resampled values: exp sums to one million
+    d = norm.lcpm(rd, varscale=0.7, seed=5)
+    np.testing.assert_allclose(torch.exp(d[0]).sum(dim=0).cpu().numpy(), 1e6, rtol=1e-10)
