@@ -337,6 +337,11 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         if single:
             P_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
             D_host = torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True)
+        elif schedule == "pairs":
+            # ONE (n_gene, n_gene) P and dot for the whole job, in a page-locked mapping shared by all ranks:
+            # every GPU writes the rectangles it computed and their transposes, rank 0 holds the reference's
+            # complete return value after the step's closing barrier
+            (P_host, D_host), shared_home = parallel.shared_host_matrices(2, (n_gene, n_gene))
         else:
             P_host = torch.empty((max(my_rows, 1), n_gene), dtype=torch.float64, pin_memory=True)
             D_host = torch.empty((max(my_rows, 1), n_gene), dtype=torch.float64, pin_memory=True)
@@ -346,6 +351,8 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         def step_e2e():
             if single:
                 norm.coex(dt_host, dc_np, precision=precision, out=(P_host, D_host))
+            elif schedule == "pairs":
+                parallel.coex_host(dt_host, dc_np, n_gene, precision=precision, out_dev=(P, D), home=(P_host, D_host))
             else:
                 parallel.coex_host(dt_host, dc_np, n_gene, precision=precision, out_dev=(P, D), out_host=(P_host, D_host),
                                    schedule=schedule)
@@ -359,17 +366,24 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
             step_e2e()
         barrier()
         sec = max_over_ranks(time.perf_counter() - t0)
-        d2h_cols = P_host.shape[1]
-        if not single and schedule == "pairs":      # only the column blocks this rank owns travel back
-            d2h_cols = my_rows + sum(parallel.block_rows(n_gene, world, src) for _, src, _ in parallel.exchange_plan(world, rank))
-        h2d_t = torch.tensor([float(dt_host.numel() * 8), float(P_host.shape[0] * d2h_cols * 16)], dtype=torch.float64,
-                             device=dev)
+        d2h_bytes = float(P_host.shape[0] * P_host.shape[1] * 16)
+        if not single and schedule == "pairs":
+            # this rank's diagonal block (both triangles) + every rectangle it computed and its transpose
+            d2h_bytes = float(my_rows * my_rows * 16)
+            for _, src, parity in parallel.exchange_plan(world, rank):
+                a0, a1, b0, b1 = parallel._segment_rect(my_rows, parallel.block_rows(n_gene, world, src), parity)
+                d2h_bytes += 2.0 * (a1 - a0) * (b1 - b0) * 16
+        h2d_t = torch.tensor([float(dt_host.numel() * 8), d2h_bytes], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(h2d_t)
         e2e = {"value": pairs / (sec / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(h2d_t[0].item()),
                "d2h_bytes_per_step": int(h2d_t[1].item()), "steps": e2e_steps, "ms_per_step": 1e3 * sec / e2e_steps,
                "api": "normalisr_b200.normalisr.coex(dt_host, dc, out=pinned)" if single else
-                      "normalisr_b200.parallel.coex_host(dt_block_host, dc, n_gene)"}
+                      ("normalisr_b200.parallel.coex_host(dt_block_host, dc, n_gene, home=(P, dot)): one complete symmetric "
+                       "P and dot for the job, both triangles, in a page-locked mapping %s" % (
+                           "shared by all ranks (rank 0 holds the reference's return value)" if shared_home else
+                           "per rank (/dev/shm too small for a shared one)") if schedule == "pairs" else
+                       "normalisr_b200.parallel.coex_host(dt_block_host, dc, n_gene)")}
 
     if rank != 0:
         if world > 1:

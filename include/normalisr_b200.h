@@ -161,7 +161,13 @@ int nsr_contract_ab(nsr_ctx* ctx, uintptr_t stream, int engine, int mode,
  *   done                 optional device counter (uint32): += 8 per finished tile of the segment (one
  *                        per epilogue warp, after its stores are visible system-wide); a copy stream
  *                        can nsr_stream_wait_geq on it and send the segment's columns home while the
- *                        launch continues with the next segment.
+ *                        launch continues with the next segment;
+ *   mirror_P / mirror_out2 / ld_mirror  optional: the lower triangle.  The reference returns the full
+ *                        symmetric matrices to one caller (association.py:1036-1057); with these every
+ *                        GPU also writes the transposed copy of what it computes - for the diagonal
+ *                        segment into its own rows (mirror_P = P + col0, ld_mirror = ld), for a block
+ *                        pair into a (rows_b x rows_a) buffer that is sent home as rows of block b - so
+ *                        the matrices are assembled without a pass over the lower triangle on the host.
  * host_tiles: n_tiles triples (segment, tile_row, tile_col), processed in list order (claimed from a
  * global counter), so list segments in the order their blocks arrive.  tcgen05 engine only; the
  * waiting launch occupies every SM, so the flags must be set by work that needs none (copy engines). */
@@ -176,6 +182,9 @@ typedef struct nsr_segment {
     uint32_t ready_value;
     const uint32_t* ready;
     uint32_t* done;
+    double* mirror_P;          /* optional transposed copy: the element of A row i and B row j also lands at  */
+    double* mirror_out2;       /* mirror_*[j * ld_mirror + i] (both or neither; ld_mirror >= rows_a).  The    */
+    int64_t ld_mirror;         /* diagonal segment skips tiles with tile_row == tile_col (already symmetric). */
 } nsr_segment;
 int nsr_contract_segments(nsr_ctx* ctx, uintptr_t stream,
                           const int8_t* a_slices, int64_t rows_a, int64_t rows_alloc_a,
@@ -363,6 +372,12 @@ int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64_t rows, in
  * host, 1 = host to device.  Pitches and width in bytes. */
 int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
                int64_t src_pitch, int64_t width_bytes, int64_t height, int kind);
+
+/* Asynchronous copy of nbytes from device `src_device` into this context's device on `stream` (a stream of
+ * the context's device): cudaMemcpyPeerAsync, peer access enabled on first use.  No kernel, no SM: the
+ * single-process multi-GPU path (normalisr_b200.parallel.coex_all_devices) pulls the digit planes of the
+ * other GPUs' gene blocks with it while the persistent contraction launch is already running. */
+int nsr_copy_peer(nsr_ctx* ctx, uintptr_t stream, void* dst, const void* src, int src_device, int64_t nbytes);
 
 /* Text I/O of the command-line layer around the hot path (run.py:10-35), host side: files are mapped and
  * parsed by a pool of threads straight into the caller's buffers (page-locked memory in the Python layer,

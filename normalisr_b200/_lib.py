@@ -60,6 +60,7 @@ _SIGNATURES = {
     "nsr_mtx_read": (c_int, [ctypes.c_char_p, c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_int]),
     "nsr_pvalue": (c_int, [c_vp, c_up, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "nsr_copy2d": (c_int, [c_vp, c_up, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_int]),
+    "nsr_copy_peer": (c_int, [c_vp, c_up, c_vp, c_vp, c_int, c_i64]),
     "nsr_unslice": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp]),
     "nsr_binnet": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_i64, c_dbl, c_vp, c_i64, c_vp]),
     "nsr_project_coef": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp]),
@@ -90,7 +91,7 @@ class Segment(ctypes.Structure):
     """struct nsr_segment (include/normalisr_b200.h)."""
     _fields_ = [("b_slices", c_vp), ("rows_b", c_i64), ("rows_alloc_b", c_i64), ("quantum_b", c_vp), ("var_b", c_vp),
                 ("col0", c_i64), ("diagonal", ctypes.c_int32), ("ready_value", ctypes.c_uint32), ("ready", c_vp),
-                ("done", c_vp)]
+                ("done", c_vp), ("mirror_P", c_vp), ("mirror_out2", c_vp), ("ld_mirror", c_i64)]
 
 
 class NsrError(RuntimeError):

@@ -299,12 +299,15 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     Extra keyword arguments understood here (all optional, none changes results beyond the
     stated tolerance): ``precision`` in {'fast','default','precise'}, ``device``,
     ``out`` = (P, dot) preallocated (pinned) CPU tensors that receive the two matrices,
-    ``engine`` (tests only)."""
+    ``devices`` = "all" | count | list of CUDA devices: host inputs are spread over those GPUs from this
+    one process and the caller gets the reference's complete return value (``parallel.coex_all_devices``
+    for dy=None, ``parallel.de_all_devices`` otherwise), ``engine`` (tests only)."""
     precision = ka.pop('precision', 'default')
     exact_groupings = ka.pop('exact_groupings', True)
     device = ka.pop('device', None)
     eng = ka.pop('engine', ENGINE_UMMA)
     out_host = ka.pop('out', None)          # optional (P, dot|gamma) host tensors to fill
+    devices = ka.pop('devices', None)       # "all" / count / list: every listed GPU of the box, one process
     dimreduce = ka.pop('dimreduce', 0)
     if single not in (0, 1, 4, 5):
         raise ValueError('Unknown value single={}'.format(single))
@@ -321,6 +324,22 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     n = dx.shape[1]
     if (not samexy and dy.shape[1] != n) or dc.shape[1] != n:
         raise ValueError('Unmatching dx/dy/dc dimensions.')
+    if devices is not None:
+        from . import parallel
+        devs = parallel.visible_devices(devices)
+        if len(devs) > 1:
+            if _is_dev(dx) or _is_dev(dy) or device is not None:
+                raise ValueError('devices= takes host inputs (the matrices are spread over the GPUs).')
+            common = dict(precision=precision, dimreduce=dimreduce)
+            if not samexy:
+                return parallel.de_all_devices(dx, dy, dc, devs, lowmem=lowmem, return_dot=return_dot, single=single,
+                                               engine=eng, exact_groupings=exact_groupings, **common, **ka)
+            if single != 0 or not (lowmem and return_dot) or ka:
+                raise NotImplementedError('devices= with dy=None covers the coex call: single=0, lowmem=True, '
+                                          'return_dot=True.')
+            P, D, var = parallel.coex_all_devices(dx, dc, devs, out=out_host, **common)
+            return (P, D, None, None, var)
+        device = devs[0]
     if single == 1:
         from .single1 import association_tests_single1
         if samexy:

@@ -328,6 +328,8 @@ extern "C" int nsr_contract_ab(nsr_ctx* ctx, uintptr_t stream, int engine, int m
     sg.rows_alloc = rows_alloc_b;
     sg.info.qb = quantum_b; sg.info.vb = var_b; sg.info.rows_b = rows_b; sg.info.col0 = 0; sg.info.mode = mode;
     sg.info.ready = nullptr; sg.info.ready_value = 0; sg.info.done = nullptr;
+    const bool mir = mode == NSR_MODE_COEX;          // both triangles of the same matrix
+    sg.info.mP = mir ? P : nullptr; sg.info.mO = mir ? out2 : nullptr; sg.info.ldm = ld;
     return contract_impl(ctx, stream, engine, mode, a_slices, rows_a, rows_alloc_a, n_slices_a, quantum_a, var_a, &sg, 1,
                          n_slices_b, n, n_pad, n_products, host_tiles, 2, n_tiles, dof_a, P, out2, ld, k_chunk);
 }
@@ -360,6 +362,9 @@ extern "C" int nsr_contract_segments(nsr_ctx* ctx, uintptr_t stream, const int8_
         sg[s].info.qb = in.quantum_b; sg[s].info.vb = in.var_b; sg[s].info.rows_b = in.rows_b; sg[s].info.col0 = in.col0;
         sg[s].info.mode = in.diagonal ? NSR_MODE_COEX_UPPER : NSR_MODE_COEX_RECT;
         sg[s].info.ready = in.ready; sg[s].info.ready_value = in.ready_value; sg[s].info.done = in.done;
+        NSR_REQUIRE((in.mirror_P == nullptr) == (in.mirror_out2 == nullptr) && (in.mirror_P == nullptr || in.ld_mirror >= rows_a),
+                    "nsr_contract_segments: segment %d: bad mirror (ld_mirror=%lld)", s, (long long)in.ld_mirror);
+        sg[s].info.mP = in.mirror_P; sg[s].info.mO = in.mirror_out2; sg[s].info.ldm = in.ld_mirror;
     }
     return contract_impl(ctx, stream, NSR_ENGINE_UMMA, NSR_MODE_COEX_RECT, a_slices, rows_a, rows_alloc_a, n_slices, quantum_a,
                          var_a, sg, n_segments, n_slices, n, n_pad, n_products, host_tiles, 3, n_tiles, dof_a, P, out2, ld,
@@ -406,6 +411,23 @@ extern "C" int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst
     NSR_CHECK(cudaSetDevice(ctx->device));
     NSR_CHECK(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes, (size_t)height,
                                 kind == 0 ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int nsr_copy_peer(nsr_ctx* ctx, uintptr_t stream, void* dst, const void* src, int src_device, int64_t nbytes) {
+    NSR_REQUIRE(ctx != nullptr && dst && src && nbytes >= 0 && src_device >= 0, "nsr_copy_peer: bad arguments");
+    if (nbytes == 0) return 0;
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    if (src_device != ctx->device) {
+        int can = 0;
+        NSR_CHECK(cudaDeviceCanAccessPeer(&can, ctx->device, src_device));
+        if (can) {                                 // direct NVLink / PCIe peer path; otherwise the driver stages through the host
+            cudaError_t e = cudaDeviceEnablePeerAccess(src_device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else NSR_CHECK(e);
+        }
+    }
+    NSR_CHECK(cudaMemcpyPeerAsync(dst, ctx->device, src, src_device, (size_t)nbytes, (cudaStream_t)stream));
     return 0;
 }
 

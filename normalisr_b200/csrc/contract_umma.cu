@@ -206,7 +206,8 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const Se
     const bool row_ok = wanted && i < ep.rows_a;
     const double qi = row_ok ? ep.qa[i] : 0.0;
     const double vi = (row_ok && ep.va) ? ep.va[i] : 1.0;
-    const bool mirror = sg.mode == NSR_MODE_COEX && tr != tc;
+    // the transposed copy: none for a tile on the diagonal of a symmetric segment (it holds both (i, j) and (j, i))
+    double* const mP = (sg.mP != nullptr && (tr != tc || sg.mode == NSR_MODE_COEX_RECT)) ? sg.mP : nullptr;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
     bool refine = false;
     if (wanted) {
@@ -229,7 +230,7 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const Se
                         // launch, but before the segment's flag: no SM has them in L1 earlier, and L1 does not
                         // survive a launch boundary - plain cached loads are safe)
                         refine |= nsr_finish(ep, sg.mode, sg.col0, i, j, qi, vi, sg.qb[j], sg.vb ? sg.vb[j] : 1.0,
-                                             nsr_combine(ep, a4), mirror);
+                                             nsr_combine(ep, a4), mP, sg.mO, sg.ldm);
                     }
                 }
             }

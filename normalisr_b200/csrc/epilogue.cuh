@@ -43,6 +43,8 @@ struct SegInfo {
     const uint32_t* ready;                   // device flag: B may be read once *ready - ready_value >= 0 (or nullptr)
     uint32_t ready_value;
     uint32_t* done;                          // incremented once per epilogue warp and finished tile (or nullptr)
+    double* mP; double* mO;                  // mirrored copy: element (i, j) also lands at m*[j * ldm + i] (or nullptr);
+    int64_t ldm;                             // tiles on the diagonal of a symmetric segment are not mirrored
 };
 
 // host-side description of a segment's operand (what the tensor map is built from) + its SegInfo
@@ -52,10 +54,12 @@ struct NsrSegOperand {
     SegInfo info;
 };
 
-// one output element (i = row in A, j = row in B); `mirror` also writes (j, i) (COEX, i != j tile).
+// one output element (i = row in A, j = row in B); with `mP` the transposed element is written too
+// (COEX, i != j tile: the other triangle of the same matrix; multi-GPU block pairs: the mirrored block).
 // Returns true when the element asks for the full-precision phase (adaptive schedule).
 __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
-                                           double qi, double vi, double qj, double vj, double acc, bool mirror) {
+                                           double qi, double vi, double qj, double vj, double acc, double* mP,
+                                           double* mO, int64_t ldm) {
     double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
     const int64_t at = i * p.ld + col0 + j;
     if (p.acc_in) sum += p.out2[at];               // earlier cell chunks
@@ -76,13 +80,13 @@ __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, in
     }
     p.P[at] = P;
     p.out2[at] = o2;
-    if (mirror) {
-        p.P[j * p.ld + i] = P;
-        p.out2[j * p.ld + i] = o2;
+    if (mP != nullptr) {
+        mP[j * ldm + i] = P;
+        mO[j * ldm + i] = o2;
     }
     return refine;
 }
 __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
                                            double vi, double qj, double vj, double acc, bool mirror) {
-    return nsr_finish(p, p.mode, 0, i, j, qi, vi, qj, vj, acc, mirror);
+    return nsr_finish(p, p.mode, 0, i, j, qi, vi, qj, vj, acc, mirror ? p.P : nullptr, p.out2, p.ld);
 }

@@ -373,8 +373,9 @@ def contract(ctx, mode, A, B, tiles, dof_a, P, out2, n_products, engine=ENGINE_U
 def contract_segments(ctx, A, segments, tiles, dof_a, P, out2, n_products, k_chunk=0):
     """Everything one GPU owns under the block-pair schedule in ONE persistent launch
     (nsr_contract_segments).  ``segments``: list of dicts with keys B (Sliced), rows_b, col0, diagonal,
-    and optionally ready = (uint32 flag tensor element pointer, value), done = pointer; ``tiles``:
-    (k, 3) int32 array of (segment, tile_row, tile_col)."""
+    and optionally ready = (uint32 flag tensor element pointer, value), done = pointer, mirror =
+    (P pointer, out2 pointer, ld) for the transposed copy; ``tiles``: (k, 3) int32 array of (segment,
+    tile_row, tile_col)."""
     assert 1 <= len(segments) <= _lib.MAX_SEGMENTS
     arr = (_lib.Segment * len(segments))()
     for i, sg in enumerate(segments):
@@ -391,6 +392,8 @@ def contract_segments(ctx, A, segments, tiles, dof_a, P, out2, n_products, k_chu
         arr[i].ready = ready[0] if ready else None
         arr[i].ready_value = int(ready[1]) & 0xFFFFFFFF if ready else 0
         arr[i].done = sg.get("done")
+        mir = sg.get("mirror")
+        arr[i].mirror_P, arr[i].mirror_out2, arr[i].ld_mirror = (mir[0], mir[1], int(mir[2])) if mir else (None, None, 0)
     tiles = np.ascontiguousarray(tiles, dtype=np.int32).reshape(-1, 3)
     ld = out2.stride(0) if out2.shape[0] > 1 else out2.shape[1]
     assert out2.stride(1) == 1 and P.shape == out2.shape and P.stride(1) == 1 and (out2.shape[0] == 1 or P.stride(0) == ld)
@@ -497,6 +500,29 @@ def copy_block_to_host(ctx, dst_host, src_dev, r0, r1, c0, c1, stream=None):
                                   dst_host.data_ptr() + (r0 * dst_host.stride(0) + c0) * es, dst_host.stride(0) * es,
                                   src_dev.data_ptr() + (r0 * src_dev.stride(0) + c0) * es, src_dev.stride(0) * es,
                                   (c1 - c0) * es, r1 - r0, 0), "nsr_copy2d")
+
+
+def copy_rect_to_host(ctx, dst_host, dr0, dc0, src_dev, sr0, sc0, rows, cols, stream=None):
+    """dst_host[dr0:dr0+rows, dc0:dc0+cols] <- src_dev[sr0:sr0+rows, sc0:sc0+cols] (2-D float64, unit
+    column stride), asynchronously on ``stream`` (default: current)."""
+    if rows <= 0 or cols <= 0:
+        return
+    es = 8
+    st = stream.cuda_stream if stream is not None else _stream()
+    _lib.check(ctx.lib.nsr_copy2d(ctx.handle, st,
+                                  dst_host.data_ptr() + (dr0 * dst_host.stride(0) + dc0) * es, dst_host.stride(0) * es,
+                                  src_dev.data_ptr() + (sr0 * src_dev.stride(0) + sc0) * es, src_dev.stride(0) * es,
+                                  cols * es, rows, 0), "nsr_copy2d")
+
+
+def copy_peer(ctx, dst, src, stream=None):
+    """dst (contiguous tensor on ctx's device) <- src (contiguous tensor of the same byte size on another
+    device of this process), asynchronously on ``stream`` of ctx's device (copy engines, no kernel)."""
+    nbytes = dst.numel() * dst.element_size()
+    assert dst.is_contiguous() and src.is_contiguous() and nbytes == src.numel() * src.element_size()
+    st = stream.cuda_stream if stream is not None else _stream()
+    _lib.check(ctx.lib.nsr_copy_peer(ctx.handle, st, dst.data_ptr(), src.data_ptr(), src.device.index, nbytes),
+               "nsr_copy_peer")
 
 
 def coex_strip_tiles(t_begin, t_end, strip=12):

@@ -287,14 +287,15 @@ def _timed(events, fn):
     events.append((e0, e1))
 
 
-def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None):
+def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None, home=None):
     """Pairs schedule on an already residualised block: post the exchange and contract everything this
     rank owns - with the copy-engine transport in ONE persistent launch that starts on the diagonal
     block and picks up each block pair when its planes have arrived.  Returns (P, dot, var_all).
     ``events`` (a list) receives one CUDA event pair per contraction launch (bench bookkeeping).
     ``out_host`` = (P, dot) pinned CPU tensors: every finished column block is copied back on a
     side stream while the next block pair is contracted (column blocks this rank does not own are
-    not written).
+    not written).  ``home`` = (P, dot) FULL (n_gene, n_gene) host tensors shared by all ranks (see
+    ``contract_plan``): every rank writes the rectangles it computed and their transposes.
 
     The int32 partial sums are bounded from the digit energies AFTER the launch is queued (the
     energies of the remote blocks travel with them): the contraction runs optimistically in one pass
@@ -310,7 +311,7 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
             rounds = start_exchange_ce(symm[0], symm[1], local, group, ctx=ctx)
         else:
             rounds = start_exchange(local, group)
-    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, events, out_host)
+    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, events, out_host, home=home)
     if world > 1:
         var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
         dist.all_gather_into_tensor(var_all, local.var, group=group)
@@ -324,12 +325,34 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
     k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_a, em_b))
     if k_chunk:
         P, D = contract_plan(ctx, local, [(r[0], r[1], r[2], []) for r in rounds], rank, world, n_gene, dof_a,
-                             n_products, k_chunk, (P, D), None, out_host)
+                             n_products, k_chunk, (P, D), None, out_host, home=home)
     return P, D, var_all[:n_gene]
 
 
+def _segment_rect(rows_a, rows_b, parity):
+    """(a0, a1, b0, b1): the rows of A x rows of B that ``pair_tiles`` covers for this parity."""
+    if parity == 0:
+        return 0, min(shared_cut(rows_a) * TILE, rows_a), 0, rows_b
+    if parity == 1:
+        return 0, rows_a, min(shared_cut(rows_b) * TILE, rows_b), rows_b
+    return 0, rows_a, 0, rows_b
+
+
+_MIRROR = {}
+
+
+def _mirror_pair(device, k, blk):
+    """(P, dot) buffers (blk x blk) that receive the transposed copy of block pair k of this device; kept
+    per device so that the device-to-host copies of one call never outlive their source."""
+    key = (torch.device(device).index, k, blk)
+    if key not in _MIRROR:
+        _MIRROR[key] = (torch.empty((blk, blk), dtype=torch.float64, device=device),
+                        torch.empty((blk, blk), dtype=torch.float64, device=device))
+    return _MIRROR[key]
+
+
 def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out=None, events=None,
-                  out_host=None, single_launch=True):
+                  out_host=None, single_launch=True, home=None):
     """Contract everything ``rank`` owns under the pairs schedule: the upper triangle of its diagonal
     block, then the block pairs of ``rounds`` = [(src, parity, Sliced of block src, works)].
     ``works``: [] when the block is already there (the one-GPU emulation of the schedule in
@@ -338,76 +361,100 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
     One persistent launch over all segments (``nsr_contract_segments``) unless a block arrives over
     NCCL - its kernels need SMs, which a waiting persistent launch would not release - or
     ``single_launch`` is off; then one launch per block.  Returns (P, dot): rows of block ``rank`` x
-    all n_gene columns, owned tiles filled in."""
+    all n_gene columns, owned tiles filled in.
+
+    Where the results go besides (P, dot), each column block as soon as its tiles are finished, on a
+    side stream, while the launch continues:
+      out_host = (P, dot) host tensors (rows of this rank, n_gene): the same layout as (P, dot);
+      home     = (P, dot) host tensors (n_gene, n_gene), the FULL symmetric matrices of the reference
+                 (association.py:1036-1057): the kernel also writes the transposed copy of everything it
+                 computes (diagonal block: into P itself; block pair: into a (rows_b x rows_a) buffer) and
+                 both rectangles are copied home, so that after all ranks are done every entry of both
+                 triangles has been written exactly once."""
     blk = local.rows_alloc
     rows_a = block_rows(n_gene, world, rank)
+    dev = local.slices.device
     if out is None:
-        P = torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=local.slices.device)
+        P = torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev)
         D = torch.zeros_like(P)
     else:
         P, D = out
     local.rows = max(rows_a, 1)
     if not rows_a:
         return P, D
-    copy_stream = _side_stream2(local.slices.device) if out_host is not None else None
-    flagged = all(len(w) == 0 or isinstance(w[0], _FlagWork) for _, _, _, w in rounds)
-    if single_launch and flagged and len(rounds) + 1 <= MAX_SEGMENTS:
+    r0 = rank * blk
+    to_host = out_host is not None or home is not None
+    copy_stream = _side_stream2(dev) if to_host else None
+    main = torch.cuda.current_stream()
+
+    segs = [dict(B=local, rows_b=rows_a, col0=r0, diagonal=True)]
+    if home is not None:
+        segs[0]["mirror"] = (P.data_ptr() + 8 * r0, D.data_ptr() + 8 * r0, P.stride(0))
+    tiles = [engine.coex_tiles(rows_a)]
+    extra = [dict(works=[], rect=(0, rows_a, 0, rows_a), mbuf=None)]
+    for k, (src, parity, buf, works) in enumerate(rounds, 1):
+        rows_b = block_rows(n_gene, world, src)
+        if not rows_b:
+            continue
+        buf.rows = rows_b
+        sg = dict(B=buf, rows_b=rows_b, col0=src * blk, diagonal=False)
+        mbuf = None
+        if home is not None:
+            mbuf = _mirror_pair(dev, k, blk)
+            sg["mirror"] = (mbuf[0].data_ptr(), mbuf[1].data_ptr(), blk)
+        segs.append(sg)
+        tiles.append(pair_tiles(rows_a, rows_b, parity))
+        extra.append(dict(works=works, rect=_segment_rect(rows_a, rows_b, parity), mbuf=mbuf))
+
+    def send(i):
+        """queue the device-to-host copies of segment i on the copy stream"""
+        sg, ex = segs[i], extra[i]
+        c0 = sg["col0"]
+        if out_host is not None:
+            for src_t, dst_t in ((P, out_host[0]), (D, out_host[1])):
+                engine.copy_rect_to_host(ctx, dst_t, 0, c0, src_t, 0, c0, rows_a, sg["rows_b"], stream=copy_stream)
+        if home is not None:
+            a0, a1, b0, b1 = ex["rect"]
+            for t, (src_t, dst_t) in enumerate(((P, home[0]), (D, home[1]))):
+                engine.copy_rect_to_host(ctx, dst_t, r0 + a0, c0 + b0, src_t, a0, c0 + b0, a1 - a0, b1 - b0,
+                                         stream=copy_stream)
+                if ex["mbuf"] is not None:
+                    engine.copy_rect_to_host(ctx, dst_t, c0 + b0, r0 + a0, ex["mbuf"][t], b0, a0, b1 - b0, a1 - a0,
+                                             stream=copy_stream)
+
+    flagged = all(len(ex["works"]) == 0 or isinstance(ex["works"][0], _FlagWork) for ex in extra)
+    if single_launch and flagged and len(segs) <= MAX_SEGMENTS:
         sync = _sync_words(ctx)
-        segs = [dict(B=local, rows_b=rows_a, col0=rank * blk, diagonal=True)]
-        tl = engine.coex_tiles(rows_a)
-        tiles = [np.concatenate([np.zeros((len(tl), 1), np.int32), tl], axis=1)]
-        for k, (src, parity, buf, works) in enumerate(rounds, 1):
-            rows_b = block_rows(n_gene, world, src)
-            if not rows_b:
-                continue
-            buf.rows = rows_b
-            sg = dict(B=buf, rows_b=rows_b, col0=src * blk, diagonal=False)
-            if works:
-                sg["ready"] = (works[0].flag_ptr, works[0].value)
-            tl = pair_tiles(rows_a, rows_b, parity)
-            tiles.append(np.concatenate([np.full((len(tl), 1), len(segs), np.int32), tl], axis=1))
-            segs.append(sg)
-        track = out_host is not None and not k_chunk
+        for sg, ex in zip(segs, extra):
+            if ex["works"]:
+                sg["ready"] = (ex["works"][0].flag_ptr, ex["works"][0].value)
+        track = to_host and not k_chunk
         if track:
             for i, sg in enumerate(segs):
                 sg["done"] = sync.done_ptr(i)
-        _timed(events, lambda: engine.contract_segments(ctx, local, segs, np.concatenate(tiles), dof_a, P, D,
-                                                        n_products, k_chunk=k_chunk))
-        if out_host is not None:
+        tl = np.concatenate([np.concatenate([np.full((len(t), 1), i, np.int32), t], axis=1) for i, t in enumerate(tiles)])
+        _timed(events, lambda: engine.contract_segments(ctx, local, segs, tl, dof_a, P, D, n_products, k_chunk=k_chunk))
+        if to_host:
             if not track:
-                copy_stream.wait_stream(torch.cuda.current_stream())
-            for i, sg in enumerate(segs):
+                copy_stream.wait_stream(main)
+            for i in range(len(segs)):
                 if track:
                     # the epilogue counts every finished tile of the segment once per epilogue warp
                     sync.done_expected[i] += EPILOGUE_WARPS * len(tiles[i])
                     engine.stream_wait_geq(ctx, sync.done_ptr(i), sync.done_expected[i], stream=copy_stream)
-                _send_home(ctx, P, D, out_host, rows_a, sg["col0"], sg["col0"] + sg["rows_b"], copy_stream)
-            torch.cuda.current_stream().wait_stream(copy_stream)
+                send(i)
+            main.wait_stream(copy_stream)
         return P, D
 
-    def send_home(c0, c1):
-        if out_host is None:
-            return
-        copy_stream.wait_stream(torch.cuda.current_stream())
-        _send_home(ctx, P, D, out_host, rows_a, c0, c1, copy_stream)
-
-    c0 = rank * blk
-    _timed(events, lambda: engine.contract(
-        ctx, MODE_COEX_UPPER, local, local, engine.coex_tiles(rows_a), dof_a,
-        P[:rows_a, c0:c0 + rows_a], D[:rows_a, c0:c0 + rows_a], n_products, k_chunk=k_chunk))
-    send_home(c0, c0 + rows_a)
-    for src, parity, buf, works in rounds:
-        wait_block(works)
-        rows_b = block_rows(n_gene, world, src)
-        if rows_b:
-            buf.rows = rows_b
-            c0 = src * blk
-            _timed(events, lambda: engine.contract(
-                ctx, MODE_COEX_RECT, local, buf, pair_tiles(rows_a, rows_b, parity), dof_a,
-                P[:rows_a, c0:c0 + rows_b], D[:rows_a, c0:c0 + rows_b], n_products, k_chunk=k_chunk))
-            send_home(c0, c0 + rows_b)
+    for i, (sg, ex) in enumerate(zip(segs, extra)):
+        wait_block(ex["works"])
+        tl = np.concatenate([np.zeros((len(tiles[i]), 1), np.int32), tiles[i]], axis=1)
+        _timed(events, lambda: engine.contract_segments(ctx, local, [sg], tl, dof_a, P, D, n_products, k_chunk=k_chunk))
+        if to_host:
+            copy_stream.wait_stream(main)
+            send(i)
     if copy_stream is not None:
-        torch.cuda.current_stream().wait_stream(copy_stream)
+        main.wait_stream(copy_stream)
     return P, D
 
 
@@ -420,11 +467,6 @@ def _side_stream2(device):
     if key not in _SIDE2:
         _SIDE2[key] = torch.cuda.Stream(device=device)
     return _SIDE2[key]
-
-
-def _send_home(ctx, P, D, out_host, rows_a, c0, c1, stream):
-    for src_t, dst_t in ((P, out_host[0]), (D, out_host[1])):
-        engine.copy_block_to_host(ctx, dst_t, src_t, 0, rows_a, c0, c1, stream=stream)
 
 
 def _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events=None):
@@ -505,11 +547,17 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
 
 
 def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimreduce=0, out_dev=None,
-              out_host=None, schedule="pairs"):
+              out_host=None, schedule="pairs", home=None):
     """``coex_sharded`` for HOST inputs and outputs: this rank's gene block is a CPU tensor / numpy
     array (pinned memory makes the staged copies asynchronous and overlapped with the projection
     kernels); the rows of P and dot are copied back into ``out_host`` (CPU tensors) if given.
-    Returns (P_rows, dot_rows, var, (row_begin, row_end)) as numpy arrays."""
+    Returns (P_rows, dot_rows, var, (row_begin, row_end)) as numpy arrays.
+
+    ``home`` = (P, dot) host tensors of the FULL (n_gene, n_gene) matrices ("pairs" schedule): every
+    rank writes the rectangles it computed AND their transposes into them.  With tensors from
+    ``shared_host_matrices`` (one page-locked mapping shared by all processes) the caller on rank 0
+    ends up with what the reference returns to its one caller - the complete symmetric P and dot
+    (coex.py:46-48) - once every rank has returned (barrier); P_rows / dot_rows are then None."""
     from .association import _residualize_any
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -533,8 +581,13 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         if schedule == "allgather":
             P, D, var, (r0, r1) = _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out_dev)
         else:
-            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host, symm=symm)
+            P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host, symm=symm,
+                                    home=home)
             r0, r1 = rank * blk, rank * blk + block_rows(n_gene, world, rank)
+        if home is not None:
+            assert schedule == "pairs"
+            torch.cuda.current_stream().synchronize()
+            return None, None, var.cpu().numpy(), (r0, r1)
         if out_host is not None:
             if schedule == "allgather":
                 out_host[0].copy_(P, non_blocking=True)
@@ -544,6 +597,261 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         else:
             Ph, Dh = P.cpu().numpy(), D.cpu().numpy()
         return Ph, Dh, var.cpu().numpy(), (r0, r1)
+
+
+_SHARED = {}
+
+
+def shared_host_matrices(count, shape, group=None, tag="nsr"):
+    """``count`` float64 host matrices of ``shape`` backed by ONE shared mapping (a file under /dev/shm
+    that rank 0 creates and unlinks once everyone has mapped it), page-locked in every process of
+    ``group``: all ranks' GPUs copy their parts of a result straight into the same memory, and the
+    caller on rank 0 reads the whole of it.  Falls back to private pinned tensors (each process then
+    holds only what its own GPU wrote) when /dev/shm is too small; returns (tensors, shared: bool).
+    Cached per (count, shape)."""
+    import mmap
+    import os
+    key = (count, tuple(shape), id(group), tag)
+    if key in _SHARED:
+        return _SHARED[key]
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    each = int(np.prod(shape)) * 8
+    nbytes = count * each
+    path = [None]
+    if rank == 0:
+        try:
+            free = os.statvfs("/dev/shm")
+            if free.f_bavail * free.f_frsize > nbytes + (1 << 28):
+                path[0] = "/dev/shm/%s_%d_%d" % (tag, os.getpid(), len(_SHARED))
+                with open(path[0], "wb") as f:
+                    f.truncate(nbytes)
+        except OSError:
+            path[0] = None
+    if world > 1:
+        dist.broadcast_object_list(path, src=0, group=group)
+    tensors, shared = None, False
+    if path[0] is not None:
+        fd = os.open(path[0], os.O_RDWR)
+        mm = mmap.mmap(fd, nbytes, mmap.MAP_SHARED, mmap.PROT_READ | mmap.PROT_WRITE)
+        os.close(fd)
+        flat = torch.frombuffer(mm, dtype=torch.float64)
+        if rank == 0:
+            flat.zero_()                       # touch the pages once, on the caller's NUMA node
+        if world > 1:
+            dist.barrier(group=group)
+        err = torch.cuda.cudart().cudaHostRegister(flat.data_ptr(), nbytes, 0)
+        if int(err) != 0:
+            raise RuntimeError("cudaHostRegister of the shared result mapping failed: %r" % (err,))
+        if world > 1:
+            dist.barrier(group=group)
+        if rank == 0:
+            os.unlink(path[0])                 # the mapping lives on until every process drops it
+        tensors = [flat[i * each // 8:(i + 1) * each // 8].view(*shape) for i in range(count)]
+        shared = True
+        _SHARED[("mm",) + key] = mm
+    else:
+        tensors = [torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True) for _ in range(count)]
+    _SHARED[key] = (tensors, shared)
+    return _SHARED[key]
+
+
+# ----------------------------------------------------------------------------------------------------
+# one process, every GPU of the box: the reference's call, the reference's return value
+# ----------------------------------------------------------------------------------------------------
+def visible_devices(devices="all"):
+    """Normalise a ``devices`` argument ("all", an int count, or a list of device specs) to a list of
+    distinct torch.device."""
+    if devices is None or devices == "all":
+        devices = list(range(torch.cuda.device_count()))
+    elif isinstance(devices, int):
+        devices = list(range(devices))
+    out = []
+    for d in devices:
+        d = torch.device("cuda", d) if isinstance(d, int) else torch.device(d)
+        if d.type != "cuda":
+            raise ValueError("devices must be CUDA devices")
+        d = torch.device("cuda", torch.cuda.current_device() if d.index is None else d.index)
+        if d in out:
+            raise ValueError("devices must be distinct (a persistent contraction launch owns its GPU)")
+        out.append(d)
+    if not out:
+        raise RuntimeError("normalisr_b200: no CUDA device visible (there is no CPU fallback).")
+    return out
+
+
+class _Team:
+    """What the per-GPU worker threads of one ``coex_all_devices`` call share."""
+
+    def __init__(self, world):
+        import threading
+        self.barrier = threading.Barrier(world)
+        self.stores = [None] * world          # peer-readable home of every device's block
+        self.ready = [None] * world           # CUDA event: block residualised
+        self.errors = [None] * world
+
+
+_STORES = {}
+
+
+def _pull_rounds(ctx, team, rank, world, local):
+    """Single-process counterpart of ``start_exchange_ce``: pull the blocks this device needs from the other
+    devices' buffers (cudaMemcpyPeerAsync on a side stream; each copy followed by the flag write the
+    persistent contraction launch waits for)."""
+    dev = local.slices.device
+    side = _side_stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    sync = _sync_words(ctx)
+    sync.epoch += 1
+    nbytes = team.stores[rank].numel()
+    rounds = []
+    for d, (_, src, parity) in enumerate(exchange_plan(world, rank)):
+        key = (dev.index, d, nbytes)
+        if key not in _STORES:
+            _STORES[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        store = _STORES[key]
+        side.wait_event(team.ready[src])
+        engine.copy_peer(ctx, store, team.stores[src], stream=side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        work = _FlagWork(ev, sync.ready_ptr(d + 1), sync.epoch)
+        engine.stream_signal(ctx, work.flag_ptr, work.value, stream=side)
+        buf = engine.Sliced(local.rows_alloc, local.n, local.n_slices, dev, storage=store, fresh=False)
+        rounds.append((src, parity, buf, [work]))
+    return rounds
+
+
+def _device_worker(team, rank, world, dev, xh, dc, n_gene, precision, dimreduce, home, var_out):
+    from .association import _residualize_any
+    try:
+        torch.cuda.set_device(dev)
+        ctx = engine.context(dev)
+        n_slices, n_products = engine.PRESETS[precision]
+        n = xh.shape[1]
+        Qt_dev, crank, _ = covariate_basis_device(ctx, dc)
+        if n <= crank + dimreduce + 1:
+            raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
+                             'removed + covariate + 1.')
+        dof_a = (n - 1 - crank - dimreduce) / 2
+        blk = row_split(n_gene, world)
+        rows_a = block_rows(n_gene, world, rank)
+        r0 = rank * blk
+        nbytes = engine.Sliced.storage_bytes(blk, n, n_slices)
+        key = (dev.index, "own", nbytes)
+        if key not in _STORES:
+            _STORES[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        store = _STORES[key]
+        local = engine.Sliced(blk, n, n_slices, dev, storage=store)
+        if rows_a < blk:
+            local.slices[:, rows_a:].zero_()
+            local.quantum[rows_a:] = 1.0
+            local.var[rows_a:] = 1.0
+        if rows_a:
+            _residualize_any(ctx, xh[r0:r0 + rows_a], Qt_dev, n_slices, False, out=local, row_offset=0)
+        ev = torch.cuda.Event()
+        ev.record()
+        team.stores[rank], team.ready[rank] = store, ev
+        team.barrier.wait()                       # every block's event exists
+        rounds = _pull_rounds(ctx, team, rank, world, local)
+        okey = (dev.index, "out", max(rows_a, 1), n_gene)
+        if okey not in _STORES:
+            _STORES[okey] = (torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev),
+                             torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev))
+        out = _STORES[okey]
+        contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, None, None, home=home)
+        # the optimistic single pass over the cells is verified like in _coex_pairs
+        for r in rounds:
+            wait_block(r[3])
+        em_a = local.energy_max.cpu().numpy()
+        em_b = em_a
+        for r in rounds:
+            em_b = np.maximum(em_b, r[2].energy_max.cpu().numpy())     # NaN (non-finite input) propagates
+        k_chunk = engine.plan_k_chunk(local, local, n_products, energies=(em_a, em_b))
+        if k_chunk:
+            contract_plan(ctx, local, [(r[0], r[1], r[2], []) for r in rounds], rank, world, n_gene, dof_a,
+                          n_products, k_chunk, out, None, None, home=home)
+        if rows_a:
+            var_out[r0:r0 + rows_a].copy_(local.var[:rows_a], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        team.barrier.wait()                       # nobody still pulls from this device's block
+    except BaseException as e:                    # noqa: BLE001 - re-raised by the caller
+        team.errors[rank] = e
+        team.barrier.abort()
+
+
+def coex_all_devices(dt, dc, devices="all", precision="default", dimreduce=0, out=None):
+    """``coex`` on every GPU of the box from ONE process: what ``normalisr.coex(dt, dc, devices="all")``
+    runs.  One worker thread + stream set per GPU; each residualises its block of genes from the host
+    matrix, pulls the digit planes it needs from its peers over NVLink (copy engines), contracts its share
+    of the block pairs in one persistent launch and copies every finished rectangle - and its transpose -
+    straight into the caller's (n_gene, n_gene) P and dot.  Returns (P, dot, var) as numpy arrays: the
+    reference's return value (coex.py:46-48 -> association.py:1036-1057), bit-identical to one GPU.
+
+    dt: (n_gene, n_cell) numpy array or CPU tensor (page-locked memory makes the copies asynchronous);
+    out: optional (P, dot) page-locked CPU tensors to fill."""
+    import threading
+    devs = visible_devices(devices)
+    world = len(devs)
+    xh = dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt))
+    if xh.is_cuda:
+        raise ValueError("coex_all_devices takes a host matrix")
+    if xh.dtype != torch.float64:
+        xh = xh.to(torch.float64)
+    n_gene = xh.shape[0]
+    if out is None:
+        out = (torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True),
+               torch.empty((n_gene, n_gene), dtype=torch.float64, pin_memory=True))
+    var_out = torch.empty(n_gene, dtype=torch.float64, pin_memory=True)
+    team = _Team(world)
+    threads = [threading.Thread(target=_device_worker, name="nsr-gpu%d" % r,
+                                args=(team, r, world, devs[r], xh, dc, n_gene, precision, dimreduce, out, var_out))
+               for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    first = [e for e in team.errors if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+    if first:
+        raise first[0]
+    if any(e is not None for e in team.errors):
+        raise RuntimeError("coex_all_devices: a worker stopped at a broken barrier")
+    return out[0].numpy(), out[1].numpy(), var_out.numpy()
+
+
+def de_all_devices(dx, dy, dc, devices="all", **ka):
+    """``association_tests(dx, dy, dc, ...)`` (dy given: DE, any ``single``) with the rows of dy - the genes -
+    dealt out to the GPUs of this process, one worker thread per GPU, no exchange at all (dg and
+    dc are small and replicated; every test is independent in y).  Host inputs, host outputs with the
+    reference's shapes: the per-device results are concatenated along the gene axis."""
+    import threading
+    from .association import association_tests
+    devs = visible_devices(devices)
+    world = len(devs)
+    ny = dy.shape[0]
+    blk = row_split(ny, world)
+    spans = [(k * blk, min((k + 1) * blk, ny)) for k in range(world) if k * blk < ny]
+    res, err = [None] * len(spans), [None] * len(spans)
+
+    def work(k):
+        try:
+            torch.cuda.set_device(devs[k])
+            res[k] = association_tests(dx, dy[spans[k][0]:spans[k][1]], dc, device=devs[k], **ka)
+        except BaseException as e:                # noqa: BLE001 - re-raised by the caller
+            err[k] = e
+
+    threads = [threading.Thread(target=work, args=(k,), name="nsr-gpu%d" % k) for k in range(len(spans))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in err:
+        if e is not None:
+            raise e
+    P = np.concatenate([r[0] for r in res], axis=1)
+    out2 = np.concatenate([r[1] for r in res], axis=1)
+    alpha = None if res[0][2] is None else np.concatenate([r[2] for r in res], axis=1)
+    vary = np.concatenate([r[4] for r in res], axis=-1)
+    return P, out2, alpha, res[0][3], vary
 
 
 def _contract_strip(ctx, mode, A, B, tiles, dof_a, P, D, row0, n_products, k_chunk=None):

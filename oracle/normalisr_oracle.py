@@ -494,13 +494,15 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, keepvar=True, normmean=False, **i
 
 
 # --------------------------------------------------------------------------------------
-# Bayesian logCPM (reference src/normalisr/lcpm.py:21-208, supported
-# configuration: varscale = 0)
+# Bayesian logCPM (reference src/normalisr/lcpm.py:21-208)
 # --------------------------------------------------------------------------------------
-def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, **ignored):
+def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, varscale=0, noise=None, **ignored):
     """(lcpm, mean|None, var|None, cov|None): digamma(1 + reads) - digamma(total + 2), per-cell
-    log-sum-exp normalisation to log counts per million, cellular covariates."""
-    from scipy.special import digamma
+    log-sum-exp normalisation to log counts per million, cellular covariates.  varscale != 0
+    (posterior resampling, :104-109, 134-150, 178-190): value = mean + sqrt(varscale * (trigamma(1 +
+    reads) - trigamma(total + 2))) * z with z = ``noise`` (the standard normal deviates; the reference
+    draws numpy.random.randn(n_gene, n_cell) once)."""
+    from scipy.special import digamma, polygamma
     d = np.asarray(reads)
     if d.ndim != 2:
         raise ValueError('reads must have 2 dimensions.')
@@ -512,9 +514,18 @@ def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, **ignored):
     t0 = d.sum() + 2 if ntot is None else ntot + 2                   # :90
     assert t0 > 2                                                    # :91
     table = digamma(1.0 + np.arange(int(d.max()) + 1)) - float(digamma(t0))   # :96-109
-    dtn = table[d]                                                   # :150
-    if normalize:                                                    # :155-157
-        dtn = dtn - (np.log(np.exp(dtn).sum(axis=0)) - np.log(1e6))
+    dmean = table[d]                                                 # :150, :176
+    dvar = np.zeros(dmean.shape)
+    if varscale != 0:
+        tvar = polygamma(1, 1.0 + np.arange(int(d.max()) + 1)) - float(polygamma(1, t0))   # :104-109
+        dvar = tvar[d] * varscale                                    # :143, :177-180
+        dtn = np.asarray(noise) * np.sqrt(dvar) + dmean              # :144-147, :181-182
+    else:
+        dtn = dmean.copy()
+    if normalize:                                                    # :155-157, :186-190
+        shift = np.log(np.exp(dtn).sum(axis=0)) - np.log(1e6)
+        dtn = dtn - shift
+        dmean = dmean - shift
     dcov = None
     if not nocov:                                                    # :193-199
         t1 = d.sum(axis=0)
@@ -524,7 +535,7 @@ def lcpm(reads, normalize=True, ntot=None, lowmem=True, nocov=False, **ignored):
         dcov = np.array([t1, nt - (d != 0).sum(axis=0), t1 ** 2])
     if lowmem:
         return dtn, None, None, dcov
-    return dtn, dtn.copy(), np.zeros(dtn.shape), dcov
+    return dtn, dmean, dvar, dcov
 
 
 def compute_var(dt, dc, stepmax=1, eps=1e-6):

