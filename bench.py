@@ -253,9 +253,12 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         # (block exchange,) contraction + P-values
         if not single:
             ev = [] if record else None
-            parallel.coex_sharded(dt_dev, dc_dev, n_gene, precision=precision, out=(P, D), schedule=schedule, events=ev)
+            pev = [] if record else None
+            parallel.coex_sharded(dt_dev, dc_dev, n_gene, precision=precision, out=(P, D), schedule=schedule, events=ev,
+                                  proj_events=pev)
             if record:
                 contract_ms.append(ev)
+                project_ms.extend(pev)
             return
         Qt_dev, crank, _ = association.covariate_basis_device(ctx, dc_dev)
         dof_a = (n_cell - 1 - crank) / 2
@@ -503,6 +506,13 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "roofline_projection": roof_proj, "cpu_baseline": cpu,
         "de": de, "binnet": binnet_info, "normvar": normvar_info, "lcpm": lcpm_info, "compute_var": cvar_info,
     }
+    if roof_proj is not None and k_ms:
+        # rank 0's step on the device clock: projection, contraction (with N > 1 one persistent launch that starts on
+        # the diagonal block while the exchange is in flight), and what is left: covariate basis, launch gaps, the
+        # host-side planning between the two, exchange set-up and barriers
+        line["timeline"] = {"step_ms": ms_step, "projection_ms": roof_proj["kernel_ms"], "contraction_ms": k_ms,
+                            "other_ms": ms_step - roof_proj["kernel_ms"] - k_ms,
+                            "rank": 0}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -4,6 +4,7 @@ PyTorch is used for device memory, streams and (in ``parallel.py``) NCCL only; e
 numerical kernel on the path is in ``libnsr_b200.so``.
 """
 import ctypes
+import functools
 import threading
 
 import numpy as np
@@ -255,6 +256,7 @@ def single1_finish(ctx, cu, yy_u, st, n_groups, nc, ci, cx, ccx, ns, vx, dof, P,
     LAUNCHES += 1
 
 
+@functools.lru_cache(maxsize=64)
 def coex_tiles(rows, strip=12):
     """Upper-triangular 128x128 tile list (tile_row <= tile_col), ordered in column strips so
     that the ~148 tiles in flight share few row blocks (L2 reuse of the operand planes)."""
@@ -268,6 +270,7 @@ def coex_tiles(rows, strip=12):
     return np.asarray(out, dtype=np.int32).reshape(-1, 2)
 
 
+@functools.lru_cache(maxsize=64)
 def rect_tiles(rows_a, rows_b, strip=12):
     ta, tb = (rows_a + TILE - 1) // TILE, (rows_b + TILE - 1) // TILE
     out = []
@@ -525,6 +528,7 @@ def copy_peer(ctx, dst, src, stream=None):
                "nsr_copy_peer")
 
 
+@functools.lru_cache(maxsize=256)
 def coex_strip_tiles(t_begin, t_end, strip=12):
     """Upper-triangular tiles whose tile column lies in [t_begin, t_end), in column sub-strips."""
     out = []

@@ -282,9 +282,10 @@ def _timed(events, fn):
         return fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    fn()
+    res = fn()
     e1.record()
     events.append((e0, e1))
+    return res
 
 
 def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None, home=None):
@@ -517,7 +518,7 @@ def _symm_for(blk, n, n_slices, device, group):
 
 
 def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduce=0, out=None,
-                 schedule="pairs", events=None):
+                 schedule="pairs", events=None, proj_events=None):
     """Co-expression over all ranks of ``group``.
 
     dt_block: this rank's genes, rows [rank*blk, min((rank+1)*blk, n_gene)) of the expression
@@ -539,7 +540,8 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
     dof_a = (n - 1 - crank - dimreduce) / 2
     blk = row_split(n_gene, world)
     symm = _symm_for(blk, n, n_slices, ctx.device, group) if (schedule == "pairs" and world > 1) else None
-    local = residualize_block(ctx, dt_block, Qt_dev, n_slices, blk, storage=None if symm is None else symm[0])
+    local = _timed(proj_events, lambda: residualize_block(ctx, dt_block, Qt_dev, n_slices, blk,
+                                                          storage=None if symm is None else symm[0]))
     if schedule == "allgather":
         return _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out, events)
     P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events, symm=symm)

@@ -30,7 +30,8 @@ def main():
     torch.cuda.empty_cache()
     ok = True
     P1, D1, v1 = norm.coex(dt, dc)
-    for devices in sorted({2, n_dev} - {0, 1}):
+    only_all = "--only-all" in sys.argv
+    for devices in sorted(({n_dev} if only_all else {2, n_dev}) - {0, 1}):
         if devices > n_dev:
             continue
         for rep in range(2):
@@ -52,7 +53,7 @@ def main():
     if "--time" in sys.argv:
         out = (torch.empty((genes, genes), dtype=torch.float64, pin_memory=True),
                torch.empty((genes, genes), dtype=torch.float64, pin_memory=True))
-        for devices in sorted({1, 2, n_dev}):
+        for devices in sorted({n_dev} if only_all else {1, 2, n_dev}):
             if devices > n_dev:
                 continue
             ka = dict(devices=devices) if devices > 1 else {}
