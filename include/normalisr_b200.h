@@ -259,8 +259,17 @@ int nsr_single1_finish(nsr_ctx* ctx, uintptr_t stream, const double* cu, const d
  *   nsr_normvar_apply  out = scale[x] * s * (dt - coef[x]^T dc), coef (genes x nc) = G+ b from the
  *                      host layer (pseudo-inverse with the rank rule of inv_rank), scale = the
  *                      keepvar factor (norm.py:251-254) or 1.
- * logw = log(w) per cell, wt per gene; s = exp(wt * logw), 1 when wt == 0.  1 <= nc <= 12. */
+ *   nsr_normvar_rhs    the part of the statistics that depends on dt, for up to 16 covariates:
+ *                      stats[x] = { b (16 columns: sum_k s^2 dt c for the rows of C16, a (16 x n) matrix:
+ *                      the covariates, zero rows up to 16), S1, S2 } - 18 doubles per gene.  The Gram
+ *                      matrices G_x depend on the gene only through the scalar wt_x and are smooth in it;
+ *                      the host layer interpolates them (normalisr_b200/norm.py: Chebyshev nodes in wt,
+ *                      barycentric evaluation), which takes 3/4 of the float64 work out of the pass.
+ * logw = log(w) per cell, wt per gene; s = w ** wt = exp(wt * logw), 1 when wt == 0.  nsr_normvar_stats:
+ * 1 <= nc <= 12; nsr_normvar_apply: 1 <= nc <= 16. */
 int nsr_normvar_width(int nc);
+int nsr_normvar_rhs(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n, int64_t ld,
+                    const double* C16, int64_t ldc, const double* logw, const double* wt, double* stats);
 int nsr_normvar_stats(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
                       int64_t ld, const double* M, int nc, int64_t ldm, const double* logw,
                       const double* wt, double* stats);
@@ -316,13 +325,18 @@ int nsr_sym_pinv(nsr_ctx* ctx, uintptr_t stream, const double* G, int64_t batch,
 int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* refined);
 
 /* Bayesian logCPM (lcpm.lcpm, src/normalisr/lcpm.py:21-208): reads is a (genes x n) matrix of
- * non-negative counts (int32 or int64, itemsize 4 / 8), lut[c] = digamma(1 + c) - digamma(total + 2) for
- * c = 0 .. lut_len - 1 (the reference's table, :96-109) and lut_exp[c] = exp(lut[c]).
- *   nsr_lcpm_scan      out3 (device, 3 x int64) = min, max and total of the counts in one pass (the
- *                      negativity check :88-89, the table length :98 and the total :95);
+ * non-negative counts (int32 or int64, itemsize 4 / 8), lut[c] = digamma(1 + c) for c = 0 .. lut_len - 1
+ * (the reference's table, :96-109, without its constant - digamma(total + 2), which the caller folds into
+ * `shift`: it is the same for every entry) and lut_exp[c] = exp(lut[c]).  Without resampling, counts
+ * >= lut_len are evaluated directly (recurrence + asymptotic series), so the table need not cover the
+ * largest count and no pass is needed to find it: the counts are read twice in all.
+ *   nsr_lcpm_scan      out3 (device, 3 x int64) = min, max and total of the counts in one pass (only needed
+ *                      with resampling, whose standard-deviation table must cover every count);
  *   nsr_lcpm_colstats  colstats = [3][n]: per cell sum_g exp(value), total reads, number of genes with a
  *                      non-zero count (per-cell normaliser :155-157 and the covariates :193-199 from one
  *                      pass over the counts; without resampling the exponentials are a table gather);
+ *                      minmax (device, 2 x int64, optional, initialised by the caller to INT64_MAX /
+ *                      INT64_MIN, accumulated): smallest NEGATIVE count (the check :88-89) and largest count;
  *   nsr_lcpm_apply     out[g][k] = value[g][k] - shift[k]  (shift may be NULL).
  * value = lut[reads] or, with posterior resampling (varscale != 0, :134-150), lut[reads] + lut_sd[reads] z
  * with lut_sd[c] = sqrt(varscale (trigamma(1 + c) - trigamma(total + 2))) and z a standard normal
@@ -335,7 +349,7 @@ int nsr_lcpm_scan(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsiz
 int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
                       int64_t n, int64_t ld, const double* lut, const double* lut_exp, int64_t lut_len,
                       const double* lut_sd, const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0,
-                      double* colstats);
+                      double* colstats, long long* minmax);
 int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
                    int64_t n, int64_t ld, const double* lut, int64_t lut_len, const double* lut_sd,
                    const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0, const double* shift,

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "nsr_group_stats": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_int, c_vp]),
     "nsr_normvar_width": (c_int, [c_int]),
     "nsr_normvar_stats": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "nsr_normvar_rhs": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nsr_normvar_apply": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp,
                                   c_vp, c_i64]),
     "nsr_sym_pinv": (c_int, [c_vp, c_up, c_vp, c_i64, c_int, c_dbl, c_vp, c_vp]),
@@ -75,7 +76,7 @@ _SIGNATURES = {
     "nsr_last_refined": (c_int, [c_vp, c_up, c_i64, c_vp]),
     "nsr_lcpm_scan": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp]),
     "nsr_lcpm_colstats": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64,
-                                  ctypes.c_uint64, c_i64, c_vp]),
+                                  ctypes.c_uint64, c_i64, c_vp, c_vp]),
     "nsr_lcpm_apply": (c_int, [c_vp, c_up, c_vp, c_int, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64,
                                ctypes.c_uint64, c_i64, c_vp, c_vp, c_i64]),
     "nsr_colvar": (c_int, [c_vp, c_up, c_vp, c_i64, c_i64, c_i64, c_vp, c_int, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),

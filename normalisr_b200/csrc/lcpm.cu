@@ -39,6 +39,22 @@ __device__ __forceinline__ double philox_normal(uint64_t index, uint64_t seed) {
     return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
 }
 
+// digamma(x), x >= 1: recurrence up to x >= 10, then the asymptotic series up to B14 (5e-16 absolute against
+// scipy on [1, 2e7]; host twin in the tests).  Only counts beyond the look-up table take this path.
+__device__ __forceinline__ double lc_digamma(double x) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    const double i = 1.0 / x, i2 = i * i;
+    double s = -1.0 / 12.0;
+    s = fma(s, i2, 691.0 / 32760.0);
+    s = fma(s, i2, -1.0 / 132.0);
+    s = fma(s, i2, 1.0 / 240.0);
+    s = fma(s, i2, -1.0 / 252.0);
+    s = fma(s, i2, 1.0 / 120.0);
+    s = fma(s, i2, -1.0 / 12.0);
+    return r + (log(x) - 0.5 * i + s * i2);
+}
+
 struct LcNoise {
     const double* lut_sd;      // sqrt(varscale * (trigamma(1 + c) - trigamma(total + 2))) per count value, or nullptr
     const double* noise;       // standard normal deviates, one per entry (ld_noise), or nullptr -> Philox
@@ -77,29 +93,46 @@ template <typename T, bool NOISY>
 __global__ void __launch_bounds__(kLcThreads)
 lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t ld,
                      const double* __restrict__ lut, const double* __restrict__ lut_exp, int64_t lut_len, LcNoise nz_,
-                     double* __restrict__ partial) {
+                     double* __restrict__ partial, long long* __restrict__ minmax) {
     const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
-    if (k >= n) return;
     const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
     double se = 0.0, tot = 0.0, nz = 0.0;
+    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    if (k < n) {
 #pragma unroll 8
-    for (int64_t g = g0; g < g1; ++g) {
-        const long long c = (long long)reads[g * ld + k];
-        const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
-        if (NOISY) {
-            const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
-                                       : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
-            se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
-        } else {
-            se += lut_exp[ci];                       // exp(lut[c]) tabulated: the pass is a pure gather
+        for (int64_t g = g0; g < g1; ++g) {
+            const long long c = (long long)reads[g * ld + k];
+            const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
+            if (NOISY) {
+                const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
+                                           : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
+                se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
+            } else {
+                // exp(lut[c]) tabulated: the pass is a pure gather (counts beyond the table: computed)
+                se += c < lut_len ? lut_exp[ci] : exp(lc_digamma(1.0 + (double)c));
+            }
+            tot += (double)c;
+            nz += c != 0 ? 1.0 : 0.0;
+            mn = c < mn ? c : mn;
+            mx = c > mx ? c : mx;
         }
-        tot += (double)c;
-        nz += c != 0 ? 1.0 : 0.0;
+        double* o = partial + ((int64_t)blockIdx.y * 3) * n + k;
+        o[0] = se;
+        o[n] = tot;
+        o[2 * n] = nz;
     }
-    double* o = partial + ((int64_t)blockIdx.y * 3) * n + k;
-    o[0] = se;
-    o[n] = tot;
-    o[2 * n] = nz;
+    if (minmax != nullptr) {                         // negativity check and largest count from the same read
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            const long long a = __shfl_xor_sync(0xffffffffu, mn, m), b = __shfl_xor_sync(0xffffffffu, mx, m);
+            mn = a < mn ? a : mn;
+            mx = b > mx ? b : mx;
+        }
+        if ((threadIdx.x & 31) == 0 && mn <= mx) {
+            if (mn < 0) atomicMin(minmax, mn);       // rare: most launches never touch the words
+            if (mx > *(volatile long long*)(minmax + 1)) atomicMax(minmax + 1, mx);
+        }
+    }
 }
 
 __global__ void lcpm_colreduce_kernel(const double* __restrict__ partial, int64_t n, int n_split, double* __restrict__ out) {
@@ -122,7 +155,7 @@ lcpm_apply_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int64_t
     for (int64_t g = g0; g < g1; ++g) {
         const long long c = (long long)reads[g * ld + k];
         const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
-        double v = lut[ci];
+        double v = (NOISY || c < lut_len) ? lut[ci] : lc_digamma(1.0 + (double)c);
         if (NOISY) {
             const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
                                        : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
@@ -152,7 +185,7 @@ extern "C" int nsr_lcpm_scan(nsr_ctx* ctx, uintptr_t stream, const void* reads, 
 extern "C" int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* reads, int itemsize, int64_t genes,
                                  int64_t n, int64_t ld, const double* lut, const double* lut_exp, int64_t lut_len,
                                  const double* lut_sd, const double* noise, int64_t ld_noise, uint64_t seed, int64_t row0,
-                                 double* colstats) {
+                                 double* colstats, long long* minmax) {
     NSR_REQUIRE(ctx && reads && lut && colstats && (lut_sd || lut_exp), "nsr_lcpm_colstats: null argument");
     NSR_REQUIRE((itemsize == 4 || itemsize == 8) && genes >= 1 && n >= 1 && ld >= n && lut_len >= 1 &&
                     (!noise || ld_noise >= n),
@@ -165,7 +198,7 @@ extern "C" int nsr_lcpm_colstats(nsr_ctx* ctx, uintptr_t stream, const void* rea
     if (nsr_scratch(ctx, (size_t)n_split * 3 * n * sizeof(double), &scratch)) return 1;
     const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
     const LcNoise nz{lut_sd, noise, ld_noise, seed, row0, n};
-#define NSR_LC(T_, N_) lcpm_colstats_kernel<T_, N_><<<grid, kLcThreads, 0, st>>>((const T_*)reads, genes, n, ld, lut, lut_exp, lut_len, nz, (double*)scratch)
+#define NSR_LC(T_, N_) lcpm_colstats_kernel<T_, N_><<<grid, kLcThreads, 0, st>>>((const T_*)reads, genes, n, ld, lut, lut_exp, lut_len, nz, (double*)scratch, minmax)
     if (itemsize == 4) { if (lut_sd) NSR_LC(int32_t, true); else NSR_LC(int32_t, false); }
     else { if (lut_sd) NSR_LC(int64_t, true); else NSR_LC(int64_t, false); }
 #undef NSR_LC
@@ -206,16 +239,20 @@ extern "C" int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads,
 namespace {
 
 constexpr int kCvRank = 16;            // covariate rank handled in registers
+constexpr int kCvCells = 2;            // cells per thread: a gene's coefficients are read once for both
 
+// RK: rank rounded up to a multiple of 4 (zero-padded coefficients): the inner product is unrolled over RK
+template <int RK>
 __global__ void __launch_bounds__(kLcThreads)
 colvar_kernel(const double* __restrict__ X, int64_t genes, int64_t n, int64_t ld, const double* __restrict__ Qt,
               int rank, int64_t ldq, const double* __restrict__ coef, int64_t ldcoef,
               const double* __restrict__ mean, const double* __restrict__ inv_std, double* __restrict__ partial) {
-    __shared__ double s_coef[kLcGeneSplit][kCvRank];
+    constexpr int RS = RK > 0 ? RK : 2;
+    __shared__ __align__(16) double s_coef[kLcGeneSplit][RS];
     __shared__ double s_mean[kLcGeneSplit], s_istd[kLcGeneSplit];
     const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
-    for (int idx = threadIdx.x; idx < kLcGeneSplit * kCvRank; idx += kLcThreads) {
-        const int g = idx / kCvRank, j = idx % kCvRank;
+    for (int idx = threadIdx.x; idx < kLcGeneSplit * RS; idx += kLcThreads) {
+        const int g = idx / RS, j = idx % RS;
         s_coef[g][j] = (g0 + g < g1 && j < rank) ? coef[(g0 + g) * ldcoef + j] : 0.0;
     }
     for (int g = threadIdx.x; g < kLcGeneSplit; g += kLcThreads) {
@@ -223,20 +260,40 @@ colvar_kernel(const double* __restrict__ X, int64_t genes, int64_t n, int64_t ld
         s_istd[g] = g0 + g < g1 ? inv_std[g0 + g] : 0.0;
     }
     __syncthreads();
-    const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
-    if (k >= n) return;
-    double q[kCvRank];
+    int64_t k[kCvCells];
+    bool ok[kCvCells];
+    double q[kCvCells][RS], acc[kCvCells];
 #pragma unroll
-    for (int j = 0; j < kCvRank; ++j) q[j] = j < rank ? Qt[(int64_t)j * ldq + k] : 0.0;
-    double acc = 0.0;
-    for (int64_t g = g0; g < g1; ++g) {
-        double r = X[g * ld + k];
+    for (int u = 0; u < kCvCells; ++u) {
+        k[u] = ((int64_t)blockIdx.x * kCvCells + u) * kLcThreads + threadIdx.x;
+        ok[u] = k[u] < n;
+        acc[u] = 0.0;
 #pragma unroll
-        for (int j = 0; j < kCvRank; ++j) r = fma(-s_coef[g - g0][j], q[j], r);
-        const double z = (r - s_mean[g - g0]) * s_istd[g - g0];
-        acc = fma(z, z, acc);
+        for (int j = 0; j < RS; ++j) q[u][j] = (ok[u] && j < rank) ? Qt[(int64_t)j * ldq + k[u]] : 0.0;
     }
-    partial[(int64_t)blockIdx.y * n + k] = acc;
+    if (!ok[0]) return;
+#pragma unroll 4
+    for (int64_t g = g0; g < g1; ++g) {
+        double r[kCvCells];
+#pragma unroll
+        for (int u = 0; u < kCvCells; ++u) r[u] = ok[u] ? X[g * ld + k[u]] : 0.0;
+        const double2* cf = reinterpret_cast<const double2*>(s_coef[g - g0]);
+#pragma unroll
+        for (int j = 0; j < RK / 2; ++j) {
+            const double2 c2 = cf[j];
+#pragma unroll
+            for (int u = 0; u < kCvCells; ++u) r[u] = fma(-c2.y, q[u][2 * j + 1], fma(-c2.x, q[u][2 * j], r[u]));
+        }
+        const double m = s_mean[g - g0], is = s_istd[g - g0];
+#pragma unroll
+        for (int u = 0; u < kCvCells; ++u) {
+            const double z = (r[u] - m) * is;
+            acc[u] = fma(z, z, acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kCvCells; ++u)
+        if (ok[u]) partial[(int64_t)blockIdx.y * n + k[u]] = acc[u];
 }
 
 __global__ void colvar_reduce_kernel(const double* __restrict__ partial, int64_t n, int n_split, double* __restrict__ out) {
@@ -261,8 +318,14 @@ extern "C" int nsr_colvar(nsr_ctx* ctx, uintptr_t stream, const double* X, int64
     NSR_REQUIRE(n_split <= 65535, "nsr_colvar: too many genes for one call");
     void* scratch = nullptr;
     if (nsr_scratch(ctx, (size_t)n_split * n * sizeof(double), &scratch)) return 1;
-    const dim3 grid((unsigned)((n + kLcThreads - 1) / kLcThreads), (unsigned)n_split);
-    colvar_kernel<<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch);
+    const dim3 grid((unsigned)((n + kCvCells * kLcThreads - 1) / (kCvCells * kLcThreads)), (unsigned)n_split);
+#define NSR_CV(RK_) colvar_kernel<RK_><<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch)
+    if (rank == 0) NSR_CV(0);
+    else if (rank <= 4) NSR_CV(4);
+    else if (rank <= 8) NSR_CV(8);
+    else if (rank <= 12) NSR_CV(12);
+    else NSR_CV(16);
+#undef NSR_CV
     colvar_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)scratch, n, n_split, out);
     NSR_CHECK(cudaGetLastError());
     return 0;

@@ -9,21 +9,45 @@
 //   (host layer: pseudo-inverse of every nc x nc G with the reference's rank rule, coef = G+ b,
 //    residual variance S2 - b^T G+ b, keepvar scale)
 //   nsr_normvar_apply   out = scale * s * (dt - coef^T dc)
-// s = exp(wt * log w).  In the apply pass a warp owns a gene and strides over the cells (coalesced
-// 8-byte accesses); the covariate chunk and log w are staged in shared memory once per CTA of 8 genes.
+// s = w ** wt = exp(wt * log w).  Both passes run on the FP64 tensor cores (DMMA) in the same fragment
+// layout; see the kernels.
 #include "nsr_common.cuh"
 
 namespace {
 
 constexpr int kNvThreads = 256;
 constexpr int kNvWarps = kNvThreads / 32;
-constexpr int kNvChunk = 384;          // cells staged per step (12 x 384 doubles + log w < 48 KB static)
-constexpr int kNvAhead = 4;            // cells per lane whose loads are issued before any arithmetic
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
     return v;
+}
+
+// s = w ** wt = 2^(wt log2(e) log w) without the library's special-case handling: round to the nearest
+// integer k, e^z on |z| <= ln(2)/2 by its Taylor polynomial of degree 13 (truncation 4e-18), 2^k added to
+// the exponent field.  0.7 ulp against exp2l on [-30, 30] (host twin of this code); arguments beyond
+// +-1000 (over / underflow territory) take the library path.  wt2 = wt * log2(e), once per gene.
+constexpr double kLog2e = 1.4426950408889634;
+__device__ __forceinline__ double nv_exp2(double y) {
+    if (!(fabs(y) < 1000.0)) return exp2(y);
+    const double kf = rint(y);
+    const double z = (y - kf) * 0.6931471805599453;
+    double p = 1.6059043836821613e-10;            // 1/13!
+    p = fma(p, z, 2.08767569878681e-09);
+    p = fma(p, z, 2.505210838544172e-08);
+    p = fma(p, z, 2.755731922398589e-07);
+    p = fma(p, z, 2.7557319223985893e-06);
+    p = fma(p, z, 2.48015873015873e-05);
+    p = fma(p, z, 1.984126984126984e-04);
+    p = fma(p, z, 1.388888888888889e-03);
+    p = fma(p, z, 8.333333333333333e-03);
+    p = fma(p, z, 4.1666666666666664e-02);
+    p = fma(p, z, 1.6666666666666666e-01);
+    p = fma(p, z, 0.5);
+    p = fma(p, z, 1.0);
+    p = fma(p, z, 1.0);
+    return __hiloint2double(__double2hiint(p) + ((int)kf << 20), __double2loint(p));
 }
 
 // ---- pass 1 on the FP64 tensor cores -------------------------------------------------------
@@ -69,7 +93,7 @@ normvar_gemm_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int
         const int64_t gene = gene_w + 8 * r + g;
         valid[r] = gene < genes;
         xr[r] = dt + (valid[r] ? gene : gene_w) * ld + 4 * t;
-        wtx[r] = valid[r] ? wt[gene] : 0.0;
+        wtx[r] = valid[r] ? wt[gene] * kLog2e : 0.0;
     }
     const int64_t n16 = (n + 15) / 16;
     const int64_t kb = n16 * blockIdx.y / ksplit, ke = n16 * (blockIdx.y + 1) / ksplit;
@@ -93,7 +117,7 @@ normvar_gemm_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int
         for (int e = 0; e < 4; ++e) {
 #pragma unroll
             for (int r = 0; r < kGmTiles; ++r) {
-                const double s = wtx[r] == 0.0 ? 1.0 : exp(wtx[r] * lw[e]);     // norm.py:238-239
+                const double s = wtx[r] == 0.0 ? 1.0 : nv_exp2(wtx[r] * lw[e]);     // w ** wt, norm.py:238-239
                 const double v = xv[r][e] * s;
                 const double a1 = s * s, a2 = s * v;
                 s1[r] += v;
@@ -131,54 +155,73 @@ __global__ void normvar_reduce_kernel(const double* __restrict__ partial, int64_
     stats[i] = s;
 }
 
-template <int NC>
+// pass 2 on the FP64 tensor cores: out = scale * s * (dt - coef^T dc).  The covariate part is a
+// (genes x covariates) x (covariates x cells) product: A = -coef (a warp's 16 genes, constant over its
+// cell loop, in registers), B = dc (4 covariates x 8 cells per DMMA, read through L1: dc is a few MB and
+// shared by every warp), accumulator initialised with the dt tile - so the residual comes out of the MMA
+// in the accumulator layout (lane (g, t): gene g, cells 2 t and 2 t + 1), where it is multiplied by
+// s = w ** wt and the keepvar scale and stored.  KS = ceil(nc / 4) k-steps.  No shared memory, no barrier.
+template <int KS>
 __global__ void __launch_bounds__(kNvThreads)
 normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int64_t ld,
                      const double* __restrict__ dc, int nc, int64_t ldc, const double* __restrict__ logw,
                      const double* __restrict__ wt, const double* __restrict__ coef, const double* __restrict__ scale,
-                     double* __restrict__ out, int64_t ldo) {
-    __shared__ double s_c[NC][kNvChunk];
-    __shared__ double s_lw[kNvChunk];
+                     double* __restrict__ out, int64_t ldo, int64_t cells_per_split) {
+    constexpr int R = 2, U = 2;                   // row tiles (8 genes) and cell tiles (8 cells) per step
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t gene = (int64_t)blockIdx.x * kNvWarps + warp;
-    const bool live = gene < genes;
-    const double wtx = live ? wt[gene] : 0.0;
-    const double sc = live ? scale[gene] : 0.0;
-    double c[NC];
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t gene_w = ((int64_t)blockIdx.x * kNvWarps + warp) * (8 * R);
+    if (gene_w >= genes) return;
+    double a[R][KS], wt2[R], sc[R];
+    const double* xr[R];
+    double* orow[R];
+    bool valid[R];
 #pragma unroll
-    for (int j = 0; j < NC; ++j) c[j] = (live && j < nc) ? coef[gene * nc + j] : 0.0;
-    const double* row = dt + (live ? gene : 0) * ld;
-    double* orow = out + (live ? gene : 0) * ldo;
-    // cells are split over blockIdx.y so that the grid fills the machine for any gene count
-    const int64_t per = ((n + gridDim.y - 1) / gridDim.y + kNvChunk - 1) / kNvChunk * kNvChunk;
-    const int64_t kb = (int64_t)blockIdx.y * per, ke = min(n, kb + per);
-    for (int64_t k0 = kb; k0 < ke; k0 += kNvChunk) {
-        const int len = (int)min((int64_t)kNvChunk, ke - k0);
-        __syncthreads();
-        for (int idx = threadIdx.x; idx < NC * kNvChunk; idx += kNvThreads) {
-            const int j = idx / kNvChunk, k = idx % kNvChunk;
-            s_c[j][k] = (j < nc && k < len) ? dc[(int64_t)j * ldc + k0 + k] : 0.0;
+    for (int r = 0; r < R; ++r) {
+        const int64_t gene = gene_w + 8 * r + g;
+        valid[r] = gene < genes;
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            const int j = 4 * kk + t;
+            a[r][kk] = (valid[r] && j < nc) ? -coef[gene * nc + j] : 0.0;
         }
-        for (int k = threadIdx.x; k < kNvChunk; k += kNvThreads) s_lw[k] = k < len ? logw[k0 + k] : 0.0;
-        __syncthreads();
-        if (live) {
-            for (int kq = lane; kq < len; kq += 32 * kNvAhead) {
-                double x[kNvAhead];
+        wt2[r] = valid[r] ? wt[gene] * kLog2e : 0.0;
+        sc[r] = valid[r] ? scale[gene] : 0.0;
+        xr[r] = dt + (valid[r] ? gene : gene_w) * ld;
+        orow[r] = out + (valid[r] ? gene : gene_w) * ldo;
+    }
+    const int64_t kb = (int64_t)blockIdx.y * cells_per_split, ke = min(n, kb + cells_per_split);
+#pragma unroll 1
+    for (int64_t c0 = kb; c0 < ke; c0 += 8 * U) {
+        double bf[U][KS], lw[U][2], d[R][U][2];
+        bool in[U][2];
 #pragma unroll
-                for (int u = 0; u < kNvAhead; ++u) {
-                    const int k = kq + 32 * u;
-                    x[u] = k < len ? row[k0 + k] : 0.0;
-                }
+        for (int u = 0; u < U; ++u) {
+            const int64_t cb = c0 + 8 * u + g;                    // B operand: column (cell) g of the tile
 #pragma unroll
-                for (int u = 0; u < kNvAhead; ++u) {
-                    const int k = kq + 32 * u;
-                    if (k < len) {
-                        const double s = wtx == 0.0 ? 1.0 : exp(wtx * s_lw[k]);
-                        double r = x[u];
+            for (int kk = 0; kk < KS; ++kk) {
+                const int j = 4 * kk + t;
+                bf[u][kk] = (j < nc && cb < ke) ? __ldg(dc + (int64_t)j * ldc + cb) : 0.0;
+            }
 #pragma unroll
-                        for (int j = 0; j < NC; ++j) r = fma(-c[j], s_c[j][k], r);
-                        orow[k0 + k] = sc * (s * r);
-                    }
+            for (int e = 0; e < 2; ++e) {
+                const int64_t k = c0 + 8 * u + 2 * t + e;         // accumulator: cells 2 t, 2 t + 1
+                in[u][e] = k < ke;
+                lw[u][e] = in[u][e] ? __ldg(logw + k) : 0.0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) d[r][u][e] = (in[u][e] && valid[r]) ? xr[r][k] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) nv_dmma(d[r][u][0], d[r][u][1], a[r][kk], bf[u][kk]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double s = wt2[r] == 0.0 ? 1.0 : nv_exp2(wt2[r] * lw[u][e]);
+                    if (in[u][e] && valid[r]) orow[r][c0 + 8 * u + 2 * t + e] = sc[r] * (s * d[r][u][e]);
                 }
             }
         }
@@ -186,15 +229,6 @@ normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
 }
 
 }  // namespace
-
-#define NSR_NV_DISPATCH(NCV, CALL)                                  \
-    do {                                                            \
-        if ((NCV) <= 4) { CALL(4); }                                \
-        else if ((NCV) <= 6) { CALL(6); }                           \
-        else if ((NCV) <= 8) { CALL(8); }                           \
-        else if ((NCV) <= 10) { CALL(10); }                         \
-        else { CALL(12); }                                          \
-    } while (0)
 
 // padded column count of the statistics for nc covariates: 8 * (D tiles + C tiles) + 2
 static int nv_d_tiles(int nc) {
@@ -235,25 +269,52 @@ extern "C" int nsr_normvar_stats(nsr_ctx* ctx, uintptr_t stream, const double* d
     return 0;
 }
 
+extern "C" int nsr_normvar_rhs(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
+                               int64_t ld, const double* C16, int64_t ldc, const double* logw, const double* wt,
+                               double* stats) {
+    NSR_REQUIRE(ctx && dt && C16 && logw && wt && stats, "nsr_normvar_rhs: null argument");
+    NSR_REQUIRE(genes >= 1 && n >= 1 && ld >= n && ldc >= n, "nsr_normvar_rhs: bad shape genes=%lld n=%lld",
+                (long long)genes, (long long)n);
+    NSR_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int cols = 18;
+    const int ksplit = nsr_cell_splits(n);
+    void* scratch = nullptr;
+    if (nsr_scratch(ctx, (size_t)ksplit * genes * cols * sizeof(double), &scratch)) return 1;
+    const dim3 grid((unsigned)((genes + kGmWarps * 8 * kGmTiles - 1) / (kGmWarps * 8 * kGmTiles)), (unsigned)ksplit);
+    normvar_gemm_kernel<0, 2><<<grid, 32 * kGmWarps, 0, st>>>(dt, genes, n, ld, C16, ldc, logw, wt, ksplit, (double*)scratch);
+    const int64_t total = genes * cols;
+    normvar_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const double*)scratch, genes, cols, ksplit, stats);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* dt, int64_t genes, int64_t n,
                                  int64_t ld, const double* dc, int nc, int64_t ldc, const double* logw,
                                  const double* wt, const double* coef, const double* scale, double* out,
                                  int64_t ldo) {
     NSR_REQUIRE(ctx && dt && dc && logw && wt && coef && scale && out, "nsr_normvar_apply: null argument");
-    NSR_REQUIRE(genes >= 1 && n >= 1 && ld >= n && ldo >= n && ldc >= n && nc >= 1 && nc <= 12,
-                "nsr_normvar_apply: bad shape genes=%lld n=%lld nc=%d (1..12 covariates)", (long long)genes,
+    NSR_REQUIRE(genes >= 1 && n >= 1 && ld >= n && ldo >= n && ldc >= n && nc >= 1 && nc <= 16,
+                "nsr_normvar_apply: bad shape genes=%lld n=%lld nc=%d (1..16 covariates)", (long long)genes,
                 (long long)n, nc);
     NSR_CHECK(cudaSetDevice(ctx->device));
-    const int64_t gx = (genes + kNvWarps - 1) / kNvWarps;
-    int64_t gy = (4 * (int64_t)ctx->sm_count + gx - 1) / gx;                 // >= 4 CTAs per SM in total
-    const int64_t max_y = (n + kNvChunk - 1) / kNvChunk;
+    const int64_t gx = (genes + kNvWarps * 16 - 1) / (kNvWarps * 16);        // 8 warps x 16 genes per CTA
+    int64_t gy = (6 * (int64_t)ctx->sm_count + gx - 1) / gx;                 // >= 6 CTAs per SM in total
+    const int64_t max_y = (n + 255) / 256;
     if (gy > max_y) gy = max_y;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
+    const int64_t per = ((n + gy - 1) / gy + 15) / 16 * 16;                  // cells per split, whole steps
+    gy = (n + per - 1) / per;
     const dim3 grid((unsigned)gx, (unsigned)gy);
     cudaStream_t st = (cudaStream_t)stream;
-#define NSR_NV_APPLY(W) normvar_apply_kernel<W><<<grid, kNvThreads, 0, st>>>(dt, genes, n, ld, dc, nc, ldc, logw, wt, coef, scale, out, ldo)
-    NSR_NV_DISPATCH(nc, NSR_NV_APPLY);
+#define NSR_NV_APPLY(KS_) normvar_apply_kernel<KS_><<<grid, kNvThreads, 0, st>>>(dt, genes, n, ld, dc, nc, ldc, logw, wt, coef, scale, out, ldo, per)
+    switch ((nc + 3) / 4) {
+        case 1: NSR_NV_APPLY(1); break;
+        case 2: NSR_NV_APPLY(2); break;
+        case 3: NSR_NV_APPLY(3); break;
+        default: NSR_NV_APPLY(4); break;
+    }
 #undef NSR_NV_APPLY
     NSR_CHECK(cudaGetLastError());
     return 0;

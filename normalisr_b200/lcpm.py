@@ -30,6 +30,32 @@ def _is_dev(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 
 
+_TABLE_LEN = 4096
+_TABLES = {}
+
+
+def _tables(dev):
+    """(digamma(1 + c), exp(digamma(1 + c))) for c < 4096 on ``dev``."""
+    key = torch.device(dev).index
+    if key not in _TABLES:
+        lut = torch.special.digamma(torch.arange(1, _TABLE_LEN + 1, dtype=torch.float64, device=dev)).contiguous()
+        _TABLES[key] = (lut, torch.exp(lut).contiguous())
+    return _TABLES[key]
+
+
+def _trigamma(x):
+    """polygamma(1, x) for x >= 1 to float64 rounding: 15 recurrence steps, then the asymptotic series up to
+    B14 at x + 15 (torch.special.polygamma stops at B6 after 6 steps: 5e-10 relative, visible in the
+    resampled values at the golden tolerance)."""
+    s = torch.zeros_like(x)
+    for i in range(15):
+        s = s + 1.0 / ((x + i) * (x + i))
+    iy = 1.0 / (x + 15.0)
+    i2 = iy * iy
+    ser = i2 * (1 / 6 + i2 * (-1 / 30 + i2 * (1 / 42 + i2 * (-1 / 30 + i2 * (5 / 66 + i2 * (-691 / 2730 + i2 * (7 / 6)))))))
+    return s + iy * (1.0 + 0.5 * iy + ser)
+
+
 def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=True, nocov=False, device=None,
          noise=None):
     """Computes Bayesian log CPM from raw read counts: ``(lcpm, mean|None, var|None, cov|None)``
@@ -79,34 +105,35 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                 held[i] = blk
             return blk
 
-        # pass 0: min / max / total in one read
-        scan = torch.empty(3, dtype=torch.int64, device=dev)
-        acc = None
-        for i, (g0, g1) in enumerate(blocks):
-            blk = block(i)
-            _lib.check(ctx.lib.nsr_lcpm_scan(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
-                                             blk.stride(0) if g1 - g0 > 1 else nc, scan.data_ptr()), "nsr_lcpm_scan")
-            engine.LAUNCHES += 1
-            cur = scan.cpu().numpy().copy() if nt and nc else np.array([0, 0, 0])
-            acc = cur if acc is None else np.array([min(acc[0], cur[0]), max(acc[1], cur[1]), acc[2] + cur[2]])
-        if acc is None:
-            acc = np.array([0, 0, 0])
-        if acc[0] < 0:
-            raise ValueError('Negative value in d detected.')                # lcpm.py:88-89
-        max_count = int(acc[1])
-        total = int(acc[2]) if ntot is None else int(ntot)
-        t0 = total + 2
-        assert t0 > 2
-        counts1 = torch.arange(1, max_count + 2, dtype=torch.float64, device=dev)
-        t0_t = torch.tensor(float(t0), dtype=torch.float64, device=dev)
-        lut = (torch.special.digamma(counts1) - torch.special.digamma(t0_t)).contiguous()       # :96-103
-        lut_exp = torch.exp(lut)
+        i64 = torch.iinfo(torch.int64)
+        minmax = torch.tensor([i64.max, i64.min], dtype=torch.int64, device=dev)
         lut_var = lut_sd = None
         noise_d = None
         key = 0
         if resample:
-            lut_var = (torch.special.polygamma(1, counts1) - torch.special.polygamma(1, t0_t)).contiguous()   # :104-109
-            lut_sd = torch.sqrt(lut_var * float(varscale)).contiguous()                                      # :148-150
+            # the standard-deviation table must cover every count and needs the total: one extra read
+            # (pass 0: min / max / total)
+            scan = torch.empty(3, dtype=torch.int64, device=dev)
+            acc = None
+            for i, (g0, g1) in enumerate(blocks):
+                blk = block(i)
+                _lib.check(ctx.lib.nsr_lcpm_scan(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
+                                                 blk.stride(0) if g1 - g0 > 1 else nc, scan.data_ptr()), "nsr_lcpm_scan")
+                engine.LAUNCHES += 1
+                cur = scan.cpu().numpy().copy() if nt and nc else np.array([0, 0, 0])
+                acc = cur if acc is None else np.array([min(acc[0], cur[0]), max(acc[1], cur[1]), acc[2] + cur[2]])
+            if acc is None:
+                acc = np.array([0, 0, 0])
+            if acc[0] < 0:
+                raise ValueError('Negative value in d detected.')                # lcpm.py:88-89
+            t0 = (int(acc[2]) if ntot is None else int(ntot)) + 2
+            assert t0 > 2
+            counts1 = torch.arange(1, int(acc[1]) + 2, dtype=torch.float64, device=dev)
+            lut = torch.special.digamma(counts1).contiguous()                                    # :96-103 (+ const)
+            lut_exp = None
+            t0_t = torch.tensor(float(t0), dtype=torch.float64, device=dev)
+            lut_var = (_trigamma(counts1) - _trigamma(t0_t)).contiguous()                        # :104-109
+            lut_sd = torch.sqrt(lut_var * float(varscale)).contiguous()                          # :148-150
             if noise is None and to_host:
                 noise = np.random.randn(nt, nc)             # the reference's own stream (:150)
             if noise is not None:
@@ -115,6 +142,10 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                     raise ValueError('noise must have the shape of reads.')
             else:
                 key = int(seed) if seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        else:
+            # digamma(1 + c) and its exponential for the counts a table serves (larger ones are evaluated in
+            # the kernels): independent of the data, built once per device
+            lut, lut_exp = _tables(dev)
 
         def noise_args(g0, g1):
             if not resample:
@@ -128,27 +159,41 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
             return lut_sd.data_ptr(), nb.data_ptr(), nb.stride(0) if g1 - g0 > 1 else nc, 0
 
         keep = []
-        # pass 1: per-cell statistics
+        # pass 1: per-cell statistics (+ smallest negative / largest count)
         col = torch.zeros((3, nc), dtype=torch.float64, device=dev)
         for i, (g0, g1) in enumerate(blocks):
             blk = block(i)
             part = torch.empty((3, nc), dtype=torch.float64, device=dev)
             sd_p, nz_p, ldn, sd_key = noise_args(g0, g1)
             _lib.check(ctx.lib.nsr_lcpm_colstats(ctx.handle, engine._stream(), blk.data_ptr(), itemsize, g1 - g0, nc,
-                                                 blk.stride(0) if g1 - g0 > 1 else nc, lut.data_ptr(), lut_exp.data_ptr(),
-                                                 lut.numel(), sd_p, nz_p, ldn, sd_key, g0, part.data_ptr()),
+                                                 blk.stride(0) if g1 - g0 > 1 else nc, lut.data_ptr(),
+                                                 lut_exp.data_ptr() if lut_exp is not None else None,
+                                                 lut.numel(), sd_p, nz_p, ldn, sd_key, g0, part.data_ptr(),
+                                                 minmax.data_ptr()),
                        "nsr_lcpm_colstats")
             engine.LAUNCHES += 2
             col += part
-        shift = None
-        if normalize:                                        # lcpm.py:155-157
-            shift = (torch.log(col[0]) - float(np.log(1e6))).contiguous()
+        # digamma(total + 2), the constant of the reference's table: on the device, no host round trip
+        total_t = col[1].sum() if ntot is None else torch.tensor(float(ntot), dtype=torch.float64, device=dev)
+        psi_t0 = torch.special.digamma(total_t + 2.0)
+        shift = psi_t0.expand(nc)                            # value = lut[c] - shift
+        if normalize:                                        # lcpm.py:155-157: the constant cancels
+            shift = torch.log(col[0]) - float(np.log(1e6))
+        shift = shift.contiguous()
         dcov = None
         if not nocov:                                        # lcpm.py:193-199
-            if bool((col[1] == 0).any()):
-                raise ValueError('Found cell with no read at all. Please remove.')
             t1 = torch.log(col[1])
             dcov = torch.stack([t1, nt - col[2], t1 ** 2])
+        # one small device->host read for the checks the reference makes up front
+        chk = torch.stack([minmax[0].to(torch.float64), total_t.to(torch.float64), (col[1] == 0).any().to(torch.float64),
+                           torch.isfinite(shift).all().to(torch.float64)]).cpu().numpy()
+        if chk[0] < 0:
+            raise ValueError('Negative value in d detected.')                    # lcpm.py:88-89
+        assert chk[1] + 2 > 2                                                    # :91
+        if not nocov and chk[2]:
+            raise ValueError('Found cell with no read at all. Please remove.')   # :195-196
+        if not chk[3]:
+            raise AssertionError('non-finite logCPM')                            # :201
         # pass 2: gather (+ resampling) + per-cell shift
         host_out = to_host
         out = torch.empty((nt, nc), dtype=torch.float64, device=dev) if not host_out else torch.empty((nt, nc), dtype=torch.float64)
@@ -182,8 +227,6 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                 dmean[g0:g1] = m.cpu() if host_out else m
                 if v is not None:
                     dvar[g0:g1] = v.cpu() if host_out else v
-        if not bool(torch.isfinite(shift).all() if shift is not None else True):
-            raise AssertionError('non-finite logCPM')        # lcpm.py:201
         if to_host:
             torch.cuda.current_stream().synchronize()
             return (out.numpy(), None if dmean is None else dmean.numpy(), None if dvar is None else dvar.numpy(),

@@ -17,6 +17,7 @@ import torch
 from . import _lib, engine
 
 _ROW_CHUNK_BYTES = 1 << 30
+_USE_CHEBYSHEV = True      # test hook: False = Gram matrices from the streaming pass (nsr_normvar_stats)
 
 
 def _is_dev(x):
@@ -43,23 +44,113 @@ def _design(ctx, dc_d):
     return M, iu, d_rows
 
 
-def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar):
-    """One block of genes resident on the device -> normalised block."""
+_CHEB_NODES = 24           # Chebyshev nodes per piece of the wt range
+_CHEB_ALPHA = 1.5          # largest half-range of the exponent within a piece
+_CHEB_PIECES = 256         # beyond this the streaming pass computes the Gram matrices
+
+
+def _gram_chebyshev(dc_d, logw, wt_d):
+    """Per-gene covariate Gram matrices G_x = sum_k w_k ** (2 wt_x) c_k c_k^T (norm.py:156-159: dc * w2[x]
+    times its transpose) for ALL genes without a pass over the expression matrix.
+
+    G depends on the gene only through the scalar wt_x:  G(wt) = e^(2 wt m) sum_k e^(2 wt (lw_k - m)) c_k c_k^T
+    with lw = log w and m the mid-range of lw.  The sum is an entire function of wt; on an interval of
+    half-width h it is a Chebyshev series in x = (wt - centre) / h whose coefficients decay like
+    I_j(alpha), alpha = h (max lw - min lw).  So: cut the range of wt into pieces with alpha <= 1.5, evaluate
+    the sum at 24 Chebyshev nodes per piece (one (24 x n) x (n x nc (nc + 1) / 2) product per piece;
+    I_24(1.5) / I_0(1.5) ~ 1e-27), and interpolate every gene with the barycentric formula (backward
+    stable; Higham 2004).  Interpolation is accurate relative to the largest value on the piece, and the
+    terms of the sum grow at rates between -alpha and +alpha across it, so the pointwise relative error is
+    about e^(2 alpha) roundings: hence the small alpha (measured: 1e-15 of sum |terms|, like a direct sum).
+    The truncated coefficients are checked; returns None if they have not decayed to rounding level or
+    the weights span too wide a range (the caller then takes the streaming-pass statistics)."""
+    dev = dc_d.device
+    nc, n = dc_d.shape
+    genes = wt_d.shape[0]
+    iu = torch.triu_indices(nc, nc, device=dev)
+    D = (dc_d[iu[0]] * dc_d[iu[1]]).t().contiguous()                # (n, tri)
+    lo, hi = float(logw.min()), float(logw.max())
+    mid, lw_half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    wmin, wmax = float(wt_d.min()), float(wt_d.max())
+    if not all(np.isfinite(v) for v in (lo, hi, wmin, wmax)):
+        return None
+    pieces = max(1, int(np.ceil(0.5 * (wmax - wmin) * 2.0 * lw_half / _CHEB_ALPHA)))
+    if pieces > _CHEB_PIECES:
+        return None
+    h = 0.5 * (wmax - wmin) / pieces
+    m = _CHEB_NODES
+    j = torch.arange(m, dtype=torch.float64, device=dev)
+    xn = torch.cos(np.pi * (j + 0.5) / m)                           # nodes (first kind)
+    bw = torch.sin(np.pi * (j + 0.5) / m) * (1.0 - 2.0 * (j % 2))    # barycentric weights
+    centres = wmin + h * (2.0 * torch.arange(pieces, dtype=torch.float64, device=dev) + 1.0)
+    piece = torch.clamp(((wt_d - wmin) / (2.0 * h)).floor().long(), 0, pieces - 1) if h > 0 else \
+        torch.zeros(genes, dtype=torch.long, device=dev)
+    x = ((wt_d - centres[piece]) / h).clamp_(-1.0, 1.0) if h > 0 else torch.zeros_like(wt_d)
+    lw0 = logw - mid
+    wt_nodes = (centres[:, None] + h * xn[None, :]).reshape(-1)     # (pieces * m,)
+    Dabs = D.abs()
+    F = torch.empty((pieces * m, D.shape[1]), dtype=torch.float64, device=dev)      # node values
+    Fabs = torch.empty_like(F)                                        # their rounding scale (sum of |terms|)
+    step = max(m, (1 << 25) // max(1, n) // m * m)                    # rows of E per batch (256 MB)
+    for r0 in range(0, pieces * m, step):
+        E = torch.exp(2.0 * wt_nodes[r0:r0 + step, None] * lw0[None, :])
+        F[r0:r0 + step] = E @ D
+        Fabs[r0:r0 + step] = E @ Dabs
+    del E
+    F, Fabs = F.reshape(pieces, m, -1), Fabs.reshape(pieces, m, -1)
+    # decay of the Chebyshev coefficients (type-II DCT of the node values): the last four must be at rounding level
+    i = torch.arange(m, dtype=torch.float64, device=dev)
+    A = (2.0 / m) * torch.einsum('ij,pjt->pit', torch.cos(np.pi * i[:, None] * (j[None, :] + 0.5) / m), F)
+    scale = Fabs.amax(dim=1)                                         # (pieces, tri)
+    if not bool((A[:, -4:].abs().amax(dim=1) <= 1e-14 * scale).all()):
+        return None
+    diff = x[:, None] - xn[None, :]                                  # (genes, m)
+    hit = diff == 0
+    wgt = bw[None, :] / torch.where(hit, torch.ones_like(diff), diff)
+    any_hit = hit.any(dim=1, keepdim=True)
+    wgt = torch.where(any_hit, hit.to(torch.float64), wgt)           # a gene exactly on a node takes the node value
+    wgt = wgt / wgt.sum(dim=1, keepdim=True)
+    tri = torch.empty((genes, D.shape[1]), dtype=torch.float64, device=dev)
+    if pieces == 1:
+        tri = wgt @ F[0]
+    else:
+        for p in range(pieces):
+            idx = (piece == p).nonzero(as_tuple=True)[0]
+            if idx.numel():
+                tri[idx] = wgt[idx] @ F[p]
+    tri = tri * torch.exp(2.0 * mid * wt_d)[:, None]
+    G = torch.zeros((genes, nc, nc), dtype=torch.float64, device=dev)
+    G[:, iu[0], iu[1]] = tri
+    return G + torch.triu(G, 1).transpose(1, 2)
+
+
+def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None):
+    """One block of genes resident on the device -> normalised block.  ``G``: the block's Gram matrices from
+    ``_gram_chebyshev``, or None: they come out of the streaming pass as well (``nsr_normvar_stats``)."""
     genes, n = dt_d.shape
     nc = dc_d.shape[0]
-    M, iu, d_rows = design
-    tri = iu.shape[1]
-    stats = torch.empty((genes, M.shape[0] + 2), dtype=torch.float64, device=dt_d.device)
     ld = dt_d.stride(0) if genes > 1 else n
     ldc = dc_d.stride(0) if nc > 1 else n
-    _lib.check(ctx.lib.nsr_normvar_stats(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, M.data_ptr(), nc,
-                                         M.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
-               "nsr_normvar_stats")
-    G = torch.zeros((genes, nc, nc), dtype=torch.float64, device=dt_d.device)
-    G[:, iu[0], iu[1]] = stats[:, :tri]
-    G = G + torch.triu(G, 1).transpose(1, 2)
-    b = stats[:, d_rows:d_rows + nc]
-    s1, s2 = stats[:, M.shape[0]], stats[:, M.shape[0] + 1]
+    if G is not None:
+        C16 = design
+        stats = torch.empty((genes, 18), dtype=torch.float64, device=dt_d.device)
+        _lib.check(ctx.lib.nsr_normvar_rhs(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, C16.data_ptr(),
+                                           C16.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
+                   "nsr_normvar_rhs")
+        b = stats[:, :nc]
+        s1, s2 = stats[:, 16], stats[:, 17]
+    else:
+        M, iu, d_rows = design
+        tri = iu.shape[1]
+        stats = torch.empty((genes, M.shape[0] + 2), dtype=torch.float64, device=dt_d.device)
+        _lib.check(ctx.lib.nsr_normvar_stats(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, M.data_ptr(), nc,
+                                             M.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
+                   "nsr_normvar_stats")
+        G = torch.zeros((genes, nc, nc), dtype=torch.float64, device=dt_d.device)
+        G[:, iu[0], iu[1]] = stats[:, :tri]
+        G = G + torch.triu(G, 1).transpose(1, 2)
+        b = stats[:, d_rows:d_rows + nc]
+        s1, s2 = stats[:, M.shape[0]], stats[:, M.shape[0] + 1]
     ci, rank = engine.sym_pinv(ctx, G)                                      # inv_rank per gene, norm.py:159-160
     if bool((rank <= 0).any()):
         raise RuntimeError('Zero-rank covariates found.')                    # norm.py:161-162
@@ -74,10 +165,11 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar):
     # finite imply it, without another pass over the matrix
     if not bool(torch.isfinite(stats).all() & torch.isfinite(coef).all() & torch.isfinite(scale).all()):
         raise AssertionError('non-finite values in the normalised expression matrix')
-    out = torch.empty((genes, n), dtype=torch.float64, device=dt_d.device)
+    if out is None:
+        out = torch.empty((genes, n), dtype=torch.float64, device=dt_d.device)
     _lib.check(ctx.lib.nsr_normvar_apply(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
                                          ldc, logw.data_ptr(), wt_d.data_ptr(), coef.data_ptr(), scale.contiguous().data_ptr(),
-                                         out.data_ptr(), n), "nsr_normvar_apply")
+                                         out.data_ptr(), out.stride(0) if genes > 1 else n), "nsr_normvar_apply")
     engine.LAUNCHES += 3
     return out
 
@@ -105,8 +197,8 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
     if cat not in (0, 1, 2):
         raise ValueError('Invalid cat value.')
     nc = dc.shape[0]
-    if nc > 12:
-        raise NotImplementedError('normvar is accelerated for up to 12 covariates.')
+    if nc > 16:
+        raise NotImplementedError('normvar is accelerated for up to 16 covariates.')
     to_host = not _is_dev(dt)
     ctx = engine.context(device if device is not None else (dt.device if _is_dev(dt) else None))
     dev = ctx.device
@@ -115,7 +207,16 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         w_d = _dev64(w, dev).contiguous()
         wt_d = _dev64(wt, dev).contiguous()
         logw = torch.log(w_d)
-        design = _design(ctx, dc_d)
+        # per-gene Gram matrices by interpolation in wt (no pass over dt); the streaming statistics otherwise
+        G_all = _gram_chebyshev(dc_d, logw, wt_d) if _USE_CHEBYSHEV else None
+        if G_all is not None:
+            design = torch.zeros((16, ns), dtype=torch.float64, device=dev)
+            design[:nc] = dc_d
+        elif nc <= 12:
+            design = _design(ctx, dc_d)
+        else:
+            raise NotImplementedError('normvar with more than 12 covariates needs weights whose range the '
+                                      'interpolation of the Gram matrices covers.')
         # covariates: continuous rows (and, for cat = 1, the intercept) are scaled by w   norm.py:257-269
         if cat == 2:
             sel = torch.ones(nc, dtype=torch.bool, device=dev)
@@ -143,11 +244,13 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         for g0 in range(0, nt, step):
             g1 = min(nt, g0 + step)
             blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
-            res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar)
+            res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar,
+                                G=None if G_all is None else G_all[g0:g1], out=None if to_host else dtn[g0:g1])
             if normmean:
                 cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
                 res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
-            dtn[g0:g1] = res if not to_host else res.cpu()
+            if to_host:
+                dtn[g0:g1] = res.cpu()
         if not bool(torch.isfinite(dcn).all()):
             raise AssertionError('non-finite values in the normalised covariates')  # norm.py:277
         ans = [dtn, dcn]
@@ -160,14 +263,15 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
 
 def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
     """Computes the variance normalisation multiplier of every cell (reference norm.py:56-128): a
-    log-linear fit of each cell's residual variance on the covariates.  Same arguments, checks and
-    return value (``(n_cell,)`` array, minimum 1).  Only ``stepmax=1`` (the reference's default, no
-    EM-like iterations) is accelerated.
+    log-linear fit of each cell's residual variance on the covariates, optionally iterated (EM-like,
+    ``stepmax`` > 1, :97-121).  Same arguments, checks and return value (``(n_cell,)`` array, minimum 1).
 
     The residual matrix is never materialised: one pass over dt gives every gene's projection
     coefficients, residual mean and variance (``nsr_project_coef`` on the orthonormal covariate
     basis plus a row of ones), a second one the per-cell sums of squared standardised residuals
-    (``nsr_colvar``); the fit of the log variances on the covariates is a rank-sized problem."""
+    (``nsr_colvar``); the fit of the log variances on the covariates is a rank-sized problem.
+    Iterations after the first work on dt / scale and dc / scale (:99-100); the scaled block is formed
+    once per iteration (one more read and write of the block), the rest is the same two passes."""
     from .association import covariate_basis_device
     if eps <= 0 or stepmax <= 0:
         raise ValueError('eps and stepmax must be positive.')
@@ -175,49 +279,60 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
         raise ValueError('dt and dc must both have 2 dimensions.')
     if dt.shape[1] != dc.shape[1]:
         raise ValueError('dt and dc must have the same cell count.')
-    if stepmax != 1:
-        raise NotImplementedError('compute_var is accelerated for stepmax=1 (no EM-like iterations).')
     to_host = not _is_dev(dt)
     ctx = engine.context(device if device is not None else (dt.device if _is_dev(dt) else None))
     dev = ctx.device
     nt, ns = dt.shape
     with torch.cuda.device(dev):
         dc_d = _dev64(dc, dev).contiguous()
-        Qt, rank, _ = covariate_basis_device(ctx, dc_d)           # least squares without intercept = projection
-        if rank > 16:
-            raise NotImplementedError('compute_var is accelerated for covariate rank <= 16.')
-        ones = torch.ones((1, ns), dtype=torch.float64, device=dev)
-        q1 = torch.cat([Qt, ones], 0).contiguous() if rank else ones
-        qsum = Qt.sum(dim=1) if rank else None
         src = dt if not to_host else (dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt)))
         step = nt if not to_host else max(1, _ROW_CHUNK_BYTES // (8 * ns))
-        col = torch.zeros(ns, dtype=torch.float64, device=dev)
-        for g0 in range(0, nt, step):
-            g1 = min(nt, g0 + step)
-            blk = src[g0:g1].to(dev, torch.float64, non_blocking=True)
-            if blk.stride(1) != 1:
-                blk = blk.contiguous()
-            cf, sxx = engine.project_coef(ctx, blk, q1)                       # (gc, rank + 1), (gc,)
-            coef = cf[:, :rank]
-            mean = (cf[:, rank] - (coef @ qsum if rank else 0.0)) / ns        # norm.py:101
-            var = (sxx - (coef * coef).sum(dim=1)) / ns - mean * mean         # :102 (Qt is orthonormal)
-            istd = (1.0 / torch.sqrt(var)).contiguous()
-            part = torch.empty(ns, dtype=torch.float64, device=dev)
-            _lib.check(ctx.lib.nsr_colvar(ctx.handle, engine._stream(), blk.data_ptr(), g1 - g0, ns,
-                                          blk.stride(0) if g1 - g0 > 1 else ns, Qt.data_ptr() if rank else None, rank,
-                                          Qt.stride(0) if rank > 1 else ns, cf.data_ptr(), cf.stride(0),
-                                          mean.contiguous().data_ptr(), istd.data_ptr(), part.data_ptr()), "nsr_colvar")
-            engine.LAUNCHES += 2
-            col += part
-        y = torch.log(torch.sqrt(col / nt))                                   # :103
-        # log-linear fit with intercept (:104-105): mean + projection on the centred covariates
+        ones = torch.ones((1, ns), dtype=torch.float64, device=dev)
+        # log-linear fit with intercept (:104-105, on the UNSCALED covariates): mean + projection on the centred covariates
         xc = dc_d - dc_d.mean(dim=1, keepdim=True)
         Qc, rc, _ = covariate_basis_device(ctx, xc)
-        ym = y.mean()
-        pred = ym + (Qc.T @ (Qc @ (y - ym)) if rc else 0.0)
-        new = torch.exp(pred)                                                 # :107 (scale was 1)
-        new = new / new.min()
-        w = 1.0 / new                                                         # :122-123
+        scale = None                       # d1sscale; None = all ones (first iteration)
+        best, bestv, it = None, 1e300, 0
+        while it < stepmax and bestv > eps:
+            inv = None if scale is None else (1.0 / scale)
+            Qt, rank, _ = covariate_basis_device(ctx, dc_d if inv is None else dc_d * inv)   # least squares without intercept = projection
+            if rank > 16:
+                raise NotImplementedError('compute_var is accelerated for covariate rank <= 16.')
+            q1 = torch.cat([Qt, ones], 0).contiguous() if rank else ones
+            qsum = Qt.sum(dim=1) if rank else None
+            col = torch.zeros(ns, dtype=torch.float64, device=dev)
+            for g0 in range(0, nt, step):
+                g1 = min(nt, g0 + step)
+                blk = src[g0:g1].to(dev, torch.float64, non_blocking=True)
+                if inv is not None:
+                    blk = blk * inv                                               # :99
+                if blk.stride(1) != 1:
+                    blk = blk.contiguous()
+                cf, sxx = engine.project_coef(ctx, blk, q1)                       # (gc, rank + 1), (gc,)
+                coef = cf[:, :rank]
+                mean = (cf[:, rank] - (coef @ qsum if rank else 0.0)) / ns        # norm.py:104
+                var = (sxx - (coef * coef).sum(dim=1)) / ns - mean * mean         # :105 (Qt is orthonormal)
+                istd = (1.0 / torch.sqrt(var)).contiguous()
+                part = torch.empty(ns, dtype=torch.float64, device=dev)
+                _lib.check(ctx.lib.nsr_colvar(ctx.handle, engine._stream(), blk.data_ptr(), g1 - g0, ns,
+                                              blk.stride(0) if g1 - g0 > 1 else ns, Qt.data_ptr() if rank else None, rank,
+                                              Qt.stride(0) if rank > 1 else ns, cf.data_ptr(), cf.stride(0),
+                                              mean.contiguous().data_ptr(), istd.data_ptr(), part.data_ptr()), "nsr_colvar")
+                engine.LAUNCHES += 2
+                col += part
+            y = torch.log(torch.sqrt(col / nt))                                   # :106
+            ym = y.mean()
+            pred = ym + (Qc.T @ (Qc @ (y - ym)) if rc else 0.0)                   # :107-108
+            new = torch.exp(pred)                                                 # :111
+            if scale is not None:
+                new = new * scale
+            new = new / new.min()                                                 # :112
+            t1 = float(((new - scale) / scale).abs().max() if scale is not None else (new - 1.0).abs().max())   # :113
+            scale = new
+            it += 1
+            if t1 < bestv:                                                        # :116-118
+                bestv, best = t1, scale
+        w = 1.0 / best                                                            # :122-123
         w = w / w.min()
         if not bool(torch.isfinite(w).all() & (w > 0).all()):
             raise AssertionError('non-finite variance normalisation multipliers')

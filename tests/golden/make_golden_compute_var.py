@@ -29,7 +29,9 @@ def main():
     w = norm.compute_var(dt, dc)
     dc2 = np.concatenate([dc, dc[:1] + 2 * dc[-1:]])               # rank-deficient covariates
     w2 = norm.compute_var(dt, dc2)
-    np.savez_compressed(os.path.join(HERE, "compute_var.npz"), dt=dt, dc=dc, w=w, dc2=dc2, w2=w2)
+    w3 = norm.compute_var(dt, dc, stepmax=4)                       # EM-like iterations (norm.py:97-121)
+    w4 = norm.compute_var(dt, dc, stepmax=50, eps=1e-3)            # stops on the tolerance
+    np.savez_compressed(os.path.join(HERE, "compute_var.npz"), dt=dt, dc=dc, w=w, dc2=dc2, w2=w2, w_step4=w3, w_eps=w4)
     print("compute_var", dt.shape, dc.shape, w[:4])
 
 

@@ -51,10 +51,14 @@ def test_normvar_golden(case):
 
 
 @gpu
-def test_normvar_against_oracle_shapes_and_chunks(monkeypatch):
+@pytest.mark.parametrize("chebyshev", [True, False])
+def test_normvar_against_oracle_shapes_and_chunks(monkeypatch, chebyshev):
+    """Both sources of the per-gene Gram matrices: interpolation in wt (default; also the only one beyond 12
+    covariates) and the streaming statistics pass."""
     from normalisr_b200 import norm as nv
+    monkeypatch.setattr(nv, "_USE_CHEBYSHEV", chebyshev)
     rng = np.random.default_rng(41)
-    for genes, n, nc in ((37, 300, 1), (500, 3000, 9), (260, 1001, 12), (64, 128, 5)):
+    for genes, n, nc in ((37, 300, 1), (500, 3000, 9), (260, 1001, 12), (64, 128, 5)) + (((90, 700, 16),) if chebyshev else ()):
         dc = np.concatenate([rng.normal(size=(nc - 1, n)), np.ones((1, n))]) if nc > 1 else np.ones((1, n))
         if nc >= 5:
             dc[1] = rng.random(n) < 0.3                       # a categorical covariate (cat = 1 leaves it alone)
@@ -76,6 +80,9 @@ def test_oracle_compute_var_matches_reference():
     g = load_golden("compute_var")
     np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc"]), g["w"], rtol=1e-12)
     np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc2"]), g["w2"], rtol=1e-12)
+    np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc"], stepmax=4), g["w_step4"], rtol=1e-12)
+    np.testing.assert_allclose(orc.compute_var(g["dt"], g["dc"], stepmax=50, eps=1e-3), g["w_eps"], rtol=1e-12)
+    assert np.abs(g["w_step4"] / g["w"] - 1).max() > 1e-3           # the iterations do move the result
     with pytest.raises(ValueError):
         orc.compute_var(g["dt"], g["dc"][:, :-1])
 
@@ -91,6 +98,11 @@ def test_compute_var_golden_and_oracle(monkeypatch):
     dev = norm.compute_var(torch.from_numpy(g["dt"]).cuda(), torch.from_numpy(g["dc"]).cuda())
     assert dev.is_cuda
     np.testing.assert_allclose(dev.cpu().numpy(), g["w"], rtol=1e-10)
+    # EM-like iterations (stepmax > 1, norm.py:97-121), fixed count and tolerance stop
+    np.testing.assert_allclose(norm.compute_var(g["dt"], g["dc"], stepmax=4), g["w_step4"], rtol=1e-9)
+    np.testing.assert_allclose(norm.compute_var(g["dt"], g["dc"], stepmax=50, eps=1e-3), g["w_eps"], rtol=1e-9)
+    dev = norm.compute_var(torch.from_numpy(g["dt"]).cuda(), torch.from_numpy(g["dc"]).cuda(), stepmax=4)
+    np.testing.assert_allclose(dev.cpu().numpy(), g["w_step4"], rtol=1e-9)
     rng = np.random.default_rng(14)
     n, genes = 3000, 900
     dc = np.concatenate([rng.normal(size=(4, n)), (rng.random((2, n)) < 0.3).astype(float), np.ones((1, n))])
@@ -103,8 +115,7 @@ def test_compute_var_golden_and_oracle(monkeypatch):
         norm.compute_var(dt, dc[:, :-1])
     with pytest.raises(ValueError):
         norm.compute_var(dt, dc, eps=0)
-    with pytest.raises(NotImplementedError):
-        norm.compute_var(dt, dc, stepmax=3)
+    np.testing.assert_allclose(norm.compute_var(dt, dc, stepmax=3), orc.compute_var(dt, dc, stepmax=3), rtol=1e-9)   # chunked + iterated
 
 
 @gpu
@@ -120,7 +131,31 @@ def test_normvar_errors():
     with pytest.raises(RuntimeError):
         norm.normvar(dt + 1, np.zeros((2, 10)), w, wt)        # zero-rank covariates (norm.py:161)
     with pytest.raises(NotImplementedError):
-        norm.normvar(np.zeros((4, 40)), np.ones((13, 40)), np.ones(40), wt)
+        norm.normvar(np.zeros((4, 40)), np.ones((17, 40)), np.ones(40), wt)
+
+
+@gpu
+def test_normvar_wide_weight_range_uses_more_pieces_or_falls_back():
+    """Weights spanning orders of magnitude: the interpolation cuts the wt range into more pieces, and beyond
+    its limit the Gram matrices come from the streaming pass - same results either way."""
+    from normalisr_b200 import norm as nv
+    rng = np.random.default_rng(43)
+    genes, n, nc = 200, 1500, 6
+    dc = np.concatenate([rng.normal(size=(nc - 1, n)), np.ones((1, n))])
+    dt = rng.normal(size=(genes, n)) - 5.0
+    for sd, top, fallback in ((1.5, 3.0, False), (3.0, 60.0, True)):
+        w = np.exp(rng.normal(size=n) * sd)
+        wt = rng.uniform(0, top, size=genes)
+        G = nv._gram_chebyshev(torch.from_numpy(dc).cuda(), torch.log(torch.from_numpy(w).cuda()), torch.from_numpy(wt).cuda())
+        assert (G is None) == fallback
+        if not fallback:
+            want = np.einsum('gk,ik,jk->gij', w[None, :] ** (2 * wt[:, None]), dc, dc)
+            scale = np.einsum('gk,ik,jk->gij', w[None, :] ** (2 * wt[:, None]), np.abs(dc), np.abs(dc))
+            assert (np.abs(G.cpu().numpy() - want) <= 1e-13 * scale).all()
+        if top <= 3.0:
+            want = orc.normvar(dt, dc, w, wt)
+            got = nv.normvar(dt, dc, w, wt)
+            np.testing.assert_allclose(got[0], want[0], rtol=1e-8, atol=1e-8 * np.abs(want[0]).max())
 
 
 @gpu
