@@ -204,7 +204,7 @@ def _residualize_groupings(ctx, dx, Qt_dev, n_slices, keep_coef, exact=True):
     instead of 8 and is exact in x; anything else takes the general route.  Returns (Sliced, raw device
     matrix)."""
     xd = _to_device_f64(ctx, dx)
-    if exact:
+    if exact and (Qt_dev is None or Qt_dev.shape[0] <= MAX_RANK):
         A, status = engine.residualize_exact(ctx, xd, Qt_dev, keep_coef=keep_coef)
         if int(status.item()) == 0:
             return A, xd
@@ -347,9 +347,10 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
         return association_tests_single1(dx, dy, dc, lowmem=lowmem, return_dot=return_dot,
                                          dimreduce=dimreduce, device=device, **ka)
     if single == 4:
-        from .single4 import association_tests_single4
-        if samexy:
-            raise NotImplementedError('single=4 with dy=None is not on the accelerated path.')  # replaced below
+        from .single4 import association_tests_single4, association_tests_single4_same
+        if samexy:                                                               # association.py:492-496
+            return association_tests_single4_same(dx, dc, lowmem=lowmem, return_dot=return_dot, dimreduce=dimreduce,
+                                                  device=device, **ka)
         return association_tests_single4(dx, dy, dc, lowmem=lowmem, return_dot=return_dot,
                                          dimreduce=dimreduce, precision=precision, device=device,
                                          engine=eng, exact_groupings=exact_groupings, **ka)
@@ -363,8 +364,6 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     if nc == 0:
         logging.warning('No covariate dc input.')
     Qt_dev, rank, W = covariate_basis_device(ctx, dc)
-    if rank > MAX_RANK:
-        raise NotImplementedError('covariate rank {} > {}'.format(rank, MAX_RANK))
     if n <= rank + dimreduce + 1:
         raise ValueError('Insufficient number of cells: must be greater than degrees of freedom '
                          'removed + covariate + 1.')

@@ -112,6 +112,19 @@ def residualize(ctx, X, Qt, n_slices, out=None, row_offset=0, keep_coef=False):
     if out is None:
         out = Sliced(rows, n, n_slices, X.device)
         row_offset = 0
+    if rank > _lib.MAX_RANK:
+        # more covariates than the fused kernels stage in shared memory (NSR_MAX_RANK): project with two
+        # float64 library GEMMs into a temporary (in row blocks), then quantise that without covariates
+        step = max(1, (1 << 28) // max(1, n))
+        for r0 in range(0, rows, step):
+            xb = X[r0:r0 + step]
+            cf = xb @ Qt.T
+            residualize(ctx, (xb - cf @ Qt).contiguous(), None, n_slices, out=out, row_offset=row_offset + r0)
+            if keep_coef:
+                if out.coef is None:
+                    out.coef = torch.zeros((out.rows, rank), dtype=torch.float64, device=X.device)
+                out.coef[row_offset + r0:row_offset + r0 + xb.shape[0]] = cf
+        return out
     assert out.n == n and out.n_slices == n_slices and row_offset + rows <= out.rows
     coef = None
     if keep_coef and rank:

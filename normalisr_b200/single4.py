@@ -114,6 +114,114 @@ def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
     return res
 
 
+def pair_stats(K, n):
+    """single=4 with dy=None (association.py:517-556 for ``prody is None``): every pair x < y is tested
+    with ALL other rows and the covariates held fixed.  With K = the inverse of the Gram matrix of the
+    covariate-residualised rows (the dx block of the precision matrix of [dx; dc]), the conditional 2 x 2
+    Gram matrix of (x, y) given the rest is the inverse of [[K_xx, K_xy], [K_xy, K_yy]], so
+        dxx = K_yy / det / n,  dyy = K_xx / det / n,  dxy = -K_xy / det / n,  det = K_xx K_yy - K_xy^2,
+        gamma = dxy / dxx = -K_xy / K_yy,   R^2 = dxy^2 / (dxx dyy) = K_xy^2 / (K_xx K_yy)
+    instead of one pseudo-inverse of an (nx + nc - 2) matrix per pair.  Returns (r2, gamma, dyy), (nx, nx),
+    meaningful for x != y."""
+    kd = torch.diagonal(K)
+    kk = kd[:, None] * kd[None, :]
+    det = kk - K * K
+    return K * K / kk, -K / kd[None, :], kd[:, None] / det / n
+
+
+def pair_alpha(K, B):
+    """alpha of the same test when lowmem is off (association.py:551-553): coefficients on the covariates of
+    the regressions of y and of x on everything but the pair, alpha = c_y - gamma c_x.  B (nx, nc) = the
+    regression coefficients of every row on the covariates alone; the covariate columns of the precision
+    matrix are -K B, and leaving one variable out of a regression is a rank-one update of it."""
+    kd = torch.diagonal(K)
+    Oc = -(K @ B)                                                    # (nx, nc)
+    ratio_y = K / kd[None, :]                                        # K_xy / K_yy
+    ratio_x = K / kd[:, None]                                        # K_xy / K_xx
+    cx = -(Oc[:, None, :] - ratio_y[:, :, None] * Oc[None, :, :]) / (kd[:, None] - K * ratio_y)[:, :, None]
+    cy = -(Oc[None, :, :] - ratio_x[:, :, None] * Oc[:, None, :]) / (kd[None, :] - K * ratio_x)[:, :, None]
+    gamma = -ratio_y
+    return cy - gamma[:, :, None] * cx
+
+
+def association_tests_single4_same(dx, dc, lowmem=True, return_dot=True, dimreduce=0, device=None, **ka):
+    """``association_tests(dx, None, dc, single=4)``: returns (P, dot|gamma, alpha|None, None, vary) with the
+    reference's assembly (association.py:1036-1065; note :1040 - the coefficient is multiplied by vary)."""
+    from .association import covariate_basis_device, _to_device_f64, _is_dev, _out
+    tol = ka.pop('tol', 1e-8)
+    if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
+        raise NotImplementedError('normalisr_b200 implements the exact SVD branch of inv_rank only '
+                                  '(method auto/scipy, mpc=0).')
+    ka.pop('qr', None)
+    for k in ('precision', 'engine', 'exact_groupings'):
+        ka.pop(k, None)
+    if ka:
+        raise TypeError("association_test_4() got an unexpected keyword argument '{}'".format(next(iter(ka))))
+    to_host = not _is_dev(dx)
+    ctx = engine.context(device if device is not None else (dx.device if _is_dev(dx) else None))
+    nx, n = dx.shape
+    nc = dc.shape[0]
+    if nx == 0 or n == 0:
+        raise ValueError('Dimensions in na==0 detected.')
+    if nc == 0:
+        logging.warning('No covariate dc input.')
+    Qt_dev, rank_c, W = covariate_basis_device(ctx, dc, tol=tol)
+    if rank_c > MAX_RANK:
+        raise NotImplementedError('covariate rank {} > {}'.format(rank_c, MAX_RANK))
+    dof = n - 1 - (max(nx - 2, 0) + rank_c) - dimreduce
+    if dof <= 0:
+        raise RuntimeError('Insufficient number of cells: must be greater than degrees of '
+                           'freedom removed + covariate + 1.')
+    with torch.cuda.device(ctx.device):
+        dev = ctx.device
+        xd = _to_device_f64(ctx, dx)
+        if rank_c:
+            cf, _ = engine.project_coef(ctx, xd, Qt_dev)
+        else:
+            cf = torch.zeros((nx, 0), dtype=torch.float64, device=dev)
+        G = engine.gram_f64(ctx, xd, cf)                             # Gram matrix of the residualised rows
+        eye = torch.eye(nx, dtype=torch.float64, device=dev)
+        K, status = engine.de4_solve(ctx, G, eye, torch.ones(nx, dtype=torch.float64, device=dev), n, rank_c, 0, tol,
+                                     False)[4:6]                     # w = G^-1 I
+        if int(status.item()) & 1:
+            raise NotImplementedError('single=4 with dy=None needs rows that are linearly independent given the '
+                                      'covariates (the rank-deficient case is not accelerated).')
+        K = 0.5 * (K + K.T)
+        r2, gamma, dyy = pair_stats(K, n)
+        off = ~torch.eye(nx, dtype=torch.bool, device=dev)
+        if not bool(((r2[off] >= 0) & (r2[off] <= 1 + 1e-8)).all()):                     # :557
+            raise AssertionError('R^2 outside [0, 1]: collinear rows?')
+        P = engine.pvalue(ctx, torch.where(off, r2, torch.zeros_like(r2)).contiguous(),
+                          torch.full((nx,), dof / 2, dtype=torch.float64, device=dev))
+        up = torch.triu(torch.ones((nx, nx), dtype=torch.bool, device=dev), 1)
+        zero = torch.zeros_like(P)
+
+        def sym(t):                                                  # triu(., 1) + transpose (:1049-1056)
+            t = torch.where(up, t, zero)
+            return t + t.T
+        P = sym(P)
+        vary = sym(dyy)
+        vary.diagonal().fill_(1.0)                                   # :1054
+        out2 = sym(gamma * dyy)                                      # :1040, :1055-1056
+        if not return_dot:
+            out2 = out2 / vary                                       # :1061
+        alpha = None
+        if not lowmem:                                               # :1063-1065
+            if rank_c:
+                al = pair_alpha(K, cf @ torch.from_numpy(W).to(dev))
+            else:
+                al = torch.zeros((nx, nx, nc), dtype=torch.float64, device=dev)
+            al = torch.where(up[:, :, None], al, torch.zeros_like(al))
+            alpha = (al + al.transpose(0, 1)).contiguous()
+        if not bool(torch.isfinite(P).all() & torch.isfinite(out2).all() & torch.isfinite(vary).all()):
+            raise AssertionError('non-finite result')                # :1077
+        res = (P, out2, alpha, None, vary)
+        if to_host:
+            torch.cuda.current_stream().synchronize()
+            res = tuple(_out(t, True) for t in res)
+    return res
+
+
 def loo_stats(Gxx, Gxy, yy, n, rank_c, tol=1e-8):
     """Leave-one-out regression statistics of association_test_4 (association.py:521-544)
     from Gram matrices of covariate-residualised rows: Gxx = Rx Rx^T (nx, nx),

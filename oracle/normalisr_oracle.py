@@ -178,6 +178,47 @@ def tile_single4(vx, prod, prody, prodyy, nx, nc, n, lenx, dimreduce=0, pvalue_b
     return pv, gam, varx, vary
 
 
+def tile_single4_same(prod, nx, nc, n, dimreduce=0, lowmem=True, pvalue_backend="auto", **ka):
+    """association_test_4 with dx == dy (``prody is None``, association.py:492-496, 517-519): every pair
+    x < y is tested with ALL other rows of [dx; dc] as covariates - neither x nor y is one (:523-526).
+    Returns (pv, gamma, vary, alpha|None) with entries for x < y only (zeros elsewhere)."""
+    m = nx + nc
+    pv = np.zeros((nx, nx))
+    gam = np.zeros((nx, nx))
+    vary = np.zeros((nx, nx))
+    rank = np.zeros((nx, nx), dtype=int)
+    alpha = None if lowmem else np.zeros((nx, nx, nc))
+    for x in range(nx):
+        for y in range(x + 1, nx):
+            oth = [k for k in range(m) if k != x and k != y]
+            r = 0
+            if oth:
+                ginv, r = pinv_rank(prod[np.ix_(oth, oth)], **ka)
+            rank[x, y] = r
+            if r == 0:
+                dxx, dyy, dxy = prod[x, x] / n, prod[y, y] / n, prod[x, y] / n
+            else:
+                cx = prod[x, oth] @ ginv
+                dxx = (prod[x, x] - cx @ prod[oth, x]) / n
+                cy = prod[oth, y] @ ginv
+                dyy = (prod[y, y] - cy @ prod[oth, y]) / n
+                dxy = (prod[x, y] - cy @ prod[oth, x]) / n
+            if dxx == 0:
+                dxx = 1
+            vary[x, y] = dyy
+            gam[x, y] = dxy / dxx
+            if not lowmem and r > 0 and nc > 0:                       # :551-553
+                alpha[x, y] = cy[-nc:] - gam[x, y] * cx[-nc:]
+            pv[x, y] = dxy * dxy / (dxx * dyy)
+    assert (pv >= 0).all() and (pv <= 1 + 1e-8).all()
+    dof = n - 1 - rank - dimreduce
+    if (dof <= 0).any():
+        raise RuntimeError("Insufficient number of cells: must be greater than degrees of "
+                           "freedom removed + covariate + 1.")
+    pv = beta_cdf(1 - pv, dof / 2, 0.5, backend=pvalue_backend)
+    return pv, gam, vary, alpha
+
+
 # --------------------------------------------------------------------------------------
 # _auto_batchsize / association_tests                     (association.py:731-1093)
 # --------------------------------------------------------------------------------------
@@ -248,7 +289,7 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     if samexy:
         dy = dx
         if single == 4:
-            raise NotImplementedError("oracle: single=4 with dy=None is not on the hot path")
+            return _single4_same(dx, dc, lowmem, return_dot, pvalue_backend, **ka)
     nx, ns = dx.shape
     ny = dy.shape[0]
     nc = dc.shape[0]
@@ -348,6 +389,31 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
     elif return_dot:
         coef = coef * varx[:, None]
     return P, coef, alpha, varx, vary
+
+
+def _single4_same(dx, dc, lowmem, return_dot, pvalue_backend, **ka):
+    """single=4 with dy=None: Gram matrix of [dx; dc] (:935-951), the pair loop, and the assembly of
+    association.py:1036-1065 for this case (note :1040: the coefficient is multiplied by vary, not varx)."""
+    nx, ns = dx.shape
+    nc = dc.shape[0]
+    dimreduce = ka.pop("dimreduce", 0)
+    A = np.concatenate([dx, dc], axis=0)
+    prod = A @ A.T
+    pv, gam, vary, alpha = tile_single4_same(prod, nx, nc, ns, dimreduce, lowmem, pvalue_backend, **ka)
+    dot = gam * vary                                   # :1040
+    P = np.triu(pv, 1)
+    P = P + P.T                                        # :1049-1050
+    vary = np.triu(vary, 1)
+    vary = vary + vary.T
+    vary[np.arange(nx), np.arange(nx)] = 1             # :1051-1054
+    dot = np.triu(dot, 1)
+    dot = dot + dot.T                                  # :1055-1056
+    if not return_dot:
+        dot = dot / vary                               # :1061
+    if not lowmem:
+        a = np.triu(alpha.transpose(2, 0, 1))
+        alpha = (a + a.transpose(0, 2, 1)).transpose(1, 2, 0)       # :1063-1065
+    return P, dot, alpha, None, vary
 
 
 # --------------------------------------------------------------------------------------

@@ -238,6 +238,22 @@ def test_many_covariates():
     _check_coex(norm.coex(dt, dc), orc.coex(dt, dc))
 
 
+def test_more_covariates_than_the_kernels_stage():
+    """rank 70 > NSR_MAX_RANK = 64: the projection falls back to float64 library GEMMs into a temporary and
+    the kernels quantise without covariates - same results (coex and de, alpha included)."""
+    rng = np.random.default_rng(23)
+    n, g = 1200, 40
+    dc = np.concatenate([rng.normal(size=(69, n)), np.ones((1, n))])
+    dt = rng.normal(size=(g, n)) + 0.3 * dc[:5].sum(0)
+    _check_coex(norm.coex(dt, dc), orc.coex(dt, dc))
+    dg = (rng.random((6, n)) < 0.2).astype(float)
+    got, want = norm.de(dg, dt, dc, lowmem=False), orc.de(dg, dt, dc, lowmem=False)
+    assert_p_close(got[0], want[0])
+    scale = np.sqrt(want[4] / want[3][:, None])           # gamma = r sqrt(vart / varg): the |delta r| <= 1e-6 bound
+    assert (np.abs(got[1] - want[1]) <= R_ATOL * scale + 1e-12).all()
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-5, atol=1e-5 * np.abs(want[2]).max())
+
+
 def test_errors_match_reference():
     x = np.random.default_rng(0).normal(size=(4, 5))
     with pytest.raises(ValueError):
@@ -615,6 +631,43 @@ def test_all_devices_one_process():
     for single in (0, 4):
         r1, rn = norm.de(dg, dt, dc, single=single), norm.de(dg, dt, dc, single=single, devices="all")
         assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(r1, rn))
+
+
+def test_single4_same_golden_and_oracle():
+    """single=4 with dy=None (association.py:492-496, 517-556, 1036-1065): one inverse of the residualised Gram
+    matrix instead of one pseudo-inverse per pair; reference goldens (incl. alpha, gamma, dimreduce,
+    rank-deficient covariates) and a larger oracle case through coex(..., single=4)."""
+    g = load_golden("single4_same")
+    nx = g["dx"].shape[0]
+    iu = np.triu_indices(nx, 1)
+    for name, ka in (("lowmem", {}), ("alpha", dict(lowmem=False)), ("gamma", dict(return_dot=False)),
+                     ("dimreduce", dict(dimreduce=3))):
+        r = association.association_tests(g["dx"], None, g["dc"], single=4, **ka)
+        assert_p_close(r[0][iu], g["P_" + name][iu])
+        np.testing.assert_allclose(r[0], g["P_" + name], rtol=1e-4, atol=1e-300)
+        np.testing.assert_allclose(r[1], g["dot_" + name], rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(r[4], g["vary_" + name], rtol=1e-9)
+        assert r[3] is None and (r[0].diagonal() == 0).all() and (r[4].diagonal() == 1).all()
+        if not ka.get("lowmem", True):
+            np.testing.assert_allclose(r[2], g["alpha_" + name], rtol=1e-7, atol=1e-10)
+    r = association.association_tests(g["dx"], None, g["dc2"], single=4, lowmem=False)
+    assert_p_close(r[0][iu], g["P_rankdef"][iu])
+    np.testing.assert_allclose(r[2], g["alpha_rankdef"], rtol=1e-7, atol=1e-10)
+    rng = np.random.default_rng(77)
+    n, nx = 2500, 40
+    dc = np.concatenate([rng.normal(size=(3, n)), np.ones((1, n))])
+    dx = rng.normal(size=(nx, n)) + rng.normal(size=(nx, 4)) @ rng.normal(size=(4, n))
+    want = orc.coex(dx, dc, single=4)
+    got = norm.coex(dx, dc, single=4)
+    iu = np.triu_indices(nx, 1)
+    assert_p_close(got[0][iu], want[0][iu])
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-9)
+    assert want[0][iu].min() < 1e-50
+    dev = association.association_tests(torch.from_numpy(dx).cuda(), None, torch.from_numpy(dc).cuda(), single=4)
+    assert dev[0].is_cuda and np.allclose(dev[0].cpu().numpy(), got[0], rtol=1e-12, atol=0)
+    with pytest.raises(NotImplementedError):                        # linearly dependent rows
+        association.association_tests(np.concatenate([dx, dx[:1] + dx[1:2]]), None, dc, single=4)
 
 
 def test_nonfinite_input_raises():

@@ -92,3 +92,22 @@ def test_errors():
         orc.coex(np.zeros((3, 4)), np.random.default_rng(0).normal(size=(3, 4)))  # n <= rank + 1
     with pytest.raises(ValueError):
         orc.association_tests(np.zeros((3, 9)), None, np.ones((1, 9)), single=7)
+
+
+def test_oracle_single4_same_matches_reference():
+    """association_tests(dx, None, dc, single=4): every pair with all other rows as covariates
+    (association.py:492-496, 517-556, 1036-1065)."""
+    g = load_golden("single4_same")
+    iu = np.triu_indices(g["dx"].shape[0], 1)
+    for name, ka in (("lowmem", {}), ("alpha", dict(lowmem=False)), ("gamma", dict(return_dot=False)),
+                     ("dimreduce", dict(dimreduce=3))):
+        r = orc.association_tests(g["dx"], None, g["dc"], single=4, **ka)
+        np.testing.assert_allclose(r[0][iu], g["P_" + name][iu], rtol=1e-10)
+        np.testing.assert_allclose(r[1], g["dot_" + name], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(r[4], g["vary_" + name], rtol=1e-10)
+        assert r[3] is None and (r[0].diagonal() == 0).all()
+        if not ka.get("lowmem", True):
+            np.testing.assert_allclose(r[2], g["alpha_" + name], rtol=1e-9, atol=1e-12)
+    r = orc.association_tests(g["dx"], None, g["dc2"], single=4, lowmem=False)
+    np.testing.assert_allclose(r[0][iu], g["P_rankdef"][iu], rtol=1e-10)
+    np.testing.assert_allclose(r[2], g["alpha_rankdef"], rtol=1e-9, atol=1e-12)
