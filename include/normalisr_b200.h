@@ -336,7 +336,7 @@ int nsr_last_refined(nsr_ctx* ctx, uintptr_t stream, int64_t n_tiles, int64_t* r
  *                      non-zero count (per-cell normaliser :155-157 and the covariates :193-199 from one
  *                      pass over the counts; without resampling the exponentials are a table gather);
  *                      minmax (device, 2 x int64, optional, initialised by the caller to INT64_MAX /
- *                      INT64_MIN, accumulated): smallest NEGATIVE count (the check :88-89) and largest count;
+ *                      INT64_MIN, accumulated): [0] turns negative if any count is (the check :88-89), [1] = largest count;
  *   nsr_lcpm_apply     out[g][k] = value[g][k] - shift[k]  (shift may be NULL).
  * value = lut[reads] or, with posterior resampling (varscale != 0, :134-150), lut[reads] + lut_sd[reads] z
  * with lut_sd[c] = sqrt(varscale (trigamma(1 + c) - trigamma(total + 2))) and z a standard normal

@@ -85,7 +85,8 @@ def covariate_basis(dc, tol=1e-8):
     return np.ascontiguousarray(Linv @ q0), rank, W
 
 
-_BASIS_CACHE = {}        # device index -> (key, result): the basis of the most recent covariate TENSOR
+_BASIS_CACHE = {}        # device index -> [(key, result, tensor)]: the bases of the most recent covariate TENSORS
+_BASIS_CACHE_LEN = 4
 
 
 def covariate_basis_device(ctx, dc, tol=1e-8):
@@ -97,16 +98,25 @@ def covariate_basis_device(ctx, dc, tol=1e-8):
     coex / de calls with the same covariates skip the two small device->host round trips of the
     factorisation."""
     nc, n = dc.shape
-    key = None
-    if _is_dev(dc) and dc.device == ctx.device:
-        key = (dc.data_ptr(), dc._version, tuple(dc.shape), tuple(dc.stride()), dc.dtype, float(tol))
-        hit = _BASIS_CACHE.get(ctx.device.index)
-        if hit is not None and hit[0] == key:
-            return hit[1]
+    key = basis_cache_key(ctx, dc, tol)
+    if key is not None:
+        for hit in _BASIS_CACHE.get(ctx.device.index, ()):
+            if hit[0] == key:
+                return hit[1]
     res = _covariate_basis_device(ctx, dc, tol)
     if key is not None:
-        _BASIS_CACHE[ctx.device.index] = (key, res, dc)      # holding dc keeps its storage from being reused
+        # holding dc keeps its storage from being reused under the same key
+        entries = _BASIS_CACHE.setdefault(ctx.device.index, [])
+        entries.insert(0, (key, res, dc))
+        del entries[_BASIS_CACHE_LEN:]
     return res
+
+
+def basis_cache_key(ctx, dc, tol=1e-8, tag=None):
+    """Identity of an unmodified CUDA covariate tensor (None for anything else)."""
+    if _is_dev(dc) and dc.device == ctx.device:
+        return (dc.data_ptr(), dc._version, tuple(dc.shape), tuple(dc.stride()), dc.dtype, float(tol), tag)
+    return None
 
 
 def _covariate_basis_device(ctx, dc, tol):

@@ -96,41 +96,48 @@ lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int6
                      double* __restrict__ partial, long long* __restrict__ minmax) {
     const int64_t k = (int64_t)blockIdx.x * kLcThreads + threadIdx.x;
     const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
-    double se = 0.0, tot = 0.0, nz = 0.0;
-    long long mn = LLONG_MAX, mx = LLONG_MIN;
+    // everything but the sum of exponentials stays in the counts' own integer type until the end (a gene
+    // range holds 64 counts: the total is kept in 64 bits); negativity = the OR of the sign bits
+    double se = 0.0;
+    unsigned long long tot = 0;
+    int nz = 0;
+    T any_or = 0, mx = 0;
+    const T len_t = (T)(lut_len > (int64_t)INT_MAX ? (int64_t)INT_MAX : lut_len);
     if (k < n) {
+        const T* col = reads + k;
 #pragma unroll 8
         for (int64_t g = g0; g < g1; ++g) {
-            const long long c = (long long)reads[g * ld + k];
-            const long long ci = c < 0 ? 0 : (c >= lut_len ? lut_len - 1 : c);
+            const T c = col[g * ld];
+            const T ci = c < 0 ? (T)0 : (c >= len_t ? (T)(len_t - 1) : c);
             if (NOISY) {
                 const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
                                            : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
                 se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
             } else {
                 // exp(lut[c]) tabulated: the pass is a pure gather (counts beyond the table: computed)
-                se += c < lut_len ? lut_exp[ci] : exp(lc_digamma(1.0 + (double)c));
+                se += c < len_t ? lut_exp[ci] : exp(lc_digamma(1.0 + (double)c));
             }
-            tot += (double)c;
-            nz += c != 0 ? 1.0 : 0.0;
-            mn = c < mn ? c : mn;
+            tot += (unsigned long long)(long long)c;
+            nz += c != 0 ? 1 : 0;
+            any_or |= c;
             mx = c > mx ? c : mx;
         }
         double* o = partial + ((int64_t)blockIdx.y * 3) * n + k;
         o[0] = se;
-        o[n] = tot;
-        o[2 * n] = nz;
+        o[n] = (double)(long long)tot;
+        o[2 * n] = (double)nz;
     }
     if (minmax != nullptr) {                         // negativity check and largest count from the same read
+        long long neg = any_or < 0 ? -1 : 0, m = (long long)mx;
 #pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            const long long a = __shfl_xor_sync(0xffffffffu, mn, m), b = __shfl_xor_sync(0xffffffffu, mx, m);
-            mn = a < mn ? a : mn;
-            mx = b > mx ? b : mx;
+        for (int d = 16; d >= 1; d >>= 1) {
+            neg |= __shfl_xor_sync(0xffffffffu, neg, d);
+            const long long b = __shfl_xor_sync(0xffffffffu, m, d);
+            m = b > m ? b : m;
         }
-        if ((threadIdx.x & 31) == 0 && mn <= mx) {
-            if (mn < 0) atomicMin(minmax, mn);       // rare: most launches never touch the words
-            if (mx > *(volatile long long*)(minmax + 1)) atomicMax(minmax + 1, mx);
+        if ((threadIdx.x & 31) == 0) {
+            if (neg < 0) atomicMin(minmax, -1ll);    // "some count is negative" (lcpm.py:88-89); rare
+            if (m > *(volatile long long*)(minmax + 1)) atomicMax(minmax + 1, m);
         }
     }
 }
@@ -238,62 +245,92 @@ extern "C" int nsr_lcpm_apply(nsr_ctx* ctx, uintptr_t stream, const void* reads,
 // blockIdx.y and combined in a fixed order.
 namespace {
 
-constexpr int kCvRank = 16;            // covariate rank handled in registers
-constexpr int kCvCells = 2;            // cells per thread: a gene's coefficients are read once for both
+constexpr int kCvRank = 16;            // covariate rank handled (4 k-steps of the FP64 MMA)
+constexpr int kCvGenes = 256;          // genes per CTA (blockIdx.y), combined in a fixed order afterwards
+constexpr int kCvWarps = kLcThreads / 32;
+constexpr int kCvCells = 16;           // cells per warp: two 8-cell MMA tiles
 
-// RK: rank rounded up to a multiple of 4 (zero-padded coefficients): the inner product is unrolled over RK
-template <int RK>
+__device__ __forceinline__ void cv_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// The residual tile X - coef Qt comes out of the FP64 tensor cores (A = -coef: 8 genes x 4 covariates per
+// MMA, B = Qt: 4 covariates x 8 cells, fixed per warp and kept in registers, accumulator initialised with the
+// X tile); lane (g, t) then holds gene g, cells 2 t and 2 t + 1 of each tile, standardises and squares
+// them, and sums over its genes; the eight lanes of a cell are combined with shuffles at the end.
+// KS = ceil(rank / 4).  FAST: rows are 16-byte aligned (vector loads for warps whose 16 cells all exist).
+template <int KS, bool FAST>
 __global__ void __launch_bounds__(kLcThreads)
 colvar_kernel(const double* __restrict__ X, int64_t genes, int64_t n, int64_t ld, const double* __restrict__ Qt,
               int rank, int64_t ldq, const double* __restrict__ coef, int64_t ldcoef,
               const double* __restrict__ mean, const double* __restrict__ inv_std, double* __restrict__ partial) {
-    constexpr int RS = RK > 0 ? RK : 2;
-    __shared__ __align__(16) double s_coef[kLcGeneSplit][RS];
-    __shared__ double s_mean[kLcGeneSplit], s_istd[kLcGeneSplit];
-    const int64_t g0 = (int64_t)blockIdx.y * kLcGeneSplit, g1 = min(genes, g0 + kLcGeneSplit);
-    for (int idx = threadIdx.x; idx < kLcGeneSplit * RS; idx += kLcThreads) {
-        const int g = idx / RS, j = idx % RS;
-        s_coef[g][j] = (g0 + g < g1 && j < rank) ? coef[(g0 + g) * ldcoef + j] : 0.0;
-    }
-    for (int g = threadIdx.x; g < kLcGeneSplit; g += kLcThreads) {
-        s_mean[g] = g0 + g < g1 ? mean[g0 + g] : 0.0;
-        s_istd[g] = g0 + g < g1 ? inv_std[g0 + g] : 0.0;
-    }
-    __syncthreads();
-    int64_t k[kCvCells];
-    bool ok[kCvCells];
-    double q[kCvCells][RS], acc[kCvCells];
+    constexpr int U = kCvCells / 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int64_t c0 = ((int64_t)blockIdx.x * kCvWarps + warp) * kCvCells;
+    if (c0 >= n) return;
+    const int64_t g0 = (int64_t)blockIdx.y * kCvGenes, g1 = min(genes, g0 + kCvGenes);
+    const bool full = FAST && c0 + kCvCells <= n;
+    double bq[U][KS > 0 ? KS : 1], acc[U][2];
 #pragma unroll
-    for (int u = 0; u < kCvCells; ++u) {
-        k[u] = ((int64_t)blockIdx.x * kCvCells + u) * kLcThreads + threadIdx.x;
-        ok[u] = k[u] < n;
-        acc[u] = 0.0;
+    for (int u = 0; u < U; ++u) {
+        acc[u][0] = acc[u][1] = 0.0;
+        const int64_t cb = c0 + 8 * u + g;
 #pragma unroll
-        for (int j = 0; j < RS; ++j) q[u][j] = (ok[u] && j < rank) ? Qt[(int64_t)j * ldq + k[u]] : 0.0;
-    }
-    if (!ok[0]) return;
-#pragma unroll 4
-    for (int64_t g = g0; g < g1; ++g) {
-        double r[kCvCells];
-#pragma unroll
-        for (int u = 0; u < kCvCells; ++u) r[u] = ok[u] ? X[g * ld + k[u]] : 0.0;
-        const double2* cf = reinterpret_cast<const double2*>(s_coef[g - g0]);
-#pragma unroll
-        for (int j = 0; j < RK / 2; ++j) {
-            const double2 c2 = cf[j];
-#pragma unroll
-            for (int u = 0; u < kCvCells; ++u) r[u] = fma(-c2.y, q[u][2 * j + 1], fma(-c2.x, q[u][2 * j], r[u]));
-        }
-        const double m = s_mean[g - g0], is = s_istd[g - g0];
-#pragma unroll
-        for (int u = 0; u < kCvCells; ++u) {
-            const double z = (r[u] - m) * is;
-            acc[u] = fma(z, z, acc[u]);
+        for (int kk = 0; kk < KS; ++kk) {
+            const int j = 4 * kk + t;
+            bq[u][kk] = (j < rank && cb < n) ? Qt[(int64_t)j * ldq + cb] : 0.0;
         }
     }
+#pragma unroll 2
+    for (int64_t gt = g0; gt < g1; gt += 8) {
+        const int64_t gene = gt + g;
+        const bool live = gene < g1;
+        const int64_t gl = live ? gene : g0;
+        double a[KS > 0 ? KS : 1];
 #pragma unroll
-    for (int u = 0; u < kCvCells; ++u)
-        if (ok[u]) partial[(int64_t)blockIdx.y * n + k[u]] = acc[u];
+        for (int kk = 0; kk < KS; ++kk) {
+            const int j = 4 * kk + t;
+            a[kk] = (live && j < rank) ? -coef[gl * ldcoef + j] : 0.0;
+        }
+        const double m = mean[gl], is = live ? inv_std[gl] : 0.0;
+        const double* row = X + gl * ld + c0 + 2 * t;
+        double d[U][2];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (full) {
+                const double2 v = *reinterpret_cast<const double2*>(row + 8 * u);
+                d[u][0] = v.x; d[u][1] = v.y;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) d[u][e] = (c0 + 8 * u + 2 * t + e < n) ? row[8 * u + e] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) cv_dmma(d[u][0], d[u][1], a[kk], bq[u][kk]);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double z = (d[u][e] - m) * is;          // is = 0 for rows beyond the range
+                acc[u][e] = fma(z, z, acc[u][e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            double v = acc[u][e];
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            const int64_t k = c0 + 8 * u + 2 * t + e;
+            if (g == 0 && k < n) partial[(int64_t)blockIdx.y * n + k] = v;
+        }
+    }
 }
 
 __global__ void colvar_reduce_kernel(const double* __restrict__ partial, int64_t n, int n_split, double* __restrict__ out) {
@@ -314,17 +351,25 @@ extern "C" int nsr_colvar(nsr_ctx* ctx, uintptr_t stream, const double* X, int64
                 "nsr_colvar: bad arguments (rank %d, at most %d)", rank, kCvRank);
     NSR_CHECK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_split = (int)((genes + kLcGeneSplit - 1) / kLcGeneSplit);
+    const int n_split = (int)((genes + kCvGenes - 1) / kCvGenes);
     NSR_REQUIRE(n_split <= 65535, "nsr_colvar: too many genes for one call");
     void* scratch = nullptr;
     if (nsr_scratch(ctx, (size_t)n_split * n * sizeof(double), &scratch)) return 1;
-    const dim3 grid((unsigned)((n + kCvCells * kLcThreads - 1) / (kCvCells * kLcThreads)), (unsigned)n_split);
-#define NSR_CV(RK_) colvar_kernel<RK_><<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch)
-    if (rank == 0) NSR_CV(0);
-    else if (rank <= 4) NSR_CV(4);
-    else if (rank <= 8) NSR_CV(8);
-    else if (rank <= 12) NSR_CV(12);
-    else NSR_CV(16);
+    const int64_t cells_per_cta = (int64_t)kCvWarps * kCvCells;
+    const dim3 grid((unsigned)((n + cells_per_cta - 1) / cells_per_cta), (unsigned)n_split);
+    const bool fast = ((uintptr_t)X % 16 == 0) && (ld % 2 == 0);          // vector loads: rows 16-byte aligned
+#define NSR_CV(KS_)                                                                                                    \
+    do {                                                                                                               \
+        if (fast) colvar_kernel<KS_, true><<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch); \
+        else colvar_kernel<KS_, false><<<grid, kLcThreads, 0, st>>>(X, genes, n, ld, Qt, rank, ldq, coef, ldcoef, mean, inv_std, (double*)scratch);     \
+    } while (0)
+    switch ((rank + 3) / 4) {
+        case 0: NSR_CV(0); break;
+        case 1: NSR_CV(1); break;
+        case 2: NSR_CV(2); break;
+        case 3: NSR_CV(3); break;
+        default: NSR_CV(4); break;
+    }
 #undef NSR_CV
     colvar_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const double*)scratch, n, n_split, out);
     NSR_CHECK(cudaGetLastError());

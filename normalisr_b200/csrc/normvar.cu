@@ -72,9 +72,14 @@ __device__ __forceinline__ void nv_load4(const double* p, int64_t k, int64_t n, 
 #pragma unroll
     for (int e = 0; e < 4; ++e) v[e] = (k + e < n) ? __ldg(p + e) : 0.0;
 }
+// the same four values with two 16-byte loads (p 16-byte aligned, all four inside the row)
+__device__ __forceinline__ void nv_load4v(const double* p, double (&v)[4]) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p)), b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
 
 // M: (8 * (NTD + NTC) x n) = [D rows, zero rows up to 8 NTD | C rows, zero rows up to 8 NTC]
-template <int NTD, int NTC>
+template <int NTD, int NTC, bool VEC = false>
 __global__ void __launch_bounds__(32 * kGmWarps)
 normvar_gemm_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int64_t ld,
                     const double* __restrict__ M, int64_t ldm, const double* __restrict__ logw,
@@ -108,11 +113,22 @@ normvar_gemm_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int
     for (int64_t kk = kb; kk < ke; ++kk) {
         const int64_t k = kk * 16 + 4 * t;
         double xv[kGmTiles][4], lw[4], mv[NT][4];
+        if (VEC && kk * 16 + 16 <= n) {              // interior step, 16-byte aligned rows: no predicates
 #pragma unroll
-        for (int r = 0; r < kGmTiles; ++r) nv_load4(xr[r] + kk * 16, k, valid[r] ? n : 0, xv[r]);
-        nv_load4(logw + k, k, n, lw);
+            for (int r = 0; r < kGmTiles; ++r) {
+                if (valid[r]) nv_load4v(xr[r] + kk * 16, xv[r]);
+                else xv[r][0] = xv[r][1] = xv[r][2] = xv[r][3] = 0.0;
+            }
+            nv_load4v(logw + k, lw);
 #pragma unroll
-        for (int j = 0; j < NT; ++j) nv_load4(M + (int64_t)(8 * j + g) * ldm + k, k, n, mv[j]);
+            for (int j = 0; j < NT; ++j) nv_load4v(M + (int64_t)(8 * j + g) * ldm + k, mv[j]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < kGmTiles; ++r) nv_load4(xr[r] + kk * 16, k, valid[r] ? n : 0, xv[r]);
+            nv_load4(logw + k, k, n, lw);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) nv_load4(M + (int64_t)(8 * j + g) * ldm + k, k, n, mv[j]);
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
 #pragma unroll
@@ -161,7 +177,7 @@ __global__ void normvar_reduce_kernel(const double* __restrict__ partial, int64_
 // shared by every warp), accumulator initialised with the dt tile - so the residual comes out of the MMA
 // in the accumulator layout (lane (g, t): gene g, cells 2 t and 2 t + 1), where it is multiplied by
 // s = w ** wt and the keepvar scale and stored.  KS = ceil(nc / 4) k-steps.  No shared memory, no barrier.
-template <int KS>
+template <int KS, bool VEC>
 __global__ void __launch_bounds__(kNvThreads)
 normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, int64_t ld,
                      const double* __restrict__ dc, int nc, int64_t ldc, const double* __restrict__ logw,
@@ -187,13 +203,45 @@ normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
         }
         wt2[r] = valid[r] ? wt[gene] * kLog2e : 0.0;
         sc[r] = valid[r] ? scale[gene] : 0.0;
-        xr[r] = dt + (valid[r] ? gene : gene_w) * ld;
-        orow[r] = out + (valid[r] ? gene : gene_w) * ldo;
+        xr[r] = dt + (valid[r] ? gene : gene_w) * ld + 2 * t;
+        orow[r] = out + (valid[r] ? gene : gene_w) * ldo + 2 * t;
     }
+    const bool rows_ok = gene_w + 8 * R <= genes;        // warp-uniform: the MMAs below need all 32 lanes on one path
     const int64_t kb = (int64_t)blockIdx.y * cells_per_split, ke = min(n, kb + cells_per_split);
 #pragma unroll 1
     for (int64_t c0 = kb; c0 < ke; c0 += 8 * U) {
         double bf[U][KS], lw[U][2], d[R][U][2];
+        if (VEC && rows_ok && c0 + 8 * U <= ke) {
+            // interior step: every row and cell exists - 16-byte loads and stores, no predicates
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk) {
+                    const int j = 4 * kk + t;
+                    bf[u][kk] = j < nc ? __ldg(dc + (int64_t)j * ldc + c0 + 8 * u + g) : 0.0;
+                }
+                const double2 l2 = __ldg(reinterpret_cast<const double2*>(logw + c0 + 8 * u + 2 * t));
+                lw[u][0] = l2.x; lw[u][1] = l2.y;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const double2 v = *reinterpret_cast<const double2*>(xr[r] + c0 + 8 * u);
+                    d[r][u][0] = v.x; d[r][u][1] = v.y;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int kk = 0; kk < KS; ++kk) nv_dmma(d[r][u][0], d[r][u][1], a[r][kk], bf[u][kk]);
+                    double2 o;
+                    o.x = sc[r] * ((wt2[r] == 0.0 ? 1.0 : nv_exp2(wt2[r] * lw[u][0])) * d[r][u][0]);
+                    o.y = sc[r] * ((wt2[r] == 0.0 ? 1.0 : nv_exp2(wt2[r] * lw[u][1])) * d[r][u][1]);
+                    *reinterpret_cast<double2*>(orow[r] + c0 + 8 * u) = o;
+                }
+            }
+            continue;
+        }
         bool in[U][2];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -209,7 +257,7 @@ normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
                 in[u][e] = k < ke;
                 lw[u][e] = in[u][e] ? __ldg(logw + k) : 0.0;
 #pragma unroll
-                for (int r = 0; r < R; ++r) d[r][u][e] = (in[u][e] && valid[r]) ? xr[r][k] : 0.0;
+                for (int r = 0; r < R; ++r) d[r][u][e] = (in[u][e] && valid[r]) ? xr[r][c0 + 8 * u + e] : 0.0;
             }
         }
 #pragma unroll
@@ -221,7 +269,7 @@ normvar_apply_kernel(const double* __restrict__ dt, int64_t genes, int64_t n, in
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double s = wt2[r] == 0.0 ? 1.0 : nv_exp2(wt2[r] * lw[u][e]);
-                    if (in[u][e] && valid[r]) orow[r][c0 + 8 * u + 2 * t + e] = sc[r] * (s * d[r][u][e]);
+                    if (in[u][e] && valid[r]) orow[r][c0 + 8 * u + e] = sc[r] * (s * d[r][u][e]);
                 }
             }
         }
@@ -282,7 +330,10 @@ extern "C" int nsr_normvar_rhs(nsr_ctx* ctx, uintptr_t stream, const double* dt,
     void* scratch = nullptr;
     if (nsr_scratch(ctx, (size_t)ksplit * genes * cols * sizeof(double), &scratch)) return 1;
     const dim3 grid((unsigned)((genes + kGmWarps * 8 * kGmTiles - 1) / (kGmWarps * 8 * kGmTiles)), (unsigned)ksplit);
-    normvar_gemm_kernel<0, 2><<<grid, 32 * kGmWarps, 0, st>>>(dt, genes, n, ld, C16, ldc, logw, wt, ksplit, (double*)scratch);
+    const bool vec = ((uintptr_t)dt % 16 == 0) && ((uintptr_t)C16 % 16 == 0) && ((uintptr_t)logw % 16 == 0) &&
+                     (ld % 2 == 0) && (ldc % 2 == 0);
+    if (vec) normvar_gemm_kernel<0, 2, true><<<grid, 32 * kGmWarps, 0, st>>>(dt, genes, n, ld, C16, ldc, logw, wt, ksplit, (double*)scratch);
+    else normvar_gemm_kernel<0, 2, false><<<grid, 32 * kGmWarps, 0, st>>>(dt, genes, n, ld, C16, ldc, logw, wt, ksplit, (double*)scratch);
     const int64_t total = genes * cols;
     normvar_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const double*)scratch, genes, cols, ksplit, stats);
     NSR_CHECK(cudaGetLastError());
@@ -308,7 +359,14 @@ extern "C" int nsr_normvar_apply(nsr_ctx* ctx, uintptr_t stream, const double* d
     gy = (n + per - 1) / per;
     const dim3 grid((unsigned)gx, (unsigned)gy);
     cudaStream_t st = (cudaStream_t)stream;
-#define NSR_NV_APPLY(KS_) normvar_apply_kernel<KS_><<<grid, kNvThreads, 0, st>>>(dt, genes, n, ld, dc, nc, ldc, logw, wt, coef, scale, out, ldo, per)
+    // 16-byte accesses: rows of dt / out and log w 16-byte aligned (cell splits are multiples of 16 cells)
+    const bool vec = ((uintptr_t)dt % 16 == 0) && ((uintptr_t)out % 16 == 0) && ((uintptr_t)logw % 16 == 0) &&
+                     (ld % 2 == 0) && (ldo % 2 == 0);
+#define NSR_NV_APPLY(KS_)                                                                                              \
+    do {                                                                                                               \
+        if (vec) normvar_apply_kernel<KS_, true><<<grid, kNvThreads, 0, st>>>(dt, genes, n, ld, dc, nc, ldc, logw, wt, coef, scale, out, ldo, per); \
+        else normvar_apply_kernel<KS_, false><<<grid, kNvThreads, 0, st>>>(dt, genes, n, ld, dc, nc, ldc, logw, wt, coef, scale, out, ldo, per);     \
+    } while (0)
     switch ((nc + 3) / 4) {
         case 1: NSR_NV_APPLY(1); break;
         case 2: NSR_NV_APPLY(2); break;

@@ -17,6 +17,7 @@ import torch
 from . import _lib, engine
 
 _ROW_CHUNK_BYTES = 1 << 30
+_CENTRED = {}              # device index -> (key, (Qc, rank), tensor): basis of the centred covariates (compute_var)
 _USE_CHEBYSHEV = True      # test hook: False = Gram matrices from the streaming pass (nsr_normvar_stats)
 
 
@@ -272,7 +273,7 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
     (``nsr_colvar``); the fit of the log variances on the covariates is a rank-sized problem.
     Iterations after the first work on dt / scale and dc / scale (:99-100); the scaled block is formed
     once per iteration (one more read and write of the block), the rest is the same two passes."""
-    from .association import covariate_basis_device
+    from .association import basis_cache_key, covariate_basis_device
     if eps <= 0 or stepmax <= 0:
         raise ValueError('eps and stepmax must be positive.')
     if dt.ndim != 2 or dc.ndim != 2:
@@ -289,8 +290,14 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
         step = nt if not to_host else max(1, _ROW_CHUNK_BYTES // (8 * ns))
         ones = torch.ones((1, ns), dtype=torch.float64, device=dev)
         # log-linear fit with intercept (:104-105, on the UNSCALED covariates): mean + projection on the centred covariates
-        xc = dc_d - dc_d.mean(dim=1, keepdim=True)
-        Qc, rc, _ = covariate_basis_device(ctx, xc)
+        ckey = basis_cache_key(ctx, dc_d, tag='centred')
+        if ckey is not None and _CENTRED.get(dev.index, (None,))[0] == ckey:
+            Qc, rc = _CENTRED[dev.index][1]
+        else:
+            xc = dc_d - dc_d.mean(dim=1, keepdim=True)
+            Qc, rc, _ = covariate_basis_device(ctx, xc)
+            if ckey is not None:
+                _CENTRED[dev.index] = (ckey, (Qc, rc), dc_d)
         scale = None                       # d1sscale; None = all ones (first iteration)
         best, bestv, it = None, 1e300, 0
         while it < stepmax and bestv > eps:
@@ -327,9 +334,12 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
             if scale is not None:
                 new = new * scale
             new = new / new.min()                                                 # :112
-            t1 = float(((new - scale) / scale).abs().max() if scale is not None else (new - 1.0).abs().max())   # :113
-            scale = new
+            prev, scale = scale, new
             it += 1
+            if stepmax == 1:                                                      # no decision depends on t1: no sync
+                best = scale
+                break
+            t1 = float(((new - prev) / prev).abs().max() if prev is not None else (new - 1.0).abs().max())      # :113
             if t1 < bestv:                                                        # :116-118
                 bestv, best = t1, scale
         w = 1.0 / best                                                            # :122-123
