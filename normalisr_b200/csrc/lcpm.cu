@@ -105,22 +105,41 @@ lcpm_colstats_kernel(const T* __restrict__ reads, int64_t genes, int64_t n, int6
     const T len_t = (T)(lut_len > (int64_t)INT_MAX ? (int64_t)INT_MAX : lut_len);
     if (k < n) {
         const T* col = reads + k;
-#pragma unroll 8
-        for (int64_t g = g0; g < g1; ++g) {
-            const T c = col[g * ld];
-            const T ci = c < 0 ? (T)0 : (c >= len_t ? (T)(len_t - 1) : c);
-            if (NOISY) {
-                const double z = nz_.noise ? nz_.noise[g * nz_.ld_noise + k]
-                                           : philox_normal((uint64_t)((nz_.row0 + g) * nz_.n_total + k), nz_.seed);
-                se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
-            } else {
-                // exp(lut[c]) tabulated: the pass is a pure gather (counts beyond the table: computed)
-                se += c < len_t ? lut_exp[ci] : exp(lc_digamma(1.0 + (double)c));
+        constexpr int kBatch = 8;                    // counts loaded before any of them is used: the table gather
+                                                     // and the rare large-count branch must not serialise the loads
+#pragma unroll 1
+        for (int64_t g = g0; g < g1; g += kBatch) {
+            T cc[kBatch];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) cc[i] = g + i < g1 ? col[(g + i) * ld] : (T)0;
+            bool big = false;
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                const T c = cc[i];
+                const bool in = g + i < g1;
+                const T ci = c < 0 ? (T)0 : (c >= len_t ? (T)(len_t - 1) : c);
+                if (NOISY) {
+                    if (in) {
+                        const double z = nz_.noise ? nz_.noise[(g + i) * nz_.ld_noise + k]
+                                                   : philox_normal((uint64_t)((nz_.row0 + g + i) * nz_.n_total + k), nz_.seed);
+                        se += exp(fma(nz_.lut_sd[ci], z, lut[ci]));
+                    }
+                } else {
+                    // exp(lut[c]) tabulated: the pass is a pure gather; counts beyond the table are added below
+                    const double v = lut_exp[ci];
+                    se += (in && c < len_t) ? v : 0.0;
+                    big = big || c >= len_t;
+                }
+                tot += (unsigned long long)(long long)c;
+                nz += c != 0 ? 1 : 0;
+                any_or |= c;
+                mx = c > mx ? c : mx;
             }
-            tot += (unsigned long long)(long long)c;
-            nz += c != 0 ? 1 : 0;
-            any_or |= c;
-            mx = c > mx ? c : mx;
+            if (!NOISY && big) {
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i)
+                    if (cc[i] >= len_t) se += exp(lc_digamma(1.0 + (double)cc[i]));
+            }
         }
         double* o = partial + ((int64_t)blockIdx.y * 3) * n + k;
         o[0] = se;

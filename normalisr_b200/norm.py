@@ -50,7 +50,16 @@ _CHEB_ALPHA = 1.5          # largest half-range of the exponent within a piece
 _CHEB_PIECES = 256         # beyond this the streaming pass computes the Gram matrices
 
 
-def _gram_chebyshev(dc_d, logw, wt_d):
+def _cheb_pieces(bounds):
+    """Number of pieces the wt range is cut into for (min w, max w, min wt, max wt); 0 = not applicable."""
+    if not all(np.isfinite(v) for v in bounds) or bounds[0] <= 0:
+        return 0
+    lw_half = 0.5 * (np.log(bounds[1]) - np.log(bounds[0])) * (1 + 1e-12)
+    pieces = max(1, int(np.ceil(0.5 * (bounds[3] - bounds[2]) * 2.0 * lw_half / _CHEB_ALPHA)))
+    return pieces if pieces <= _CHEB_PIECES else 0
+
+
+def _gram_chebyshev(dc_d, logw, wt_d, bounds=None):
     """Per-gene covariate Gram matrices G_x = sum_k w_k ** (2 wt_x) c_k c_k^T (norm.py:156-159: dc * w2[x]
     times its transpose) for ALL genes without a pass over the expression matrix.
 
@@ -63,21 +72,23 @@ def _gram_chebyshev(dc_d, logw, wt_d):
     stable; Higham 2004).  Interpolation is accurate relative to the largest value on the piece, and the
     terms of the sum grow at rates between -alpha and +alpha across it, so the pointwise relative error is
     about e^(2 alpha) roundings: hence the small alpha (measured: 1e-15 of sum |terms|, like a direct sum).
-    The truncated coefficients are checked; returns None if they have not decayed to rounding level or
-    the weights span too wide a range (the caller then takes the streaming-pass statistics)."""
+    Returns (G, ok): ok is a device flag - the truncated Chebyshev coefficients have decayed to rounding
+    level (read later by the caller, so that nothing here waits for the device) - or None when the weights
+    span too wide a range (the caller then takes the streaming-pass statistics).  ``bounds`` = (min w,
+    max w, min wt, max wt) if the caller already has them on the host."""
     dev = dc_d.device
     nc, n = dc_d.shape
     genes = wt_d.shape[0]
     iu = torch.triu_indices(nc, nc, device=dev)
     D = (dc_d[iu[0]] * dc_d[iu[1]]).t().contiguous()                # (n, tri)
-    lo, hi = float(logw.min()), float(logw.max())
-    mid, lw_half = 0.5 * (lo + hi), 0.5 * (hi - lo)
-    wmin, wmax = float(wt_d.min()), float(wt_d.max())
-    if not all(np.isfinite(v) for v in (lo, hi, wmin, wmax)):
+    if bounds is None:
+        bounds = torch.stack([torch.exp(logw.min()), torch.exp(logw.max()), wt_d.min(), wt_d.max()]).cpu().tolist()
+    pieces = _cheb_pieces(bounds)
+    if not pieces:
         return None
-    pieces = max(1, int(np.ceil(0.5 * (wmax - wmin) * 2.0 * lw_half / _CHEB_ALPHA)))
-    if pieces > _CHEB_PIECES:
-        return None
+    lo, hi = float(np.log(bounds[0])), float(np.log(bounds[1]))
+    mid = 0.5 * (lo + hi)
+    wmin, wmax = float(bounds[2]), float(bounds[3])
     h = 0.5 * (wmax - wmin) / pieces
     m = _CHEB_NODES
     j = torch.arange(m, dtype=torch.float64, device=dev)
@@ -103,8 +114,7 @@ def _gram_chebyshev(dc_d, logw, wt_d):
     i = torch.arange(m, dtype=torch.float64, device=dev)
     A = (2.0 / m) * torch.einsum('ij,pjt->pit', torch.cos(np.pi * i[:, None] * (j[None, :] + 0.5) / m), F)
     scale = Fabs.amax(dim=1)                                         # (pieces, tri)
-    if not bool((A[:, -4:].abs().amax(dim=1) <= 1e-14 * scale).all()):
-        return None
+    ok = (A[:, -4:].abs().amax(dim=1) <= 1e-14 * scale).all()
     diff = x[:, None] - xn[None, :]                                  # (genes, m)
     hit = diff == 0
     wgt = bw[None, :] / torch.where(hit, torch.ones_like(diff), diff)
@@ -122,12 +132,15 @@ def _gram_chebyshev(dc_d, logw, wt_d):
     tri = tri * torch.exp(2.0 * mid * wt_d)[:, None]
     G = torch.zeros((genes, nc, nc), dtype=torch.float64, device=dev)
     G[:, iu[0], iu[1]] = tri
-    return G + torch.triu(G, 1).transpose(1, 2)
+    return G + torch.triu(G, 1).transpose(1, 2), ok
 
 
-def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None):
-    """One block of genes resident on the device -> normalised block.  ``G``: the block's Gram matrices from
-    ``_gram_chebyshev``, or None: they come out of the streaming pass as well (``nsr_normvar_stats``)."""
+def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None, flags=None):
+    """One block of genes resident on the device -> normalised block.  ``G``: a callable returning the
+    block's Gram matrices (``_gram_chebyshev``; called AFTER the statistics kernel is queued, so its many
+    small launches are prepared while that kernel runs), or None: they come out of the streaming pass as
+    well (``nsr_normvar_stats``).  ``flags``: dict of lists that receive device booleans (zero-rank
+    covariates, non-finite results) for the caller to read once, instead of a synchronisation each."""
     genes, n = dt_d.shape
     nc = dc_d.shape[0]
     ld = dt_d.stride(0) if genes > 1 else n
@@ -138,6 +151,7 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None
         _lib.check(ctx.lib.nsr_normvar_rhs(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, C16.data_ptr(),
                                            C16.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
                    "nsr_normvar_rhs")
+        G = G()
         b = stats[:, :nc]
         s1, s2 = stats[:, 16], stats[:, 17]
     else:
@@ -153,8 +167,6 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None
         b = stats[:, d_rows:d_rows + nc]
         s1, s2 = stats[:, M.shape[0]], stats[:, M.shape[0] + 1]
     ci, rank = engine.sym_pinv(ctx, G)                                      # inv_rank per gene, norm.py:159-160
-    if bool((rank <= 0).any()):
-        raise RuntimeError('Zero-rank covariates found.')                    # norm.py:161-162
     coef = torch.einsum('gij,gj->gi', ci, b).contiguous()
     if keepvar:                                                              # norm.py:241-243, 251-254
         dv = torch.sqrt(s2 / n - (s1 / n) ** 2)
@@ -162,10 +174,18 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None
         scale = (dv / dv2) ** wt_d
     else:
         scale = torch.ones(genes, dtype=torch.float64, device=dt_d.device)
-    # the reference asserts that its output is finite (norm.py:277); S2 = sum (s dt)^2, coef and scale
-    # finite imply it, without another pass over the matrix
-    if not bool(torch.isfinite(stats).all() & torch.isfinite(coef).all() & torch.isfinite(scale).all()):
-        raise AssertionError('non-finite values in the normalised expression matrix')
+    # zero-rank covariates (norm.py:161-162); the reference asserts that its output is finite (norm.py:277):
+    # S2 = sum (s dt)^2, coef and scale finite imply it, without another pass over the matrix
+    zero_rank = (rank <= 0).any()
+    finite = torch.isfinite(stats).all() & torch.isfinite(coef).all() & torch.isfinite(scale).all()
+    if flags is None:
+        if bool(zero_rank):
+            raise RuntimeError('Zero-rank covariates found.')
+        if not bool(finite):
+            raise AssertionError('non-finite values in the normalised expression matrix')
+    else:
+        flags["zero_rank"].append(zero_rank)
+        flags["finite"].append(finite)
     if out is None:
         out = torch.empty((genes, n), dtype=torch.float64, device=dt_d.device)
     _lib.check(ctx.lib.nsr_normvar_apply(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, dc_d.data_ptr(), nc,
@@ -175,7 +195,8 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None
     return out
 
 
-def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, normmean=False, device=None):
+def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, normmean=False, device=None,
+            _chebyshev=None):
     """Performs mean and variance normalisations; same arguments, checks and return value as the
     reference (norm.py:169-289): ``[dtn, dcn]`` or ``[dtn, dcn, dextran]``.  ``nth`` / ``bs`` are
     accepted and ignored."""
@@ -191,9 +212,14 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         raise ValueError('Unmatched gene or cell counts.')
     if dextra is not None and (dextra.ndim != 2 or dextra.shape[0] == 0 or dextra.shape[1] != ns):
         raise ValueError('Unmatched shape or size for dextra.')
-    if float(w.min()) <= 0:
+    def min_max(x):                       # the checks here and the interpolation below need the four bounds
+        if _is_dev(x):
+            return torch.stack([x.min(), x.max()]).double().cpu().tolist()
+        return [float(x.min()), float(x.max())]
+    bounds = min_max(w) + min_max(wt)
+    if not bounds[0] > 0 and not np.isnan(bounds[0]):
         raise ValueError('w must be positive.')
-    if float(wt.min()) < 0:
+    if bounds[2] < 0:
         raise ValueError('wt must be non-negative.')
     if cat not in (0, 1, 2):
         raise ValueError('Invalid cat value.')
@@ -208,9 +234,17 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         w_d = _dev64(w, dev).contiguous()
         wt_d = _dev64(wt, dev).contiguous()
         logw = torch.log(w_d)
-        # per-gene Gram matrices by interpolation in wt (no pass over dt); the streaming statistics otherwise
-        G_all = _gram_chebyshev(dc_d, logw, wt_d) if _USE_CHEBYSHEV else None
-        if G_all is not None:
+        # per-gene Gram matrices by interpolation in wt (no pass over dt); the streaming statistics otherwise.
+        # The interpolation is queued after the first block's statistics kernel (see _normvar_rows).
+        cheb = {"G": None, "ok": None}
+        use_cheb = (_USE_CHEBYSHEV if _chebyshev is None else _chebyshev) and _cheb_pieces(bounds) > 0
+
+        def gram_block(g0, g1):
+            if cheb["G"] is None:
+                cheb["G"], cheb["ok"] = _gram_chebyshev(dc_d, logw, wt_d, bounds)
+            return cheb["G"][g0:g1]
+        flags = {"zero_rank": [], "finite": []}
+        if use_cheb:
             design = torch.zeros((16, ns), dtype=torch.float64, device=dev)
             design[:nc] = dc_d
         elif nc <= 12:
@@ -246,13 +280,27 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
             g1 = min(nt, g0 + step)
             blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
             res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar,
-                                G=None if G_all is None else G_all[g0:g1], out=None if to_host else dtn[g0:g1])
+                                G=(lambda a=g0, b=g1: gram_block(a, b)) if use_cheb else None,
+                                out=None if to_host else dtn[g0:g1], flags=flags)
             if normmean:
                 cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
                 res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
             if to_host:
                 dtn[g0:g1] = res.cpu()
-        if not bool(torch.isfinite(dcn).all()):
+        # every deferred check in one read
+        chk = torch.stack([torch.stack(flags["zero_rank"]).any(), torch.stack(flags["finite"]).all(),
+                           torch.isfinite(dcn).all(),
+                           cheb["ok"] if cheb["ok"] is not None else torch.ones((), dtype=torch.bool, device=dev)]).cpu().tolist()
+        if not chk[3]:
+            # the interpolation did not reach rounding level (not observed; the pieces are sized for it): take
+            # the Gram matrices from the streaming pass instead
+            return normvar(dt, dc, w, wt, dextra=dextra, cat=cat, keepvar=keepvar, normmean=normmean, device=device,
+                           _chebyshev=False)
+        if chk[0]:
+            raise RuntimeError('Zero-rank covariates found.')                        # norm.py:161-162
+        if not chk[1]:
+            raise AssertionError('non-finite values in the normalised expression matrix')
+        if not chk[2]:
             raise AssertionError('non-finite values in the normalised covariates')  # norm.py:277
         ans = [dtn, dcn]
         if dextra is not None:

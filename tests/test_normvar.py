@@ -149,6 +149,8 @@ def test_normvar_wide_weight_range_uses_more_pieces_or_falls_back():
         G = nv._gram_chebyshev(torch.from_numpy(dc).cuda(), torch.log(torch.from_numpy(w).cuda()), torch.from_numpy(wt).cuda())
         assert (G is None) == fallback
         if not fallback:
+            G, ok = G
+            assert bool(ok)
             want = np.einsum('gk,ik,jk->gij', w[None, :] ** (2 * wt[:, None]), dc, dc)
             scale = np.einsum('gk,ik,jk->gij', w[None, :] ** (2 * wt[:, None]), np.abs(dc), np.abs(dc))
             assert (np.abs(G.cpu().numpy() - want) <= 1e-13 * scale).all()
