@@ -592,10 +592,11 @@ def run_de_reference(args, wl_name):
     print(json.dumps(line), flush=True)
 
 
-def de_phase_times(torch, ctx, p, single, n_slices, n_products, reps=3):
+def de_phase_times(torch, ctx, p, single, n_slices, n_products, reps=5, skip=2):
     """Device times of the phases of one de() call on device-resident inputs (CUDA events around the same
     engine calls the public API makes): covariate basis, projection of the groupings, projection of the
-    genes, contraction(s), solve (single=4)."""
+    genes, contraction(s), solve (single=4).  The first ``skip`` repetitions are not counted: their event
+    brackets include the first device allocations of the outputs (the GPU idles while cudaMalloc runs)."""
     from normalisr_b200 import association, engine
     out = {}
 
@@ -632,7 +633,7 @@ def de_phase_times(torch, ctx, p, single, n_slices, n_products, reps=3):
             g = timed("contract", grams)
             timed("solve", lambda: engine.de4_solve(ctx, g, Gxy, Ry.var * n, n, rank_c, 0, 1e-8, False))
     torch.cuda.synchronize()
-    return {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in out.items()}, Rx.n_slices
+    return {k: float(np.mean([a.elapsed_time(b) for a, b in v[skip:]])) for k, v in out.items()}, Rx.n_slices
 
 
 def de_roofline(phases, planes_x, genes, cells, groups, single, n_slices, n_products):
