@@ -31,6 +31,40 @@ def test_strips_partition_upper_triangle(rows, world):
         assert max(counts) <= 1.25 * (sum(counts) / world) + t      # balanced up to one tile row
 
 
+@pytest.mark.parametrize("rows", [130, 1900, 5000, 20000])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+def test_home_rectangles_write_every_entry_exactly_once(rows, world):
+    """The single-caller result: every rank copies home its diagonal block (both triangles, the lower one from
+    the kernel's mirrored stores), and for every block pair it owns the rectangle it computed plus the
+    transpose.  Together these must cover the (rows x rows) matrices exactly once - no entry left to a
+    second pass on the host, none written by two GPUs - and each rectangle must consist of whole tiles the
+    rank really computes (``pair_tiles``)."""
+    blk = parallel.row_split(rows, world)
+    count = np.zeros((rows, rows), dtype=np.int32)
+    for rank in range(world):
+        ra = parallel.block_rows(rows, world, rank)
+        r0 = rank * blk
+        if not ra:
+            continue
+        count[r0:r0 + ra, r0:r0 + ra] += 1
+        for _, src, parity in parallel.exchange_plan(world, rank):
+            rb = parallel.block_rows(rows, world, src)
+            if not rb:
+                continue
+            c0 = src * blk
+            a0, a1, b0, b1 = parallel._segment_rect(ra, rb, parity)
+            count[r0 + a0:r0 + a1, c0 + b0:c0 + b1] += 1                 # direct
+            count[c0 + b0:c0 + b1, r0 + a0:r0 + a1] += 1                 # transposed copy
+            tl = parallel.pair_tiles(ra, rb, parity)
+            cover = np.zeros((ra, rb), dtype=bool)
+            for ti, tj in tl:
+                cover[ti * 128:(ti + 1) * 128, tj * 128:(tj + 1) * 128] = True
+            want = np.zeros((ra, rb), dtype=bool)
+            want[a0:a1, b0:b1] = True
+            assert np.array_equal(cover, want)
+    assert (count == 1).all()
+
+
 def test_row_split():
     # equal blocks, multiples of the 128-row tile
     assert parallel.row_split(20000, 8) == 2560 and parallel.row_split(10, 4) == 128
