@@ -415,7 +415,9 @@ int nsr_mtx_read(const char* path, int64_t nnz, int32_t* row, int32_t* col, doub
 /* Test hooks: "hadamard" (0/1, default 1), "umma_pair" (1 = cta_group::2 kernel;
  * 0 = single-CTA kernel, default), "umma_kblock" (64 or 128 cells per pipeline stage of the single-CTA
  * kernel, default 128), "umma_dynamic" (1 = tiles claimed from a global counter, default; 0 = static
- * round-robin), "adaptive_min_cells" (see nsr_last_refined), "prefetch" (1 = L2 prefetch of the next
+ * round-robin), "split_k" (1 = launches with fewer than two waves of tiles split the cells into parts - work
+ * items (tile, part) over all SMs, partial sums added in a fixed order by a second small kernel; default 1),
+ * "adaptive_min_cells" (see nsr_last_refined), "prefetch" (1 = L2 prefetch of the next
  * cell block in the residual pass; measured neutral, default 0). Process-wide. */
 int nsr_set_option(const char* name, int value);
 

@@ -17,7 +17,11 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
                              int64_t n_pad, int n_slices_b, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
-                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev);
+                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev, int n_parts = 1,
+                             double* part_out = nullptr, int64_t part_stride = 0);
+int nsr_launch_contract_finish(cudaStream_t st, const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                               const SegInfo& sg, int n_parts, const double* part, int64_t part_stride);
+int nsr_umma_parts(int64_t cells, int n_slices_a, int n_slices_b, int n_parts);
 extern int nsr_use_hadamard;
 extern int nsr_prefetch;
 extern int nsr_umma_kblock;
@@ -25,6 +29,7 @@ extern int nsr_umma_pair;
 extern int nsr_epi_warps;
 extern int nsr_umma_stack;
 extern int nsr_umma_dynamic;
+int nsr_split_k = 1;          // 1: few-tile launches split the cells over work items (see contract_impl)
 extern int nsr_epi_sleep_ns;
 
 // Adaptive digit-product schedule, OPT-IN (tcgen05 engine, 3 planes / 8 products, one pass over the
@@ -124,6 +129,7 @@ extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "prefetch")) { nsr_prefetch = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_pair")) { nsr_umma_pair = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_dynamic")) { nsr_umma_dynamic = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "split_k")) { nsr_split_k = value ? 1 : 0; return 0; }
     if (!strcmp(name, "adaptive_min_cells")) { nsr_adaptive_min_cells = value < 0 ? 0 : value; return 0; }
     if (!strcmp(name, "umma_stack")) { nsr_umma_stack = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_warps")) {
@@ -294,6 +300,35 @@ static int contract_impl(nsr_ctx* ctx, uintptr_t stream, int engine, int mode, c
         NSR_CHECK(cudaGetLastError());
         return nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, 3, segs, 1, n_pad, 3, 5, list, n_tiles, ep,
                                         0, n_pad, count);
+    }
+    // Few tiles, many cells (de: a few hundred groupings against every gene; the groupings' own Gram matrix):
+    // with one CTA per tile the last wave of tiles leaves most SMs idle.  Split the cells into parts instead -
+    // work items (tile, part) over all SMs, partial sums into per-part slabs, one small kernel that adds the
+    // slabs in a fixed order and finishes.  The parts also serve as the overflow chunks (each part <= chunk).
+    // Only the rectangular modes: their sums (two different variables, or an exact small-integer operand) stay
+    // below 2^53, so the parts add up exactly and the result is the single-pass one bit for bit; co-expression
+    // keeps its one-pass tiles (self-products of 24-bit values over 1e5 cells exceed 2^53, and its results are
+    // promised to be identical across tilings and GPU counts).
+    if (engine == NSR_ENGINE_UMMA && !pair && n_segs == 1 && nsr_split_k != 0 && n_tiles < 2 * (int64_t)ctx->sm_count &&
+        (mode == NSR_MODE_DE || mode == NSR_MODE_RAW)) {
+        const int64_t target = 4 * (int64_t)ctx->sm_count;                  // ~4 waves of work items
+        int64_t want = (target + n_tiles - 1) / n_tiles;
+        const int64_t for_overflow = (n_pad + chunk - 1) / chunk;
+        if (want < for_overflow) want = for_overflow;
+        const int64_t max_parts = n_pad / (8 * NSR_KBLOCK) > 0 ? n_pad / (8 * NSR_KBLOCK) : 1;   // >= 1024 cells per part
+        if (want > max_parts && max_parts >= for_overflow) want = max_parts;
+        const int64_t slab = rows_a * ld;                                   // one (rows_a x ld) image of out2 per part
+        const int parts = nsr_umma_parts(n_pad, n_slices_a, n_slices_b, (int)want);
+        if (parts > 1 && parts >= for_overflow && (size_t)parts * (size_t)slab * sizeof(double) <= ((size_t)1 << 30)) {
+            void* scratch = nullptr;
+            if (nsr_scratch(ctx, (size_t)parts * (size_t)slab * sizeof(double), &scratch)) return 1;
+            int rc = nsr_launch_contract_umma(ctx, st, a_slices, rows_a, rows_alloc_a, n_slices_a, segs, 1, n_pad, n_slices_b,
+                                              wmax, ctx->tiles_dev, n_tiles, ep, 0, n_pad, nullptr, parts, (double*)scratch,
+                                              slab);
+            if (rc) return rc;
+            return nsr_launch_contract_finish(st, ctx->tiles_dev, n_tiles, ep, segs[0].info, parts, (const double*)scratch,
+                                              slab);
+        }
     }
     for (int64_t c0 = 0; c0 < n_pad; c0 += chunk) {
         const int64_t c1 = c0 + chunk < n_pad ? c0 + chunk : n_pad;

@@ -50,6 +50,12 @@ struct UmmaArgs {
     const int* n_tiles_dev;       // if set, the tile count is read from device memory (second phase of the
                                   // adaptive schedule: the list was compacted on the device)
     int n_segs;
+    // split over the cells: work item w = (tile w % n_tiles, part w / n_tiles); part p contracts k-blocks
+    // [p * kb_per_part, (p + 1) * kb_per_part) and stores its scaled partial sums in slab p of part_out
+    int n_parts;                  // 1 = off
+    int kb_per_part;
+    double* part_out;
+    int64_t part_stride;          // doubles per slab
     SegInfo seg[kMaxSegs];
     ContractParams ep;
 };
@@ -197,7 +203,7 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
 template <int GROUPS, int EW>
 __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const SegInfo& sg, uint32_t tmem_base, int warp,
                                               int lane, int tr, int tc, bool wanted, uint32_t empty_bar, bool remote,
-                                              int tile_idx = -1) {
+                                              int tile_idx = -1, double* part = nullptr) {
     constexpr int kCols = NSR_TILE / (EW / 4);          // columns per epilogue warp
     constexpr int CH = EW > 8 ? 8 : 16;                 // columns per TMEM read (register budget)
     const int quad = warp & 3;
@@ -230,7 +236,7 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const Se
                         // launch, but before the segment's flag: no SM has them in L1 earlier, and L1 does not
                         // survive a launch boundary - plain cached loads are safe)
                         refine |= nsr_finish(ep, sg.mode, sg.col0, i, j, qi, vi, sg.qb[j], sg.vb ? sg.vb[j] : 1.0,
-                                             nsr_combine(ep, a4), mP, sg.mO, sg.ldm);
+                                             nsr_combine(ep, a4), mP, sg.mO, sg.ldm, part);
                     }
                 }
             }
@@ -346,12 +352,16 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             uint32_t phase = 0;
             uint32_t seg_seen = 0;                        // segments whose ready flag this CTA has observed
             const int n_tiles = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
+            const int n_items = n_tiles * g.n_parts;
             for (int it = 0;; ++it) {
-                int t = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
-                if (t >= n_tiles) t = -1;
-                s_tile[it % kTileRing] = t;
+                int w = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
+                if (w >= n_items) w = -1;
+                s_tile[it % kTileRing] = w;
                 mbar_arrive(smem_u32(&bar_tile[it % kTileRing]));
-                if (t < 0) break;
+                if (w < 0) break;
+                const int t = w % n_tiles;
+                const int kb0 = (w / n_tiles) * g.kb_per_part;
+                const int kb1 = g.n_parts > 1 ? min(g.num_kb, kb0 + g.kb_per_part) : g.num_kb;
                 const int tcs = g.tiles[2 * t + 1];
                 const int sidx = tcs >> 24;
                 const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = (tcs & 0xFFFFFF) * NSR_TILE;
@@ -360,7 +370,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                     seg_seen |= 1u << sidx;
                 }
                 const CUtensorMap* mb = &maps.b[sidx];
-                for (int kb = 0; kb < g.num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&bar_empty[stage]), phase ^ 1);
                     const uint32_t full = smem_u32(&bar_full[stage]);
                     mbar_expect_tx(full, C::kStageBytes);
@@ -382,10 +392,14 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             uint32_t phase = 0, tphase = 0;
             for (int it = 0;; ++it) {
                 mbar_wait(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1);
-                if (s_tile[it % kTileRing] < 0) break;
+                const int w = s_tile[it % kTileRing];
+                if (w < 0) break;
+                const int n_tiles_m = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
+                const int kb0 = (w / n_tiles_m) * g.kb_per_part;
+                const int kb1 = g.n_parts > 1 ? min(g.num_kb, kb0 + g.kb_per_part) : g.num_kb;
                 mbar_wait(smem_u32(&bar_tmem_empty), tphase ^ 1);
                 tc_fence_after();
-                for (int kb = 0; kb < g.num_kb; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(smem_u32(&bar_full[stage]), phase);
                     tc_fence_after();
                     const uint32_t base = ring_u32 + stage * C::kStageBytes;
@@ -403,7 +417,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                                 const int a = sc.a[e], b = sc.b[e];
                                 const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
                                 const uint64_t db = make_smem_desc<KB>(base + (SA + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                const uint32_t acc = (kb > 0 || ks > 0 || !sc.first[e]) ? 1u : 0u;
+                                const uint32_t acc = (kb > kb0 || ks > 0 || !sc.first[e]) ? 1u : 0u;
                                 tc_mma_i8(tmem_base + (a + b) * NSR_TILE, da, db, sc.wide[e] ? kInstrDescN256 : kInstrDesc, acc);
                             }
                         } else {
@@ -417,7 +431,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                                         const bool first = (a == (grp > SB - 1 ? grp - (SB - 1) : 0));
                                         const uint64_t da = make_smem_desc<KB>(base + a * C::kSliceBytes) + (uint64_t)(2 * ks);
                                         const uint64_t db = make_smem_desc<KB>(base + (SA + b) * C::kSliceBytes) + (uint64_t)(2 * ks);
-                                        const uint32_t acc = (kb > 0 || ks > 0 || !first) ? 1u : 0u;
+                                        const uint32_t acc = (kb > kb0 || ks > 0 || !first) ? 1u : 0u;
                                         tc_mma_i8(tmem_base + grp * NSR_TILE, da, db, kInstrDesc, acc);
                                     }
                                 }
@@ -436,13 +450,16 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
         uint32_t tphase = 0;
         for (int it = 0;; ++it) {
             mbar_wait_backoff(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1, g.epi_sleep_ns);
-            const int t = s_tile[it % kTileRing];
-            if (t < 0) break;
+            const int w = s_tile[it % kTileRing];
+            if (w < 0) break;
+            const int n_tiles_e = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
+            const int t = w % n_tiles_e;
             const int tr = g.tiles[2 * t], tcs = g.tiles[2 * t + 1];
+            double* part = g.n_parts > 1 ? g.part_out + (int64_t)(w / n_tiles_e) * g.part_stride : nullptr;
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
             epilogue_tile<C::kGroups, EW>(g.ep, g.seg[tcs >> 24], tmem_base, warp, lane, tr, tcs & 0xFFFFFF, true,
-                                          smem_u32(&bar_tmem_empty), false, t);
+                                          smem_u32(&bar_tmem_empty), false, t, part);
             tphase ^= 1;
         }
     }
@@ -662,7 +679,8 @@ int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const SegMap
     const int smem = C::kStages * C::kStageBytes + 1024;
     auto kern = contract_umma_kernel<SA, SB, WMAX, KB, EW>;
     NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = (g.n_tiles_dev == nullptr && g.n_tiles < ctx->sm_count) ? g.n_tiles : ctx->sm_count;
+    const int64_t items = (int64_t)g.n_tiles * g.n_parts;
+    const int grid = (g.n_tiles_dev == nullptr && items < ctx->sm_count) ? (int)items : ctx->sm_count;
     kern<<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, g);
     NSR_CHECK(cudaGetLastError());
     return 0;
@@ -687,7 +705,42 @@ int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensor
     return 0;
 }
 
+// Split over the cells, second step: one CTA per output tile adds the parts' slabs in a fixed order and
+// turns the sum into the stored statistics (the same nsr_finish_sum as the fused epilogue).
+__global__ void __launch_bounds__(256)
+contract_finish_kernel(const int32_t* __restrict__ tiles, ContractParams ep, SegInfo sg, int n_parts,
+                       const double* __restrict__ part, int64_t part_stride) {
+    const int tr = tiles[2 * blockIdx.x], tc = tiles[2 * blockIdx.x + 1] & 0xFFFFFF;
+    double* const mP = (sg.mP != nullptr && (tr != tc || sg.mode == NSR_MODE_COEX_RECT)) ? sg.mP : nullptr;
+    for (int idx = threadIdx.x; idx < NSR_TILE * NSR_TILE; idx += 256) {
+        const int64_t i = (int64_t)tr * NSR_TILE + (idx >> 7), j = (int64_t)tc * NSR_TILE + (idx & 127);
+        if (i >= ep.rows_a || j >= sg.rows_b) continue;
+        const int64_t at = i * ep.ld + sg.col0 + j;
+        double acc = 0.0;                        // integer-valued partial sums: exact additions below 2^53
+        for (int p = 0; p < n_parts; ++p) acc += part[(int64_t)p * part_stride + at];
+        nsr_finish_sum(ep, sg.mode, sg.col0, i, j, ep.va ? ep.va[i] : 1.0, sg.vb ? sg.vb[j] : 1.0,
+                       (ep.qa[i] * sg.qb[j]) * acc, mP, sg.mO, sg.ldm);
+    }
+}
+
 }  // namespace
+
+int nsr_launch_contract_finish(cudaStream_t st, const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                               const SegInfo& sg, int n_parts, const double* part, int64_t part_stride) {
+    contract_finish_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(tiles_dev, ep, sg, n_parts, part, part_stride);
+    NSR_CHECK(cudaGetLastError());
+    return 0;
+}
+
+extern int nsr_umma_kblock;
+// number of parts the kernel will really use for a request of n_parts over `cells` cells
+int nsr_umma_parts(int64_t cells, int n_slices_a, int n_slices_b, int n_parts) {
+    const int kb = (n_slices_a + n_slices_b > 6) ? 64 : nsr_umma_kblock;
+    const int num_kb = (int)(cells / kb);
+    if (n_parts <= 1 || num_kb < 1) return 1;
+    const int per = (num_kb + n_parts - 1) / n_parts;
+    return (num_kb + per - 1) / per;
+}
 
 int nsr_umma_stack = 1;      // test hook: stacked-B N = 256 MMAs in the single-CTA kernel
 int nsr_epi_warps = 8;       // test hook: epilogue warps of the single-CTA kernel (8 or 16)
@@ -700,7 +753,8 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
                              int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
                              int64_t n_pad, int n_slices_b, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
-                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev) {
+                             int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev, int n_parts,
+                             double* part_out, int64_t part_stride) {
     if (n_tiles < 0) {
         // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
         if (n_segs != 1 || n_slices_a != n_slices_b) {
@@ -721,6 +775,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.n_tiles_dev = nullptr;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.n_segs = 1;
+        g.n_parts = 1; g.kb_per_part = 0; g.part_out = nullptr; g.part_stride = 0;
         g.seg[0] = segs[0].info;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
@@ -749,6 +804,13 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     g.n_tiles = (int)n_tiles;
     g.num_kb = (int)((cell_end - cell_begin) / kb);
     g.kb_begin = (int)(cell_begin / kb);
+    g.n_parts = 1; g.kb_per_part = g.num_kb; g.part_out = nullptr; g.part_stride = 0;
+    if (n_parts > 1 && part_out != nullptr) {
+        g.kb_per_part = (g.num_kb + n_parts - 1) / n_parts;
+        g.n_parts = (g.num_kb + g.kb_per_part - 1) / g.kb_per_part;      // no empty part
+        g.part_out = part_out;
+        g.part_stride = part_stride;
+    }
     g.stack_b = (nsr_umma_stack != 0 && kb == 128) ? 1 : 0;
     g.tile_counter = nullptr;
     g.n_tiles_dev = n_tiles_dev;

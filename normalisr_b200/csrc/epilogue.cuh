@@ -54,16 +54,14 @@ struct NsrSegOperand {
     SegInfo info;
 };
 
-// one output element (i = row in A, j = row in B); with `mP` the transposed element is written too
-// (COEX, i != j tile: the other triangle of the same matrix; multi-GPU block pairs: the mirrored block).
-// Returns true when the element asks for the full-precision phase (adaptive schedule).
-__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
-                                           double qi, double vi, double qj, double vj, double acc, double* mP,
-                                           double* mO, int64_t ldm) {
-    double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
+// From sum = sum_k res_i res_j over ALL cells to the stored statistics of one output element (i = row in A,
+// j = row in B); with `mP` the transposed element is written too (COEX, i != j tile: the other triangle of the
+// same matrix; multi-GPU block pairs: the mirrored block).  Returns true when the element asks for the
+// full-precision phase (adaptive schedule).
+__device__ __forceinline__ bool nsr_finish_sum(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
+                                               double vi, double vj, double sum, double* mP, double* mO, int64_t ldm) {
     const int64_t at = i * p.ld + col0 + j;
-    if (p.acc_in) sum += p.out2[at];               // earlier cell chunks
-    if (mode == NSR_MODE_RAW || p.raw_out) {
+    if (mode == NSR_MODE_RAW) {
         p.out2[at] = sum;
         return false;
     }
@@ -85,6 +83,28 @@ __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, in
         mO[j * ldm + i] = o2;
     }
     return refine;
+}
+
+// One output element from the exact integer sum `acc` of this launch's cells.  `part` (split over the cells,
+// several CTAs per tile): the UNSCALED integer-valued sum goes to that slab; contract_finish_kernel adds the
+// slabs in a fixed order (exactly, while the total stays below 2^53 - every DE-type sum does) and scales once,
+// so the result equals the single-pass one.  Otherwise: running sum over sequential cell chunks (acc_in /
+// raw_out), then the statistics.
+__device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
+                                           double qi, double vi, double qj, double vj, double acc, double* mP,
+                                           double* mO, int64_t ldm, double* part = nullptr) {
+    const int64_t at = i * p.ld + col0 + j;
+    if (part != nullptr) {
+        part[at] = acc;
+        return false;
+    }
+    double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
+    if (p.acc_in) sum += p.out2[at];               // earlier cell chunks
+    if (p.raw_out) {
+        p.out2[at] = sum;
+        return false;
+    }
+    return nsr_finish_sum(p, mode, col0, i, j, vi, vj, sum, mP, mO, ldm);
 }
 __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
                                            double vi, double qj, double vj, double acc, bool mirror) {

@@ -670,6 +670,45 @@ def test_single4_same_golden_and_oracle():
         association.association_tests(np.concatenate([dx, dx[:1] + dx[1:2]]), None, dc, single=4)
 
 
+def test_split_over_cells_is_bit_identical_for_de():
+    """Launches with fewer than two waves of tiles split the cells over work items (tile, part) and add the
+    parts' integer sums in a second kernel (option "split_k"): same bits as the one-pass launch for the
+    rectangular modes, for general and for exact one-plane groupings, with and without overflow chunks."""
+    ctx = engine.context(0)
+    n, nx, ny = 40000, 300, 900
+    p = synth.device_problem(1021, ny, n, "cuda")
+    rng = torch.Generator(device="cuda")
+    rng.manual_seed(3)
+    dg = (torch.rand((nx, n), generator=rng, device="cuda") < 0.02).to(torch.float64)
+    xg = torch.randn((nx, n), generator=rng, device="cuda", dtype=torch.float64) + 0.05 * p["dt"][:nx]
+    Qt, crank, _ = association.covariate_basis_device(ctx, p["dc"])
+    S, prods = engine.PRESETS["default"]
+    B = engine.residualize(ctx, p["dt"], Qt, S)
+    A_exact, status = engine.residualize_exact(ctx, dg, Qt)
+    assert int(status.item()) == 0
+    A_gen = engine.residualize(ctx, xg, Qt, S)
+    dof = (n - 1 - crank) / 2
+    tiles = engine.rect_tiles(nx, ny)
+    for A in (A_exact, A_gen):
+        for mode in (engine.MODE_DE, engine.MODE_RAW):
+            for kc in (0, 8192):
+                outs = []
+                for split in (1, 0):
+                    engine.set_option("split_k", split)
+                    P = torch.zeros((nx, ny), dtype=torch.float64, device="cuda")
+                    D = torch.zeros_like(P)
+                    engine.contract(ctx, mode, A, B, tiles, dof, None if mode == engine.MODE_RAW else P, D, prods, k_chunk=kc)
+                    outs.append((P, D))
+                engine.set_option("split_k", 1)
+                torch.cuda.synchronize()
+                if kc == 0:
+                    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+                else:       # sequential chunks add SCALED partial sums: equal to rounding only
+                    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=1e-13, atol=1e-13 * float(outs[1][1].abs().max()))
+                    torch.testing.assert_close(outs[0][0], outs[1][0], rtol=1e-9, atol=0)
+                assert float(outs[0][1].abs().max()) > 0
+
+
 def test_nonfinite_input_raises():
     """The reference asserts finite outputs (association.py:252-255, 1077): a NaN / Inf in dt must not
     come back as 'not significant'."""
