@@ -309,8 +309,14 @@ static int contract_impl(nsr_ctx* ctx, uintptr_t stream, int engine, int mode, c
     // below 2^53, so the parts add up exactly and the result is the single-pass one bit for bit; co-expression
     // keeps its one-pass tiles (self-products of 24-bit values over 1e5 cells exceed 2^53, and its results are
     // promised to be identical across tilings and GPU counts).
+    // Worth it when the one-CTA-per-tile launch would leave more than a quarter of the machine idle (its last wave):
+    // the second kernel and the slabs cost about as much as a 20 % imbalance on these short launches (measured at
+    // 300 x 10k x 50k cells: 237 tiles = 1.6 waves ran 0.52 ms one-pass, 0.6 ms split; 160 tiles over 1M cells ran
+    // 10.6 ms one-pass, 7.9 ms split).
+    const int64_t waves = (n_tiles + ctx->sm_count - 1) / ctx->sm_count;
+    const bool unbalanced = 4 * n_tiles < 3 * waves * (int64_t)ctx->sm_count;
     if (engine == NSR_ENGINE_UMMA && !pair && n_segs == 1 && nsr_split_k != 0 && n_tiles < 2 * (int64_t)ctx->sm_count &&
-        (mode == NSR_MODE_DE || mode == NSR_MODE_RAW)) {
+        unbalanced && (mode == NSR_MODE_DE || mode == NSR_MODE_RAW)) {
         const int64_t target = 4 * (int64_t)ctx->sm_count;                  // ~4 waves of work items
         int64_t want = (target + n_tiles - 1) / n_tiles;
         const int64_t for_overflow = (n_pad + chunk - 1) / chunk;
