@@ -6,8 +6,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsr_b200.so")
-SOURCES = ["api.cu", "basis.cu", "binnet.cu", "de4.cu", "grouped.cu", "lcpm.cu", "normvar.cu", "sympinv.cu", "textio.cu", "residual.cu", "contract_simt.cu", "contract_umma.cu"]
+SOURCES = ["api.cu", "basis.cu", "binnet.cu", "de4.cu", "grouped.cu", "lcpm.cu", "normvar.cu", "sympinv.cu", "textio.cu", "residual.cu", "contract_simt.cu", "contract_umma.cu", "contract_umma_splitk.cu"]
 HEADERS = ["nsr_common.cuh", "epilogue.cuh", "pvalue.cuh", os.path.join("..", "..", "include", "normalisr_b200.h")]
+INCLUDES = {"contract_umma_splitk.cu": ["contract_umma.cu"]}      # sources that #include another source
 
 
 def _nvcc():
@@ -51,7 +52,8 @@ def build(force=False, verbose=False):
         src = os.path.join(CSRC, sname)
         obj = os.path.join(objdir, sname[:-3] + ".o")
         objs.append(obj)
-        if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_t, os.path.getmtime(src)):
+        src_t = max([os.path.getmtime(src)] + [os.path.getmtime(os.path.join(CSRC, d)) for d in INCLUDES.get(sname, ())])
+        if force or verbose or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_t, src_t):
             jobs.append((src, obj, verbose, env))
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         results = list(ex.map(_compile_one, jobs))

@@ -15,7 +15,16 @@
 //   warps 2..9     epilogue: warp w reads TMEM lane quadrant w%4, columns 64*((w-2)/4)..+64.
 // The P-value arithmetic is latency-bound float64 (~330 us per tile with 4 epilogue warps, as long
 // as 40 % of a 100k-cell tile), hence 8 epilogue warps, two per scheduler.
+//
+// This file is compiled twice.  contract_umma.cu itself is the one-pass kernel and everything on the host side;
+// contract_umma_splitk.cu defines NSR_SPLITK_TU and includes it: the same kernel with work items (tile, part
+// of the cells) - see UmmaArgs::n_parts - exported as nsr_launch_contract_umma_splitk.  Two translation units
+// rather than a template flag so that the one-pass kernel's argument block, code and registers are exactly
+// what they are without the split (power-bound at the headline size: profiles/r02_splitk_ab.md).
 #include <cuda.h>
+#ifndef NSR_SPLITK_TU
+#define NSR_SPLITK_TU 0
+#endif
 
 #include "epilogue.cuh"
 
@@ -50,12 +59,14 @@ struct UmmaArgs {
     const int* n_tiles_dev;       // if set, the tile count is read from device memory (second phase of the
                                   // adaptive schedule: the list was compacted on the device)
     int n_segs;
+#if NSR_SPLITK_TU
     // split over the cells: work item w = (tile w % n_tiles, part w / n_tiles); part p contracts k-blocks
-    // [p * kb_per_part, (p + 1) * kb_per_part) and stores its scaled partial sums in slab p of part_out
-    int n_parts;                  // 1 = off
+    // [p * kb_per_part, (p + 1) * kb_per_part) and stores its unscaled partial sums in slab p of part_out
+    int n_parts;
     int kb_per_part;
     double* part_out;
     int64_t part_stride;          // doubles per slab
+#endif
     SegInfo seg[kMaxSegs];
     ContractParams ep;
 };
@@ -203,7 +214,11 @@ __device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t cluster_addr) 
 template <int GROUPS, int EW>
 __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const SegInfo& sg, uint32_t tmem_base, int warp,
                                               int lane, int tr, int tc, bool wanted, uint32_t empty_bar, bool remote,
-                                              int tile_idx = -1, double* part = nullptr) {
+#if NSR_SPLITK_TU
+                                              int tile_idx, double* part) {
+#else
+                                              int tile_idx = -1) {
+#endif
     constexpr int kCols = NSR_TILE / (EW / 4);          // columns per epilogue warp
     constexpr int CH = EW > 8 ? 8 : 16;                 // columns per TMEM read (register budget)
     const int quad = warp & 3;
@@ -235,8 +250,13 @@ __device__ __forceinline__ void epilogue_tile(const ContractParams& ep, const Se
                         // (the per-row scales of a remote segment are written by a copy engine during this
                         // launch, but before the segment's flag: no SM has them in L1 earlier, and L1 does not
                         // survive a launch boundary - plain cached loads are safe)
+#if NSR_SPLITK_TU
+                        // split over the cells: the unscaled integer sum of this part (contract_finish_kernel adds them)
+                        part[i * ep.ld + sg.col0 + j] = nsr_combine(ep, a4);
+#else
                         refine |= nsr_finish(ep, sg.mode, sg.col0, i, j, qi, vi, sg.qb[j], sg.vb ? sg.vb[j] : 1.0,
-                                             nsr_combine(ep, a4), mP, sg.mO, sg.ldm, part);
+                                             nsr_combine(ep, a4), mP, sg.mO, sg.ldm);
+#endif
                     }
                 }
             }
@@ -352,16 +372,25 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             uint32_t phase = 0;
             uint32_t seg_seen = 0;                        // segments whose ready flag this CTA has observed
             const int n_tiles = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
+#if NSR_SPLITK_TU
             const int n_items = n_tiles * g.n_parts;
+#else
+            const int n_items = n_tiles;
+#endif
             for (int it = 0;; ++it) {
                 int w = g.tile_counter ? atomicAdd(g.tile_counter, 1) : (int)(blockIdx.x + it * gridDim.x);
                 if (w >= n_items) w = -1;
                 s_tile[it % kTileRing] = w;
                 mbar_arrive(smem_u32(&bar_tile[it % kTileRing]));
                 if (w < 0) break;
+#if NSR_SPLITK_TU
                 const int t = w % n_tiles;
-                const int kb0 = (w / n_tiles) * g.kb_per_part;
-                const int kb1 = g.n_parts > 1 ? min(g.num_kb, kb0 + g.kb_per_part) : g.num_kb;
+                const int kb0 = (w / n_tiles) * g.kb_per_part, kb1 = min(g.num_kb, kb0 + g.kb_per_part);
+#else
+                const int t = w;
+                constexpr int kb0 = 0;
+                const int kb1 = g.num_kb;
+#endif
                 const int tcs = g.tiles[2 * t + 1];
                 const int sidx = tcs >> 24;
                 const int row_a = g.tiles[2 * t] * NSR_TILE, row_b = (tcs & 0xFFFFFF) * NSR_TILE;
@@ -394,9 +423,12 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
                 mbar_wait(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1);
                 const int w = s_tile[it % kTileRing];
                 if (w < 0) break;
-                const int n_tiles_m = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
-                const int kb0 = (w / n_tiles_m) * g.kb_per_part;
-                const int kb1 = g.n_parts > 1 ? min(g.num_kb, kb0 + g.kb_per_part) : g.num_kb;
+#if NSR_SPLITK_TU
+                const int kb0 = (w / g.n_tiles) * g.kb_per_part, kb1 = min(g.num_kb, kb0 + g.kb_per_part);
+#else
+                constexpr int kb0 = 0;
+                const int kb1 = g.num_kb;
+#endif
                 mbar_wait(smem_u32(&bar_tmem_empty), tphase ^ 1);
                 tc_fence_after();
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -452,14 +484,22 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
             mbar_wait_backoff(smem_u32(&bar_tile[it % kTileRing]), (it / kTileRing) & 1, g.epi_sleep_ns);
             const int w = s_tile[it % kTileRing];
             if (w < 0) break;
-            const int n_tiles_e = g.n_tiles_dev ? *g.n_tiles_dev : g.n_tiles;
-            const int t = w % n_tiles_e;
+#if NSR_SPLITK_TU
+            const int t = w % g.n_tiles;
+#else
+            const int t = w;
+#endif
             const int tr = g.tiles[2 * t], tcs = g.tiles[2 * t + 1];
-            double* part = g.n_parts > 1 ? g.part_out + (int64_t)(w / n_tiles_e) * g.part_stride : nullptr;
             mbar_wait_backoff(smem_u32(&bar_tmem_full), tphase, g.epi_sleep_ns);
             tc_fence_after();
+#if NSR_SPLITK_TU
             epilogue_tile<C::kGroups, EW>(g.ep, g.seg[tcs >> 24], tmem_base, warp, lane, tr, tcs & 0xFFFFFF, true,
-                                          smem_u32(&bar_tmem_empty), false, t, part);
+                                          smem_u32(&bar_tmem_empty), false, t,
+                                          g.part_out + (int64_t)(w / g.n_tiles) * g.part_stride);
+#else
+            epilogue_tile<C::kGroups, EW>(g.ep, g.seg[tcs >> 24], tmem_base, warp, lane, tr, tcs & 0xFFFFFF, true,
+                                          smem_u32(&bar_tmem_empty), false, t);
+#endif
             tphase ^= 1;
         }
     }
@@ -473,6 +513,7 @@ contract_umma_kernel(const __grid_constant__ CUtensorMap map_a,
 }
 
 
+#if !NSR_SPLITK_TU
 // =============================================================================================
 // cta_group::2 variant: a CTA pair (one cluster) computes a 256 x 128 output tile.  CTA r of the
 // pair stages its own 128 rows of A and half (64 rows) of B, so per MMA each SM reads 6 KB of
@@ -652,6 +693,8 @@ contract_umma2_kernel(const __grid_constant__ CUtensorMap map_a,
     }
 }
 
+#endif  // !NSR_SPLITK_TU
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -679,8 +722,12 @@ int launch_ew(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const SegMap
     const int smem = C::kStages * C::kStageBytes + 1024;
     auto kern = contract_umma_kernel<SA, SB, WMAX, KB, EW>;
     NSR_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#if NSR_SPLITK_TU
     const int64_t items = (int64_t)g.n_tiles * g.n_parts;
     const int grid = (g.n_tiles_dev == nullptr && items < ctx->sm_count) ? (int)items : ctx->sm_count;
+#else
+    const int grid = (g.n_tiles_dev == nullptr && g.n_tiles < ctx->sm_count) ? g.n_tiles : ctx->sm_count;
+#endif
     kern<<<grid, 64 + 32 * EW, smem, st>>>(ma, mb, g);
     NSR_CHECK(cudaGetLastError());
     return 0;
@@ -692,6 +739,7 @@ int launch(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const SegMaps& 
     return launch_ew<SA, SB, WMAX, KB, 8>(ctx, st, ma, mb, g);
 }
 
+#if !NSR_SPLITK_TU
 template <int S, int WMAX>
 int launch2(nsr_ctx* ctx, cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const UmmaArgs& g) {
     using C = Cfg2<S, WMAX>;
@@ -742,6 +790,13 @@ int nsr_umma_parts(int64_t cells, int n_slices_a, int n_slices_b, int n_parts) {
     return (num_kb + per - 1) / per;
 }
 
+int nsr_launch_contract_umma_splitk(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
+                                    int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
+                                    int64_t n_pad, int n_slices_b, int wmax,
+                                    const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                                    int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev, int n_parts,
+                                    double* part_out, int64_t part_stride);
+
 int nsr_umma_stack = 1;      // test hook: stacked-B N = 256 MMAs in the single-CTA kernel
 int nsr_epi_warps = 8;       // test hook: epilogue warps of the single-CTA kernel (8 or 16)
 int nsr_umma_pair = 0;       // 0 -> single-CTA kernel (default: 3 % faster sustained), 1 -> cta_group::2 kernel
@@ -749,12 +804,34 @@ int nsr_epi_sleep_ns = 500;  // test hook: epilogue wait back-off
 int nsr_umma_kblock = 128;   // test hook (nsr_set_option): 128 -> SWIZZLE_128B stages, 64 -> SWIZZLE_64B
 int nsr_umma_dynamic = 1;    // 1: tiles claimed from a global counter, 0: static round-robin (single-CTA kernel)
 
+#else   // NSR_SPLITK_TU
+}  // namespace
+extern int nsr_umma_kblock;
+extern int nsr_epi_sleep_ns;
+#endif
+
+#if NSR_SPLITK_TU
+int nsr_launch_contract_umma_splitk(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
+                                    int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
+                                    int64_t n_pad, int n_slices_b, int wmax,
+                                    const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
+                                    int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev, int n_parts,
+                                    double* part_out, int64_t part_stride) {
+    if (n_tiles < 0 || n_parts < 2 || part_out == nullptr) {
+        nsr_set_error("nsr_contract: the split-over-cells launch takes a plain tile list and at least two parts");
+        return 2;
+    }
+#else
 int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int64_t rows_a,
                              int64_t rows_alloc_a, int n_slices_a, const NsrSegOperand* segs, int n_segs,
                              int64_t n_pad, int n_slices_b, int wmax,
                              const int32_t* tiles_dev, int64_t n_tiles, const ContractParams& ep,
                              int64_t cell_begin, int64_t cell_end, const int* n_tiles_dev, int n_parts,
                              double* part_out, int64_t part_stride) {
+    if (n_parts > 1 && part_out != nullptr)
+        return nsr_launch_contract_umma_splitk(ctx, st, a, rows_a, rows_alloc_a, n_slices_a, segs, n_segs, n_pad, n_slices_b,
+                                               wmax, tiles_dev, n_tiles, ep, cell_begin, cell_end, n_tiles_dev, n_parts,
+                                               part_out, part_stride);
     if (n_tiles < 0) {
         // pair-tile list (tile_row/2, tile_col, mask), -n_tiles entries: cta_group::2 kernel
         if (n_segs != 1 || n_slices_a != n_slices_b) {
@@ -775,7 +852,6 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         g.n_tiles_dev = nullptr;
         g.epi_sleep_ns = nsr_epi_sleep_ns;
         g.n_segs = 1;
-        g.n_parts = 1; g.kb_per_part = 0; g.part_out = nullptr; g.part_stride = 0;
         g.seg[0] = segs[0].info;
         g.ep = ep;
         if (n_slices == 3 && wmax == 4) return launch2<3, 4>(ctx, st, ma, mb, g);
@@ -784,6 +860,7 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
         nsr_set_error("nsr_contract: unsupported (n_slices=%d, wmax=%d) for the tcgen05 pair engine", n_slices, wmax);
         return 2;
     }
+#endif
     if (n_segs < 1 || n_segs > kMaxSegs) {
         nsr_set_error("nsr_contract: %d segments (1..%d)", n_segs, kMaxSegs);
         return 2;
@@ -804,13 +881,12 @@ int nsr_launch_contract_umma(nsr_ctx* ctx, cudaStream_t st, const int8_t* a, int
     g.n_tiles = (int)n_tiles;
     g.num_kb = (int)((cell_end - cell_begin) / kb);
     g.kb_begin = (int)(cell_begin / kb);
-    g.n_parts = 1; g.kb_per_part = g.num_kb; g.part_out = nullptr; g.part_stride = 0;
-    if (n_parts > 1 && part_out != nullptr) {
-        g.kb_per_part = (g.num_kb + n_parts - 1) / n_parts;
-        g.n_parts = (g.num_kb + g.kb_per_part - 1) / g.kb_per_part;      // no empty part
-        g.part_out = part_out;
-        g.part_stride = part_stride;
-    }
+#if NSR_SPLITK_TU
+    g.kb_per_part = (g.num_kb + n_parts - 1) / n_parts;
+    g.n_parts = (g.num_kb + g.kb_per_part - 1) / g.kb_per_part;      // no empty part
+    g.part_out = part_out;
+    g.part_stride = part_stride;
+#endif
     g.stack_b = (nsr_umma_stack != 0 && kb == 128) ? 1 : 0;
     g.tile_counter = nullptr;
     g.n_tiles_dev = n_tiles_dev;

@@ -85,26 +85,41 @@ __device__ __forceinline__ bool nsr_finish_sum(const ContractParams& p, int mode
     return refine;
 }
 
-// One output element from the exact integer sum `acc` of this launch's cells.  `part` (split over the cells,
-// several CTAs per tile): the UNSCALED integer-valued sum goes to that slab; contract_finish_kernel adds the
-// slabs in a fixed order (exactly, while the total stays below 2^53 - every DE-type sum does) and scales once,
-// so the result equals the single-pass one.  Otherwise: running sum over sequential cell chunks (acc_in /
-// raw_out), then the statistics.
+// One output element from the exact integer sum `acc` of this launch's cells: running sum over sequential
+// cell chunks (acc_in / raw_out), then the statistics.  Kept as ONE function with its own copy of the
+// statistics (not a call into nsr_finish_sum): the fused epilogue is power-bound at the headline size and the
+// refactored form compiled to a 2.5 % slower step (profiles/r02_splitk_ab.md).  Launches split over the cells
+// store the UNSCALED integer-valued sums per part instead (epilogue_tile<.., SPLIT>); contract_finish_kernel
+// adds the parts in a fixed order, exactly while the total stays below 2^53, scales once and calls
+// nsr_finish_sum: the single-pass result.
 __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int mode, int64_t col0, int64_t i, int64_t j,
                                            double qi, double vi, double qj, double vj, double acc, double* mP,
-                                           double* mO, int64_t ldm, double* part = nullptr) {
-    const int64_t at = i * p.ld + col0 + j;
-    if (part != nullptr) {
-        part[at] = acc;
-        return false;
-    }
+                                           double* mO, int64_t ldm) {
     double sum = (qi * qj) * acc;                  // sum_k res_i res_j over this launch's cells
+    const int64_t at = i * p.ld + col0 + j;
     if (p.acc_in) sum += p.out2[at];               // earlier cell chunks
-    if (p.raw_out) {
+    if (mode == NSR_MODE_RAW || p.raw_out) {
         p.out2[at] = sum;
         return false;
     }
-    return nsr_finish_sum(p, mode, col0, i, j, vi, vj, sum, mP, mO, ldm);
+    const double dot = sum * p.inv_n;
+    double P, o2;
+    bool refine = false;
+    if ((mode == NSR_MODE_COEX || mode == NSR_MODE_COEX_UPPER) && i == j) {
+        P = 0.0; o2 = 0.0;                         // triu(.,1) + transpose leaves a zero diagonal
+    } else {
+        const double r2 = (dot * dot) / (vi * vj);
+        refine = p.refine_r2 >= 0.0 && !(r2 <= p.refine_r2);
+        P = nsr_pvalue_r2(r2, p.pv);
+        o2 = (mode == NSR_MODE_DE) ? dot / vi : dot;
+    }
+    p.P[at] = P;
+    p.out2[at] = o2;
+    if (mP != nullptr) {
+        mP[j * ldm + i] = P;
+        mO[j * ldm + i] = o2;
+    }
+    return refine;
 }
 __device__ __forceinline__ bool nsr_finish(const ContractParams& p, int64_t i, int64_t j, double qi,
                                            double vi, double qj, double vj, double acc, bool mirror) {
