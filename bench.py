@@ -827,6 +827,21 @@ def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    edges = int(stats[0].item()) // reps
+    # the same rows through the first-generation kernel (8-byte row staged per SM with one bulk copy), for comparison
+    from normalisr_b200 import engine as _engine
+    _engine.set_option("binnet_keys", 0)
+    try:
+        bn.binnet_rows(ctx, P, qcut, 0, out=out, stats=stats)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            bn.binnet_rows(ctx, P, qcut, 0, out=out, stats=stats)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_values = e0.elapsed_time(e1) / reps
+    finally:
+        _engine.set_option("binnet_keys", 1)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -834,7 +849,7 @@ def bench_binnet(torch, ctx, P, n_gene, qcut=0.05, reps=5):
         pass
     peak = peaks.get("hbm_gbs") or peaks.get("hbm_GBs") or 6545.0
     gbs = 9.0 * n_gene * n_gene / (ms * 1e-3) / 1e9
-    return {"workload": "binnet_%dk" % (n_gene // 1000), "qcut": qcut, "ms": ms, "edges": int(stats[0].item()) // reps,
+    return {"workload": "binnet_%dk" % (n_gene // 1000), "qcut": qcut, "ms": ms, "ms_values_kernel": ms_values, "edges": edges,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                          "algorithmic_bytes": 9 * n_gene * n_gene}}
 

@@ -28,6 +28,7 @@ extern int nsr_umma_kblock;
 extern int nsr_umma_pair;
 extern int nsr_epi_warps;
 extern int nsr_umma_stack;
+extern int nsr_binnet_keys;
 extern int nsr_umma_dynamic;
 int nsr_split_k = 1;          // 1: few-tile launches split the cells over work items (see contract_impl)
 extern int nsr_epi_sleep_ns;
@@ -131,6 +132,7 @@ extern "C" int nsr_set_option(const char* name, int value) {
     if (!strcmp(name, "umma_dynamic")) { nsr_umma_dynamic = value ? 1 : 0; return 0; }
     if (!strcmp(name, "split_k")) { nsr_split_k = value ? 1 : 0; return 0; }
     if (!strcmp(name, "adaptive_min_cells")) { nsr_adaptive_min_cells = value < 0 ? 0 : value; return 0; }
+    if (!strcmp(name, "binnet_keys")) { nsr_binnet_keys = value ? 1 : 0; return 0; }
     if (!strcmp(name, "umma_stack")) { nsr_umma_stack = value ? 1 : 0; return 0; }
     if (!strcmp(name, "epi_warps")) {
         NSR_REQUIRE(value == 8 || value == 16, "epi_warps must be 8 or 16");

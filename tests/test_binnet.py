@@ -77,9 +77,19 @@ def test_sort_free_rule_equals_bh_threshold():
 gpu = pytest.mark.gpu
 
 
+@pytest.fixture(params=["keys", "values"])
+def row_kernel(request):
+    """Both row kernels of csrc/binnet.cu: 4-byte keys in shared memory, two rows per SM (the default) and
+    the 8-byte row staged with one bulk copy."""
+    from normalisr_b200 import engine
+    engine.set_option("binnet_keys", 1 if request.param == "keys" else 0)
+    yield request.param
+    engine.set_option("binnet_keys", 1)
+
+
 @gpu
 @pytest.mark.parametrize("name", ["binnet_coex", "binnet_ties"])
-def test_binnet_golden_bit_identical(name):
+def test_binnet_golden_bit_identical(name, row_kernel):
     from normalisr_b200 import normalisr as norm
     P, qcuts, nets = _golden_nets(name)
     for q, want in zip(qcuts, nets):
@@ -95,7 +105,7 @@ def test_binnet_golden_bit_identical(name):
 
 
 @gpu
-def test_binnet_large_against_oracle_and_row_chunks(monkeypatch):
+def test_binnet_large_against_oracle_and_row_chunks(monkeypatch, row_kernel):
     """1,500 genes: coex P from the CUDA path, a hub row with > 6000... candidates is exercised at
     7,000 columns separately; host input staged in several row chunks."""
     from normalisr_b200 import binnet as bn, normalisr as norm, synth
@@ -118,13 +128,14 @@ def test_binnet_large_against_oracle_and_row_chunks(monkeypatch):
 
 
 @gpu
-def test_binnet_rows_wider_than_shared_memory():
-    """Rows of more than 25,000 entries take the kernel variant that re-reads the row from L2;
-    also rows of a row block whose diagonal sits at an offset, or outside the block."""
+def test_binnet_rows_wider_than_shared_memory(row_kernel):
+    """Rows of more than 25,000 entries (100,000 for the key kernel) take the kernel variant that re-reads the row
+    from L2; also rows of a row block whose diagonal sits at an offset, or outside the block."""
     from normalisr_b200 import binnet as bn, engine
     rng = np.random.default_rng(9)
     ctx = engine.context(0)
-    for cols, diag0 in ((30011, 0), (30011, 29990), (30011, -5), (5000, 4990), (4999, 3), (24999, 100), (25000, 7)):
+    for cols, diag0 in ((30011, 0), (30011, 29990), (30011, -5), (5000, 4990), (4999, 3), (24999, 100), (25000, 7), (49999, 3),
+                        (50000, 11), (50001, 49000), (100003, 5)):
         Pm = rng.random((24, cols)) ** rng.integers(1, 8, size=(24, 1))
         out, stats = bn.binnet_rows(ctx, torch.from_numpy(Pm).cuda(), 0.1, diag0)
         got = out.cpu().numpy().astype(bool)
@@ -142,7 +153,7 @@ def test_binnet_rows_wider_than_shared_memory():
 
 
 @gpu
-def test_binnet_slowly_converging_and_tied_rows():
+def test_binnet_slowly_converging_and_tied_rows(row_kernel):
     """Rows on which the plain fixed-point iteration needs many steps (a staircase just under the BH
     line), rows packed with ties (window overflow -> fallback path), negative zero, all-equal rows."""
     from normalisr_b200 import binnet as bn, engine
@@ -164,6 +175,37 @@ def test_binnet_slowly_converging_and_tied_rows():
         got = out.cpu().numpy().astype(bool)
         for i in range(len(rows)):
             assert np.array_equal(got[i], orc.bh(Pm[i]) <= q), (i, q)
+
+
+@gpu
+def test_binnet_threshold_ties_in_the_high_word(row_kernel):
+    """Entries that share the high 32 bits of the BH threshold (the key kernel decides those from the value in
+    global memory), rows at odd offsets (no 16-byte alignment), odd widths, a diagonal inside the cluster."""
+    from normalisr_b200 import binnet as bn, engine
+    rng = np.random.default_rng(12)
+    ctx = engine.context(0)
+    for cols, ld, off in ((4000, 4000, 0), (4001, 4001, 0), (4000, 4003, 1), (3999, 4002, 3)):
+        rows = []
+        for centre in (0.01, 0.05 * 1000 / cols, 3e-5):
+            k = rng.integers(-2000, 2000, size=cols)
+            cluster = centre * (1.0 + k * 2.0 ** -44)                      # equal high words, different low words
+            rows.append(np.where(rng.random(cols) < 0.4, cluster, rng.random(cols) ** 3))
+        rows.append(np.where(rng.random(cols) < 0.5, np.float64(0.05) * 1200 / cols, rng.random(cols)))
+        Pm = np.array(rows)
+        buf = torch.zeros(len(rows) * ld + 8, dtype=torch.float64, device="cuda")
+        view = buf[off:off + len(rows) * ld].view(len(rows), ld)[:, :cols]
+        view.copy_(torch.from_numpy(Pm))
+        for q, diag0 in ((0.05, -cols - 5), (0.05, 7), (0.3, 1000)):
+            out, stats = bn.binnet_rows(ctx, view, q, diag0)
+            got = out.cpu().numpy().astype(bool)
+            for i in range(len(rows)):
+                d = i + diag0
+                keep = np.ones(cols, dtype=bool)
+                if 0 <= d < cols:
+                    keep[d] = False
+                    assert not got[i, d]
+                assert np.array_equal(got[i, keep], orc.bh(Pm[i, keep]) <= q), (cols, ld, off, q, diag0, i)
+            assert int(stats[1]) == 0
 
 
 @gpu
