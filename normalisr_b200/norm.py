@@ -135,6 +135,57 @@ def _gram_chebyshev(dc_d, logw, wt_d, bounds=None):
     return G + torch.triu(G, 1).transpose(1, 2), ok
 
 
+_WIDE_BYTES = 1 << 28      # bound on each (genes, cells) temporary of the wide fallbacks below
+
+
+def _pinv_rank_sym(G, tol=1e-8):
+    """inv_rank (association.py:66-80) for a stack of symmetric matrices on the device: the singular values of a
+    symmetric matrix are the absolute eigenvalues and its right singular vectors the eigenvectors, so
+    ``(Vt.T / s) @ Vt`` with values below tol * largest dropped is V diag(1 / |lambda|) V^T over the kept ones."""
+    lam, V = torch.linalg.eigh(G)
+    a = lam.abs()
+    keep = (a >= tol * a.amax(dim=-1, keepdim=True)) & (a > 0)
+    inv = torch.where(keep, 1.0 / torch.where(keep, a, torch.ones_like(a)), torch.zeros_like(a))
+    return (V * inv[..., None, :]) @ V.transpose(-1, -2), keep.sum(dim=-1)
+
+
+def _normvar_rows_wide(dt_d, dc_d, logw, wt_d, keepvar, G, out, flags):
+    """normvar for more covariates than the kernels stage (nc > 16): the same algebra as ``_normvar_rows`` with
+    library products (float64 GEMMs, batched symmetric eigendecompositions) in gene chunks.  ``G``: the chunk's
+    Gram matrices if the interpolation supplies them, else None (formed here, one GEMM on the products c_i c_j)."""
+    genes, n = dt_d.shape
+    nc = dc_d.shape[0]
+    step = max(1, _WIDE_BYTES // (8 * n))
+    D = None
+    for g0 in range(0, genes, step):
+        g1 = min(genes, g0 + step)
+        wt = wt_d[g0:g1]
+        s = torch.exp(wt[:, None] * logw[None, :])                          # w ** wt (1 where wt == 0), norm.py:238-239
+        xs = dt_d[g0:g1] * s
+        b = (xs * s) @ dc_d.T                                               # sum_k (s dt) (s c)
+        if G is not None:
+            Gc = G[g0:g1]
+        else:
+            if D is None:
+                iu = torch.triu_indices(nc, nc, device=dc_d.device)
+                D = (dc_d[iu[0]] * dc_d[iu[1]]).T.contiguous()              # (n, tri)
+            tri = (s * s) @ D
+            Gc = torch.zeros((g1 - g0, nc, nc), dtype=torch.float64, device=dc_d.device)
+            Gc[:, iu[0], iu[1]] = tri
+            Gc = Gc + torch.triu(Gc, 1).transpose(1, 2)
+        ci, rank = _pinv_rank_sym(Gc)                                        # norm.py:159-160
+        coef = torch.einsum('gij,gj->gi', ci, b)
+        res = xs - s * (coef @ dc_d)                                         # norm.py:163 with dc * w2[x]
+        if keepvar:                                                          # norm.py:241-243, 251-254
+            dv = torch.sqrt(((xs - xs.mean(dim=1, keepdim=True)) ** 2).mean(dim=1))
+            dv2 = torch.sqrt((res * res).mean(dim=1))
+            res = res * ((dv / dv2) ** wt)[:, None]
+        flags["zero_rank"].append((rank <= 0).any())
+        flags["finite"].append(torch.isfinite(res).all())
+        out[g0:g1] = res
+    return out
+
+
 def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None, flags=None):
     """One block of genes resident on the device -> normalised block.  ``G``: a callable returning the
     block's Gram matrices (``_gram_chebyshev``; called AFTER the statistics kernel is queued, so its many
@@ -224,8 +275,7 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
     if cat not in (0, 1, 2):
         raise ValueError('Invalid cat value.')
     nc = dc.shape[0]
-    if nc > 16:
-        raise NotImplementedError('normvar is accelerated for up to 16 covariates.')
+    wide = nc > 16                       # more covariates than the kernels stage: library products (_normvar_rows_wide)
     to_host = not _is_dev(dt)
     ctx = engine.context(device if device is not None else (dt.device if _is_dev(dt) else None))
     dev = ctx.device
@@ -244,7 +294,9 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
                 cheb["G"], cheb["ok"] = _gram_chebyshev(dc_d, logw, wt_d, bounds)
             return cheb["G"][g0:g1]
         flags = {"zero_rank": [], "finite": []}
-        if use_cheb:
+        if wide:
+            design = None
+        elif use_cheb:
             design = torch.zeros((16, ns), dtype=torch.float64, device=dev)
             design[:nc] = dc_d
         elif nc <= 12:
@@ -279,9 +331,15 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         for g0 in range(0, nt, step):
             g1 = min(nt, g0 + step)
             blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
-            res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar,
-                                G=(lambda a=g0, b=g1: gram_block(a, b)) if use_cheb else None,
-                                out=None if to_host else dtn[g0:g1], flags=flags)
+            if wide:
+                res = _normvar_rows_wide(blk, dc_d, logw, wt_d[g0:g1].contiguous(), keepvar,
+                                         gram_block(g0, g1) if use_cheb else None,
+                                         torch.empty((g1 - g0, ns), dtype=torch.float64, device=dev) if to_host else dtn[g0:g1],
+                                         flags)
+            else:
+                res = _normvar_rows(ctx, blk, dc_d, design, logw, wt_d[g0:g1].contiguous(), keepvar,
+                                    G=(lambda a=g0, b=g1: gram_block(a, b)) if use_cheb else None,
+                                    out=None if to_host else dtn[g0:g1], flags=flags)
             if normmean:
                 cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
                 res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
@@ -351,8 +409,6 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
         while it < stepmax and bestv > eps:
             inv = None if scale is None else (1.0 / scale)
             Qt, rank, _ = covariate_basis_device(ctx, dc_d if inv is None else dc_d * inv)   # least squares without intercept = projection
-            if rank > 16:
-                raise NotImplementedError('compute_var is accelerated for covariate rank <= 16.')
             q1 = torch.cat([Qt, ones], 0).contiguous() if rank else ones
             qsum = Qt.sum(dim=1) if rank else None
             col = torch.zeros(ns, dtype=torch.float64, device=dev)
@@ -368,6 +424,14 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
                 mean = (cf[:, rank] - (coef @ qsum if rank else 0.0)) / ns        # norm.py:104
                 var = (sxx - (coef * coef).sum(dim=1)) / ns - mean * mean         # :105 (Qt is orthonormal)
                 istd = (1.0 / torch.sqrt(var)).contiguous()
+                if rank > 16:
+                    # more basis rows than nsr_colvar keeps in registers: the residual block in gene chunks (library GEMM)
+                    sub = max(1, _WIDE_BYTES // (8 * ns))
+                    for h0 in range(0, g1 - g0, sub):
+                        h1 = min(g1 - g0, h0 + sub)
+                        r = blk[h0:h1] - coef[h0:h1] @ Qt
+                        col += (((r - mean[h0:h1, None]) * istd[h0:h1, None]) ** 2).sum(dim=0)
+                    continue
                 part = torch.empty(ns, dtype=torch.float64, device=dev)
                 _lib.check(ctx.lib.nsr_colvar(ctx.handle, engine._stream(), blk.data_ptr(), g1 - g0, ns,
                                               blk.stride(0) if g1 - g0 > 1 else ns, Qt.data_ptr() if rank else None, rank,

@@ -42,7 +42,7 @@ def _pinv_rank_batched(m, tol=1e-8):
 
 
 def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduce=0, device=None, **ka):
-    from .association import inv_rank, _as_host_f64, _is_dev, _out
+    from .association import inv_rank, _as_host_f64, _is_dev, _outs
     if ka:
         raise TypeError("association_test_2() got an unexpected keyword argument '{}'".format(next(iter(ka))))
     to_host = not _is_dev(dy)
@@ -154,6 +154,5 @@ def association_tests_single1(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
         out2 = gamma * t_vx[:, None] if return_dot else gamma                    # association.py:1058-1061
         res = (P, out2, alpha, t_vx, vy)
         if to_host:
-            torch.cuda.current_stream().synchronize()
-            res = tuple(_out(t, True) for t in res)
+            res = _outs(res)
     return res

@@ -37,15 +37,26 @@ from . import engine
 from ._lib import MODE_RAW, MAX_RANK
 
 
+def _exact_inverse_only(ka, size):
+    """The keyword arguments single=4 hands to inv_rank (association.py:528: ``method``, ``mpc``, ``qr``).  ``mpc``
+    exists to make the reference's per-grouping SVD affordable by truncating it; here every leave-one-out inverse
+    comes from one factorisation, so only the settings under which the reference computes the exact pseudo-inverse
+    are taken: method 'auto' / 'scipy' with mpc = 0 or mpc >= the size of the matrices inverted (then :64 picks
+    the exact SVD and :78-79 truncates nothing).  ``qr`` only concerns the randomised SVD."""
+    mpc = ka.pop('mpc', 0)
+    method = ka.pop('method', 'auto')
+    ka.pop('qr', None)
+    if method not in ('auto', 'scipy') or (mpc != 0 and mpc < size):
+        raise NotImplementedError('normalisr_b200 computes the exact leave-one-out inverses of single=4; a truncated '
+                                  'or randomised SVD (method={!r}, mpc={} < {}) is not reproduced.'.format(method, mpc, size))
+
+
 def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduce=0,
                               precision='default', device=None, engine_id=None, exact_groupings=True, **ka):
-    from .association import covariate_basis_device, _residualize_any, _residualize_groupings, _is_dev, _out
+    from .association import covariate_basis_device, _residualize_any, _residualize_groupings, _is_dev, _outs
     eng = ka.pop('engine', engine.ENGINE_UMMA) if engine_id is None else engine_id
     tol = ka.pop('tol', 1e-8)
-    if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
-        raise NotImplementedError('normalisr_b200 implements the exact SVD branch of inv_rank only '
-                                  '(method auto/scipy, mpc=0).')
-    ka.pop('qr', None)
+    _exact_inverse_only(ka, dx.shape[0] - 1 + dc.shape[0])
     if ka:
         raise TypeError("association_test_4() got an unexpected keyword argument '{}'".format(
             next(iter(ka))))
@@ -109,8 +120,7 @@ def association_tests_single4(dx, dy, dc, lowmem=True, return_dot=True, dimreduc
             alpha = al[None, :, :].expand(nx, ny, nc).contiguous()
         res = (P, out2, alpha, dxx, dyy)
         if to_host:
-            torch.cuda.current_stream().synchronize()
-            res = tuple(_out(t, True) for t in res)
+            res = _outs(res)
     return res
 
 
@@ -147,12 +157,9 @@ def pair_alpha(K, B):
 def association_tests_single4_same(dx, dc, lowmem=True, return_dot=True, dimreduce=0, device=None, **ka):
     """``association_tests(dx, None, dc, single=4)``: returns (P, dot|gamma, alpha|None, None, vary) with the
     reference's assembly (association.py:1036-1065; note :1040 - the coefficient is multiplied by vary)."""
-    from .association import covariate_basis_device, _to_device_f64, _is_dev, _out
+    from .association import covariate_basis_device, _to_device_f64, _is_dev, _outs
     tol = ka.pop('tol', 1e-8)
-    if ka.pop('mpc', 0) != 0 or ka.pop('method', 'auto') not in ('auto', 'scipy'):
-        raise NotImplementedError('normalisr_b200 implements the exact SVD branch of inv_rank only '
-                                  '(method auto/scipy, mpc=0).')
-    ka.pop('qr', None)
+    _exact_inverse_only(ka, max(dx.shape[0] - 2, 0) + dc.shape[0])
     for k in ('precision', 'engine', 'exact_groupings'):
         ka.pop(k, None)
     if ka:
@@ -217,8 +224,7 @@ def association_tests_single4_same(dx, dc, lowmem=True, return_dot=True, dimredu
             raise AssertionError('non-finite result')                # :1077
         res = (P, out2, alpha, None, vary)
         if to_host:
-            torch.cuda.current_stream().synchronize()
-            res = tuple(_out(t, True) for t in res)
+            res = _outs(res)
     return res
 
 

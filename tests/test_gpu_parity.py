@@ -195,6 +195,22 @@ def test_host_pipeline_many_chunks_equals_device_path(monkeypatch):
     assert np.array_equal(Po, Pd) and np.array_equal(Do, Dd)
 
 
+@pytest.mark.parametrize("single", [0, 4])
+def test_de_host_genes_streamed_in_row_chunks_equal_device_path(monkeypatch, single):
+    """de() with a HOST expression matrix larger than one staging buffer (config 5 on one GPU: the 160 GB matrix
+    never sits in HBM, only its digit planes do): the genes arrive in row chunks on a copy stream while the
+    previous chunk is projected; same bits as the device-resident call."""
+    p = synth.host_problem(1021, 3001, 2000, n_group=10, group_p=0.1)
+    dev = norm.de(*[torch.from_numpy(p[k]).cuda() for k in ("dg", "dt", "dc")], single=single)
+    monkeypatch.setattr(association, "_ROW_CHUNK_BYTES", 8 * 2000 * 257)     # 12 chunks of 257 genes
+    host = norm.de(p["dg"], p["dt"], p["dc"], single=single)
+    for a, b in zip(host, dev):
+        if a is not None:
+            assert np.array_equal(a, b.cpu().numpy())
+    pinned = norm.de(p["dg"], torch.from_numpy(p["dt"]).pin_memory(), p["dc"], single=single)
+    assert all(np.array_equal(a, b) for a, b in zip(pinned, host) if a is not None)
+
+
 def test_device_tensors_in_device_tensors_out():
     g = load_golden("coex_chain")
     dt = torch.from_numpy(g["dt"]).cuda()
@@ -841,6 +857,24 @@ def test_de_single4_rank_deficient_groupings_fall_back():
         assert np.isfinite(got[0]).all() and ((got[0] >= 0) & (got[0] <= 1)).all()
     except AssertionError:
         pass            # like the reference (association.py:557)
+
+
+def test_de_single4_mpc_that_truncates_nothing():
+    """single=4 hands method / mpc / qr to inv_rank (association.py:528).  An mpc at least as large as the matrices
+    inverted selects the exact SVD and truncates nothing (:64, :78-79): same results as mpc = 0 (golden made by
+    the reference with mpc = n_group - 1 + n_cov); a truncating mpc or the randomised SVD is refused."""
+    g = load_golden("inv_rank")
+    dg, dt, dc = g["de_dg"], g["de_dt"], g["de_dc"]
+    for ka in (dict(mpc=dg.shape[0] - 1 + dc.shape[0], method="scipy"), dict(mpc=100, qr=2), dict()):
+        P, gamma, _, varg, vart = norm.de(dg, dt, dc, single=4, **ka)
+        assert_p_close(P, g["de_P"])
+        scale = np.sqrt(g["de_vart"] / g["de_varg"][:, None])
+        assert (np.abs(gamma - g["de_gamma"]) <= R_ATOL * scale + 1e-12).all()
+        np.testing.assert_allclose(varg, g["de_varg"], rtol=1e-7)
+        np.testing.assert_allclose(vart, g["de_vart"], rtol=1e-7)
+    for ka in (dict(mpc=3), dict(method="sklearn")):
+        with pytest.raises(NotImplementedError):
+            norm.de(dg, dt, dc, single=4, **ka)
 
 
 def test_segments_flags_and_done_counters():

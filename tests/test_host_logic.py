@@ -43,7 +43,30 @@ def test_inv_rank_matches_oracle():
     with pytest.raises(ValueError):
         association.inv_rank(np.zeros((2, 3)))
     with pytest.raises(NotImplementedError):
-        association.inv_rank(np.eye(3), mpc=2)
+        association.inv_rank(np.stack([np.eye(3)] * 2), mpc=2)               # association.py:58-60
+    with pytest.raises(ValueError):
+        association.inv_rank(np.eye(3), method='scipys')
+    for bad in (dict(tol=0), dict(qr=-1), dict(qr=1.5)):
+        with pytest.raises(ValueError):
+            association.inv_rank(np.eye(3), **bad)
+
+
+def test_inv_rank_every_option_matches_reference():
+    """Rank cap, exact and randomised truncated SVD (random_state 0), QR-normalised power iterations, stacks
+    (association.py:4-134), against tests/golden/inv_rank.npz made by the unmodified reference."""
+    import json
+    from conftest import load_golden
+    g = load_golden("inv_rank")
+    options = json.loads(str(g["options"]))
+    for i in range(4):
+        for j, ka in enumerate(options):
+            inv, rank = association.inv_rank(g["m%d" % i], **ka)
+            want = g["inv%d_%d" % (i, j)]
+            assert rank == int(g["rank%d_%d" % (i, j)]), (i, ka)
+            np.testing.assert_allclose(inv, want, rtol=1e-9, atol=1e-11 * np.abs(want).max(), err_msg=str((i, ka)))
+    inv, rank = association.inv_rank(g["stack"])
+    np.testing.assert_allclose(inv, g["stack_inv"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(rank, g["stack_rank"])
 
 
 def test_tile_lists_cover_exactly_once():

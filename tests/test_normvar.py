@@ -119,6 +119,40 @@ def test_compute_var_golden_and_oracle(monkeypatch):
 
 
 @gpu
+@pytest.mark.parametrize("chebyshev", [True, False])
+def test_normvar_and_compute_var_many_covariates(monkeypatch, chebyshev):
+    """More covariates than the kernels stage (16): same results through the library-product fallbacks
+    (normvar: 20 and 33 covariates, rank-deficient; compute_var: covariate rank 24)."""
+    from normalisr_b200 import norm as nv
+    monkeypatch.setattr(nv, "_USE_CHEBYSHEV", chebyshev)
+    monkeypatch.setattr(nv, "_WIDE_BYTES", 8 * 1200 * 64)                       # several gene chunks
+    rng = np.random.default_rng(47)
+    for genes, n, nc in ((150, 1200, 20), (70, 900, 33)):
+        dc = np.concatenate([rng.normal(size=(nc - 1, n)), np.ones((1, n))])
+        dc[1] = rng.random(n) < 0.3
+        dc[2] = 2 * dc[0] - dc[-1]                                             # rank-deficient covariates
+        dt = rng.normal(size=(genes, n)) * rng.uniform(0.2, 3, size=(genes, 1)) - 6.0
+        w = np.exp(rng.normal(size=n) * 0.3)
+        wt = rng.uniform(0, 1.5, size=genes)
+        wt[::7] = 0
+        for ka in ({}, {"keepvar": False, "cat": 0}, {"normmean": True, "cat": 2, "dextra": rng.normal(size=(3, n))}):
+            want = orc.normvar(dt, dc, w, wt, **ka)
+            monkeypatch.setattr(nv, "_ROW_CHUNK_BYTES", 8 * n * 100)
+            got = nv.normvar(dt, dc, w, wt, **ka)
+            for a, b in zip(got, want):
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(b).max()))
+        dev = nv.normvar(*[torch.from_numpy(x).cuda() for x in (dt, dc, w, wt)])
+        np.testing.assert_allclose(dev[0].cpu().numpy(), orc.normvar(dt, dc, w, wt)[0], rtol=1e-9, atol=1e-8)
+    if chebyshev:
+        n, genes = 2000, 500
+        dc = np.concatenate([rng.normal(size=(23, n)), np.ones((1, n))])
+        dt = rng.normal(size=(genes, n)) * np.exp(0.3 * dc[0]) * rng.uniform(0.5, 2, size=(genes, 1)) + 0.5 * dc[1] - 7.0
+        monkeypatch.setattr(nv, "_ROW_CHUNK_BYTES", 8 * n * 200)
+        for stepmax in (1, 3):
+            np.testing.assert_allclose(nv.compute_var(dt, dc, stepmax=stepmax), orc.compute_var(dt, dc, stepmax=stepmax), rtol=1e-9)
+
+
+@gpu
 def test_normvar_errors():
     from normalisr_b200 import normalisr as norm
     dt, dc, w, wt = np.zeros((4, 10)), np.ones((2, 10)), np.ones(10), np.ones(4)
@@ -130,8 +164,6 @@ def test_normvar_errors():
         norm.normvar(dt, dc, w, wt, cat=3)
     with pytest.raises(RuntimeError):
         norm.normvar(dt + 1, np.zeros((2, 10)), w, wt)        # zero-rank covariates (norm.py:161)
-    with pytest.raises(NotImplementedError):
-        norm.normvar(np.zeros((4, 40)), np.ones((17, 40)), np.ones(40), wt)
 
 
 @gpu
