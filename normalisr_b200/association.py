@@ -18,6 +18,14 @@ from . import engine
 from ._lib import MODE_COEX, MODE_DE, MODE_RAW, ENGINE_UMMA, MAX_RANK
 
 _ROW_CHUNK_BYTES = 1 << 30       # host->device staging granularity for numpy inputs
+# Streamed co-expression pipeline: row chunks of about _PIPE_CHUNK_BYTES, in multiples of _STRIP_TILES 128-row tiles.
+# Small chunks on purpose: the output that becomes final with a chunk can only leave once the chunk's strip is
+# contracted, and final output is produced fastest at the end (it grows with the square of the rows seen), so the
+# device->host leg trails the host->device leg by about one chunk + one strip.  100k cells x 20k genes, one B200:
+# 1.2 GB chunks 330 ms, 0.4 GB 318 ms, 0.2 GB (256 rows) 315 ms per call.
+_PIPE_CHUNK_BYTES = 1 << 28
+_STRIP_TILES = 2
+_TIMELINE = None                 # profiling hook (tools/coex_e2e_profile.py): a list that receives (label, chunk, timing event)
 
 
 # --------------------------------------------------------------------------------------
@@ -254,6 +262,13 @@ def _residualize_groupings(ctx, dx, Qt_dev, n_slices, keep_coef, exact=True):
     return engine.residualize(ctx, xd, Qt_dev, n_slices, keep_coef=keep_coef), xd
 
 
+def _mark(label, chunk, stream):
+    if _TIMELINE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream)
+        _TIMELINE.append((label, chunk, ev))
+
+
 def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef, out_host):
     """Co-expression of a HOST matrix with the three legs overlapped:
       copy stream : chunk c+1 of the expression matrix, host -> device
@@ -268,8 +283,8 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
     A = engine.Sliced(rows, n, n_slices, dev)
     P = torch.empty((rows, rows), dtype=torch.float64, device=dev)
     D = torch.empty((rows, rows), dtype=torch.float64, device=dev)
-    strip_rows = 12 * engine.TILE
-    base = max(strip_rows, (_ROW_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
+    strip_rows = _STRIP_TILES * engine.TILE
+    base = max(strip_rows, (_PIPE_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
     # row chunks: `base` rows while plenty remain, then geometrically smaller ones, so that the work
     # left after the last host->device copy (the last strip's tiles and its device->host copy) is small
     bounds = [0]
@@ -289,17 +304,21 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
         with torch.cuda.stream(copy_stream):
             if done[i & 1] is not None:
                 copy_stream.wait_event(done[i & 1])
+            _mark("h2d_begin", i, copy_stream)
             b[:r1 - r0].copy_(xh[r0:r1], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy_stream)
+            _mark("h2d_end", i, copy_stream)
         main.wait_event(ready)
         engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=A, row_offset=r0, keep_coef=keep_coef)
         done[i & 1] = torch.cuda.Event()
         done[i & 1].record(main)
+        _mark("projected", i, main)
         tiles = engine.coex_strip_tiles(r0 // engine.TILE, (r1 + engine.TILE - 1) // engine.TILE)
         # optimistic single pass over the cells (planning would need a device->host sync per chunk
         # and stall the copy stream); the int32 bound is verified once at the end
         engine.contract(ctx, MODE_COEX, A, A, tiles, dof_a, P, D, n_products, eng, k_chunk=0)
+        _mark("contracted", i, main)
         if out_host is not None:
             fin = torch.cuda.Event()
             fin.record(main)
@@ -307,6 +326,7 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
             for dst, src in zip(out_host, (P, D)):
                 engine.copy_block_to_host(ctx, dst, src, 0, r1, r0, r1, d2h_stream)
                 engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
+            _mark("d2h_end", i, d2h_stream)
     main.synchronize()
     d2h_stream.synchronize()
     k_chunk = engine.plan_k_chunk(A, A, n_products)

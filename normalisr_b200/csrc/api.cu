@@ -151,6 +151,12 @@ extern "C" int nsr_set_option(const char* name, int value) {
 
 // Shared implementation of nsr_contract / nsr_contract_ab / nsr_contract_segments.
 // tile_stride = 2: host_tiles holds (tile_row, tile_col), one segment; 3: (segment, tile_row, tile_col).
+// tile list: page-locked host memory (read over PCIe, zero-copy) -> device memory
+__global__ void tiles_upload_kernel(int4* __restrict__ dst, const int4* __restrict__ src, int64_t n_vec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 static int contract_impl(nsr_ctx* ctx, uintptr_t stream, int engine, int mode, const int8_t* a_slices, int64_t rows_a,
                          int64_t rows_alloc_a, int n_slices_a, const double* quantum_a, const double* var_a,
                          const NsrSegOperand* segs, int n_segs, int n_slices_b, int64_t n, int64_t n_pad, int n_products,
@@ -248,8 +254,17 @@ static int contract_impl(nsr_ctx* ctx, uintptr_t stream, int engine, int mode, c
     if (ctx->tiles_event == nullptr) NSR_CHECK(cudaEventCreateWithFlags(&ctx->tiles_event, cudaEventDisableTiming));
     else NSR_CHECK(cudaEventSynchronize(ctx->tiles_event));       // previous upload has left the staging buffer
     memcpy(ctx->tiles_pinned, upload, (size_t)n_upload * sizeof(int32_t));
-    NSR_CHECK(cudaMemcpyAsync(ctx->tiles_dev, ctx->tiles_pinned, (size_t)n_upload * sizeof(int32_t),
-                              cudaMemcpyHostToDevice, st));
+    // NOT a cudaMemcpyAsync: a host-to-device copy queues on the H2D copy engine, and in the streamed pipelines that
+    // engine is busy with the next gigabyte-sized chunk of the expression matrix - the tile list then waits ~22 ms
+    // behind it and so does the contraction (measured: every strip's launch started one chunk late, 350 -> 3xx ms
+    // end to end at 100k x 20k).  A small kernel reads the page-locked list over PCIe instead.
+    {
+        const int64_t n_vec = (n_upload + 3) / 4;            // the buffers are allocated with twice the room asked for
+        const int blocks = (int)((n_vec + 255) / 256 < 16 ? (n_vec + 255) / 256 : 16);
+        tiles_upload_kernel<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(reinterpret_cast<int4*>(ctx->tiles_dev),
+                                                                    reinterpret_cast<const int4*>(ctx->tiles_pinned), n_vec);
+        NSR_CHECK(cudaGetLastError());
+    }
     NSR_CHECK(cudaEventRecord(ctx->tiles_event, st));
 
     ContractParams ep;

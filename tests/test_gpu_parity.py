@@ -180,7 +180,7 @@ def test_host_pipeline_many_chunks_equals_device_path(monkeypatch):
     as their columns arrive, finished blocks copied back on a third stream, geometric tail chunks)
     gives the same bits as the device-resident path, with and without caller-provided pinned
     output buffers."""
-    monkeypatch.setattr(association, "_ROW_CHUNK_BYTES", 1)                # smallest row chunks: 1,536 rows, then a tail
+    monkeypatch.setattr(association, "_PIPE_CHUNK_BYTES", 1)               # smallest row chunks: 256 rows each
     p = synth.host_problem(1007, 5003, 1200)
     dt_d, dc_d = torch.from_numpy(p["dt"]).cuda(), torch.from_numpy(p["dc"]).cuda()
     Pd, Dd, vd = norm.coex(dt_d, dc_d)
