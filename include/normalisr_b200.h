@@ -418,7 +418,8 @@ int nsr_mtx_read(const char* path, int64_t nnz, int32_t* row, int32_t* col, doub
  * round-robin), "split_k" (1 = launches with fewer than two waves of tiles split the cells into parts - work
  * items (tile, part) over all SMs, partial sums added in a fixed order by a second small kernel; default 1),
  * "adaptive_min_cells" (see nsr_last_refined), "prefetch" (1 = L2 prefetch of the next
- * cell block in the residual pass; measured neutral, default 0). Process-wide. */
+ * cell block in the residual pass; measured neutral, default 0), "binnet_keys" (1 = nsr_binnet keeps rows as 2-byte
+ * bin keys, four rows per SM, default; 0 = the 8-byte row staged with one bulk copy).  Process-wide. */
 int nsr_set_option(const char* name, int value);
 
 /* Debug / test helper: reconstruct z' (float64, rows x n_pad) from slices and quantum. */

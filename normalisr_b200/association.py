@@ -269,7 +269,7 @@ def _mark(label, chunk, stream):
         _TIMELINE.append((label, chunk, ev))
 
 
-def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef, out_host):
+def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef, out_host, into=None):
     """Co-expression of a HOST matrix with the three legs overlapped:
       copy stream : chunk c+1 of the expression matrix, host -> device
       main stream : projection of chunk c, then every output tile whose columns lie in chunk c
@@ -277,12 +277,21 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
       d2h stream  : the blocks of P / dot that became final with chunk c, device -> host
     After strip c the square [0, end_c)^2 is complete (mirrored entries included), so the newly
     final part is the column block [0:end_c, begin_c:end_c] plus the row block
-    [begin_c:end_c, 0:begin_c].  Returns (A, P_dev, dot_dev, P_host|None, dot_host|None)."""
+    [begin_c:end_c, 0:begin_c].  Returns (A, P_dev, dot_dev).
+
+    ``into`` = (A, P, D): the diagonal block of a multi-GPU job (``parallel``): project into the rank's own Sliced
+    block and write the (rows, rows) square into the given views of the rank's output rows (``out_host``: the
+    matching views of the job's host matrices).  Nothing waits for the device then: the int32 bound is the caller's
+    to verify with the other blocks' energies, and the function returns (A, P, D, event) with the event recorded
+    behind the last device->host copy."""
     dev = ctx.device
     rows, n = xh.shape
-    A = engine.Sliced(rows, n, n_slices, dev)
-    P = torch.empty((rows, rows), dtype=torch.float64, device=dev)
-    D = torch.empty((rows, rows), dtype=torch.float64, device=dev)
+    if into is None:
+        A = engine.Sliced(rows, n, n_slices, dev)
+        P = torch.empty((rows, rows), dtype=torch.float64, device=dev)
+        D = torch.empty((rows, rows), dtype=torch.float64, device=dev)
+    else:
+        A, P, D = into
     strip_rows = _STRIP_TILES * engine.TILE
     base = max(strip_rows, (_PIPE_CHUNK_BYTES // max(1, n * 8)) // strip_rows * strip_rows)
     # row chunks: `base` rows while plenty remain, then geometrically smaller ones, so that the work
@@ -327,6 +336,11 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
                 engine.copy_block_to_host(ctx, dst, src, 0, r1, r0, r1, d2h_stream)
                 engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
             _mark("d2h_end", i, d2h_stream)
+    if into is not None:
+        main.wait_stream(copy_stream)          # the staging buffers go back to the allocator of this stream
+        tail = torch.cuda.Event()
+        tail.record(d2h_stream)
+        return A, P, D, tail
     main.synchronize()
     d2h_stream.synchronize()
     k_chunk = engine.plan_k_chunk(A, A, n_products)

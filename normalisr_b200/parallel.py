@@ -164,6 +164,8 @@ _SYMM = {}            # (bytes, device, group) -> (symmetric uint8 buffer, handl
 # contraction; N = 2: 67.5 vs 72.9 ms per step), "nccl" = point-to-point send/recv kernels,
 # "auto" = "ce" when peer-mapped (symmetric) memory can be set up on all ranks, else "nccl".
 TRANSPORT = "auto"
+PAIR_STRIPS = 8            # column strips per block pair when results go to the host (see contract_plan)
+STREAM_DIAGONAL = True     # host inputs with one home matrix: the diagonal block is contracted while the block's rows arrive
 
 
 def _symm_block(nbytes, device, group):
@@ -288,7 +290,8 @@ def _timed(events, fn):
     return res
 
 
-def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None, home=None):
+def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, out_host=None, symm=None, home=None,
+                skip_diag=False):
     """Pairs schedule on an already residualised block: post the exchange and contract everything this
     rank owns - with the copy-engine transport in ONE persistent launch that starts on the diagonal
     block and picks up each block pair when its planes have arrived.  Returns (P, dot, var_all).
@@ -312,7 +315,8 @@ def _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out, events=None, 
             rounds = start_exchange_ce(symm[0], symm[1], local, group, ctx=ctx)
         else:
             rounds = start_exchange(local, group)
-    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, events, out_host, home=home)
+    P, D = contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, events, out_host, home=home,
+                         skip_diag=skip_diag)
     if world > 1:
         var_all = torch.empty(blk * world, dtype=torch.float64, device=local.var.device)
         dist.all_gather_into_tensor(var_all, local.var, group=group)
@@ -353,7 +357,7 @@ def _mirror_pair(device, k, blk):
 
 
 def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_chunk, out=None, events=None,
-                  out_host=None, single_launch=True, home=None):
+                  out_host=None, single_launch=True, home=None, skip_diag=False):
     """Contract everything ``rank`` owns under the pairs schedule: the upper triangle of its diagonal
     block, then the block pairs of ``rounds`` = [(src, parity, Sliced of block src, works)].
     ``works``: [] when the block is already there (the one-GPU emulation of the schedule in
@@ -371,7 +375,9 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
                  (association.py:1036-1057): the kernel also writes the transposed copy of everything it
                  computes (diagonal block: into P itself; block pair: into a (rows_b x rows_a) buffer) and
                  both rectangles are copied home, so that after all ranks are done every entry of both
-                 triangles has been written exactly once."""
+                 triangles has been written exactly once.
+    ``skip_diag``: the diagonal block is already done and on its way home (``diag_block_streamed``: contracted
+    in strips while the block's rows were still arriving from the host); only the block pairs are launched."""
     blk = local.rows_alloc
     rows_a = block_rows(n_gene, world, rank)
     dev = local.slices.device
@@ -388,11 +394,16 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
     copy_stream = _side_stream2(dev) if to_host else None
     main = torch.cuda.current_stream()
 
-    segs = [dict(B=local, rows_b=rows_a, col0=r0, diagonal=True)]
-    if home is not None:
-        segs[0]["mirror"] = (P.data_ptr() + 8 * r0, D.data_ptr() + 8 * r0, P.stride(0))
-    tiles = [engine.coex_tiles(rows_a)]
-    extra = [dict(works=[], rect=(0, rows_a, 0, rows_a), mbuf=None)]
+    segs, tiles, extra = [], [], []
+    if not skip_diag:
+        segs.append(dict(B=local, rows_b=rows_a, col0=r0, diagonal=True))
+        if home is not None:
+            segs[0]["mirror"] = (P.data_ptr() + 8 * r0, D.data_ptr() + 8 * r0, P.stride(0))
+        tiles.append(engine.coex_tiles(rows_a))
+        extra.append(dict(works=[], rect=(0, rows_a, 0, rows_a), mbuf=None))
+    n_pairs = sum(1 for r in rounds if block_rows(n_gene, world, r[0]))
+    pairs_done = 0
+    flag_driven = single_launch and not k_chunk and all(len(r[3]) == 0 or isinstance(r[3][0], _FlagWork) for r in rounds)
     for k, (src, parity, buf, works) in enumerate(rounds, 1):
         rows_b = block_rows(n_gene, world, src)
         if not rows_b:
@@ -403,9 +414,24 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
         if home is not None:
             mbuf = _mirror_pair(dev, k, blk)
             sg["mirror"] = (mbuf[0].data_ptr(), mbuf[1].data_ptr(), blk)
-        segs.append(sg)
-        tiles.append(pair_tiles(rows_a, rows_b, parity))
-        extra.append(dict(works=works, rect=_segment_rect(rows_a, rows_b, parity), mbuf=mbuf))
+        tl = pair_tiles(rows_a, rows_b, parity)
+        a0, a1, b0, b1 = _segment_rect(rows_a, rows_b, parity)
+        # results travelling to the host: the block pair is cut into column strips, each a segment of its own
+        # (same operands, its own `done` counter), so that a strip leaves while the next one is contracted
+        # instead of the whole rectangle waiting for its last tile
+        n_sub = 1
+        if home is not None and len(tl) and flag_driven:
+            n_sub = max(1, min(PAIR_STRIPS, (MAX_SEGMENTS - len(segs)) // max(1, n_pairs - pairs_done)))
+        pairs_done += 1
+        cols = np.unique(tl[:, 1]) if len(tl) else np.zeros(0, np.int32)
+        for part in np.array_split(cols, min(n_sub, max(1, len(cols)))):
+            if n_sub > 1 and not len(part):
+                continue
+            sel = tl if n_sub == 1 else tl[(tl[:, 1] >= part[0]) & (tl[:, 1] <= part[-1])]
+            c_lo, c_hi = (b0, b1) if n_sub == 1 else (max(b0, int(part[0]) * TILE), min(b1, (int(part[-1]) + 1) * TILE))
+            segs.append(dict(sg))
+            tiles.append(np.ascontiguousarray(sel))
+            extra.append(dict(works=works, rect=(a0, a1, c_lo, c_hi), mbuf=mbuf))
 
     def send(i):
         """queue the device-to-host copies of segment i on the copy stream"""
@@ -423,6 +449,8 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
                     engine.copy_rect_to_host(ctx, dst_t, c0 + b0, r0 + a0, ex["mbuf"][t], b0, a0, b1 - b0, a1 - a0,
                                              stream=copy_stream)
 
+    if not segs:
+        return P, D
     flagged = all(len(ex["works"]) == 0 or isinstance(ex["works"][0], _FlagWork) for ex in extra)
     if single_launch and flagged and len(segs) <= MAX_SEGMENTS:
         sync = _sync_words(ctx)
@@ -548,6 +576,24 @@ def coex_sharded(dt_block, dc, n_gene, group=None, precision="default", dimreduc
     return P, D, var, (rank * blk, rank * blk + block_rows(n_gene, world, rank))
 
 
+def diag_block_streamed(ctx, xh_block, Qt_dev, n_slices, n_products, dof_a, local, out, home, r0):
+    """This rank's gene block from the HOST, with its diagonal block of the output done on the way: the rows
+    arrive in chunks, each chunk is projected into ``local`` and the tiles of the diagonal block whose columns it
+    completes are contracted at once (``association._coex_host_pipeline``), while the next chunk is still on the
+    wire and the finished squares leave for ``home`` on a third stream.  The tensor cores would otherwise idle
+    until the whole block is in (1 / world of the rank's contraction, and as much of its copy-out, overlap the
+    copy-in).  Same bits as the diagonal segment of ``contract_plan``: exact integer sums, symmetric epilogue.
+    Returns the event behind the last device->host copy."""
+    from .association import _coex_host_pipeline
+    rows_a = xh_block.shape[0]
+    P, D = out
+    local.rows = rows_a
+    views = (P[:rows_a, r0:r0 + rows_a], D[:rows_a, r0:r0 + rows_a])
+    host = tuple(h[r0:r0 + rows_a, r0:r0 + rows_a] for h in home)
+    return _coex_host_pipeline(ctx, xh_block, Qt_dev, n_slices, n_products, dof_a, engine.ENGINE_UMMA, False, host,
+                               into=(local, views[0], views[1]))[3]
+
+
 def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimreduce=0, out_dev=None,
               out_host=None, schedule="pairs", home=None):
     """``coex_sharded`` for HOST inputs and outputs: this rank's gene block is a CPU tensor / numpy
@@ -578,17 +624,26 @@ def coex_host(dt_block_host, dc, n_gene, group=None, precision="default", dimred
         local = engine.Sliced(blk, n, n_slices, ctx.device, storage=None if symm is None else symm[0])
         if xh.shape[0] < blk:
             local.slices.zero_(); local.quantum.fill_(1.0); local.var.fill_(1.0)
-        if xh.shape[0]:
+        tail = None
+        streamed = home is not None and schedule == "pairs" and xh.shape[0] > 0 and STREAM_DIAGONAL
+        if streamed:
+            if out_dev is None:
+                out_dev = (torch.zeros((xh.shape[0], n_gene), dtype=torch.float64, device=ctx.device),
+                           torch.zeros((xh.shape[0], n_gene), dtype=torch.float64, device=ctx.device))
+            tail = diag_block_streamed(ctx, xh, Qt_dev, n_slices, n_products, dof_a, local, out_dev, home, rank * blk)
+        elif xh.shape[0]:
             _residualize_any(ctx, xh, Qt_dev, n_slices, False, out=local, row_offset=0)
         if schedule == "allgather":
             P, D, var, (r0, r1) = _coex_strip(ctx, local, n_gene, dof_a, n_products, group, out_dev)
         else:
             P, D, var = _coex_pairs(ctx, local, n_gene, dof_a, n_products, group, out_dev, out_host=out_host, symm=symm,
-                                    home=home)
+                                    home=home, skip_diag=streamed)
             r0, r1 = rank * blk, rank * blk + block_rows(n_gene, world, rank)
         if home is not None:
             assert schedule == "pairs"
             torch.cuda.current_stream().synchronize()
+            if tail is not None:
+                tail.synchronize()
             return None, None, var.cpu().numpy(), (r0, r1)
         if out_host is not None:
             if schedule == "allgather":
@@ -748,19 +803,24 @@ def _device_worker(team, rank, world, dev, xh, dc, n_gene, precision, dimreduce,
             local.slices[:, rows_a:].zero_()
             local.quantum[rows_a:] = 1.0
             local.var[rows_a:] = 1.0
-        if rows_a:
+        okey = (dev.index, "out", max(rows_a, 1), n_gene)
+        if okey not in _STORES:
+            _STORES[okey] = (torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev),
+                             torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev))
+        out = _STORES[okey]
+        tail = None
+        streamed = rows_a > 0 and STREAM_DIAGONAL
+        if streamed:
+            tail = diag_block_streamed(ctx, xh[r0:r0 + rows_a], Qt_dev, n_slices, n_products, dof_a, local, out, home, r0)
+        elif rows_a:
             _residualize_any(ctx, xh[r0:r0 + rows_a], Qt_dev, n_slices, False, out=local, row_offset=0)
         ev = torch.cuda.Event()
         ev.record()
         team.stores[rank], team.ready[rank] = store, ev
         team.barrier.wait()                       # every block's event exists
         rounds = _pull_rounds(ctx, team, rank, world, local)
-        okey = (dev.index, "out", max(rows_a, 1), n_gene)
-        if okey not in _STORES:
-            _STORES[okey] = (torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev),
-                             torch.zeros((max(rows_a, 1), n_gene), dtype=torch.float64, device=dev))
-        out = _STORES[okey]
-        contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, None, None, home=home)
+        contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, 0, out, None, None, home=home,
+                      skip_diag=streamed)
         # the optimistic single pass over the cells is verified like in _coex_pairs
         for r in rounds:
             wait_block(r[3])
@@ -775,6 +835,8 @@ def _device_worker(team, rank, world, dev, xh, dc, n_gene, precision, dimreduce,
         if rows_a:
             var_out[r0:r0 + rows_a].copy_(local.var[:rows_a], non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        if tail is not None:
+            tail.synchronize()
         team.barrier.wait()                       # nobody still pulls from this device's block
     except BaseException as e:                    # noqa: BLE001 - re-raised by the caller
         team.errors[rank] = e
