@@ -59,16 +59,57 @@ def cpu_sample_genes(cores, n_gene):
 # clocks
 # --------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons of one GPU DURING the timed region: an NVML polling thread (20 ms; no
+    start-up latency, so even a 100 ms region gets samples), nvidia-smi -lms as the fallback."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.rows = []
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+
+    def _poll(self, nv, h):
+        import threading
+        self.stop_flag = threading.Event()
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    try:
+                        bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), float(mx),
+                                      nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(bits)))
+                except Exception:
+                    pass
+                self.stop_flag.wait(0.02)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            self._poll(nv, h)
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -80,6 +121,19 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.rows:
+                pw = [r[2] for r in self.rows]
+                load = [r[0] for r in self.rows if r[2] >= 0.5 * max(pw)] or [r[0] for r in self.rows]
+                bits = 0
+                for r in self.rows:
+                    bits |= r[3]
+                out.update(sm_mhz=float(np.median(load)), sm_max_mhz=float(max(r[1] for r in self.rows)),
+                           reasons=sorted(k for k, b in self.REASON_BITS.items() if bits & b), samples=len(self.rows),
+                           power_w_max=float(max(pw)), how="nvml, 20 ms")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
