@@ -387,6 +387,15 @@ int nsr_binnet(nsr_ctx* ctx, uintptr_t stream, const double* P, int64_t rows, in
 int nsr_copy2d(nsr_ctx* ctx, uintptr_t stream, void* dst, int64_t dst_pitch, const void* src,
                int64_t src_pitch, int64_t width_bytes, int64_t height, int kind);
 
+/* Host-to-host strided copy by a team of threads (threads <= 0: all cores): the staging step between a caller's
+ * ordinary (pageable) arrays and the page-locked ring the copy engines work on, so that plain numpy input and
+ * freshly allocated numpy results run the same overlapped pipeline as page-locked buffers (a pageable
+ * cudaMemcpy stages through one driver thread at ~3 GB/s and takes the result array's page faults one by one).
+ * Replaces nothing in the reference: it is what keeps `normalisr.coex(dt, dc)` (coex.py:4) a drop-in for numpy
+ * callers.  Pitches and width in bytes; no CUDA call inside. */
+int nsr_host_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                    int64_t height, int threads);
+
 /* Asynchronous copy of nbytes from device `src_device` into this context's device on `stream` (a stream of
  * the context's device): cudaMemcpyPeerAsync, peer access enabled on first use.  No kernel, no SM: the
  * single-process multi-GPU path (normalisr_b200.parallel.coex_all_devices) pulls the digit planes of the

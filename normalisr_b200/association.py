@@ -14,10 +14,11 @@ import numpy as np
 import scipy.linalg
 import torch
 
-from . import engine
+from . import engine, hoststage
 from ._lib import MODE_COEX, MODE_DE, MODE_RAW, ENGINE_UMMA, MAX_RANK
 
-_ROW_CHUNK_BYTES = 1 << 30       # host->device staging granularity for numpy inputs
+_ROW_CHUNK_BYTES = 1 << 30       # host->device granularity for page-locked host inputs
+_STAGED_CHUNK_BYTES = 1 << 28    # ... for pageable ones (they pass through two page-locked slots of this size)
 # Streamed co-expression pipeline: row chunks of about _PIPE_CHUNK_BYTES, in multiples of _STRIP_TILES 128-row tiles.
 # Small chunks on purpose: the output that becomes final with a chunk can only leave once the chunk's strip is
 # contracted, and final output is produced fastest at the end (it grows with the square of the rows seen), so the
@@ -216,20 +217,21 @@ def _residualize_any(ctx, x, Qt_dev, n_slices, keep_coef, out=None, row_offset=0
     if out is None:
         out = engine.Sliced(rows, n, n_slices, dev)
         row_offset = 0
-    chunk = max(1, min(rows, _ROW_CHUNK_BYTES // max(1, n * 8)))
+    pageable = not xh.is_pinned()
+    chunk = max(1, min(rows, (_STAGED_CHUNK_BYTES if pageable else _ROW_CHUNK_BYTES) // max(1, n * 8)))
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     bufs = [torch.empty((chunk, n), dtype=torch.float64, device=dev) for _ in range(2)]
+    stager = hoststage.InputStager(xh, chunk, dev)           # pageable input goes through page-locked slots
     done = [None, None]
     for i, r0 in enumerate(range(0, rows, chunk)):
         r1 = min(r0 + chunk, rows)
         b = bufs[i & 1]
-        with torch.cuda.stream(copy_stream):
-            if done[i & 1] is not None:
-                copy_stream.wait_event(done[i & 1])      # buffer free again
-            b[:r1 - r0].copy_(xh[r0:r1], non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
+        if done[i & 1] is not None:
+            copy_stream.wait_event(done[i & 1])          # buffer free again
+        stager.copy_rows(b, r0, r1, copy_stream)
+        ready = torch.cuda.Event()
+        ready.record(copy_stream)
         main.wait_event(ready)
         engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=out, row_offset=row_offset + r0,
                            keep_coef=keep_coef)
@@ -306,18 +308,23 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
     d2h_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     bufs = [torch.empty((min(chunk, rows), n), dtype=torch.float64, device=dev) for _ in range(2)]
+    stager = hoststage.InputStager(xh, min(chunk, rows), dev)
+    # results into ordinary (pageable) host matrices leave through a ring of page-locked slots and a worker thread
+    drain = None
+    if out_host is not None and not all(t.is_pinned() for t in out_host):
+        widest = max(bounds[i + 1] - bounds[i] for i in range(len(bounds) - 1))
+        drain = hoststage.OutputDrain(ctx, 4 * 8 * rows * widest)
     done = [None, None]
     for i in range(len(bounds) - 1):
         r0, r1 = bounds[i], bounds[i + 1]
         b = bufs[i & 1]
-        with torch.cuda.stream(copy_stream):
-            if done[i & 1] is not None:
-                copy_stream.wait_event(done[i & 1])
-            _mark("h2d_begin", i, copy_stream)
-            b[:r1 - r0].copy_(xh[r0:r1], non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(copy_stream)
-            _mark("h2d_end", i, copy_stream)
+        if done[i & 1] is not None:
+            copy_stream.wait_event(done[i & 1])
+        _mark("h2d_begin", i, copy_stream)
+        stager.copy_rows(b, r0, r1, copy_stream)
+        ready = torch.cuda.Event()
+        ready.record(copy_stream)
+        _mark("h2d_end", i, copy_stream)
         main.wait_event(ready)
         engine.residualize(ctx, b[:r1 - r0], Qt_dev, n_slices, out=A, row_offset=r0, keep_coef=keep_coef)
         done[i & 1] = torch.cuda.Event()
@@ -332,10 +339,16 @@ def _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_
             fin = torch.cuda.Event()
             fin.record(main)
             d2h_stream.wait_event(fin)
-            for dst, src in zip(out_host, (P, D)):
-                engine.copy_block_to_host(ctx, dst, src, 0, r1, r0, r1, d2h_stream)
-                engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
+            if drain is not None:
+                drain.send(d2h_stream, [(dst[a0:a1, b0:b1], src[a0:a1, b0:b1]) for dst, src in zip(out_host, (P, D))
+                                        for a0, a1, b0, b1 in ((0, r1, r0, r1), (r0, r1, 0, r0))])
+            else:
+                for dst, src in zip(out_host, (P, D)):
+                    engine.copy_block_to_host(ctx, dst, src, 0, r1, r0, r1, d2h_stream)
+                    engine.copy_block_to_host(ctx, dst, src, r0, r1, 0, r0, d2h_stream)
             _mark("d2h_end", i, d2h_stream)
+    if drain is not None:
+        drain.close()
     if into is not None:
         main.wait_stream(copy_stream)          # the staging buffers go back to the allocator of this stream
         tail = torch.cuda.Event()
@@ -468,6 +481,11 @@ def association_tests(dx, dy, dc, bsx=0, bsy=0, nth=1, lowmem=True, return_dot=T
             if xh.dtype != torch.float64:
                 xh = xh.to(torch.float64)
             direct = out_host if (out_host is not None and lowmem and return_dot) else None
+            if direct is None and out_host is None and lowmem and return_dot:
+                # the caller gets fresh (pageable) matrices, like from the reference; they are filled block by
+                # block while the pipeline runs
+                direct = (torch.empty((dx.shape[0], dx.shape[0]), dtype=torch.float64),
+                          torch.empty((dx.shape[0], dx.shape[0]), dtype=torch.float64))
             A, P, out2 = _coex_host_pipeline(ctx, xh, Qt_dev, n_slices, n_products, dof_a, eng, keep_coef,
                                              direct)
             B = A

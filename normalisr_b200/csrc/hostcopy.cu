@@ -1,0 +1,51 @@
+// Host-side strided copy with a team of threads: the staging step between a caller's ordinary (pageable) numpy
+// arrays and the page-locked buffers the copy engines read and write.  A pageable cudaMemcpy moves ~3 GB/s here
+// (driver-internal staging, one thread; fresh result pages fault one by one): norm.coex(dt, dc) on plain numpy
+// arrays took 4.4 - 5.4 s at 100k cells x 20k genes against 0.32 s with page-locked buffers.  With this copy
+// feeding a ring of page-locked slots, the plain call runs the same three-stream pipeline.
+#include <algorithm>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "nsr_common.cuh"
+
+extern "C" int nsr_host_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t width_bytes,
+                               int64_t height, int threads) {
+    NSR_REQUIRE(dst && src && width_bytes >= 0 && height >= 0 && dst_pitch >= width_bytes && src_pitch >= width_bytes,
+                "nsr_host_copy2d: bad arguments");
+    if (width_bytes == 0 || height == 0) return 0;
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(nt, 64));
+    const int64_t total = width_bytes * height;
+    // work units of about 1 MB: whole rows when rows are long, groups of rows otherwise
+    const bool contiguous = dst_pitch == width_bytes && src_pitch == width_bytes;
+    const int64_t unit_bytes = 1 << 20;
+    if (total < 4 * unit_bytes) nt = 1;
+    auto body = [&](int t) {
+        if (contiguous) {
+            const int64_t per = (total + nt - 1) / nt;
+            const int64_t lo = std::min<int64_t>(total, (int64_t)t * per), hi = std::min<int64_t>(total, lo + per);
+            if (hi > lo) std::memcpy((char*)dst + lo, (const char*)src + lo, (size_t)(hi - lo));
+            return;
+        }
+        // rows interleaved in blocks, so that every thread touches a spread of the destination (first-touch page
+        // faults of a fresh result array are taken by all threads at once)
+        const int64_t rows_per = std::max<int64_t>(1, unit_bytes / std::max<int64_t>(1, width_bytes));
+        for (int64_t r0 = (int64_t)t * rows_per; r0 < height; r0 += (int64_t)nt * rows_per) {
+            const int64_t r1 = std::min(height, r0 + rows_per);
+            for (int64_t r = r0; r < r1; ++r)
+                std::memcpy((char*)dst + r * dst_pitch, (const char*)src + r * src_pitch, (size_t)width_bytes);
+        }
+    };
+    if (nt == 1) {
+        body(0);
+        return 0;
+    }
+    std::vector<std::thread> team;
+    team.reserve(nt - 1);
+    for (int t = 1; t < nt; ++t) team.emplace_back(body, t);
+    body(0);
+    for (auto& th : team) th.join();
+    return 0;
+}

@@ -249,3 +249,22 @@ def test_every_module_imports_without_a_gpu():
         importlib.import_module("normalisr_b200." + name)
     import normalisr_b200.normalisr as norm
     assert set(norm.__all__) == {"coex", "de", "binnet", "normvar", "lcpm", "compute_var"}
+
+
+def test_host_copy2d_thread_team():
+    """nsr_host_copy2d (the staging copy between pageable arrays and page-locked slots): strided source and
+    destination, short and long rows, one thread and many; a host function, no CUDA call inside."""
+    import torch
+    from normalisr_b200 import hoststage
+    g = torch.Generator().manual_seed(5)
+    for rows, cols, threads in ((1, 7, 0), (3000, 600, 0), (40, 300000, 3), (2500, 1100, 1), (0, 5, 0)):
+        src_big = torch.randn((rows + 3, cols + 5), generator=g, dtype=torch.float64)
+        dst_big = torch.zeros((rows + 2, cols + 9), dtype=torch.float64)
+        src, dst = src_big[2:2 + rows, 1:1 + cols], dst_big[1:1 + rows, 4:4 + cols]
+        hoststage.host_copy2d(dst, src, threads)
+        assert torch.equal(dst, src)
+        assert int((dst_big != 0).sum()) == int((src != 0).sum())           # nothing written outside the block
+    a = torch.arange(12, dtype=torch.float64).reshape(3, 4)
+    b = torch.empty_like(a)
+    hoststage.host_copy2d(b, a)
+    assert torch.equal(a, b)
