@@ -247,6 +247,17 @@ def _to_device_f64(ctx, x):
         xd = x.to(ctx.device, torch.float64)
     else:
         xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        if xh.dtype == torch.float64 and xh.dim() == 2 and xh.stride(1) == 1 and not xh.is_pinned() and xh.numel() >= (1 << 22):
+            # a large pageable matrix: through the page-locked slots, in row chunks
+            rows, n = xh.shape
+            xd = torch.empty((rows, n), dtype=torch.float64, device=ctx.device)
+            chunk = max(1, min(rows, _STAGED_CHUNK_BYTES // max(1, n * 8)))
+            stager = hoststage.InputStager(xh, chunk, ctx.device)
+            st = torch.cuda.current_stream(ctx.device)
+            for r0 in range(0, rows, chunk):
+                stager.copy_rows(xd[r0:], r0, min(rows, r0 + chunk), st)
+            st.synchronize()
+            return xd
         xd = xh.to(ctx.device, torch.float64, non_blocking=True)
     return xd if xd.stride(1) == 1 else xd.contiguous()
 

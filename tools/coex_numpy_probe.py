@@ -21,3 +21,14 @@ for rep in range(3):
     P, D, var = norm.coex(dt, dc)
     print("numpy in / numpy out: %.1f ms" % ((time.perf_counter() - t0) * 1e3), flush=True)
     del P, D
+
+# the same for de(single=4) at the CRISPRi-screen shape (config 3)
+del dt
+p = synth.device_problem(1002, 10000, 50000, dev, n_group=300, group_p=0.02, n_module=0)
+h = {k: p[k].cpu().numpy() for k in ("dg", "dt", "dc")}
+del p
+torch.cuda.empty_cache()
+for rep in range(3):
+    t0 = time.perf_counter()
+    res = norm.de(h["dg"], h["dt"], h["dc"], single=4)
+    print("de(single=4), numpy in / numpy out: %.1f ms" % ((time.perf_counter() - t0) * 1e3), flush=True)
