@@ -70,6 +70,22 @@ def pair_tiles(rows_a, rows_b, parity=None):
     return np.ascontiguousarray(tl, dtype=np.int32).reshape(-1, 2)
 
 
+def pair_strips(tl, rect, n_sub):
+    """Cut the tiles ``tl`` of one block pair (covering rows x columns ``rect`` = (a0, a1, b0, b1) of the pair) into
+    at most ``n_sub`` strips of whole tile columns: [(tiles, (a0, a1, c_lo, c_hi))], the tiles of every strip in
+    their original order, the strips' column ranges a partition of [b0, b1).  One strip = the input."""
+    a0, a1, b0, b1 = rect
+    cols = np.unique(tl[:, 1]) if len(tl) else np.zeros(0, np.int32)
+    if n_sub <= 1 or len(cols) <= 1:
+        return [(np.ascontiguousarray(tl, dtype=np.int32).reshape(-1, 2), rect)]
+    out = []
+    for part in np.array_split(cols, min(n_sub, len(cols))):
+        sel = tl[(tl[:, 1] >= part[0]) & (tl[:, 1] <= part[-1])]
+        out.append((np.ascontiguousarray(sel, dtype=np.int32).reshape(-1, 2),
+                    (a0, a1, max(b0, int(part[0]) * TILE), min(b1, (int(part[-1]) + 1) * TILE))))
+    return out
+
+
 def shared_cut(rows_lo):
     """Tile row of block lo at which a shared block pair is cut between its two owners."""
     return ((rows_lo + TILE - 1) // TILE + 1) // 2
@@ -423,15 +439,10 @@ def contract_plan(ctx, local, rounds, rank, world, n_gene, dof_a, n_products, k_
         if home is not None and len(tl) and flag_driven:
             n_sub = max(1, min(PAIR_STRIPS, (MAX_SEGMENTS - len(segs)) // max(1, n_pairs - pairs_done)))
         pairs_done += 1
-        cols = np.unique(tl[:, 1]) if len(tl) else np.zeros(0, np.int32)
-        for part in np.array_split(cols, min(n_sub, max(1, len(cols)))):
-            if n_sub > 1 and not len(part):
-                continue
-            sel = tl if n_sub == 1 else tl[(tl[:, 1] >= part[0]) & (tl[:, 1] <= part[-1])]
-            c_lo, c_hi = (b0, b1) if n_sub == 1 else (max(b0, int(part[0]) * TILE), min(b1, (int(part[-1]) + 1) * TILE))
+        for sel, rect in pair_strips(tl, (a0, a1, b0, b1), n_sub):
             segs.append(dict(sg))
-            tiles.append(np.ascontiguousarray(sel))
-            extra.append(dict(works=works, rect=(a0, a1, c_lo, c_hi), mbuf=mbuf))
+            tiles.append(sel)
+            extra.append(dict(works=works, rect=rect, mbuf=mbuf))
 
     def send(i):
         """queue the device-to-host copies of segment i on the copy stream"""

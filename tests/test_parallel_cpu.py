@@ -65,6 +65,35 @@ def test_home_rectangles_write_every_entry_exactly_once(rows, world):
     assert (count == 1).all()
 
 
+@pytest.mark.parametrize("rows_a,rows_b,parity", [(2560, 2560, None), (2560, 2440, 0), (2500, 2560, 1), (130, 100, None),
+                                                  (10000, 10000, 0), (128, 128, 1)])
+@pytest.mark.parametrize("n_sub", [1, 2, 4, 8, 50])
+def test_pair_strips_partition_tiles_and_columns(rows_a, rows_b, parity, n_sub):
+    """Column strips of a block pair (each leaves for the host as soon as it is contracted): together they hold
+    every tile of the pair once, in the original order within a strip, and their rectangles tile the pair's
+    rectangle without gaps or overlaps, each rectangle covered by its own tiles."""
+    tl = parallel.pair_tiles(rows_a, rows_b, parity)
+    rect = parallel._segment_rect(rows_a, rows_b, parity)
+    strips = parallel.pair_strips(tl, rect, n_sub)
+    assert 1 <= len(strips) <= max(1, n_sub)
+    assert sorted(map(tuple, np.concatenate([t for t, _ in strips]))) == sorted(map(tuple, tl))
+    a0, a1, b0, b1 = rect
+    if not len(tl):                                   # the other owner took the only tile row / column
+        assert strips[0][1] == rect and (a1 - a0) * (b1 - b0) == 0
+        return
+    count = np.zeros((rows_a, rows_b), dtype=np.int32)
+    for tiles, (s0, s1, c0, c1) in strips:
+        assert (s0, s1) == (a0, a1) and b0 <= c0 < c1 <= b1
+        count[s0:s1, c0:c1] += 1
+        cover = np.zeros((rows_a, rows_b), dtype=bool)
+        for ti, tj in tiles:
+            cover[ti * 128:(ti + 1) * 128, tj * 128:(tj + 1) * 128] = True
+        assert cover[s0:s1, c0:c1].all()
+        order = [tuple(x) for x in tl if c0 <= x[1] * 128 < c1]
+        assert [tuple(x) for x in tiles] == order
+    assert (count[a0:a1, b0:b1] == 1).all() and count.sum() == (a1 - a0) * (b1 - b0)
+
+
 def test_row_split():
     # equal blocks, multiples of the 128-row tile
     assert parallel.row_split(20000, 8) == 2560 and parallel.row_split(10, 4) == 128
