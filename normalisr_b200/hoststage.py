@@ -74,7 +74,11 @@ class InputStager:
         if self.events[i] is not None:
             self.events[i].synchronize()
         slot = self.slots[i][:r1 - r0]
-        host_copy2d(slot, self.src[r0:r1])
+        rows = self.src[r0:r1]
+        if rows.dtype == torch.float64 and (rows.shape[1] <= 1 or rows.stride(1) == 1):
+            host_copy2d(slot, rows)
+        else:
+            slot.copy_(rows)                       # other dtypes / column strides: torch's own (converting) copy
         with torch.cuda.stream(stream):
             dst_dev[:r1 - r0].copy_(slot, non_blocking=True)
             ev = torch.cuda.Event()

@@ -211,6 +211,22 @@ def test_de_host_genes_streamed_in_row_chunks_equal_device_path(monkeypatch, sin
     assert all(np.array_equal(a, b) for a, b in zip(pinned, host) if a is not None)
 
 
+def test_host_inputs_of_any_layout_and_pinning():
+    """Host matrices as the caller happens to hold them - C-ordered numpy (pageable: staged through page-locked slots
+    by the thread team), Fortran-ordered numpy, a transposed CPU tensor view, page-locked tensors - give the same bits."""
+    p = synth.host_problem(1023, 700, 900, n_group=8, group_p=0.1)
+    want = norm.coex(p["dt"], p["dc"])
+    variants = [np.asfortranarray(p["dt"]), torch.from_numpy(np.ascontiguousarray(p["dt"].T)).T,
+                torch.from_numpy(p["dt"]).pin_memory()]
+    for dt in variants:
+        got = norm.coex(dt, p["dc"])
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    want = norm.de(p["dg"], p["dt"], p["dc"], single=4)
+    for dt in variants:
+        got = norm.de(np.asfortranarray(p["dg"]), dt, p["dc"], single=4)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want) if a is not None)
+
+
 def test_device_tensors_in_device_tensors_out():
     g = load_golden("coex_chain")
     dt = torch.from_numpy(g["dt"]).cuda()
