@@ -13,7 +13,7 @@ numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.  The per-row procedure
 import numpy as np
 import torch
 
-from . import _lib, engine
+from . import _lib, engine, hoststage
 
 _ROW_CHUNK_BYTES = 1 << 29
 
@@ -68,17 +68,21 @@ def binnet(net, qcut, device=None):
             if src.dtype != torch.float64:
                 src = src.to(torch.float64)
             out = torch.empty((nt, nt), dtype=torch.uint8, device=ctx.device)
-            step = max(1, _ROW_CHUNK_BYTES // (8 * nt))
+            step = max(1, min(nt, min(_ROW_CHUNK_BYTES, hoststage.STAGE_BYTES) // (8 * nt)))
+            blocks = hoststage.RowBlocks(ctx, src, step, tag="binnet")       # pageable P through page-locked slots
             for r0 in range(0, nt, step):
                 r1 = min(nt, r0 + step)
-                binnet_rows(ctx, src[r0:r1].to(ctx.device, non_blocking=True), qcut, r0, out=out[r0:r1], stats=stats)
+                binnet_rows(ctx, blocks.fetch(r0, r1), qcut, r0, out=out[r0:r1], stats=stats)
         edges, invalid = (int(x) for x in stats.cpu())
         if invalid:
             raise AssertionError('net must be finite with values in [0, 1].')
         if edges == 0:
             raise RuntimeError("Empty binary network.")
         out = out.view(torch.bool)
-        return out.cpu().numpy() if to_host else out
+        if to_host:
+            from .association import _outs
+            return _outs((out,))[0]
+        return out
 
 
 def bh(pv, weight=None, device=None):

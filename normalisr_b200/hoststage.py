@@ -17,6 +17,7 @@ import torch
 
 from . import _lib
 
+STAGE_BYTES = 1 << 28      # row blocks of the host loops: each is staged through page-locked slots of this size
 _SLOTS = {}        # (tag, device index, bytes, count) -> list of page-locked uint8 tensors, kept for the next call
 
 
@@ -49,16 +50,17 @@ def pinned_slots(tag, device, nbytes, count):
 
 
 class InputStager:
-    """Rows [r0, r1) of a 2-D host float64 matrix -> a device buffer, asynchronously on a copy stream."""
+    """Rows [r0, r1) of a 2-D host matrix (any dtype) -> a device buffer of the same dtype, asynchronously on a
+    stream."""
 
     def __init__(self, src, rows_max, device, tag="in"):
         self.src = src
         self.pinned = src.is_pinned()
         self.k = 0
         if not self.pinned:
-            n = src.shape[1]
-            self.slots = [s[:rows_max * n * 8].view(torch.float64).view(rows_max, n)
-                          for s in pinned_slots(tag, device, max(1, rows_max * n * 8), 2)]
+            n, es = src.shape[1], src.element_size()
+            self.slots = [s[:rows_max * n * es].view(src.dtype).view(rows_max, n)
+                          for s in pinned_slots(tag, device, max(1, rows_max * n * es), 2)]
             self.events = [None, None]
 
     def copy_rows(self, dst_dev, r0, r1, stream):
@@ -75,7 +77,7 @@ class InputStager:
             self.events[i].synchronize()
         slot = self.slots[i][:r1 - r0]
         rows = self.src[r0:r1]
-        if rows.dtype == torch.float64 and (rows.shape[1] <= 1 or rows.stride(1) == 1):
+        if rows.shape[1] <= 1 or rows.stride(1) == 1:
             host_copy2d(slot, rows)
         else:
             slot.copy_(rows)                       # other dtypes / column strides: torch's own (converting) copy
@@ -104,16 +106,17 @@ class OutputDrain:
         self.thread.start()
 
     def send(self, stream, blocks):
-        """blocks: list of (dst host 2-D view, src device 2-D view) of equal shapes (float64, unit column stride)."""
+        """blocks: list of (dst host 2-D view, src device 2-D view) of equal shapes and dtypes (unit column stride)."""
         batch, used = [], 0
         for dst, src in blocks:
             rows, cols = src.shape
             if rows == 0 or cols == 0:
                 continue
-            rows_fit = max(1, self.slot_bytes // (cols * 8))
+            es = src.element_size()
+            rows_fit = max(1, self.slot_bytes // (cols * es))
             for a in range(0, rows, rows_fit):                 # a block larger than a slot goes in row pieces
                 b = min(rows, a + rows_fit)
-                nb = (b - a) * cols * 8
+                nb = -(-((b - a) * cols * es) // 16) * 16       # keep every piece 16-byte aligned in the slot
                 if used + nb > self.slot_bytes and batch:
                     self._flush(stream, batch)
                     batch, used = [], 0
@@ -131,9 +134,10 @@ class OutputDrain:
         lib = self.ctx.lib
         for dst, src, nb in batch:
             rows, cols = src.shape
-            stage = slot[off:off + nb].view(torch.float64).view(rows, cols)
-            _lib.check(lib.nsr_copy2d(self.ctx.handle, stream.cuda_stream, stage.data_ptr(), cols * 8, src.data_ptr(),
-                                      (src.stride(0) if rows > 1 else cols) * 8, cols * 8, rows, 0), "nsr_copy2d")
+            es = src.element_size()
+            stage = slot[off:off + rows * cols * es].view(src.dtype).view(rows, cols)
+            _lib.check(lib.nsr_copy2d(self.ctx.handle, stream.cuda_stream, stage.data_ptr(), cols * es, src.data_ptr(),
+                                      (src.stride(0) if rows > 1 else cols) * es, cols * es, rows, 0), "nsr_copy2d")
             parts.append((dst, stage))
             off += nb
         ev = torch.cuda.Event()
@@ -160,3 +164,29 @@ class OutputDrain:
         self.thread.join()
         if self.error is not None:
             raise self.error
+
+
+class RowBlocks:
+    """The row-block loop of the functions around the hot path (normvar, lcpm, compute_var, binnet) on HOST
+    matrices: ``fetch(g0, g1)`` returns rows [g0, g1) of the source on the device (pageable sources through the
+    page-locked slots), ``store(dst_rows, res_dev)`` sends a result block to its rows of a pageable host matrix
+    through the drain, ``close()`` waits for everything."""
+
+    def __init__(self, ctx, src, rows_max, out_row_bytes=0, tag="blocks"):
+        self.ctx = ctx
+        self.src = src
+        self.stager = InputStager(src, rows_max, ctx.device, tag=tag + "-in")
+        self.drain = OutputDrain(ctx, max(1 << 20, rows_max * out_row_bytes), count=2, tag=tag + "-out") \
+            if out_row_bytes else None
+
+    def fetch(self, g0, g1):
+        dst = torch.empty((g1 - g0, self.src.shape[1]), dtype=self.src.dtype, device=self.ctx.device)
+        self.stager.copy_rows(dst, g0, g1, torch.cuda.current_stream(self.ctx.device))
+        return dst
+
+    def store(self, dst_rows, res_dev):
+        self.drain.send(torch.cuda.current_stream(self.ctx.device), [(dst_rows, res_dev)])
+
+    def close(self):
+        if self.drain is not None:
+            self.drain.close()

@@ -21,7 +21,7 @@ import logging
 import numpy as np
 import torch
 
-from . import _lib, engine
+from . import _lib, engine, hoststage
 
 _ROW_CHUNK_BYTES = 1 << 30
 
@@ -91,16 +91,18 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
     itemsize = src.element_size()
     resample = varscale != 0
     with torch.cuda.device(dev):
-        step = max(1, _ROW_CHUNK_BYTES // max(1, itemsize * nc)) if to_host else nt
+        step = max(1, min(nt, min(_ROW_CHUNK_BYTES, hoststage.STAGE_BYTES) // max(1, 8 * nc))) if to_host else nt
         blocks = [(g0, min(nt, g0 + step)) for g0 in range(0, nt, step)]
         single = len(blocks) == 1
         held = {}
+        n_out = 1 + (0 if lowmem else 2)
+        stage = hoststage.RowBlocks(ctx, src, step, out_row_bytes=8 * nc * n_out, tag="lcpm") if to_host else None
 
         def block(i):
             g0, g1 = blocks[i]
             if i in held:
                 return held[i]
-            blk = src[g0:g1].to(dev, non_blocking=True) if to_host else src[g0:g1]
+            blk = stage.fetch(g0, g1) if to_host else src[g0:g1]
             if single:
                 held[i] = blk
             return blk
@@ -212,7 +214,7 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                        "nsr_lcpm_apply")
             engine.LAUNCHES += 1
             if host_out:
-                out[g0:g1] = res.cpu()
+                stage.store(out[g0:g1], res)
             if not lowmem:
                 if resample:
                     m = torch.empty((g1 - g0, nc), dtype=torch.float64, device=dev)
@@ -224,10 +226,16 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
                     v = lut_var[blk.long().clamp_(0, lut_var.numel() - 1)] * float(varscale)
                 else:
                     m, v = res, None
-                dmean[g0:g1] = m.cpu() if host_out else m
-                if v is not None:
-                    dvar[g0:g1] = v.cpu() if host_out else v
+                if host_out:
+                    stage.store(dmean[g0:g1], m)
+                    if v is not None:
+                        stage.store(dvar[g0:g1], v)
+                else:
+                    dmean[g0:g1] = m
+                    if v is not None:
+                        dvar[g0:g1] = v
         if to_host:
+            stage.close()
             torch.cuda.current_stream().synchronize()
             return (out.numpy(), None if dmean is None else dmean.numpy(), None if dvar is None else dvar.numpy(),
                     None if dcov is None else dcov.cpu().numpy())

@@ -14,7 +14,7 @@ third pass.  numpy in -> numpy out, CUDA tensors in -> CUDA tensors out.
 import numpy as np
 import torch
 
-from . import _lib, engine
+from . import _lib, engine, hoststage
 
 _ROW_CHUNK_BYTES = 1 << 30
 _CENTRED = {}              # device index -> (key, (Qc, rank), tensor): basis of the centred covariates (compute_var)
@@ -315,8 +315,11 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
         # expression, in row blocks (genes are independent)
         if to_host:
             src = dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt))
+            if src.dtype != torch.float64:
+                src = src.to(torch.float64)
             dtn = torch.empty((nt, ns), dtype=torch.float64)
-            step = max(1, _ROW_CHUNK_BYTES // (8 * ns))
+            step = max(1, min(nt, min(_ROW_CHUNK_BYTES, hoststage.STAGE_BYTES) // (8 * ns)))
+            blocks = hoststage.RowBlocks(ctx, src, step, out_row_bytes=8 * ns, tag="normvar")
         else:
             src = dt.to(torch.float64)
             if src.stride(1) != 1:
@@ -330,7 +333,7 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
             gi_d = torch.from_numpy(gi).to(dev)
         for g0 in range(0, nt, step):
             g1 = min(nt, g0 + step)
-            blk = src[g0:g1].to(dev, torch.float64, non_blocking=True) if to_host else src[g0:g1]
+            blk = blocks.fetch(g0, g1) if to_host else src[g0:g1]
             if wide:
                 res = _normvar_rows_wide(blk, dc_d, logw, wt_d[g0:g1].contiguous(), keepvar,
                                          gram_block(g0, g1) if use_cheb else None,
@@ -344,7 +347,9 @@ def normvar(dt, dc, w, wt, dextra=None, cat=1, nth=1, bs=500, keepvar=True, norm
                 cf, _ = engine.project_coef(ctx, res, dcn.contiguous())
                 res.addmm_(cf @ gi_d, dcn, alpha=-1.0)
             if to_host:
-                dtn[g0:g1] = res.cpu()
+                blocks.store(dtn[g0:g1], res)
+        if to_host:
+            blocks.close()
         # every deferred check in one read
         chk = torch.stack([torch.stack(flags["zero_rank"]).any(), torch.stack(flags["finite"]).all(),
                            torch.isfinite(dcn).all(),
@@ -393,7 +398,10 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
     with torch.cuda.device(dev):
         dc_d = _dev64(dc, dev).contiguous()
         src = dt if not to_host else (dt if isinstance(dt, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(dt)))
-        step = nt if not to_host else max(1, _ROW_CHUNK_BYTES // (8 * ns))
+        if to_host and src.dtype != torch.float64:
+            src = src.to(torch.float64)
+        step = nt if not to_host else max(1, min(nt, min(_ROW_CHUNK_BYTES, hoststage.STAGE_BYTES) // (8 * ns)))
+        blocks = hoststage.RowBlocks(ctx, src, step, tag="compute_var") if to_host else None
         ones = torch.ones((1, ns), dtype=torch.float64, device=dev)
         # log-linear fit with intercept (:104-105, on the UNSCALED covariates): mean + projection on the centred covariates
         ckey = basis_cache_key(ctx, dc_d, tag='centred')
@@ -414,7 +422,7 @@ def compute_var(dt, dc, stepmax=1, eps=1E-6, device=None):
             col = torch.zeros(ns, dtype=torch.float64, device=dev)
             for g0 in range(0, nt, step):
                 g1 = min(nt, g0 + step)
-                blk = src[g0:g1].to(dev, torch.float64, non_blocking=True)
+                blk = blocks.fetch(g0, g1) if to_host else src[g0:g1].to(dev, torch.float64, non_blocking=True)
                 if inv is not None:
                     blk = blk * inv                                               # :99
                 if blk.stride(1) != 1:
