@@ -24,6 +24,7 @@ import torch
 from . import _lib, engine, hoststage
 
 _ROW_CHUNK_BYTES = 1 << 30
+_HOLD_BYTES = 1 << 35          # host counts up to this size are copied to the device once for both passes
 
 
 def _is_dev(x):
@@ -95,6 +96,8 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
         blocks = [(g0, min(nt, g0 + step)) for g0 in range(0, nt, step)]
         single = len(blocks) == 1
         held = {}
+        # both passes read the counts: a host matrix that fits comfortably stays on the device in between
+        keep_on_device = to_host and nt * nc * itemsize <= _HOLD_BYTES
         n_out = 1 + (0 if lowmem else 2)
         stage = hoststage.RowBlocks(ctx, src, step, out_row_bytes=8 * nc * n_out, tag="lcpm") if to_host else None
 
@@ -103,7 +106,7 @@ def lcpm(reads, normalize=True, nth=0, ntot=None, varscale=0, seed=None, lowmem=
             if i in held:
                 return held[i]
             blk = stage.fetch(g0, g1) if to_host else src[g0:g1]
-            if single:
+            if single or keep_on_device:
                 held[i] = blk
             return blk
 

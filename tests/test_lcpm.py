@@ -47,8 +47,10 @@ def test_oracle_lcpm_resampling_matches_reference():
 def test_lcpm_golden(monkeypatch):
     from normalisr_b200 import lcpm as lc, normalisr as norm
     g = load_golden("lcpm_counts")
-    for chunk in (1 << 30, 8 * 300 * 50):                           # one block / several row blocks
+    for chunk, hold in ((1 << 30, 1 << 35), (8 * 300 * 50, 1 << 35), (8 * 300 * 50, 0)):
+        # one block / several row blocks kept on the device between the passes / several blocks fetched twice
         monkeypatch.setattr(lc, "_ROW_CHUNK_BYTES", chunk)
+        monkeypatch.setattr(lc, "_HOLD_BYTES", hold)
         out = norm.lcpm(g["reads"])
         assert isinstance(out[0], np.ndarray) and out[1] is None and out[2] is None
         np.testing.assert_allclose(out[0], g["lcpm"], rtol=1e-12, atol=1e-12)
