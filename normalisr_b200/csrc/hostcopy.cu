@@ -43,9 +43,17 @@ extern "C" int nsr_host_copy2d(void* dst, int64_t dst_pitch, const void* src, in
         return 0;
     }
     std::vector<std::thread> team;
+    std::vector<int> own;                        // shares this thread copies itself (its own, and any whose thread
+    own.push_back(0);                            // could not be started: no exception leaves an extern "C" function)
     team.reserve(nt - 1);
-    for (int t = 1; t < nt; ++t) team.emplace_back(body, t);
-    body(0);
+    for (int t = 1; t < nt; ++t) {
+        try {
+            team.emplace_back(body, t);
+        } catch (...) {
+            own.push_back(t);
+        }
+    }
+    for (int t : own) body(t);
     for (auto& th : team) th.join();
     return 0;
 }
