@@ -21,6 +21,16 @@ _CENTRED = {}              # device index -> (key, (Qc, rank), tensor): basis of
 _USE_CHEBYSHEV = True      # test hook: False = Gram matrices from the streaming pass (nsr_normvar_stats)
 
 
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device, priority=-1)
+    return _SIDE[key]
+
+
 def _is_dev(x):
     return isinstance(x, torch.Tensor) and x.is_cuda
 
@@ -199,10 +209,20 @@ def _normvar_rows(ctx, dt_d, dc_d, design, logw, wt_d, keepvar, G=None, out=None
     if G is not None:
         C16 = design
         stats = torch.empty((genes, 18), dtype=torch.float64, device=dt_d.device)
+        cur = torch.cuda.current_stream(dt_d.device)
+        inputs_ready = torch.cuda.Event()
+        inputs_ready.record(cur)
         _lib.check(ctx.lib.nsr_normvar_rhs(ctx.handle, engine._stream(), dt_d.data_ptr(), genes, n, ld, C16.data_ptr(),
                                            C16.stride(0), logw.data_ptr(), wt_d.data_ptr(), stats.data_ptr()),
                    "nsr_normvar_rhs")
-        G = G()
+        # the Gram matrices do not depend on the statistics kernel: their ~60 small launches run on a high-priority
+        # side stream, in the gaps of that kernel instead of behind it
+        side = _side_stream(dt_d.device)
+        side.wait_event(inputs_ready)
+        with torch.cuda.stream(side):
+            G = G()
+        cur.wait_stream(side)
+        G.record_stream(cur)
         b = stats[:, :nc]
         s1, s2 = stats[:, 16], stats[:, 17]
     else:
