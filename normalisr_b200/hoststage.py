@@ -49,6 +49,11 @@ def pinned_slots(tag, device, nbytes, count):
     return _SLOTS[head + (nbytes,)]
 
 
+def release():
+    """Give the page-locked rings back (they are otherwise kept for the next call: up to ~1.5 GB per device)."""
+    _SLOTS.clear()
+
+
 class InputStager:
     """Rows [r0, r1) of a 2-D host matrix (any dtype) -> a device buffer of the same dtype, asynchronously on a
     stream."""
