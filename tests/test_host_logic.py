@@ -268,3 +268,27 @@ def test_host_copy2d_thread_team():
     b = torch.empty_like(a)
     hoststage.host_copy2d(b, a)
     assert torch.equal(a, b)
+
+
+def test_constant_rows_filter_and_single4_keyword_rules():
+    """de.py:92-93 (len(np.unique(x)) > 1 per grouping) without full passes over the matrix; the inv_rank keywords
+    single=4 accepts (those under which the reference computes the exact pseudo-inverse)."""
+    from normalisr_b200 import de as de_mod, single4
+    rng = np.random.default_rng(2)
+    d = (rng.random((40, 9000)) < 0.01).astype(float)
+    d[3] = 0
+    d[5] = 1
+    d[7] = 0
+    d[7, -1] = 2.5                                   # differs only in the last column
+    d[9] = -3.25
+    want = np.array([len(np.unique(x)) > 1 for x in d])
+    assert np.array_equal(de_mod._rows_that_vary(d), want)
+    assert np.array_equal(de_mod._rows_that_vary(d[:, :1]), np.zeros(40, dtype=bool))
+    assert de_mod._rows_that_vary(np.zeros((3, 0))).tolist() == [False] * 3
+    for ka in (dict(), dict(mpc=0), dict(mpc=12, method="scipy"), dict(mpc=500, qr=3), dict(method="auto")):
+        ka = dict(ka)
+        single4._exact_inverse_only(ka, 12)
+        assert not ka                                 # consumed
+    for ka in (dict(mpc=11), dict(method="sklearn"), dict(mpc=3, method="scipy")):
+        with pytest.raises(NotImplementedError):
+            single4._exact_inverse_only(dict(ka), 12)
