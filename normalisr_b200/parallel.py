@@ -14,7 +14,14 @@ The path shards naturally:
     flight.  The older schedule ("allgather": one all-gather, then a strip of tile rows per rank)
     is kept for comparison;
   * no further communication: rank r ends with the rows of its block of P / dot for the column
-    blocks it owns; ``gather_dense`` mirrors them into the full symmetric matrices.
+    blocks it owns; ``gather_dense`` mirrors them into the full symmetric matrices;
+  * one result for one caller (``home``): every GPU also writes the transposes of what it computes and copies
+    its rectangles straight into ONE (n_gene, n_gene) host P and dot - under torchrun a page-locked mapping
+    shared by the ranks (``coex_host`` + ``shared_host_matrices``), from one process the caller's own arrays
+    (``coex_all_devices``, one worker thread per GPU; ``de_all_devices`` for de);
+  * host inputs: the diagonal block of a rank is contracted in strips while its rows are still arriving
+    (``diag_block_streamed``), and block pairs leave for the host in column strips with their own completion
+    counters (``pair_strips``), so copy-in, tensor work and copy-out overlap.
 Because the sums over cells are exact integers, every schedule gives bit-identical results.
 """
 import logging
