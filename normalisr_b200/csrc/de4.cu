@@ -15,7 +15,7 @@
 // Kernels (all float64, fixed summation orders):
 //   gemm_f64_kernel        C = op(A) op(B), 64 x 64 tiles, 4 x 4 per thread, optional split over K
 //   chol_panel / chol_update  blocked right-looking Cholesky, 32-column panels
-//   tri_inverse_kernel     L^-1, one warp per column
+//   tri_inverse_(smem_)kernel  L^-1, one warp per column (the column in shared memory up to n = 3,200)
 //   de4_colsum / de4_finish   the closed form above + the P-value
 #include "epilogue.cuh"
 
@@ -236,6 +236,74 @@ tri_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double*
     }
 }
 
+// The same substitution with the column being built kept in shared memory (8 columns x n doubles per CTA): the
+// dependent chain of a step is a shared-memory read, a shuffle tree and a division instead of a round trip through
+// L2 for what the previous step wrote.  Same lane partition, same tree, same arithmetic: identical bits.
+__global__ void __launch_bounds__(256)
+tri_inverse_smem_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __restrict__ Linv, int64_t ldi) {
+    extern __shared__ double s_cols[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * 8 + warp;
+    if (j >= n) return;
+    double* x = s_cols + (int64_t)warp * n;
+    for (int64_t i = lane; i < j; i += 32) Linv[i * ldi + j] = 0.0;
+    if (lane == 0) x[j] = 1.0 / L[j * ldl + j];
+    __syncwarp();
+    for (int64_t i = j + 1; i < n; ++i) {
+        const double diag = L[i * ldl + i];                       // (not on the dependent chain)
+        double s = 0.0;
+        for (int64_t k = j + lane; k < i; k += 32) s = fma(L[i * ldl + k], x[k], s);
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0) x[i] = -s / diag;
+        __syncwarp();
+    }
+    for (int64_t i = j + lane; i < n; i += 32) Linv[i * ldi + j] = x[i];
+}
+
+// ... and with the next row of L already on its way while a step's chain (shared-memory reads, shuffle tree,
+// division) runs: the row segments live in registers, MAXK per lane (n <= 32 MAXK).  Terms beyond the row's length
+// are fma(0, 0, s) = s, so the sums are the same bits as above.
+template <int MAXK>
+__global__ void __launch_bounds__(256)
+tri_inverse_pipe_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __restrict__ Linv, int64_t ldi) {
+    extern __shared__ double s_cols[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * 8 + warp;
+    if (j >= n) return;
+    double* x = s_cols + (int64_t)warp * n;
+    for (int64_t i = lane; i < j; i += 32) Linv[i * ldi + j] = 0.0;
+    if (lane == 0) x[j] = 1.0 / L[j * ldl + j];
+    __syncwarp();
+    double cur[MAXK], nxt[MAXK], dcur = 1.0, dnxt = 1.0;
+    auto load_row = [&](int64_t i, double (&v)[MAXK], double& dg) {
+#pragma unroll
+        for (int m = 0; m < MAXK; ++m) {
+            const int64_t k = j + lane + 32 * m;
+            v[m] = k < i ? L[i * ldl + k] : 0.0;
+        }
+        dg = L[i * ldl + i];
+    };
+    if (j + 1 < n) load_row(j + 1, cur, dcur);
+    for (int64_t i = j + 1; i < n; ++i) {
+        if (i + 1 < n) load_row(i + 1, nxt, dnxt);
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < MAXK; ++m) {
+            const int64_t k = j + lane + 32 * m;
+            s = fma(cur[m], k < i ? x[k] : 0.0, s);
+        }
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+        if (lane == 0) x[i] = -s / dcur;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MAXK; ++m) cur[m] = nxt[m];
+        dcur = dnxt;
+    }
+    for (int64_t i = j + lane; i < n; i += 32) Linv[i * ldi + j] = x[i];
+}
+
 __global__ void diag_kernel(const double* __restrict__ K, int64_t n, int64_t ldk, double* __restrict__ kd) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) kd[i] = K[i * ldk + i];
@@ -429,7 +497,21 @@ extern "C" int nsr_de4_solve(nsr_ctx* ctx, uintptr_t stream, double* Gxx, int nx
             chol_update_kernel<<<dim3(tb, tb), 256, 0, st>>>(Gxx, n, n, k0, nb);
         }
     }
-    tri_inverse_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(Gxx, n, n, Linv, n);
+    if (8 * n * (int64_t)sizeof(double) <= 200 * 1024) {
+        const int smem = (int)(8 * n * sizeof(double));
+        const unsigned blocks = (unsigned)((n + 7) / 8);
+        if (n <= 320) {
+            tri_inverse_pipe_kernel<10><<<blocks, 256, smem, st>>>(Gxx, n, n, Linv, n);
+        } else if (n <= 640) {
+            NSR_CHECK(cudaFuncSetAttribute(tri_inverse_pipe_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            tri_inverse_pipe_kernel<20><<<blocks, 256, smem, st>>>(Gxx, n, n, Linv, n);
+        } else {
+            NSR_CHECK(cudaFuncSetAttribute(tri_inverse_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            tri_inverse_smem_kernel<<<blocks, 256, smem, st>>>(Gxx, n, n, Linv, n);
+        }
+    } else {
+        tri_inverse_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(Gxx, n, n, Linv, n);
+    }
     NSR_CHECK(cudaGetLastError());
     // K = Linv^T Linv (symmetric), w = K Gxy
     if (launch_gemm(ctx, st, Linv, 1, n, Linv, n, 1, K, n, n, n, n, 0, 1.0, nullptr, 0, 0.0, work, n_work)) return 1;
