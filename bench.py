@@ -442,6 +442,26 @@ def run_ours(args, n_gene, n_cell, wl_name, wl_desc):
                            "per rank (/dev/shm too small for a shared one)") if schedule == "pairs" else
                        "normalisr_b200.parallel.coex_host(dt_block_host, dc, n_gene)")}
 
+        # the same call as a user of the reference makes it: ordinary (pageable) numpy arrays in, fresh numpy
+        # arrays out; informational, not the headline (the contract's e2e uses page-locked input)
+        if single and e2e_steps >= 2 and not args.no_numpy_e2e:
+            try:
+                dt_np = np.empty(tuple(dt_host.shape), dtype=np.float64)
+                dt_np[...] = dt_host.numpy()
+                del P_host, D_host
+                norm.coex(dt_np, dc_np, precision=precision)
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    res_np = norm.coex(dt_np, dc_np, precision=precision)
+                sec_np = (time.perf_counter() - t0) / 2
+                e2e["numpy_in_numpy_out"] = {"value": pairs / sec_np, "unit": UNIT, "ms_per_step": 1e3 * sec_np, "steps": 2,
+                                             "api": "normalisr_b200.normalisr.coex(dt, dc) on pageable numpy arrays, fresh "
+                                                    "numpy P / dot / var returned (staged through page-locked slots by a "
+                                                    "host thread team)"}
+                del res_np, dt_np
+            except Exception as e:
+                e2e["numpy_in_numpy_out"] = {"error": repr(e)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1101,6 +1121,7 @@ def main():
     ap.add_argument("--transport", default=None, choices=["nccl", "ce", "auto"],
                     help="multi-GPU plane exchange: NCCL send/recv or copy-engine pulls from peer-mapped memory")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numpy-e2e", action="store_true", help="skip the informational pageable-numpy end-to-end call")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-de", action="store_true", help="skip the secondary DE tests/s measurement")
     ap.add_argument("--umma-pair", type=int, default=None, help="test hook: 1 = cta_group::2 kernel, 0 = single-CTA")
